@@ -1,0 +1,219 @@
+/*
+ * powerpaint_b200.h — C ABI of the B200-native PowerPaint denoising hot path.
+ *
+ * The reference (open-mmlab/PowerPaint) is pure Python over diffusers; it has no FFI of
+ * its own. The boundary a maintainer binds is therefore the set of *operators* its
+ * per-step hot path executes, each entry point citing the reference call site it
+ * replaces (paths relative to the reference checkout):
+ *
+ *   pp_gemm_conv      nn.Conv2d 3x3 / 1x1 and nn.Linear inside ResnetBlock2D,
+ *                     Transformer2DModel, Downsample2D, Upsample2D, conv_in/conv_out,
+ *                     BrushNet zero-convs  (powerpaint/models/unet_2d_blocks.py:789,807,
+ *                     1274,1289,1319,1428,2499,2514,2542,2672,2689;
+ *                     unet_2d_condition.py:256,477; BrushNet_CA.py:223-228,330-376,446-454)
+ *                     with bias / time-embedding broadcast / skip add / BrushNet add /
+ *                     output scale / GEGLU fused into the epilogue
+ *                     (unet_2d_condition.py:1223,1300; unet_2d_blocks.py:1388-1398,2627-2638)
+ *   pp_attention      Attention + AttnProcessor2_0 -> F.scaled_dot_product_attention
+ *                     (processors referenced at unet_2d_condition.py:24-31)
+ *   pp_group_norm     nn.GroupNorm(32)+SiLU in ResnetBlock2D / Transformer2DModel.norm /
+ *                     conv_norm_out (unet_2d_condition.py:466,1351-1353), also performs the
+ *                     up-path torch.cat (unet_2d_blocks.py:2589,2732) while normalising
+ *   pp_layer_norm     nn.LayerNorm x3 per BasicTransformerBlock
+ *   pp_upsample2x     Upsample2D's F.interpolate(scale_factor=2, mode="nearest")
+ *   pp_time_embed     Timesteps(320, flip_sin_to_cos=True, shift=0)
+ *                     (unet_2d_condition.py:914-938)
+ *   pp_cfg_ddim_step  CFG combine + DDIMScheduler.step + next-step input build
+ *                     (pipelines/pipeline_PowerPaint.py:990-996,1018-1023;
+ *                      pipeline_PowerPaint_Brushnet_CA.py:1390,1444-1449)
+ *   pp_program_*      a recorded list of the above, replayed per denoising step
+ *                     (the `for i, t in enumerate(timesteps)` loops,
+ *                      pipeline_PowerPaint.py:988-1041, Brushnet_CA.py:1384-1466,
+ *                      ControlNet.py:1663-1741)
+ *
+ * Conventions: all pointers are DEVICE pointers unless named host_*; activations are
+ * bf16, channels-last (NHWC == [batch, tokens, channels]); every call enqueues on the
+ * given cudaStream_t and never synchronises the host; no allocation happens inside a
+ * call; a non-zero return code means nothing was enqueued and pp_last_error() holds the
+ * reason. Handles are thread-compatible (one thread per handle at a time).
+ */
+#ifndef POWERPAINT_B200_H_
+#define POWERPAINT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int pp_status; /* 0 = ok, 1 = invalid argument, 2 = CUDA error, 3 = unsupported */
+typedef void* pp_stream; /* cudaStream_t */
+
+const char* pp_last_error(void);
+/* ABI version of this library (bumped on incompatible struct changes). */
+int pp_abi_version(void);
+/* 1 if the current device is sm_100 (B200) and the kernels can run on it. */
+int pp_device_supported(void);
+
+/* ------------------------------------------------------------------ GEMM / conv */
+enum {
+    PP_A_MATRIX = 0,    /* A is [M, K] row-major (a Linear or 1x1 conv over tokens) */
+    PP_A_CONV3X3 = 1,   /* implicit GEMM, 3x3 stride 1 pad 1 over NHWC [nb, h, w, c] */
+    PP_A_CONV3X3_S2 = 2 /* implicit GEMM, 3x3 stride 2 pad 1 (Downsample2D); h, w even */
+};
+enum {
+    PP_EPI_PLAIN = 0,
+    PP_EPI_GEGLU = 1,      /* out[:, j] = (acc_a + bias_a) * gelu(acc_g + bias_g); weights tile-interleaved */
+    PP_EPI_TRANSPOSED = 2  /* out[(m / t_rows) * N + n][m % t_rows], row pitch t_ld (V^T for attention) */
+};
+enum { PP_ACT_NONE = 0, PP_ACT_SILU = 1 };
+
+typedef struct pp_gemm_desc {
+    int32_t a_mode;
+    int32_t epilogue;
+    /* A operand: up to two sources concatenated along K / channels (skip-concat without torch.cat) */
+    const void* a0;
+    const void* a1;      /* may be NULL */
+    int32_t c0, c1;      /* channels (K per tap) of each source; c1 = 0 if a1 is NULL */
+    int64_t lda0, lda1;  /* PP_A_MATRIX: row pitch in elements; conv modes: ignored (tight NHWC) */
+    int32_t nb, h, w;    /* conv modes: INPUT batch / height / width */
+    int32_t M;           /* PP_A_MATRIX: rows. conv modes: ignored (= nb*ho*wo) */
+    int32_t N;           /* GEMM N (for GEGLU: 2x the output width) */
+    /* B operand: weights [N, Kw] bf16 row-major, Kw = taps * (pad64(c0) + pad64(c1)) when
+       taps == 9 or a1 != NULL, else row pitch ldb >= c0 */
+    const void* b;
+    int64_t ldb;
+    /* epilogue: v = acc + bias[n] + rowvec[m / rows_per_group][n] + res1[m][n];
+                 v = v * alpha + res2[m][n]; v = act(v) */
+    const float* bias;
+    const float* rowvec;
+    int32_t rows_per_group;
+    const void* res1; /* bf16 */
+    int64_t ldr1;
+    const void* res2; /* bf16 */
+    int64_t ldr2;
+    float alpha;
+    int32_t act;
+    void* out;
+    int64_t ldc;
+    int32_t out_fp32; /* 0: bf16 output, 1: fp32 output */
+    int32_t t_rows;   /* PP_EPI_TRANSPOSED */
+    int64_t t_ld;
+    int32_t block_n;  /* 0 = auto, else one of 64/128/160/256 */
+} pp_gemm_desc;
+
+pp_status pp_gemm_conv(const pp_gemm_desc* d, pp_stream stream);
+
+/* ------------------------------------------------------------------ attention */
+typedef struct pp_attn_desc {
+    /* q: [batch, nq, heads, d] with token pitch q_ld (elements); k likewise with nk, k_ld.
+       vt: V transposed, [batch, heads*d, vt_ld] (keys contiguous, vt_ld >= nk, vt_ld % 8 == 0).
+       out: [batch, nq, heads*d] row pitch o_ld. softmax(q k^T * scale) v, no mask. */
+    const void* q;
+    const void* k;
+    const void* vt;
+    void* out;
+    int32_t batch, heads, d, nq, nk;
+    int64_t q_ld, k_ld, vt_ld, o_ld;
+    int64_t q_batch_stride, k_batch_stride; /* elements between batches */
+    float scale;
+} pp_attn_desc;
+
+pp_status pp_attention(const pp_attn_desc* d, pp_stream stream);
+
+/* ------------------------------------------------------------------ norms */
+typedef struct pp_gn_desc {
+    /* GroupNorm over NHWC x = concat(x0[..., :c0], x1[..., :c1]) -> y [.., c0+c1] bf16 */
+    const void* x0;
+    const void* x1; /* may be NULL */
+    int32_t c0, c1;
+    int32_t batch, hw, groups;
+    const float* gamma;
+    const float* beta;
+    float eps;
+    int32_t silu;
+    float* stats; /* scratch [batch, groups, 2] fp32; zeroed by the call */
+    void* y;
+} pp_gn_desc;
+pp_status pp_group_norm(const pp_gn_desc* d, pp_stream stream);
+
+pp_status pp_layer_norm(const void* x, void* y, const float* gamma, const float* beta,
+                        int32_t rows, int32_t c, float eps, pp_stream stream);
+
+/* ------------------------------------------------------------------ small ops */
+/* nearest 2x upsample of NHWC bf16 [nb,h,w,c] -> [nb,2h,2w,c] */
+pp_status pp_upsample2x(const void* x, void* y, int32_t nb, int32_t h, int32_t w, int32_t c,
+                        pp_stream stream);
+/* y = a + b (bf16, n elements, n % 8 == 0) — ControlNet skip residuals */
+pp_status pp_add(const void* a, const void* b, void* y, int64_t n, pp_stream stream);
+/* sinusoidal timestep embedding [batch, dim] bf16: cat(cos, sin) (flip_sin_to_cos=True, shift 0).
+   t comes from timesteps[*step_idx] when step_idx != NULL, else timesteps[0..batch). */
+pp_status pp_time_embed(const float* timesteps, const int32_t* step_idx, void* out, int32_t batch,
+                        int32_t dim, pp_stream stream);
+/* NCHW fp32 <-> NHWC bf16 (c padded to c_pad with zeros on the way in) */
+pp_status pp_nchw_to_nhwc(const float* x, void* y, int32_t nb, int32_t c, int32_t hw,
+                          int32_t c_pad, pp_stream stream);
+pp_status pp_nhwc_to_nchw(const void* x, int32_t x_is_fp32, float* y, int32_t nb, int32_t c,
+                          int32_t hw, int32_t c_ld, pp_stream stream);
+
+/* ------------------------------------------------------------------ CFG + DDIM */
+typedef struct pp_cfg_ddim_desc {
+    /* eps: model output for the 2*batch CFG-duplicated samples (unconditional half first),
+       NHWC [2*batch, hw, eps_ld] (fp32 or bf16), channels 0..3 used.
+       latents: fp32 NHWC [batch, hw, 4], updated in place (x_t -> x_{t-1}).
+       coef: [n_steps, 8] fp32 rows {sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2),
+             sigma, 0, 0, 0}; row *step_idx is used, then *step_idx is incremented when
+             advance_step != 0 (so a captured CUDA graph can be replayed once per step).
+       noise: optional fp32 NHWC [batch, hw, 4] variance noise (eta > 0).
+       next_in: optional bf16 NHWC [n_copies*batch, hw, next_c]: channels 0..3 = x_{t-1},
+             channels 4..4+extra_c = extra[b] (mask + masked-image latents, fp32 NHWC
+             [batch, hw, extra_c]), rest zero; written for both CFG halves. */
+    const void* eps;
+    int32_t eps_fp32;
+    int32_t eps_ld;
+    float* latents;
+    const float* coef;
+    int32_t* step_idx;
+    int32_t advance_step;
+    const float* noise;
+    float guidance_scale;
+    int32_t do_cfg; /* 0: eps has `batch` samples and is used as is */
+    int32_t batch, hw;
+    void* next_in;
+    int32_t next_c, n_copies;
+    const float* extra;
+    int32_t extra_c;
+} pp_cfg_ddim_desc;
+pp_status pp_cfg_ddim_step(const pp_cfg_ddim_desc* d, pp_stream stream);
+
+/* ------------------------------------------------------------------ programs */
+/* A program records op descriptors once (tensor maps are encoded at record time) and
+   replays them with one call per denoising step; it can be instantiated as a CUDA graph. */
+typedef struct pp_program pp_program;
+pp_status pp_program_create(pp_program** out);
+void pp_program_destroy(pp_program* p);
+pp_status pp_program_add_gemm(pp_program* p, const pp_gemm_desc* d);
+pp_status pp_program_add_attention(pp_program* p, const pp_attn_desc* d);
+pp_status pp_program_add_group_norm(pp_program* p, const pp_gn_desc* d);
+pp_status pp_program_add_layer_norm(pp_program* p, const void* x, void* y, const float* gamma,
+                                    const float* beta, int32_t rows, int32_t c, float eps);
+pp_status pp_program_add_upsample2x(pp_program* p, const void* x, void* y, int32_t nb, int32_t h,
+                                    int32_t w, int32_t c);
+pp_status pp_program_add_add(pp_program* p, const void* a, const void* b, void* y, int64_t n);
+pp_status pp_program_add_time_embed(pp_program* p, const float* timesteps,
+                                    const int32_t* step_idx, void* out, int32_t batch, int32_t dim);
+pp_status pp_program_add_cfg_ddim(pp_program* p, const pp_cfg_ddim_desc* d);
+pp_status pp_program_add_memset(pp_program* p, void* ptr, int64_t bytes);
+int32_t pp_program_num_ops(const pp_program* p);
+/* number of kernel launches one run enqueues */
+int32_t pp_program_num_launches(const pp_program* p);
+/* enqueue every recorded op on `stream` (plain launches) */
+pp_status pp_program_run(pp_program* p, pp_stream stream);
+/* capture the program into a CUDA graph (once), then replay it with pp_program_graph_launch */
+pp_status pp_program_graph_build(pp_program* p, pp_stream stream);
+pp_status pp_program_graph_launch(pp_program* p, pp_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POWERPAINT_B200_H_ */

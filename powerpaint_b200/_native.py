@@ -1,0 +1,148 @@
+"""ctypes binding of include/powerpaint_b200.h (the C-ABI boundary).
+
+The product path has no CPU fallback: if the shared library is missing or cannot be
+loaded, `lib()` raises, and every op raises `RuntimeError` with `pp_last_error()` on a
+non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "libpowerpaint_b200.so"
+_lib = None
+
+# enums (mirror include/powerpaint_b200.h)
+PP_A_MATRIX, PP_A_CONV3X3, PP_A_CONV3X3_S2 = 0, 1, 2
+PP_EPI_PLAIN, PP_EPI_GEGLU, PP_EPI_TRANSPOSED = 0, 1, 2
+PP_ACT_NONE, PP_ACT_SILU = 0, 1
+
+vp = C.c_void_p
+i32 = C.c_int32
+i64 = C.c_int64
+f32 = C.c_float
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("a_mode", i32), ("epilogue", i32),
+        ("a0", vp), ("a1", vp),
+        ("c0", i32), ("c1", i32),
+        ("lda0", i64), ("lda1", i64),
+        ("nb", i32), ("h", i32), ("w", i32),
+        ("M", i32), ("N", i32),
+        ("b", vp), ("ldb", i64),
+        ("bias", vp), ("rowvec", vp), ("rows_per_group", i32),
+        ("res1", vp), ("ldr1", i64),
+        ("res2", vp), ("ldr2", i64),
+        ("alpha", f32), ("act", i32),
+        ("out", vp), ("ldc", i64),
+        ("out_fp32", i32), ("t_rows", i32), ("t_ld", i64),
+        ("block_n", i32),
+    ]
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("q", vp), ("k", vp), ("vt", vp), ("out", vp),
+        ("batch", i32), ("heads", i32), ("d", i32), ("nq", i32), ("nk", i32),
+        ("q_ld", i64), ("k_ld", i64), ("vt_ld", i64), ("o_ld", i64),
+        ("q_batch_stride", i64), ("k_batch_stride", i64),
+        ("scale", f32),
+    ]
+
+
+class GnDesc(C.Structure):
+    _fields_ = [
+        ("x0", vp), ("x1", vp), ("c0", i32), ("c1", i32),
+        ("batch", i32), ("hw", i32), ("groups", i32),
+        ("gamma", vp), ("beta", vp), ("eps", f32), ("silu", i32),
+        ("stats", vp), ("y", vp),
+    ]
+
+
+class CfgDdimDesc(C.Structure):
+    _fields_ = [
+        ("eps", vp), ("eps_fp32", i32), ("eps_ld", i32),
+        ("latents", vp), ("coef", vp), ("step_idx", vp), ("advance_step", i32),
+        ("noise", vp), ("guidance_scale", f32), ("do_cfg", i32),
+        ("batch", i32), ("hw", i32),
+        ("next_in", vp), ("next_c", i32), ("n_copies", i32),
+        ("extra", vp), ("extra_c", i32),
+    ]
+
+
+# every exported symbol of include/powerpaint_b200.h with (restype, argtypes)
+_SIGNATURES = {
+    "pp_last_error": (C.c_char_p, []),
+    "pp_abi_version": (C.c_int, []),
+    "pp_device_supported": (C.c_int, []),
+    "pp_gemm_conv": (C.c_int, [C.POINTER(GemmDesc), vp]),
+    "pp_attention": (C.c_int, [C.POINTER(AttnDesc), vp]),
+    "pp_group_norm": (C.c_int, [C.POINTER(GnDesc), vp]),
+    "pp_layer_norm": (C.c_int, [vp, vp, vp, vp, i32, i32, f32, vp]),
+    "pp_upsample2x": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
+    "pp_add": (C.c_int, [vp, vp, vp, i64, vp]),
+    "pp_time_embed": (C.c_int, [vp, vp, vp, i32, i32, vp]),
+    "pp_nchw_to_nhwc": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
+    "pp_nhwc_to_nchw": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, vp]),
+    "pp_cfg_ddim_step": (C.c_int, [C.POINTER(CfgDdimDesc), vp]),
+    "pp_program_create": (C.c_int, [C.POINTER(vp)]),
+    "pp_program_destroy": (None, [vp]),
+    "pp_program_add_gemm": (C.c_int, [vp, C.POINTER(GemmDesc)]),
+    "pp_program_add_attention": (C.c_int, [vp, C.POINTER(AttnDesc)]),
+    "pp_program_add_group_norm": (C.c_int, [vp, C.POINTER(GnDesc)]),
+    "pp_program_add_layer_norm": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, f32]),
+    "pp_program_add_upsample2x": (C.c_int, [vp, vp, vp, i32, i32, i32, i32]),
+    "pp_program_add_add": (C.c_int, [vp, vp, vp, vp, i64]),
+    "pp_program_add_time_embed": (C.c_int, [vp, vp, vp, vp, i32, i32]),
+    "pp_program_add_cfg_ddim": (C.c_int, [vp, C.POINTER(CfgDdimDesc)]),
+    "pp_program_add_memset": (C.c_int, [vp, vp, i64]),
+    "pp_program_num_ops": (i32, [vp]),
+    "pp_program_num_launches": (i32, [vp]),
+    "pp_program_run": (C.c_int, [vp, vp]),
+    "pp_program_graph_build": (C.c_int, [vp, vp]),
+    "pp_program_graph_launch": (C.c_int, [vp, vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def lib():
+    """Load (once) and return the C-ABI library; raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise RuntimeError(
+                f"{_LIB_PATH} is not built: run `python -m powerpaint_b200.build` "
+                "(there is no CPU fallback for the hot path)"
+            )
+        L = C.CDLL(str(_LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = lib().pp_last_error()
+        raise RuntimeError(f"powerpaint_b200 native call failed ({what} status {status}): "
+                           f"{msg.decode() if msg else '?'}")
+
+
+def ptr(t) -> int | None:
+    """data_ptr of a torch tensor (or None)."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

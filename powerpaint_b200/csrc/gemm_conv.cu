@@ -1,0 +1,593 @@
+// tcgen05 GEMM / implicit-GEMM convolution for the PowerPaint UNet hot path (sm_100a).
+//
+//   D[M, N] = epilogue( A[M, K] * W[N, K]^T )        bf16 operands, fp32 accumulate in TMEM
+//
+// One kernel serves every dense contraction of the per-step UNet / BrushNet forward
+// (reference call sites: nn.Linear / nn.Conv2d inside ResnetBlock2D, Transformer2DModel,
+// Downsample2D, Upsample2D — powerpaint/models/unet_2d_blocks.py:789,807,1274,1289,1319,
+// 1428,2499,2514,2542,2672,2689 — conv_in / conv_out unet_2d_condition.py:256,477, and the
+// BrushNet zero-convs BrushNet_CA.py:330-376,446-454):
+//
+//  * A operand. PP_A_MATRIX: 2-D TMA tiles of a token-major matrix. PP_A_CONV3X3: the
+//    activation stays NHWC in HBM and each of the 9 filter taps is one 4-D TMA box
+//    (64 channels x bw x bh x bn pixels) shifted by the tap offset; the halo and every
+//    ragged edge (channels, width, height, batch) are zero-filled by TMA's out-of-bounds
+//    rule, so there is no im2col buffer and no padding copy. PP_A_CONV3X3_S2 (Downsample2D)
+//    uses four parity-plane tensor maps so a stride-2 tap is again a dense box.
+//    Up to two A sources are walked back to back along K: the up-path skip concat
+//    (unet_2d_blocks.py:2589,2732) never materialises.
+//  * B operand: weights [N, K] K-major, K ordered (tap, source, channel) to match.
+//  * Pipeline: warp 0 = TMA producer, warp 1 = single-thread tcgen05.mma issuer,
+//    warps 2..5 = epilogue (tcgen05.ld -> registers -> global). STAGES-deep smem ring with
+//    full/empty mbarriers; tcgen05.commit releases ring slots and publishes the accumulator.
+//    Two CTAs co-reside per SM for the 128/160-wide tiles so one CTA's epilogue overlaps the
+//    other's main loop.
+//  * Epilogue (fused): + bias[n] + time-embedding row vector + residual (skip / shortcut)
+//    → × alpha (1/output_scale_factor or BrushNet conditioning_scale) → + second residual
+//    (BrushNet / ControlNet feature injection, unet_2d_condition.py:1223,1300) → SiLU /
+//    GEGLU gate → bf16 or fp32 store, optionally transposed (V^T for the attention kernel).
+#include <algorithm>
+
+#include "common.cuh"
+#include "ops.h"
+
+namespace pp {
+
+static constexpr int BLOCK_M = 128;
+static constexpr int BLOCK_K = 64;
+static constexpr int UMMA_K = 16;
+static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+static constexpr int GEMM_THREADS = 192;
+
+__host__ __device__ constexpr int tmem_cols_for(int n) {
+    return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    return act == PP_ACT_SILU ? silu_f(v) : v;
+}
+
+// Epilogue for 8 consecutive output columns of one row. v[] holds acc (+ nothing yet).
+template <bool kVec>
+__device__ __forceinline__ void epilogue_store8(const GemmKParams& p, float (&v)[8], int64_t row,
+                                                int grp, int n0) {
+    // bias
+    if (p.bias) {
+        if (kVec) {
+            float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0));
+            float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
+        }
+    }
+    if (p.rowvec) {
+        const float* rv = p.rowvec + (int64_t)grp * p.N + n0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (kVec || n0 + j < p.N) v[j] += __ldg(rv + j);
+    }
+    if (p.res1) {
+        const __nv_bfloat16* r = p.res1 + row * p.ldr1 + n0;
+        if (kVec) {
+            uint4 q = __ldg(reinterpret_cast<const uint4*>(r));
+            v[0] += bf16_lo(q.x); v[1] += bf16_hi(q.x); v[2] += bf16_lo(q.y); v[3] += bf16_hi(q.y);
+            v[4] += bf16_lo(q.z); v[5] += bf16_hi(q.z); v[6] += bf16_lo(q.w); v[7] += bf16_hi(q.w);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (n0 + j < p.N) v[j] += __bfloat162float(r[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= p.alpha;
+    if (p.res2) {
+        const __nv_bfloat16* r = p.res2 + row * p.ldr2 + n0;
+        if (kVec) {
+            uint4 q = __ldg(reinterpret_cast<const uint4*>(r));
+            v[0] += bf16_lo(q.x); v[1] += bf16_hi(q.x); v[2] += bf16_lo(q.y); v[3] += bf16_hi(q.y);
+            v[4] += bf16_lo(q.z); v[5] += bf16_hi(q.z); v[6] += bf16_lo(q.w); v[7] += bf16_hi(q.w);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (n0 + j < p.N) v[j] += __bfloat162float(r[j]);
+        }
+    }
+    if (p.act != PP_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act);
+    }
+    if (p.epilogue == PP_EPI_TRANSPOSED) {
+        // out[(row / t_rows) * N + n][row % t_rows]; lanes of a warp hold consecutive rows,
+        // so each per-column store is a 64-byte contiguous run across the warp.
+        const int64_t b = row / p.t_rows;
+        const int64_t t = row - b * p.t_rows;
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (b * p.N + n0) * p.t_ld + t;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (kVec || n0 + j < p.N) o[(int64_t)j * p.t_ld] = __float2bfloat16_rn(v[j]);
+        return;
+    }
+    if (p.out_fp32) {
+        float* o = reinterpret_cast<float*>(p.out) + row * p.ldc + n0;
+        if (kVec) {
+            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (n0 + j < p.N) o[j] = v[j];
+        }
+    } else {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + n0;
+        if (kVec) {
+            uint4 q;
+            q.x = pack_bf16x2(v[0], v[1]);
+            q.y = pack_bf16x2(v[2], v[3]);
+            q.z = pack_bf16x2(v[4], v[5]);
+            q.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(o) = q;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (n0 + j < p.N) o[j] = __float2bfloat16_rn(v[j]);
+        }
+    }
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_conv_kernel(const __grid_constant__ GemmKParams p) {
+    constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+    constexpr int TMEM_COLS = tmem_cols_for(BLOCK_N);
+    constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = smem_base;
+    const uint32_t sB = sA + STAGES * A_STAGE_BYTES;
+    const uint32_t bar_base = sB + STAGES * B_STAGE_BYTES;
+    // barriers: full[STAGES], empty[STAGES], tmem_full; then the TMEM base address slot
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+    uint32_t* tmem_slot_ptr =
+        reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int m_tile = blockIdx.x;
+    const int n_tile = blockIdx.y;
+
+    // tile origin
+    int x0 = 0, y0 = 0, nb0 = 0;
+    if (p.a_mode != PP_A_MATRIX) {
+        const int tx = m_tile % p.tiles_x;
+        const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+        const int tn = m_tile / (p.tiles_x * p.tiles_y);
+        x0 = tx * p.bw;
+        y0 = ty * p.bh;
+        nb0 = tn * p.bn;
+    }
+
+    if (warp == 0 && elect_one()) {
+        prefetch_tmap(&p.tmA[0]);
+        prefetch_tmap(&p.tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int num_k_iters = p.num_k_iters;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            const int cpt = p.chunks0 + p.chunks1;  // chunks per tap
+            for (int it = 0; it < num_k_iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_arrive_expect_tx(full_bar(s), p.a_bytes + B_STAGE_BYTES);
+                const uint32_t dstA = sA + s * A_STAGE_BYTES;
+                const uint32_t dstB = sB + s * B_STAGE_BYTES;
+                const int tap = it / cpt;
+                const int ch = it - tap * cpt;
+                const int src = ch >= p.chunks0 ? 1 : 0;
+                const int cc = (src ? ch - p.chunks0 : ch) * BLOCK_K;
+                if (p.a_mode == PP_A_MATRIX) {
+                    tma_load_2d(dstA, &p.tmA[src], full_bar(s), cc, m_tile * BLOCK_M);
+                } else if (p.a_mode == PP_A_CONV3X3) {
+                    const int ky = tap / 3, kx = tap - ky * 3;
+                    tma_load_4d(dstA, &p.tmA[src], full_bar(s), cc, x0 + kx - 1, y0 + ky - 1, nb0);
+                } else {
+                    // stride 2: input (2*oy + ky - 1, 2*ox + kx - 1) = parity plane (py, px) at
+                    // (oy + dy, ox + dx) with d = -1 for k == 0 else 0, parity = (k != 1)
+                    const int ky = tap / 3, kx = tap - ky * 3;
+                    const int py = (ky != 1), px = (kx != 1);
+                    const int dy = (ky == 0) ? -1 : 0, dx = (kx == 0) ? -1 : 0;
+                    tma_load_4d(dstA, &p.tmA[py * 2 + px], full_bar(s), cc, x0 + dx, y0 + dy, nb0);
+                }
+                tma_load_2d(dstB, &p.tmB, full_bar(s), it * BLOCK_K, n_tile * BLOCK_N);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            for (int it = 0; it < num_k_iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint64_t da = umma_desc_kmajor_sw128(sA + s * A_STAGE_BYTES);
+                const uint64_t db = umma_desc_kmajor_sw128(sB + s * B_STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    umma_bf16_ss(tmem_base, umma_desc_advance_k(da, k * UMMA_K),
+                                 umma_desc_advance_k(db, k * UMMA_K), IDESC, (it | k) != 0);
+                }
+                umma_commit(empty_bar(s));  // frees the smem slot once these MMAs retire
+            }
+            umma_commit(tmem_full_bar);  // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue warps =====================
+        const int quarter = warp & 3;  // TMEM lanes this warp may read: [32*quarter, +32)
+        const int r = quarter * 32 + lane_id();  // accumulator row handled by this thread
+        // output row for this thread
+        bool valid;
+        int64_t row;
+        int grp;
+        if (p.a_mode == PP_A_MATRIX) {
+            row = (int64_t)m_tile * BLOCK_M + r;
+            valid = row < p.M;
+            grp = p.rowvec ? (int)(row / p.rows_per_group) : 0;
+        } else {
+            const int ix = r % p.bw;
+            const int iy = (r / p.bw) % p.bh;
+            const int in = r / (p.bw * p.bh);
+            const int ox = x0 + ix, oy = y0 + iy, on = nb0 + in;
+            valid = in < p.bn && ox < p.wo && oy < p.ho && on < p.nb;
+            row = ((int64_t)on * p.ho + oy) * p.wo + ox;
+            grp = on;
+        }
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const int n_base = n_tile * BLOCK_N;
+        if (p.epilogue == PP_EPI_GEGLU) {
+            constexpr int HALF = BLOCK_N / 2;
+            const int o_base = n_tile * HALF;  // output column of this tile
+            const int n_out = p.N / 2;
+#pragma unroll 1
+            for (int c0 = 0; c0 < HALF; c0 += 16) {
+                uint32_t ra[16], rg[16];
+                tmem_ld16(taddr + c0, ra);
+                tmem_ld16(taddr + HALF + c0, rg);
+                tmem_wait_ld();
+                if (valid && o_base + c0 < n_out) {
+#pragma unroll
+                    for (int h8 = 0; h8 < 16; h8 += 8) {
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float a = __uint_as_float(ra[h8 + j]);
+                            float g = __uint_as_float(rg[h8 + j]);
+                            if (p.bias) {
+                                a += __ldg(p.bias + n_base + c0 + h8 + j);
+                                g += __ldg(p.bias + n_base + HALF + c0 + h8 + j);
+                            }
+                            v[j] = a * gelu_erf_f(g);
+                        }
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + o_base + c0 + h8;
+                        uint4 q;
+                        q.x = pack_bf16x2(v[0], v[1]);
+                        q.y = pack_bf16x2(v[2], v[3]);
+                        q.z = pack_bf16x2(v[4], v[5]);
+                        q.w = pack_bf16x2(v[6], v[7]);
+                        *reinterpret_cast<uint4*>(o) = q;
+                    }
+                }
+            }
+        } else {
+            const bool vec_ok = (p.N % 8 == 0);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t acc[32];
+                tmem_ld32(taddr + c0, acc);
+                tmem_wait_ld();
+                if (valid) {
+#pragma unroll
+                    for (int g8 = 0; g8 < 32; g8 += 8) {
+                        const int n0 = n_base + c0 + g8;
+                        if (n0 >= p.N) break;
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g8 + j]);
+                        if (vec_ok && n0 + 8 <= p.N)
+                            epilogue_store8<true>(p, v, row, grp, n0);
+                        else
+                            epilogue_store8<false>(p, v, row, grp, n0);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int pad64(int c) { return ceil_div(c, 64) * 64; }
+
+template <int BLOCK_N, int STAGES>
+static size_t gemm_smem_bytes() {
+    return (size_t)STAGES * (A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2) + 8 * (2 * STAGES + 2) + 1024;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_variant(const GemmLaunch& l, cudaStream_t s) {
+    gemm_conv_kernel<BLOCK_N, STAGES><<<l.grid, GEMM_THREADS, l.smem, s>>>(l.p);
+    PP_CUDA_CHECK(cudaGetLastError());
+    return PP_OK;
+}
+
+// opt the kernel variant into its dynamic shared memory size (done at prepare time so that
+// launches are pure and can be stream-captured)
+template <int BLOCK_N, int STAGES>
+static int ensure_attr() {
+    static bool done = false;
+    if (!done) {
+        PP_CUDA_CHECK(cudaFuncSetAttribute(gemm_conv_kernel<BLOCK_N, STAGES>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)gemm_smem_bytes<BLOCK_N, STAGES>()));
+        done = true;
+    }
+    return PP_OK;
+}
+
+static int ensure_attr_for(int block_n) {
+    switch (block_n) {
+        case 64: return ensure_attr<64, 4>();
+        case 128: return ensure_attr<128, 3>();
+        case 160: return ensure_attr<160, 3>();
+        case 256: return ensure_attr<256, 4>();
+    }
+    return PP_ERR_INVALID;
+}
+
+int gemm_launch(const GemmLaunch& l, cudaStream_t s) {
+    switch (l.block_n) {
+        case 64: return launch_variant<64, 4>(l, s);
+        case 128: return launch_variant<128, 3>(l, s);
+        case 160: return launch_variant<160, 3>(l, s);
+        case 256: return launch_variant<256, 4>(l, s);
+    }
+    set_last_error("gemm_launch: unsupported block_n %d", l.block_n);
+    return PP_ERR_INVALID;
+}
+
+static size_t smem_for_block_n(int bn) {
+    switch (bn) {
+        case 64: return gemm_smem_bytes<64, 4>();
+        case 128: return gemm_smem_bytes<128, 3>();
+        case 160: return gemm_smem_bytes<160, 3>();
+        case 256: return gemm_smem_bytes<256, 4>();
+    }
+    return 0;
+}
+
+static int pick_block_n(int N, int m_tiles, bool geglu) {
+    const int cands[4] = {256, 160, 128, 64};
+    if (N <= 64) return 64;
+    // smallest padded N first, then the widest tile that still fills the machine
+    int best = 0, best_pad = 1 << 30;
+    for (int c : cands) {
+        if (geglu && c == 64) continue;
+        int padn = ceil_div(N, c) * c;
+        if (padn < best_pad) best_pad = padn;
+    }
+    for (int c : cands) {
+        if (geglu && c == 64) continue;
+        int padn = ceil_div(N, c) * c;
+        if (padn != best_pad) continue;
+        if (!best) best = c;  // widest with minimal padding
+        if (m_tiles * (padn / c) >= 148) return c;
+    }
+    // cannot fill the machine: prefer the most tiles among minimal-padding candidates
+    int most = best, most_tiles = 0;
+    for (int c : cands) {
+        if (geglu && c == 64) continue;
+        int padn = ceil_div(N, c) * c;
+        if (padn > best_pad + best_pad / 8) continue;
+        int t = m_tiles * (padn / c);
+        if (t > most_tiles) { most_tiles = t; most = c; }
+    }
+    return most;
+}
+
+int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
+    GemmLaunch l;
+    memset(&l, 0, sizeof(l));
+    GemmKParams& p = l.p;
+    PP_REQUIRE(d.a_mode >= PP_A_MATRIX && d.a_mode <= PP_A_CONV3X3_S2, "gemm: bad a_mode %d", d.a_mode);
+    PP_REQUIRE(d.epilogue >= PP_EPI_PLAIN && d.epilogue <= PP_EPI_TRANSPOSED, "gemm: bad epilogue %d", d.epilogue);
+    PP_REQUIRE(d.a0 && d.b && d.out, "gemm: null operand pointer");
+    PP_REQUIRE(d.c0 > 0 && d.c0 % 8 == 0, "gemm: c0=%d must be a positive multiple of 8", d.c0);
+    PP_REQUIRE((d.a1 == nullptr) == (d.c1 == 0), "gemm: a1/c1 mismatch");
+    PP_REQUIRE(d.c1 % 8 == 0, "gemm: c1=%d must be a multiple of 8", d.c1);
+    PP_REQUIRE(d.N > 0, "gemm: N must be positive");
+    const int taps = d.a_mode == PP_A_MATRIX ? 1 : 9;
+    const bool packed_k = taps == 9 || d.a1 != nullptr;
+    p.a_mode = d.a_mode;
+    p.chunks0 = ceil_div(d.c0, 64);
+    p.chunks1 = d.a1 ? ceil_div(d.c1, 64) : 0;
+    p.num_k_iters = taps * (p.chunks0 + p.chunks1);
+    const int64_t kw = packed_k ? (int64_t)taps * (pad64(d.c0) + pad64(d.c1)) : d.c0;
+    const int64_t ldb = packed_k ? kw : d.ldb;
+    PP_REQUIRE(ldb >= kw && ldb % 8 == 0, "gemm: ldb=%lld invalid for K=%lld", (long long)ldb, (long long)kw);
+
+    int m_tiles;
+    if (d.a_mode == PP_A_MATRIX) {
+        PP_REQUIRE(d.M > 0, "gemm: M must be positive");
+        PP_REQUIRE(d.lda0 >= d.c0 && d.lda0 % 8 == 0, "gemm: lda0=%lld invalid", (long long)d.lda0);
+        p.M = d.M;
+        m_tiles = ceil_div(d.M, BLOCK_M);
+        p.a_bytes = A_STAGE_BYTES;
+        uint64_t dims[2] = {(uint64_t)d.c0, (uint64_t)d.M};
+        uint64_t str[1] = {(uint64_t)d.lda0 * 2};
+        uint32_t box[2] = {64, BLOCK_M};
+        int rc = make_tmap_bf16(&p.tmA[0], d.a0, 2, dims, str, box, true);
+        if (rc) return rc;
+        if (d.a1) {
+            PP_REQUIRE(d.lda1 >= d.c1 && d.lda1 % 8 == 0, "gemm: lda1=%lld invalid", (long long)d.lda1);
+            uint64_t dims1[2] = {(uint64_t)d.c1, (uint64_t)d.M};
+            uint64_t str1[1] = {(uint64_t)d.lda1 * 2};
+            rc = make_tmap_bf16(&p.tmA[1], d.a1, 2, dims1, str1, box, true);
+            if (rc) return rc;
+        }
+    } else {
+        PP_REQUIRE(d.nb > 0 && d.h > 0 && d.w > 0, "gemm: conv dims must be positive");
+        const bool s2 = d.a_mode == PP_A_CONV3X3_S2;
+        if (s2) {
+            PP_REQUIRE(d.h % 2 == 0 && d.w % 2 == 0, "gemm: stride-2 conv needs even h, w (got %d x %d)", d.h, d.w);
+            PP_REQUIRE(d.a1 == nullptr, "gemm: stride-2 conv takes a single source");
+        }
+        p.nb = d.nb;
+        p.ho = s2 ? d.h / 2 : d.h;
+        p.wo = s2 ? d.w / 2 : d.w;
+        p.M = d.nb * p.ho * p.wo;
+        // pick the pixel box (bw, bh, bn), bw*bh*bn <= 128, minimising padded volume
+        int64_t best_cost = -1;
+        for (int bw = 128; bw >= 1; bw >>= 1) {
+            for (int bh = 128 / bw; bh >= 1; bh >>= 1) {
+                int bn = 128 / (bw * bh);
+                int64_t cost = (int64_t)ceil_div(p.wo, bw) * ceil_div(p.ho, bh) * ceil_div(p.nb, bn);
+                if (best_cost < 0 || cost < best_cost) {
+                    best_cost = cost;
+                    p.bw = bw; p.bh = bh; p.bn = bn;
+                }
+            }
+        }
+        p.tiles_x = ceil_div(p.wo, p.bw);
+        p.tiles_y = ceil_div(p.ho, p.bh);
+        m_tiles = p.tiles_x * p.tiles_y * ceil_div(p.nb, p.bn);
+        p.a_bytes = (uint32_t)(p.bw * p.bh * p.bn) * 128u;
+        uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+        if (!s2) {
+            const void* srcs[2] = {d.a0, d.a1};
+            const int cs[2] = {d.c0, d.c1};
+            for (int i = 0; i < 2; ++i) {
+                if (!srcs[i]) continue;
+                uint64_t dims[4] = {(uint64_t)cs[i], (uint64_t)d.w, (uint64_t)d.h, (uint64_t)d.nb};
+                uint64_t str[3] = {(uint64_t)cs[i] * 2, (uint64_t)cs[i] * 2 * d.w, (uint64_t)cs[i] * 2 * d.w * d.h};
+                int rc = make_tmap_bf16(&p.tmA[i], srcs[i], 4, dims, str, box, true);
+                if (rc) return rc;
+            }
+        } else {
+            for (int py = 0; py < 2; ++py)
+                for (int px = 0; px < 2; ++px) {
+                    const __nv_bfloat16* base =
+                        reinterpret_cast<const __nv_bfloat16*>(d.a0) + ((int64_t)py * d.w + px) * d.c0;
+                    uint64_t dims[4] = {(uint64_t)d.c0, (uint64_t)d.w / 2, (uint64_t)d.h / 2, (uint64_t)d.nb};
+                    uint64_t str[3] = {(uint64_t)d.c0 * 2 * 2, (uint64_t)d.c0 * 2 * d.w * 2,
+                                       (uint64_t)d.c0 * 2 * d.w * d.h};
+                    int rc = make_tmap_bf16(&p.tmA[py * 2 + px], base, 4, dims, str, box, true);
+                    if (rc) return rc;
+                }
+        }
+    }
+    p.N = d.N;
+    const bool geglu = d.epilogue == PP_EPI_GEGLU;
+    int bn = d.block_n ? d.block_n : pick_block_n(d.N, m_tiles, geglu);
+    PP_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "gemm: block_n %d unsupported", bn);
+    if (geglu) {
+        PP_REQUIRE(d.N % bn == 0, "gemm: GEGLU needs N %% block_n == 0 (N=%d, block_n=%d)", d.N, bn);
+        PP_REQUIRE(!d.out_fp32 && !d.rowvec && !d.res1 && !d.res2, "gemm: GEGLU epilogue takes bias only");
+        PP_REQUIRE(d.ldc % 8 == 0, "gemm: GEGLU ldc must be a multiple of 8");
+    }
+    l.block_n = bn;
+    {
+        uint64_t dims[2] = {(uint64_t)kw, (uint64_t)d.N};
+        uint64_t str[1] = {(uint64_t)ldb * 2};
+        uint32_t box[2] = {64, (uint32_t)bn};
+        int rc = make_tmap_bf16(&p.tmB, d.b, 2, dims, str, box, true);
+        if (rc) return rc;
+    }
+    // epilogue
+    p.epilogue = d.epilogue;
+    p.act = d.act;
+    p.out_fp32 = d.out_fp32;
+    p.bias = d.bias;
+    p.rowvec = d.rowvec;
+    p.rows_per_group = d.rows_per_group;
+    if (d.rowvec && d.a_mode == PP_A_MATRIX)
+        PP_REQUIRE(d.rows_per_group > 0, "gemm: rowvec needs rows_per_group > 0");
+    p.res1 = reinterpret_cast<const __nv_bfloat16*>(d.res1);
+    p.ldr1 = d.ldr1;
+    p.res2 = reinterpret_cast<const __nv_bfloat16*>(d.res2);
+    p.ldr2 = d.ldr2;
+    p.alpha = d.alpha;
+    p.out = d.out;
+    p.ldc = d.ldc;
+    p.t_rows = d.t_rows;
+    p.t_ld = d.t_ld;
+    if (d.epilogue == PP_EPI_TRANSPOSED) {
+        PP_REQUIRE(d.t_rows > 0 && d.t_ld >= d.t_rows, "gemm: transposed store needs t_rows/t_ld");
+        PP_REQUIRE(!d.out_fp32, "gemm: transposed store is bf16 only");
+    } else {
+        PP_REQUIRE(d.ldc >= (geglu ? d.N / 2 : d.N), "gemm: ldc=%lld too small", (long long)d.ldc);
+        if (d.N % 8 == 0) {
+            PP_REQUIRE(d.ldc % (d.out_fp32 ? 4 : 8) == 0, "gemm: ldc=%lld breaks 16-byte store alignment", (long long)d.ldc);
+            PP_REQUIRE((reinterpret_cast<uintptr_t>(d.out) & 15) == 0, "gemm: out pointer not 16-byte aligned");
+        }
+    }
+    if (d.N % 8 == 0) {
+        if (d.res1) PP_REQUIRE(d.ldr1 % 8 == 0 && (reinterpret_cast<uintptr_t>(d.res1) & 15) == 0, "gemm: res1 alignment");
+        if (d.res2) PP_REQUIRE(d.ldr2 % 8 == 0 && (reinterpret_cast<uintptr_t>(d.res2) & 15) == 0, "gemm: res2 alignment");
+        if (d.bias) PP_REQUIRE((reinterpret_cast<uintptr_t>(d.bias) & 15) == 0, "gemm: bias alignment");
+    }
+    l.grid = dim3((unsigned)m_tiles, (unsigned)ceil_div(d.N, bn), 1);
+    l.smem = smem_for_block_n(bn);
+    {
+        int rc = ensure_attr_for(bn);
+        if (rc) return rc;
+    }
+    *out = l;
+    return PP_OK;
+}
+
+}  // namespace pp
+
+extern "C" pp_status pp_gemm_conv(const pp_gemm_desc* d, pp_stream stream) {
+    if (!d) {
+        pp::set_last_error("pp_gemm_conv: null descriptor");
+        return pp::PP_ERR_INVALID;
+    }
+    pp::GemmLaunch l;
+    int rc = pp::gemm_prepare(*d, &l);
+    if (rc) return rc;
+    return pp::gemm_launch(l, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,264 @@
+// GroupNorm(+SiLU)(+channel concat) and LayerNorm over channels-last bf16 activations.
+//
+// Reference semantics: nn.GroupNorm(groups, C, eps, affine=True) followed by SiLU in
+// ResnetBlock2D (norm1/norm2), Transformer2DModel.norm (eps 1e-6, no SiLU) and
+// conv_norm_out (powerpaint/models/unet_2d_condition.py:466,1351-1353); nn.LayerNorm(C)
+// x3 per BasicTransformerBlock. Statistics are biased (divide by count), computed in fp32.
+//
+// These kernels are HBM-bound: GroupNorm reads x twice (stats pass + apply pass; the second
+// read is normally an L2 hit on B200's 126 MB L2) and writes y once; LayerNorm reads once
+// (row held in registers) and writes once. Algorithmic bytes: GN 2*|x|*2B (+1 re-read),
+// LN 2*|x|*2B.
+//
+// GroupNorm also performs the up-path `torch.cat([hidden, skip], dim=1)`
+// (unet_2d_blocks.py:2589,2732): it normalises over the virtual concat of two sources and
+// writes one dense tensor, so the concat never exists un-normalised.
+#include "common.cuh"
+#include "ops.h"
+
+namespace pp {
+
+// ------------------------------------------------------------------------------------
+// GroupNorm pass 1: per-(sample, group) sum and sum of squares.
+// grid = (chunks, batch); block = CV * k threads where CV = C/8 channel vectors; each thread
+// owns one 8-channel vector and strides over pixels, so loads are 16-byte and coalesced along
+// channels. Per-thread partials are folded per group through shared-memory atomics, then one
+// global atomicAdd per (group, stat) per block.
+// ------------------------------------------------------------------------------------
+__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, const __nv_bfloat16* __restrict__ x1,
+                                int c0, int c1, int hw, int groups, int pix_per_block,
+                                float* __restrict__ stats) {
+    extern __shared__ float sh[];  // [groups][2]
+    const int C = c0 + c1;
+    const int CV = C / 8;
+    const int cpg = C / groups;
+    const int n = blockIdx.y;
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    const int lanes = blockDim.x / CV;  // pixel lanes
+    const int cv = threadIdx.x % CV;
+    const int pl = threadIdx.x / CV;
+    if (pl < lanes) {
+        const int c = cv * 8;
+        const __nv_bfloat16* src;
+        int cs, co;
+        if (c < c0) { src = x0; cs = c0; co = c; } else { src = x1; cs = c1; co = c - c0; }
+        const int p_begin = blockIdx.x * pix_per_block;
+        const int p_end = min(hw, p_begin + pix_per_block);
+        float s[8], ss[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
+        for (int p = p_begin + pl; p < p_end; p += lanes) {
+            uint4 q = __ldg(reinterpret_cast<const uint4*>(src + ((int64_t)n * hw + p) * cs + co));
+            float v[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
+                          bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s[j] += v[j]; ss[j] += v[j] * v[j]; }
+        }
+        // fold the 8 channels into their groups (a vector may straddle a group boundary)
+        int g_prev = c / cpg;
+        float as = 0.f, ass = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = (c + j) / cpg;
+            if (g != g_prev) {
+                atomicAdd(&sh[g_prev * 2], as);
+                atomicAdd(&sh[g_prev * 2 + 1], ass);
+                as = 0.f; ass = 0.f; g_prev = g;
+            }
+            as += s[j]; ass += ss[j];
+        }
+        atomicAdd(&sh[g_prev * 2], as);
+        atomicAdd(&sh[g_prev * 2 + 1], ass);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
+        atomicAdd(&stats[(int64_t)n * groups * 2 + i], sh[i]);
+}
+
+// GroupNorm pass 2: y = (x - mean) * rstd * gamma + beta, optional SiLU; writes the concat.
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, const __nv_bfloat16* __restrict__ x1,
+                                int c0, int c1, int hw, int groups, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float eps, int silu,
+                                const float* __restrict__ stats, __nv_bfloat16* __restrict__ y,
+                                int64_t total_vec) {
+    const int C = c0 + c1;
+    const int CV = C / 8;
+    const int cpg = C / groups;
+    const float inv_cnt = 1.0f / ((float)cpg * (float)hw);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % CV);
+        const int64_t pix = i / CV;  // n*hw + p
+        const int n = (int)(pix / hw);
+        const int c = cv * 8;
+        const __nv_bfloat16* src;
+        int cs, co;
+        if (c < c0) { src = x0; cs = c0; co = c; } else { src = x1; cs = c1; co = c - c0; }
+        uint4 q = __ldg(reinterpret_cast<const uint4*>(src + pix * cs + co));
+        float v[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
+                      bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
+        float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+        float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c));
+        float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+        const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        int g_prev = -1;
+        float mean = 0.f, rstd = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = (c + j) / cpg;
+            if (g != g_prev) {
+                const float s = __ldg(&stats[((int64_t)n * groups + g) * 2]);
+                const float ss = __ldg(&stats[((int64_t)n * groups + g) * 2 + 1]);
+                mean = s * inv_cnt;
+                const float var = fmaxf(ss * inv_cnt - mean * mean, 0.f);
+                rstd = rsqrtf(var + eps);
+                g_prev = g;
+            }
+            float o = (v[j] - mean) * rstd * ga[j] + be[j];
+            v[j] = silu ? silu_f(o) : o;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]);
+        o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]);
+        o.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(y + pix * C + c) = o;
+    }
+}
+
+int group_norm_validate(const pp_gn_desc& d) {
+    PP_REQUIRE(d.x0 && d.y && d.gamma && d.beta && d.stats, "group_norm: null pointer");
+    PP_REQUIRE((d.x1 == nullptr) == (d.c1 == 0), "group_norm: x1/c1 mismatch");
+    const int C = d.c0 + d.c1;
+    PP_REQUIRE(d.c0 > 0 && d.c0 % 8 == 0 && d.c1 % 8 == 0, "group_norm: channels must be multiples of 8 (c0=%d c1=%d)", d.c0, d.c1);
+    PP_REQUIRE(d.groups > 0 && C % d.groups == 0, "group_norm: C=%d not divisible by groups=%d", C, d.groups);
+    PP_REQUIRE(C / 8 <= 1024, "group_norm: C=%d too large", C);
+    PP_REQUIRE(d.batch > 0 && d.hw > 0, "group_norm: empty input");
+    return PP_OK;
+}
+
+int group_norm_launch(const pp_gn_desc& d, cudaStream_t s) {
+    int rc = group_norm_validate(d);
+    if (rc) return rc;
+    const int C = d.c0 + d.c1;
+    const int CV = C / 8;
+    PP_CUDA_CHECK(cudaMemsetAsync(d.stats, 0, sizeof(float) * 2 * d.groups * d.batch, s));
+    int k = 256 / CV;
+    if (k < 1) k = 1;
+    const int threads = CV * k;
+    // ~4 waves of blocks over the machine, at least 32 pixels per lane-stride
+    int chunks = (148 * 4 + d.batch - 1) / d.batch;
+    int ppb = (d.hw + chunks - 1) / chunks;
+    if (ppb < k * 8) ppb = k * 8;
+    chunks = (d.hw + ppb - 1) / ppb;
+    gn_stats_kernel<<<dim3(chunks, d.batch), threads, sizeof(float) * 2 * d.groups, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(d.x0), reinterpret_cast<const __nv_bfloat16*>(d.x1), d.c0,
+        d.c1, d.hw, d.groups, ppb, d.stats);
+    PP_CUDA_CHECK(cudaGetLastError());
+    const int64_t total_vec = (int64_t)d.batch * d.hw * CV;
+    int blocks = (int)std::min<int64_t>((total_vec + 255) / 256, 148 * 16);
+    gn_apply_kernel<<<blocks, 256, 0, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(d.x0), reinterpret_cast<const __nv_bfloat16*>(d.x1), d.c0,
+        d.c1, d.hw, d.groups, d.gamma, d.beta, d.eps, d.silu, d.stats,
+        reinterpret_cast<__nv_bfloat16*>(d.y), total_vec);
+    PP_CUDA_CHECK(cudaGetLastError());
+    return PP_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, the row lives in registers (two-pass mean/variance).
+// ------------------------------------------------------------------------------------
+template <int MAX_VEC>
+__global__ void layer_norm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  int rows, int c, float eps) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int CV = c / 8;
+    for (int64_t row = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows;
+         row += (int64_t)gridDim.x * warps_per_block) {
+        float v[MAX_VEC][8];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAX_VEC; ++i) {
+            const int cv = lane + 32 * i;
+            if (cv < CV) {
+                uint4 q = __ldg(reinterpret_cast<const uint4*>(x + row * c + cv * 8));
+                v[i][0] = bf16_lo(q.x); v[i][1] = bf16_hi(q.x); v[i][2] = bf16_lo(q.y); v[i][3] = bf16_hi(q.y);
+                v[i][4] = bf16_lo(q.z); v[i][5] = bf16_hi(q.z); v[i][6] = bf16_lo(q.w); v[i][7] = bf16_hi(q.w);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sum += v[i][j];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum / (float)c;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAX_VEC; ++i) {
+            const int cv = lane + 32 * i;
+            if (cv < CV) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float t = v[i][j] - mean; sq += t * t; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float rstd = rsqrtf(sq / (float)c + eps);
+#pragma unroll
+        for (int i = 0; i < MAX_VEC; ++i) {
+            const int cv = lane + 32 * i;
+            if (cv < CV) {
+                const int cc = cv * 8;
+                float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + cc));
+                float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + cc + 4));
+                float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + cc));
+                float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + cc + 4));
+                float o[8];
+                o[0] = (v[i][0] - mean) * rstd * g0.x + b0.x; o[1] = (v[i][1] - mean) * rstd * g0.y + b0.y;
+                o[2] = (v[i][2] - mean) * rstd * g0.z + b0.z; o[3] = (v[i][3] - mean) * rstd * g0.w + b0.w;
+                o[4] = (v[i][4] - mean) * rstd * g1.x + b1.x; o[5] = (v[i][5] - mean) * rstd * g1.y + b1.y;
+                o[6] = (v[i][6] - mean) * rstd * g1.z + b1.z; o[7] = (v[i][7] - mean) * rstd * g1.w + b1.w;
+                uint4 q;
+                q.x = pack_bf16x2(o[0], o[1]); q.y = pack_bf16x2(o[2], o[3]);
+                q.z = pack_bf16x2(o[4], o[5]); q.w = pack_bf16x2(o[6], o[7]);
+                *reinterpret_cast<uint4*>(y + row * c + cc) = q;
+            }
+        }
+    }
+}
+
+int layer_norm_launch(const void* x, void* y, const float* gamma, const float* beta, int rows, int c,
+                      float eps, cudaStream_t s) {
+    PP_REQUIRE(x && y && gamma && beta, "layer_norm: null pointer");
+    PP_REQUIRE(rows > 0 && c > 0 && c % 8 == 0, "layer_norm: rows=%d c=%d invalid", rows, c);
+    const int CV = c / 8;
+    PP_REQUIRE(CV <= 32 * 8, "layer_norm: c=%d too large", c);
+    const int warps = 8;
+    int blocks = std::min((rows + warps - 1) / warps, 148 * 8);
+    auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
+    auto yb = reinterpret_cast<__nv_bfloat16*>(y);
+    if (CV <= 32) layer_norm_kernel<1><<<blocks, warps * 32, 0, s>>>(xb, yb, gamma, beta, rows, c, eps);
+    else if (CV <= 64) layer_norm_kernel<2><<<blocks, warps * 32, 0, s>>>(xb, yb, gamma, beta, rows, c, eps);
+    else if (CV <= 96) layer_norm_kernel<3><<<blocks, warps * 32, 0, s>>>(xb, yb, gamma, beta, rows, c, eps);
+    else if (CV <= 160) layer_norm_kernel<5><<<blocks, warps * 32, 0, s>>>(xb, yb, gamma, beta, rows, c, eps);
+    else layer_norm_kernel<8><<<blocks, warps * 32, 0, s>>>(xb, yb, gamma, beta, rows, c, eps);
+    PP_CUDA_CHECK(cudaGetLastError());
+    return PP_OK;
+}
+
+}  // namespace pp
+
+extern "C" {
+pp_status pp_group_norm(const pp_gn_desc* d, pp_stream stream) {
+    if (!d) { pp::set_last_error("pp_group_norm: null descriptor"); return pp::PP_ERR_INVALID; }
+    return pp::group_norm_launch(*d, reinterpret_cast<cudaStream_t>(stream));
+}
+pp_status pp_layer_norm(const void* x, void* y, const float* gamma, const float* beta, int32_t rows,
+                        int32_t c, float eps, pp_stream stream) {
+    return pp::layer_norm_launch(x, y, gamma, beta, rows, c, eps, reinterpret_cast<cudaStream_t>(stream));
+}
+}

@@ -1,0 +1,90 @@
+// Internal host-side op interface: each op is "prepared" once from its C-ABI descriptor
+// (validation, tile selection, TMA tensor-map encoding) into a launch record, and the
+// record is launched any number of times. pp_program stores launch records.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/powerpaint_b200.h"
+
+namespace pp {
+
+// ---------------------------------------------------------------- GEMM / conv
+struct GemmKParams {
+    CUtensorMap tmA[4];  // matrix/conv: [src0, src1]; stride-2 conv: 4 parity maps
+    CUtensorMap tmB;
+    int32_t a_mode;
+    int32_t M, N;            // GEMM extents (conv: M = nb*ho*wo)
+    int32_t num_k_iters;     // total 64-wide K chunks
+    int32_t chunks0, chunks1;  // per tap: chunks of src0 then src1
+    // conv tiling
+    int32_t nb, ho, wo;
+    int32_t bw, bh, bn;
+    int32_t tiles_x, tiles_y;
+    uint32_t a_bytes;  // bytes one A stage receives (box volume * 128)
+    // epilogue
+    int32_t epilogue, act, out_fp32;
+    const float* bias;
+    const float* rowvec;
+    int32_t rows_per_group;
+    const __nv_bfloat16* res1;
+    int64_t ldr1;
+    const __nv_bfloat16* res2;
+    int64_t ldr2;
+    float alpha;
+    void* out;
+    int64_t ldc;
+    int32_t t_rows;
+    int64_t t_ld;
+};
+
+struct GemmLaunch {
+    GemmKParams p;
+    int block_n;
+    dim3 grid;
+    size_t smem;
+};
+
+int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out);
+int gemm_launch(const GemmLaunch& l, cudaStream_t s);
+
+// ---------------------------------------------------------------- attention
+struct AttnKParams {
+    CUtensorMap tmQ, tmK, tmV;
+    int32_t batch, heads, d, nq, nk;
+    int32_t d_chunks;  // ceil(d / 64)
+    int32_t k_steps;   // ceil(d / 16)
+    int32_t dv;        // ceil16(d): UMMA N of the PV product
+    float scale_log2;  // scale * log2(e)
+    __nv_bfloat16* out;
+    int64_t o_ld;
+};
+struct AttnLaunch {
+    AttnKParams p;
+    dim3 grid;
+    size_t smem;
+    int kv_stages;
+    int variant;  // d_chunks (1, 2 or 3)
+};
+int attn_prepare(const pp_attn_desc& d, AttnLaunch* out);
+int attn_launch(const AttnLaunch& l, cudaStream_t s);
+
+// ---------------------------------------------------------------- simple ops
+int group_norm_launch(const pp_gn_desc& d, cudaStream_t s);
+int group_norm_validate(const pp_gn_desc& d);
+int layer_norm_launch(const void* x, void* y, const float* gamma, const float* beta, int rows,
+                      int c, float eps, cudaStream_t s);
+int upsample2x_launch(const void* x, void* y, int nb, int h, int w, int c, cudaStream_t s);
+int add_launch(const void* a, const void* b, void* y, int64_t n, cudaStream_t s);
+int time_embed_launch(const float* timesteps, const int32_t* step_idx, void* out, int batch,
+                      int dim, cudaStream_t s);
+int nchw_to_nhwc_launch(const float* x, void* y, int nb, int c, int hw, int c_pad, cudaStream_t s);
+int nhwc_to_nchw_launch(const void* x, int x_is_fp32, float* y, int nb, int c, int hw, int c_ld,
+                        cudaStream_t s);
+int cfg_ddim_validate(const pp_cfg_ddim_desc& d);
+int cfg_ddim_launch(const pp_cfg_ddim_desc& d, cudaStream_t s);
+
+}  // namespace pp

@@ -1,0 +1,285 @@
+"""Descriptor builders and immediate-mode wrappers over the C ABI (include/powerpaint_b200.h).
+
+Every function takes torch CUDA tensors (device memory + stream plumbing only), fills the
+C descriptor with raw pointers / pitches, and either launches on torch's current stream
+(`gemm`, `attention`, ...) or returns the descriptor for recording into a `Program`.
+There is no fallback: a failure raises `RuntimeError` carrying `pp_last_error()`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _native as N
+
+BF16 = torch.bfloat16
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+# --------------------------------------------------------------------------- weights
+def pack_linear_weight(w: torch.Tensor) -> torch.Tensor:
+    """nn.Linear / 1x1 conv weight [N, K(,1,1)] -> bf16 [N, K] K-major."""
+    return w.reshape(w.shape[0], -1).to(BF16).contiguous()
+
+
+def pad64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+def pack_conv3x3_weight(w: torch.Tensor, split: Optional[int] = None) -> torch.Tensor:
+    """Conv2d weight [Cout, Cin, 3, 3] -> bf16 [Cout, 9 * (pad64(c0) + pad64(c1))], K ordered
+    (tap = ky*3+kx, source, channel) with each (tap, source) segment zero-padded to 64.
+    `split` = channels of source 0 when the input is a concat of two tensors."""
+    cout, cin = w.shape[0], w.shape[1]
+    c0 = cin if split is None else split
+    c1 = cin - c0
+    p0, p1 = pad64(c0), (pad64(c1) if c1 else 0)
+    out = torch.zeros(cout, 9, p0 + p1, dtype=BF16, device=w.device)
+    wt = w.permute(0, 2, 3, 1).reshape(cout, 9, cin).to(BF16)  # [cout, tap, cin]
+    out[:, :, :c0] = wt[:, :, :c0]
+    if c1:
+        out[:, :, p0:p0 + c1] = wt[:, :, c0:]
+    return out.reshape(cout, 9 * (p0 + p1)).contiguous()
+
+
+def pack_concat_linear_weight(w: torch.Tensor, split: int) -> torch.Tensor:
+    """1x1 conv weight over a two-source concat: [N, c0 + c1] -> [N, pad64(c0) + pad64(c1)]."""
+    w = w.reshape(w.shape[0], -1)
+    n, cin = w.shape
+    c0, c1 = split, cin - split
+    p0, p1 = pad64(c0), pad64(c1)
+    out = torch.zeros(n, p0 + p1, dtype=BF16, device=w.device)
+    out[:, :c0] = w[:, :c0].to(BF16)
+    out[:, p0:p0 + c1] = w[:, c0:].to(BF16)
+    return out.contiguous()
+
+
+def pack_geglu_weight(w: torch.Tensor, b: torch.Tensor, block_n: int = 128):
+    """GEGLU proj weight [2*F, K] (rows 0..F = value, F..2F = gate) -> tile-interleaved so every
+    block_n-row tile holds block_n/2 value rows followed by their block_n/2 gate rows."""
+    f2, k = w.shape
+    f = f2 // 2
+    half = block_n // 2
+    assert f % half == 0, (f, half)
+    wv, wg = w[:f].reshape(f // half, half, k), w[f:].reshape(f // half, half, k)
+    wi = torch.cat([wv, wg], dim=1).reshape(f2, k)
+    bv, bg = b[:f].reshape(f // half, half), b[f:].reshape(f // half, half)
+    bi = torch.cat([bv, bg], dim=1).reshape(f2)
+    return wi.to(BF16).contiguous(), bi.float().contiguous()
+
+
+# --------------------------------------------------------------------------- descriptors
+class Desc:
+    """A filled C descriptor plus the tensors it points into (kept alive)."""
+
+    def __init__(self, kind: str, c_struct, keep):
+        self.kind = kind
+        self.c = c_struct
+        self.keep = keep
+
+
+def gemm_desc(*, a0: torch.Tensor, w: torch.Tensor, out: torch.Tensor, N_: int,
+              a_mode: int = N.PP_A_MATRIX, a1: Optional[torch.Tensor] = None,
+              c0: Optional[int] = None, c1: int = 0, M: int = 0, lda0: int = 0, lda1: int = 0,
+              nb: int = 0, h: int = 0, w_: int = 0, ldb: int = 0,
+              bias: Optional[torch.Tensor] = None, rowvec: Optional[torch.Tensor] = None,
+              rows_per_group: int = 0, res1: Optional[torch.Tensor] = None, ldr1: int = 0,
+              res2: Optional[torch.Tensor] = None, ldr2: int = 0, alpha: float = 1.0,
+              act: int = N.PP_ACT_NONE, epilogue: int = N.PP_EPI_PLAIN, ldc: int = 0,
+              out_fp32: bool = False, t_rows: int = 0, t_ld: int = 0, block_n: int = 0) -> Desc:
+    d = N.GemmDesc()
+    d.a_mode, d.epilogue = a_mode, epilogue
+    d.a0, d.a1 = N.ptr(a0), N.ptr(a1)
+    d.c0 = c0 if c0 is not None else a0.shape[-1]
+    d.c1 = c1
+    d.lda0 = lda0 or d.c0
+    d.lda1 = lda1 or c1
+    d.nb, d.h, d.w = nb, h, w_
+    d.M, d.N = M, N_
+    d.b = N.ptr(w)
+    d.ldb = ldb or w.shape[-1]
+    d.bias, d.rowvec, d.rows_per_group = N.ptr(bias), N.ptr(rowvec), rows_per_group
+    d.res1, d.ldr1 = N.ptr(res1), (ldr1 or N_)
+    d.res2, d.ldr2 = N.ptr(res2), (ldr2 or N_)
+    d.alpha, d.act = alpha, act
+    d.out = N.ptr(out)
+    d.ldc = ldc or (N_ // 2 if epilogue == N.PP_EPI_GEGLU else N_)
+    d.out_fp32 = 1 if out_fp32 else 0
+    d.t_rows, d.t_ld = t_rows, t_ld
+    d.block_n = block_n
+    return Desc("gemm", d, (a0, a1, w, out, bias, rowvec, res1, res2))
+
+
+def attn_desc(*, q, k, vt, out, batch, heads, d, nq, nk, q_ld, k_ld, vt_ld, o_ld,
+              q_batch_stride, k_batch_stride, scale) -> Desc:
+    a = N.AttnDesc()
+    a.q, a.k, a.vt, a.out = N.ptr(q), N.ptr(k), N.ptr(vt), N.ptr(out)
+    a.batch, a.heads, a.d, a.nq, a.nk = batch, heads, d, nq, nk
+    a.q_ld, a.k_ld, a.vt_ld, a.o_ld = q_ld, k_ld, vt_ld, o_ld
+    a.q_batch_stride, a.k_batch_stride = q_batch_stride, k_batch_stride
+    a.scale = scale
+    return Desc("attn", a, (q, k, vt, out))
+
+
+def gn_desc(*, x0, x1, c0, c1, batch, hw, groups, gamma, beta, eps, silu, stats, y) -> Desc:
+    g = N.GnDesc()
+    g.x0, g.x1, g.c0, g.c1 = N.ptr(x0), N.ptr(x1), c0, c1
+    g.batch, g.hw, g.groups = batch, hw, groups
+    g.gamma, g.beta, g.eps, g.silu = N.ptr(gamma), N.ptr(beta), eps, 1 if silu else 0
+    g.stats, g.y = N.ptr(stats), N.ptr(y)
+    return Desc("gn", g, (x0, x1, gamma, beta, stats, y))
+
+
+def cfg_ddim_desc(*, eps, eps_fp32, eps_ld, latents, coef, step_idx, advance_step, noise,
+                  guidance_scale, do_cfg, batch, hw, next_in=None, next_c=0, n_copies=0,
+                  extra=None, extra_c=0) -> Desc:
+    d = N.CfgDdimDesc()
+    d.eps, d.eps_fp32, d.eps_ld = N.ptr(eps), 1 if eps_fp32 else 0, eps_ld
+    d.latents, d.coef, d.step_idx = N.ptr(latents), N.ptr(coef), N.ptr(step_idx)
+    d.advance_step = 1 if advance_step else 0
+    d.noise = N.ptr(noise)
+    d.guidance_scale, d.do_cfg = guidance_scale, 1 if do_cfg else 0
+    d.batch, d.hw = batch, hw
+    d.next_in, d.next_c, d.n_copies = N.ptr(next_in), next_c, n_copies
+    d.extra, d.extra_c = N.ptr(extra), extra_c
+    return Desc("cfg_ddim", d, (eps, latents, coef, step_idx, noise, next_in, extra))
+
+
+# --------------------------------------------------------------------------- immediate mode
+def run(desc: Desc) -> None:
+    L = N.lib()
+    s = N.current_stream()
+    if desc.kind == "gemm":
+        N.check(L.pp_gemm_conv(C.byref(desc.c), s), "pp_gemm_conv")
+    elif desc.kind == "attn":
+        N.check(L.pp_attention(C.byref(desc.c), s), "pp_attention")
+    elif desc.kind == "gn":
+        N.check(L.pp_group_norm(C.byref(desc.c), s), "pp_group_norm")
+    elif desc.kind == "cfg_ddim":
+        N.check(L.pp_cfg_ddim_step(C.byref(desc.c), s), "pp_cfg_ddim_step")
+    else:
+        raise ValueError(desc.kind)
+
+
+def layer_norm(x, y, gamma, beta, eps):
+    rows = x.numel() // x.shape[-1]
+    N.check(N.lib().pp_layer_norm(N.ptr(x), N.ptr(y), N.ptr(gamma), N.ptr(beta), rows, x.shape[-1],
+                                  eps, N.current_stream()), "pp_layer_norm")
+
+
+def upsample2x(x, y):
+    nb, h, w, c = x.shape
+    N.check(N.lib().pp_upsample2x(N.ptr(x), N.ptr(y), nb, h, w, c, N.current_stream()), "pp_upsample2x")
+
+
+def add(a, b, y):
+    N.check(N.lib().pp_add(N.ptr(a), N.ptr(b), N.ptr(y), a.numel(), N.current_stream()), "pp_add")
+
+
+def time_embed(timesteps, out, step_idx=None):
+    batch, dim = out.shape
+    N.check(N.lib().pp_time_embed(N.ptr(timesteps), N.ptr(step_idx), N.ptr(out), batch, dim,
+                                  N.current_stream()), "pp_time_embed")
+
+
+def nchw_to_nhwc(x: torch.Tensor, c_pad: Optional[int] = None) -> torch.Tensor:
+    """fp32 NCHW -> bf16 NHWC (channels zero-padded to c_pad)."""
+    _req(x, torch.float32, "x")
+    nb, c, h, w = x.shape
+    c_pad = c_pad or c
+    y = torch.empty(nb, h, w, c_pad, dtype=BF16, device=x.device)
+    N.check(N.lib().pp_nchw_to_nhwc(N.ptr(x), N.ptr(y), nb, c, h * w, c_pad, N.current_stream()),
+            "pp_nchw_to_nhwc")
+    return y
+
+
+def nhwc_to_nchw(x: torch.Tensor, c: Optional[int] = None) -> torch.Tensor:
+    """bf16/fp32 NHWC [nb, h, w, c_ld] -> fp32 NCHW [nb, c, h, w]."""
+    nb, h, w, c_ld = x.shape
+    c = c or c_ld
+    y = torch.empty(nb, c, h, w, dtype=torch.float32, device=x.device)
+    N.check(N.lib().pp_nhwc_to_nchw(N.ptr(x), 1 if x.dtype == torch.float32 else 0, N.ptr(y), nb, c,
+                                    h * w, c_ld, N.current_stream()), "pp_nhwc_to_nchw")
+    return y
+
+
+# --------------------------------------------------------------------------- programs
+class Program:
+    """A recorded op list (pp_program). Keeps every referenced tensor alive."""
+
+    def __init__(self):
+        self._h = N.vp()
+        N.check(N.lib().pp_program_create(C.byref(self._h)), "pp_program_create")
+        self._keep = []
+        self._graph = False
+
+    def __del__(self):
+        try:
+            if self._h:
+                N.lib().pp_program_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def add(self, desc: Desc) -> None:
+        L = N.lib()
+        fn = {"gemm": L.pp_program_add_gemm, "attn": L.pp_program_add_attention,
+              "gn": L.pp_program_add_group_norm, "cfg_ddim": L.pp_program_add_cfg_ddim}[desc.kind]
+        N.check(fn(self._h, C.byref(desc.c)), f"pp_program_add_{desc.kind}")
+        self._keep.append(desc.keep)
+
+    def add_layer_norm(self, x, y, gamma, beta, rows, c, eps):
+        N.check(N.lib().pp_program_add_layer_norm(self._h, N.ptr(x), N.ptr(y), N.ptr(gamma), N.ptr(beta),
+                                                  rows, c, eps), "pp_program_add_layer_norm")
+        self._keep.append((x, y, gamma, beta))
+
+    def add_upsample2x(self, x, y, nb, h, w, c):
+        N.check(N.lib().pp_program_add_upsample2x(self._h, N.ptr(x), N.ptr(y), nb, h, w, c),
+                "pp_program_add_upsample2x")
+        self._keep.append((x, y))
+
+    def add_add(self, a, b, y, n):
+        N.check(N.lib().pp_program_add_add(self._h, N.ptr(a), N.ptr(b), N.ptr(y), n), "pp_program_add_add")
+        self._keep.append((a, b, y))
+
+    def add_time_embed(self, timesteps, step_idx, out, batch, dim):
+        N.check(N.lib().pp_program_add_time_embed(self._h, N.ptr(timesteps), N.ptr(step_idx), N.ptr(out),
+                                                  batch, dim), "pp_program_add_time_embed")
+        self._keep.append((timesteps, step_idx, out))
+
+    def add_memset(self, t: torch.Tensor):
+        N.check(N.lib().pp_program_add_memset(self._h, N.ptr(t), t.numel() * t.element_size()),
+                "pp_program_add_memset")
+        self._keep.append((t,))
+
+    @property
+    def num_ops(self) -> int:
+        return N.lib().pp_program_num_ops(self._h)
+
+    @property
+    def num_launches(self) -> int:
+        return N.lib().pp_program_num_launches(self._h)
+
+    def run(self) -> None:
+        N.check(N.lib().pp_program_run(self._h, N.current_stream()), "pp_program_run")
+
+    def build_graph(self) -> None:
+        N.check(N.lib().pp_program_graph_build(self._h, N.current_stream()), "pp_program_graph_build")
+        self._graph = True
+
+    def launch(self) -> None:
+        """Replay: CUDA graph if built, plain launches otherwise."""
+        if self._graph:
+            N.check(N.lib().pp_program_graph_launch(self._h, N.current_stream()), "pp_program_graph_launch")
+        else:
+            self.run()

@@ -1,0 +1,350 @@
+"""GPU parity tests of the individual CUDA kernels, called through the C ABI, against plain
+PyTorch fp32 references of the same op (inputs rounded to bf16 first so only accumulation
+order / output rounding differ)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16 = torch.bfloat16
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from powerpaint_b200 import _native, ops as o
+
+    assert _native.lib().pp_device_supported() == 1, "tests need an sm_100 device"
+    return o
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 0), (256, 320, 320, 0), (1000, 640, 768, 0),
+                                      (4096, 1280, 320, 256), (77, 320, 768, 0), (300, 64, 1280, 64),
+                                      (512, 320, 2560, 160), (16, 1280, 320, 0), (2048, 4, 320, 0)])
+def test_gemm_plain(ops, M, N, K, bn):
+    from powerpaint_b200 import _native as nat
+
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    a = torch.randn(M, K, device=_dev(), generator=g).to(BF16)
+    w = (torch.randn(N, K, device=_dev(), generator=g) / math.sqrt(K)).to(BF16)
+    bias = torch.randn(N, device=_dev(), generator=g)
+    out = torch.full((M, N), float("nan"), device=_dev(), dtype=BF16)
+    ops.run(ops.gemm_desc(a0=a, w=w, out=out, N_=N, M=M, bias=bias, block_n=bn))
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < 6e-3, _rel(out, ref)
+    assert (out.float() - ref).abs().max().item() < 0.05 * ref.abs().max().item() + 0.02
+
+
+def test_gemm_epilogue_full(ops):
+    from powerpaint_b200 import _native as nat
+
+    M, N, K = 640, 320, 640
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn(M, K, device=_dev(), generator=g).to(BF16)
+    w = (torch.randn(N, K, device=_dev(), generator=g) / math.sqrt(K)).to(BF16)
+    bias = torch.randn(N, device=_dev(), generator=g)
+    rowvec = torch.randn(5, N, device=_dev(), generator=g)
+    r1 = torch.randn(M, N, device=_dev(), generator=g).to(BF16)
+    r2 = torch.randn(M, N, device=_dev(), generator=g).to(BF16)
+    for fp32 in (False, True):
+        out = torch.zeros(M, N, device=_dev(), dtype=torch.float32 if fp32 else BF16)
+        ops.run(ops.gemm_desc(a0=a, w=w, out=out, N_=N, M=M, bias=bias, rowvec=rowvec, rows_per_group=128,
+                              res1=r1, res2=r2, alpha=0.5, act=nat.PP_ACT_SILU, out_fp32=fp32))
+        torch.cuda.synchronize()
+        v = a.float() @ w.float().t() + bias + rowvec.repeat_interleave(128, 0) + r1.float()
+        v = v * 0.5 + r2.float()
+        ref = F.silu(v)
+        assert _rel(out, ref) < (2e-4 if fp32 else 6e-3), _rel(out, ref)
+
+
+def test_gemm_two_sources_and_transposed(ops):
+    from powerpaint_b200 import _native as nat
+
+    M, N, c0, c1 = 512, 320, 320, 96
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a0 = torch.randn(M, c0, device=_dev(), generator=g).to(BF16)
+    a1 = torch.randn(M, c1, device=_dev(), generator=g).to(BF16)
+    wfull = torch.randn(N, c0 + c1, device=_dev(), generator=g) / math.sqrt(c0 + c1)
+    w = ops.pack_concat_linear_weight(wfull, c0)
+    out = torch.zeros(M, N, device=_dev(), dtype=BF16)
+    ops.run(ops.gemm_desc(a0=a0, a1=a1, c1=c1, w=w, out=out, N_=N, M=M))
+    ref = torch.cat([a0, a1], 1).float() @ wfull.to(BF16).float().t()
+    assert _rel(out, ref) < 6e-3
+    # transposed store: out_t[b, n, t]
+    t_rows, t_ld = 128, 136
+    out_t = torch.zeros(M // t_rows, N, t_ld, device=_dev(), dtype=BF16)
+    ops.run(ops.gemm_desc(a0=a0, a1=a1, c1=c1, w=w, out=out_t, N_=N, M=M, epilogue=nat.PP_EPI_TRANSPOSED,
+                          t_rows=t_rows, t_ld=t_ld))
+    torch.cuda.synchronize()
+    ref_t = ref.reshape(M // t_rows, t_rows, N).permute(0, 2, 1)
+    assert _rel(out_t[:, :, :t_rows], ref_t) < 6e-3
+    assert (out_t[:, :, t_rows:] == 0).all()
+
+
+@pytest.mark.parametrize("bn", [128, 160, 256])
+def test_gemm_geglu(ops, bn):
+    from powerpaint_b200 import _native as nat
+
+    M, C = 384, 320
+    F_ = 4 * C
+    g = torch.Generator(device="cuda").manual_seed(11)
+    a = torch.randn(M, C, device=_dev(), generator=g).to(BF16)
+    w = torch.randn(2 * F_, C, device=_dev(), generator=g) / math.sqrt(C)
+    b = torch.randn(2 * F_, device=_dev(), generator=g)
+    wi, bi = ops.pack_geglu_weight(w, b, bn)
+    out = torch.zeros(M, F_, device=_dev(), dtype=BF16)
+    ops.run(ops.gemm_desc(a0=a, w=wi, out=out, N_=2 * F_, M=M, bias=bi, epilogue=nat.PP_EPI_GEGLU, block_n=bn))
+    torch.cuda.synchronize()
+    h = a.float() @ w.to(BF16).float().t() + b
+    ref = h[:, :F_] * F.gelu(h[:, F_:])
+    assert _rel(out, ref) < 6e-3, _rel(out, ref)
+
+
+@pytest.mark.parametrize("nb,h,w,cin,cout", [(2, 64, 64, 320, 320), (3, 16, 16, 640, 1280), (5, 8, 8, 1280, 1280),
+                                              (2, 32, 32, 16, 320), (2, 64, 64, 320, 4), (1, 24, 40, 32, 64),
+                                              (3, 4, 4, 64, 64), (4, 2, 2, 128, 128), (9, 1, 1, 128, 64)])
+def test_conv3x3(ops, nb, h, w, cin, cout):
+    from powerpaint_b200 import _native as nat
+
+    g = torch.Generator(device="cuda").manual_seed(nb * 100 + cin)
+    x = torch.randn(nb, cin, h, w, device=_dev(), generator=g).to(BF16)
+    wt = (torch.randn(cout, cin, 3, 3, device=_dev(), generator=g) / math.sqrt(9 * cin)).to(BF16)
+    bias = torch.randn(cout, device=_dev(), generator=g)
+    temb = torch.randn(nb, cout, device=_dev(), generator=g)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    wp = ops.pack_conv3x3_weight(wt.float())
+    out = torch.full((nb, h, w, cout), float("nan"), device=_dev(), dtype=BF16)
+    ops.run(ops.gemm_desc(a0=x_nhwc, w=wp, out=out, N_=cout, a_mode=nat.PP_A_CONV3X3, c0=cin, nb=nb, h=h, w_=w,
+                          bias=bias, rowvec=temb))
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float(), wt.float(), bias, padding=1) + temb[:, :, None, None]
+    got = out.permute(0, 3, 1, 2).float()
+    assert torch.isfinite(got).all()
+    assert _rel(got, ref) < 6e-3, _rel(got, ref)
+
+
+def test_conv3x3_two_sources(ops):
+    from powerpaint_b200 import _native as nat
+
+    nb, h, w, c0, c1, cout = 2, 16, 16, 640, 320, 640
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x0 = torch.randn(nb, h, w, c0, device=_dev(), generator=g).to(BF16)
+    x1 = torch.randn(nb, h, w, c1, device=_dev(), generator=g).to(BF16)
+    wt = (torch.randn(cout, c0 + c1, 3, 3, device=_dev(), generator=g) / math.sqrt(9 * (c0 + c1))).to(BF16)
+    wp = ops.pack_conv3x3_weight(wt.float(), split=c0)
+    res = torch.randn(nb, h, w, cout, device=_dev(), generator=g).to(BF16)
+    out = torch.zeros(nb, h, w, cout, device=_dev(), dtype=BF16)
+    ops.run(ops.gemm_desc(a0=x0, a1=x1, c0=c0, c1=c1, w=wp, out=out, N_=cout, a_mode=nat.PP_A_CONV3X3, nb=nb,
+                          h=h, w_=w, res1=res))
+    torch.cuda.synchronize()
+    xin = torch.cat([x0, x1], -1).permute(0, 3, 1, 2).float()
+    ref = F.conv2d(xin, wt.float(), None, padding=1) + res.permute(0, 3, 1, 2).float()
+    assert _rel(out.permute(0, 3, 1, 2), ref) < 6e-3
+
+
+@pytest.mark.parametrize("nb,h,w,c", [(2, 64, 64, 320), (3, 16, 16, 1280), (2, 8, 8, 64), (1, 2, 2, 128), (2, 12, 20, 32)])
+def test_conv3x3_stride2(ops, nb, h, w, c):
+    from powerpaint_b200 import _native as nat
+
+    g = torch.Generator(device="cuda").manual_seed(31 + c)
+    x = torch.randn(nb, c, h, w, device=_dev(), generator=g).to(BF16)
+    wt = (torch.randn(c, c, 3, 3, device=_dev(), generator=g) / math.sqrt(9 * c)).to(BF16)
+    bias = torch.randn(c, device=_dev(), generator=g)
+    wp = ops.pack_conv3x3_weight(wt.float())
+    out = torch.zeros(nb, h // 2, w // 2, c, device=_dev(), dtype=BF16)
+    ops.run(ops.gemm_desc(a0=x.permute(0, 2, 3, 1).contiguous(), w=wp, out=out, N_=c, a_mode=nat.PP_A_CONV3X3_S2,
+                          c0=c, nb=nb, h=h, w_=w, bias=bias))
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float(), wt.float(), bias, stride=2, padding=1)
+    assert _rel(out.permute(0, 3, 1, 2), ref) < 6e-3
+
+
+@pytest.mark.parametrize("B,H,d,nq,nk", [(2, 8, 40, 4096, 4096), (2, 8, 80, 1024, 1024), (3, 8, 160, 256, 256),
+                                          (2, 8, 160, 64, 64), (2, 8, 40, 4096, 77), (2, 8, 80, 1024, 77),
+                                          (2, 8, 160, 64, 77), (2, 4, 8, 64, 64), (2, 4, 16, 16, 77),
+                                          (3, 4, 32, 4, 4), (2, 4, 32, 1, 77), (1, 2, 64, 300, 333)])
+def test_attention(ops, B, H, d, nq, nk):
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + d + nq)
+    C_ = H * d
+    q = (torch.randn(B, nq, C_, device=_dev(), generator=g)).to(BF16)
+    k = (torch.randn(B, nk, C_, device=_dev(), generator=g)).to(BF16)
+    v = (torch.randn(B, nk, C_, device=_dev(), generator=g)).to(BF16)
+    vt_ld = (nk + 7) // 8 * 8
+    vt = torch.full((B, C_, vt_ld), float("nan"), device=_dev(), dtype=BF16)
+    vt[:, :, :nk] = v.permute(0, 2, 1)
+    out = torch.full((B, nq, C_), float("nan"), device=_dev(), dtype=BF16)
+    scale = 1.0 / math.sqrt(d)
+    ops.run(ops.attn_desc(q=q, k=k, vt=vt, out=out, batch=B, heads=H, d=d, nq=nq, nk=nk, q_ld=C_, k_ld=C_,
+                          vt_ld=vt_ld, o_ld=C_, q_batch_stride=nq * C_, k_batch_stride=nk * C_, scale=scale))
+    torch.cuda.synchronize()
+    qh = q.float().reshape(B, nq, H, d).transpose(1, 2)
+    kh = k.float().reshape(B, nk, H, d).transpose(1, 2)
+    vh = v.float().reshape(B, nk, H, d).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(B, nq, C_)
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < 1e-2, _rel(out, ref)
+
+
+def test_attention_large_logits(ops):
+    """rows whose running max jumps by far more than the lazy-rescale threshold"""
+    B, H, d, nq, nk = 1, 2, 40, 256, 1024
+    g = torch.Generator(device="cuda").manual_seed(77)
+    C_ = H * d
+    q = (torch.randn(B, nq, C_, device=_dev(), generator=g) * 4).to(BF16)
+    k = torch.randn(B, nk, C_, device=_dev(), generator=g)
+    k = (k * torch.linspace(0.2, 6.0, nk, device=_dev())[None, :, None]).to(BF16)  # later keys dominate
+    v = torch.randn(B, nk, C_, device=_dev(), generator=g).to(BF16)
+    vt = v.permute(0, 2, 1).contiguous()
+    out = torch.zeros(B, nq, C_, device=_dev(), dtype=BF16)
+    ops.run(ops.attn_desc(q=q, k=k, vt=vt, out=out, batch=B, heads=H, d=d, nq=nq, nk=nk, q_ld=C_, k_ld=C_,
+                          vt_ld=nk, o_ld=C_, q_batch_stride=nq * C_, k_batch_stride=nk * C_, scale=1 / math.sqrt(d)))
+    torch.cuda.synchronize()
+    qh = q.float().reshape(B, nq, H, d).transpose(1, 2)
+    kh = k.float().reshape(B, nk, H, d).transpose(1, 2)
+    vh = v.float().reshape(B, nk, H, d).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(B, nq, C_)
+    assert _rel(out, ref) < 1.5e-2, _rel(out, ref)
+
+
+@pytest.mark.parametrize("B,hw,c0,c1,groups,silu", [(2, 4096, 320, 0, 32, True), (3, 256, 1280, 1280, 32, True),
+                                                    (2, 1024, 640, 320, 32, False), (2, 64, 32, 0, 32, True),
+                                                    (2, 64, 1280, 640, 32, True), (1, 4, 64, 64, 8, True)])
+def test_group_norm(ops, B, hw, c0, c1, groups, silu):
+    g = torch.Generator(device="cuda").manual_seed(hw + c0)
+    C_ = c0 + c1
+    x0 = (torch.randn(B, hw, c0, device=_dev(), generator=g) * 2 + 0.5).to(BF16)
+    x1 = (torch.randn(B, hw, c1, device=_dev(), generator=g) - 0.3).to(BF16) if c1 else None
+    gamma = torch.randn(C_, device=_dev(), generator=g)
+    beta = torch.randn(C_, device=_dev(), generator=g)
+    stats = torch.empty(B, groups, 2, device=_dev())
+    y = torch.zeros(B, hw, C_, device=_dev(), dtype=BF16)
+    ops.run(ops.gn_desc(x0=x0, x1=x1, c0=c0, c1=c1, batch=B, hw=hw, groups=groups, gamma=gamma, beta=beta,
+                        eps=1e-5, silu=silu, stats=stats, y=y))
+    torch.cuda.synchronize()
+    x = torch.cat([x0, x1], -1) if c1 else x0
+    ref = F.group_norm(x.float().permute(0, 2, 1), groups, gamma, beta, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    assert _rel(y.permute(0, 2, 1), ref) < 5e-3, _rel(y.permute(0, 2, 1), ref)
+
+
+@pytest.mark.parametrize("rows,c", [(4096, 320), (1000, 640), (77, 1280), (5, 32), (64, 128)])
+def test_layer_norm(ops, rows, c):
+    g = torch.Generator(device="cuda").manual_seed(rows + c)
+    x = (torch.randn(rows, c, device=_dev(), generator=g) * 3 + 1).to(BF16)
+    gamma = torch.randn(c, device=_dev(), generator=g)
+    beta = torch.randn(c, device=_dev(), generator=g)
+    y = torch.zeros_like(x)
+    ops.layer_norm(x, y, gamma, beta, 1e-5)
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x.float(), (c,), gamma, beta, 1e-5)
+    assert _rel(y, ref) < 4e-3
+
+
+def test_small_ops(ops):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(2, 6, 10, 64, device=_dev(), generator=g).to(BF16)
+    y = torch.zeros(2, 12, 20, 64, device=_dev(), dtype=BF16)
+    ops.upsample2x(x, y)
+    ref = F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(y.float(), ref)
+    a = torch.randn(4096, device=_dev(), generator=g).to(BF16)
+    b = torch.randn(4096, device=_dev(), generator=g).to(BF16)
+    c = torch.zeros_like(a)
+    ops.add(a, b, c)
+    assert torch.equal(c, (a.float() + b.float()).to(BF16))
+    # layout conversion round trip
+    z = torch.randn(3, 9, 7, 5, device=_dev(), generator=g)
+    zn = ops.nchw_to_nhwc(z, 16)
+    assert zn.shape == (3, 7, 5, 16)
+    assert torch.equal(zn[..., :9].float(), z.to(BF16).float().permute(0, 2, 3, 1))
+    assert (zn[..., 9:] == 0).all()
+    back = ops.nhwc_to_nchw(zn, 9)
+    assert torch.equal(back, z.to(BF16).float())
+    # timestep embedding
+    t = torch.tensor([981.0, 1.0, 500.0], device=_dev())
+    e = torch.zeros(3, 320, device=_dev(), dtype=BF16)
+    ops.time_embed(t, e)
+    half = 160
+    f = torch.exp(-math.log(10000.0) * torch.arange(half, device=_dev(), dtype=torch.float32) / half)
+    arg = t[:, None] * f[None]
+    ref = torch.cat([torch.cos(arg), torch.sin(arg)], -1)
+    assert (e.float() - ref).abs().max().item() < 1e-2
+    torch.cuda.synchronize()
+
+
+def test_cfg_ddim(ops):
+    B, hw = 3, 64 * 64
+    g = torch.Generator(device="cuda").manual_seed(9)
+    eps = torch.randn(2 * B, hw, 4, device=_dev(), generator=g)
+    lat = torch.randn(B, hw, 4, device=_dev(), generator=g)
+    extra = torch.randn(B, hw, 5, device=_dev(), generator=g)
+    noise = torch.randn(B, hw, 4, device=_dev(), generator=g)
+    a_t, a_p, sigma = 0.3, 0.45, 0.1
+    coef = torch.tensor([[0] * 8, [math.sqrt(a_t), math.sqrt(1 - a_t), math.sqrt(a_p),
+                                   math.sqrt(1 - a_p - sigma ** 2), sigma, 0, 0, 0]], device=_dev(), dtype=torch.float32)
+    step = torch.tensor([1], device=_dev(), dtype=torch.int32)
+    nxt = torch.full((2 * B, hw, 16), float("nan"), device=_dev(), dtype=BF16)
+    lat_in = lat.clone()
+    ops.run(ops.cfg_ddim_desc(eps=eps, eps_fp32=True, eps_ld=4, latents=lat, coef=coef, step_idx=step,
+                              advance_step=True, noise=noise, guidance_scale=7.5, do_cfg=True, batch=B, hw=hw,
+                              next_in=nxt, next_c=16, n_copies=2, extra=extra, extra_c=5))
+    torch.cuda.synchronize()
+    e = eps[:B] + 7.5 * (eps[B:] - eps[:B])
+    x0 = (lat_in - math.sqrt(1 - a_t) * e) / math.sqrt(a_t)
+    ref = math.sqrt(a_p) * x0 + math.sqrt(1 - a_p - sigma ** 2) * e + sigma * noise
+    assert (lat - ref).abs().max().item() < 1e-4
+    assert step.item() == 2
+    for cpy in range(2):
+        blk = nxt[cpy * B:(cpy + 1) * B].float()
+        assert torch.equal(blk[..., :4], lat.to(BF16).float())
+        assert torch.equal(blk[..., 4:9], extra.to(BF16).float())
+        assert (blk[..., 9:] == 0).all()
+
+
+def test_program_and_graph(ops):
+    """record GN -> conv -> LN in a program, replay as launches and as a CUDA graph"""
+    from powerpaint_b200 import _native as nat
+
+    nb, h, w, c = 2, 16, 16, 64
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(nb, h, w, c, device=_dev(), generator=g).to(BF16)
+    gamma = torch.ones(c, device=_dev()); beta = torch.zeros(c, device=_dev())
+    stats = torch.zeros(nb, 32, 2, device=_dev())
+    xn = torch.zeros_like(x)
+    wt = (torch.randn(c, c, 3, 3, device=_dev(), generator=g) / math.sqrt(9 * c)).to(BF16)
+    wp = ops.pack_conv3x3_weight(wt.float())
+    y = torch.zeros_like(x)
+    z = torch.zeros_like(x)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        prog = ops.Program()
+        prog.add(ops.gn_desc(x0=x, x1=None, c0=c, c1=0, batch=nb, hw=h * w, groups=32, gamma=gamma, beta=beta,
+                             eps=1e-5, silu=True, stats=stats, y=xn))
+        prog.add(ops.gemm_desc(a0=xn, w=wp, out=y, N_=c, a_mode=nat.PP_A_CONV3X3, c0=c, nb=nb, h=h, w_=w))
+        prog.add_layer_norm(y, z, gamma, beta, nb * h * w, c, 1e-5)
+        assert prog.num_ops == 3 and prog.num_launches == 4
+        prog.run()
+        s.synchronize()
+        z1 = z.clone()
+        z.zero_()
+        prog.build_graph()
+        prog.launch()
+        s.synchronize()
+    assert torch.equal(z, z1)
+    ref = F.silu(F.group_norm(x.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)).to(BF16).float()
+    ref = F.conv2d(ref, wt.float(), None, padding=1).to(BF16).float().permute(0, 2, 3, 1)
+    ref = F.layer_norm(ref, (c,), gamma, beta, 1e-5)
+    assert _rel(z, ref) < 2e-2
