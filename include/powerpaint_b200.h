@@ -88,6 +88,7 @@ typedef struct pp_gemm_desc {
     const float* bias;
     const float* rowvec;
     int32_t rows_per_group;
+    int64_t rowvec_ld; /* row pitch of rowvec in elements; 0 = N */
     const void* res1; /* bf16 */
     int64_t ldr1;
     const void* res2; /* bf16 */
@@ -183,6 +184,7 @@ typedef struct pp_cfg_ddim_desc {
     int32_t next_c, n_copies;
     const float* extra;
     int32_t extra_c;
+    int32_t guidance_from_coef; /* != 0: guidance scale = coef[row][5] (graph-replay friendly) */
 } pp_cfg_ddim_desc;
 pp_status pp_cfg_ddim_step(const pp_cfg_ddim_desc* d, pp_stream stream);
 

@@ -32,7 +32,7 @@ class GemmDesc(C.Structure):
         ("nb", i32), ("h", i32), ("w", i32),
         ("M", i32), ("N", i32),
         ("b", vp), ("ldb", i64),
-        ("bias", vp), ("rowvec", vp), ("rows_per_group", i32),
+        ("bias", vp), ("rowvec", vp), ("rows_per_group", i32), ("rowvec_ld", i64),
         ("res1", vp), ("ldr1", i64),
         ("res2", vp), ("ldr2", i64),
         ("alpha", f32), ("act", i32),
@@ -68,7 +68,7 @@ class CfgDdimDesc(C.Structure):
         ("noise", vp), ("guidance_scale", f32), ("do_cfg", i32),
         ("batch", i32), ("hw", i32),
         ("next_in", vp), ("next_c", i32), ("n_copies", i32),
-        ("extra", vp), ("extra_c", i32),
+        ("extra", vp), ("extra_c", i32), ("guidance_from_coef", i32),
     ]
 
 

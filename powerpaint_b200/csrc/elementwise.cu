@@ -27,6 +27,7 @@ __global__ void cfg_ddim_kernel(pp_cfg_ddim_desc d) {
     const float* cf = d.coef + (int64_t)step * 8;
     const float sa_t = cf[0], s1a_t = cf[1], sa_p = cf[2], dir_c = cf[3], sigma = cf[4];
     const float inv_sa_t = 1.0f / sa_t;
+    const float gscale = d.guidance_from_coef ? cf[5] : d.guidance_scale;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         float eu[4], ec[4];
@@ -53,7 +54,7 @@ __global__ void cfg_ddim_kernel(pp_cfg_ddim_desc d) {
         float xp[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float eps = d.do_cfg ? eu[j] + d.guidance_scale * (ec[j] - eu[j]) : eu[j];
+            const float eps = d.do_cfg ? eu[j] + gscale * (ec[j] - eu[j]) : eu[j];
             const float x0 = (x[j] - s1a_t * eps) * inv_sa_t;
             xp[j] = sa_p * x0 + dir_c * eps + sigma * nz[j];
         }

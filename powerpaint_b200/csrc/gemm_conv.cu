@@ -65,7 +65,7 @@ __device__ __forceinline__ void epilogue_store8(const GemmKParams& p, float (&v)
         }
     }
     if (p.rowvec) {
-        const float* rv = p.rowvec + (int64_t)grp * p.N + n0;
+        const float* rv = p.rowvec + (int64_t)grp * p.rowvec_ld + n0;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             if (kVec || n0 + j < p.N) v[j] += __ldg(rv + j);
@@ -543,6 +543,7 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
     p.bias = d.bias;
     p.rowvec = d.rowvec;
     p.rows_per_group = d.rows_per_group;
+    p.rowvec_ld = d.rowvec_ld ? d.rowvec_ld : d.N;
     if (d.rowvec && d.a_mode == PP_A_MATRIX)
         PP_REQUIRE(d.rows_per_group > 0, "gemm: rowvec needs rows_per_group > 0");
     p.res1 = reinterpret_cast<const __nv_bfloat16*>(d.res1);

@@ -30,6 +30,7 @@ struct GemmKParams {
     const float* bias;
     const float* rowvec;
     int32_t rows_per_group;
+    int64_t rowvec_ld;
     const __nv_bfloat16* res1;
     int64_t ldr1;
     const __nv_bfloat16* res2;

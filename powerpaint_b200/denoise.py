@@ -1,0 +1,184 @@
+"""The fused denoising loop: one recorded CUDA program per step, replayed as a CUDA graph.
+
+Replaces the body of the reference loops
+  v1          powerpaint/pipelines/pipeline_PowerPaint.py:988-1035
+  v2 BrushNet powerpaint/pipelines/pipeline_PowerPaint_Brushnet_CA.py:1384-1449
+  ControlNet  powerpaint/pipelines/pipeline_PowerPaint_ControlNet.py:1663-1735
+i.e. per step: CFG duplication + channel concat -> [BrushNet | ControlNet] -> UNet -> CFG combine ->
+DDIMScheduler.step. Here the step is a single `pp_program`:
+
+    [side net forward]  ->  UNet forward (side-net residuals ride the UNet epilogues)
+                        ->  pp_cfg_ddim_step: eps = u + s (c - u); x_{t-1}; writes the NEXT step's
+                            bf16 channels-last net input for both CFG halves; bumps the step counter
+
+The per-step scalars (timestep, DDIM coefficients, guidance scale) live in device tables indexed
+by a device-side step counter, so one captured graph serves all steps; nothing crosses PCIe
+inside the loop (the reference uploads `t` every step, unet_2d_condition.py:926). Step-invariant
+work is hoisted: cross-attention K/V of the prompt(s), ControlNet's conditioning embedding, and
+the constant input channels (mask, masked-image latents, BrushNet condition) are converted once.
+
+All nets read ONE shared input buffer [n, h*w, 16]: channels 0..3 = latents, 4.. = the constant
+channels of whichever net consumes them; nets that do not consume a channel carry zero weights
+for it (weights are zero-padded at pack time), so no per-net concat exists.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional
+
+import torch
+
+from . import ops
+from .engine import NetEngine, Plan
+
+MAX_STEPS = 1000
+X_IN_C = 16
+
+
+class FusedDenoiser:
+    """mode: 'v1' (UNet, 9-ch), 'brushnet' (BrushNet + 4-ch UNet), 'controlnet' (ControlNet + 9-ch UNet)"""
+
+    def __init__(self, unet, side=None, mode: str = "v1"):
+        if mode not in ("v1", "brushnet", "controlnet"):
+            raise ValueError(mode)
+        if (mode == "v1") != (side is None):
+            raise ValueError("side net must be given exactly for modes 'brushnet' / 'controlnet'")
+        self.unet = unet
+        self.side = side
+        self.mode = mode
+        self._cache: Dict[tuple, dict] = {}
+
+    # ------------------------------------------------------------------ plan
+    def _get(self, B: int, h: int, w: int, do_cfg: bool, ctx_len: int, side_scale: float) -> dict:
+        key = (B, h, w, do_cfg, ctx_len, float(side_scale), id(self.unet.engine()),
+               id(self.side.engine()) if self.side is not None else 0)
+        st = self._cache.get(key)
+        if st is not None:
+            return st
+        dev = self.unet.device
+        nb = 2 * B if do_cfg else B
+        ue: NetEngine = self.unet.engine()
+        prog, ctxprog = ops.Program(), ops.Program()
+        x_in = torch.zeros(nb, h * w, X_IN_C, dtype=torch.bfloat16, device=dev)
+        timesteps = torch.zeros(MAX_STEPS, dtype=torch.float32, device=dev)
+        step_idx = torch.zeros(1, dtype=torch.int32, device=dev)
+        coef = torch.zeros(MAX_STEPS, 8, dtype=torch.float32, device=dev)
+        shared = dict(program=prog, ctx_program=ctxprog, x_in=x_in, timesteps=timesteps, step_idx=step_idx)
+        st = dict(B=B, nb=nb, h=h, w=w, do_cfg=do_cfg, x_in=x_in, timesteps=timesteps, step_idx=step_idx, coef=coef,
+                  program=prog, ctx_program=ctxprog, graph=False)
+        side_plan: Optional[Plan] = None
+        if self.mode == "brushnet":
+            se: NetEngine = self.side.engine()
+            side_plan = se._build_plan(nb, h, w, ctx_len, False, False, True, 0, shared=shared)
+            se.append_brushnet_outputs(side_plan, float(side_scale))
+            shared_u = dict(shared, adds=(side_plan.outputs["down"], side_plan.outputs["mid"], side_plan.outputs["up"]))
+            uplan = ue._build_plan(nb, h, w, ctx_len, True, False, True, 0, shared=shared_u)
+        elif self.mode == "controlnet":
+            se = self.side.engine()
+            side_plan = se._build_plan(nb, h, w, ctx_len, False, False, True, 0,
+                                       shared=dict(shared, cn_scale=float(side_scale)))
+            shared_u = dict(shared, cn=(side_plan.outputs["down"], side_plan.outputs["mid"]))
+            uplan = ue._build_plan(nb, h, w, ctx_len, False, True, True, 0, shared=shared_u)
+        else:
+            uplan = ue._build_plan(nb, h, w, ctx_len, False, False, True, 0, shared=shared)
+        st["uplan"], st["side_plan"] = uplan, side_plan
+        # fp32 master latents and the constant channels (channels-last)
+        st["latents"] = torch.zeros(B, h * w, 4, dtype=torch.float32, device=dev)
+        st["extra"] = torch.zeros(B, h * w, 5, dtype=torch.float32, device=dev)
+        st["noise"] = torch.zeros(B, h * w, 4, dtype=torch.float32, device=dev)
+        self._add_step_tail(st, with_noise=False)
+        st["bytes"] = uplan.bytes + (side_plan.bytes if side_plan else 0)
+        self._cache[key] = st
+        return st
+
+    def _add_step_tail(self, st: dict, with_noise: bool):
+        d = ops.cfg_ddim_desc(eps=st["uplan"].outputs["eps"], eps_fp32=True, eps_ld=4, latents=st["latents"],
+                              coef=st["coef"], step_idx=st["step_idx"], advance_step=True,
+                              noise=st["noise"] if with_noise else None, guidance_scale=0.0,
+                              guidance_from_coef=True, do_cfg=st["do_cfg"], batch=st["B"], hw=st["h"] * st["w"],
+                              next_in=st["x_in"], next_c=X_IN_C, n_copies=2 if st["do_cfg"] else 1,
+                              extra=st["extra"], extra_c=5)
+        st["program"].add(d)
+        st["with_noise"] = with_noise
+
+    @property
+    def launches_per_step(self) -> int:
+        return max((s["program"].num_launches for s in self._cache.values()), default=0)
+
+    # ------------------------------------------------------------------ run
+    @torch.no_grad()
+    def run(self, *, latents: torch.Tensor, prompt_embeds: torch.Tensor, timesteps, coef: torch.Tensor,
+            guidance_scale: float, extra: Optional[torch.Tensor] = None,
+            side_prompt_embeds: Optional[torch.Tensor] = None, control_image: Optional[torch.Tensor] = None,
+            side_scale: float = 1.0, noise_fn: Optional[Callable[[int], torch.Tensor]] = None,
+            callback: Optional[Callable[[int, int, torch.Tensor], Optional[torch.Tensor]]] = None,
+            use_graph: bool = True) -> torch.Tensor:
+        """latents [B,4,h,w]; prompt_embeds [nb,77,768] for the UNet (negative half first when CFG);
+        extra [B,5,h,w] = constant channels (v1/controlnet: mask + masked-image latents; brushnet:
+        conditioning latents + mask); side_prompt_embeds for the side net; coef [n,8] from
+        `DDIMScheduler.step_coefficients`. `callback(i, t, latents_nchw)` may return replacement
+        latents. Returns final latents [B,4,h,w] fp32."""
+        B, _, h, w = latents.shape
+        nb = prompt_embeds.shape[0]
+        do_cfg = nb == 2 * B
+        if not do_cfg and nb != B:
+            raise ValueError("prompt_embeds batch must be B or 2B")
+        n_steps = len(timesteps)
+        if n_steps > MAX_STEPS:
+            raise ValueError(f"at most {MAX_STEPS} steps")
+        st = self._get(B, h, w, do_cfg, prompt_embeds.shape[1], side_scale)
+        dev = st["x_in"].device
+        eta_noise = noise_fn is not None
+        if eta_noise != st["with_noise"]:
+            raise NotImplementedError("eta > 0 needs a plan recorded with noise; use FusedDenoiser(..., ) per eta mode")
+        # ---- per-call inputs (all outside the loop)
+        st["latents"].copy_(ops.nhwc_fp32_from_nchw(latents.to(dev)))
+        if extra is not None:
+            st["extra"].copy_(ops.nhwc_fp32_from_nchw(extra.to(dev)))
+        else:
+            st["extra"].zero_()
+        lat16 = st["latents"].to(torch.bfloat16)
+        ex16 = st["extra"].to(torch.bfloat16)
+        x_in = st["x_in"]
+        for cpy in range(2 if do_cfg else 1):
+            x_in[cpy * B:(cpy + 1) * B, :, :4] = lat16
+            x_in[cpy * B:(cpy + 1) * B, :, 4:9] = ex16
+        ts = torch.as_tensor([float(t) for t in timesteps], dtype=torch.float32)
+        st["timesteps"][:n_steps].copy_(ts.to(dev))
+        cf = coef.clone().float()
+        cf[:, 5] = float(guidance_scale)
+        st["coef"][:n_steps].copy_(cf.to(dev))
+        st["step_idx"].zero_()
+        st["uplan"].inputs["ctx"].copy_(prompt_embeds.to(dev, torch.bfloat16))
+        if st["side_plan"] is not None:
+            if side_prompt_embeds is None:
+                raise ValueError("side_prompt_embeds required")
+            st["side_plan"].inputs["ctx"].copy_(side_prompt_embeds.to(dev, torch.bfloat16))
+            if self.mode == "controlnet":
+                if control_image is None:
+                    raise ValueError("control_image required")
+                ci = st["side_plan"].inputs["cond_in"]
+                ci.copy_(ops.nchw_to_nhwc(control_image.to(dev).float().contiguous(), ci.shape[-1]).view_as(ci))
+                st["side_plan"].cond_program.run()
+        st["ctx_program"].run()
+        # ---- the loop
+        prog = st["program"]
+        if use_graph and callback is None and not eta_noise:
+            if not st["graph"]:
+                prog.build_graph()  # capture does not execute: device state is untouched
+                st["graph"] = True
+            for _ in range(n_steps):
+                prog.launch()
+        else:
+            for i in range(n_steps):
+                if eta_noise:
+                    st["noise"].copy_(ops.nhwc_fp32_from_nchw(noise_fn(i).to(dev)))
+                prog.run()
+                if callback is not None:
+                    cur = ops.nchw_from_nhwc_fp32(st["latents"], h, w)
+                    new = callback(i, timesteps[i], cur)
+                    if new is not None and new is not cur:
+                        st["latents"].copy_(ops.nhwc_fp32_from_nchw(new.to(dev)))
+                        l16 = st["latents"].to(torch.bfloat16)
+                        for cpy in range(2 if do_cfg else 1):
+                            x_in[cpy * B:(cpy + 1) * B, :, :4] = l16
+        return ops.nchw_from_nhwc_fp32(st["latents"], h, w).clone()

@@ -1,0 +1,583 @@
+"""Host-side planner of the per-step UNet / BrushNet / ControlNet forward.
+
+`NetEngine` takes a diffusers-named state dict for one of the three nets
+of the hot path, repacks the weights once (bf16, K-major, conv taps unrolled along K, GEGLU
+rows tile-interleaved, all `time_emb_proj` layers stacked into one matrix), and for a given
+(batch, h, w) records the whole forward as a `pp_program` of CUDA launches over static
+channels-last bf16 buffers:
+
+  reference dataflow                               here
+  ------------------------------------------------ ---------------------------------------------
+  GroupNorm -> SiLU -> Conv2d (ResnetBlock2D)      pp_group_norm (also does the skip concat)
+                                                   -> implicit-GEMM conv with bias + time-embedding
+                                                   row + shortcut + BrushNet add in the epilogue
+  NCHW<->token permutes (Transformer2DModel)       none: NHWC *is* the token layout
+  to_q/to_k/to_v, SDPA, to_out + residual          QK GEMM + V^T GEMM -> pp_attention -> GEMM(+res)
+  cross-attn K/V of the prompt, every step         projected once per prompt (`set_context`)
+  GEGLU proj, chunk, gelu, mul, Linear + residual  one GEMM with the gate in the epilogue + GEMM(+res)
+  22 x time_emb_proj(silu(emb))                    one stacked GEMM per step
+  BrushNet 28 zero-convs * scale, 28 adds in UNet  1x1 GEMMs with alpha; adds ride the producer's
+                                                   epilogue as the second residual
+
+Reference anchors: powerpaint/models/unet_2d_condition.py:1040-1363 (UNet forward and BrushNet /
+ControlNet hooks), powerpaint/models/unet_2d_blocks.py:756,1237,1405,2458,2646 (blocks),
+powerpaint/models/BrushNet_CA.py:690-952 (BrushNet forward), SURVEY.md App. A (diffusers blocks).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _native as N
+from . import ops
+
+BF16 = torch.bfloat16
+
+
+def _ceil(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+@dataclass
+class NetConfig:
+    """The diffusers config keys the hot path reads."""
+    in_channels: int = 9
+    out_channels: int = 4
+    block_out_channels: Tuple[int, ...] = (320, 640, 1280, 1280)
+    layers_per_block: int = 2
+    attention_head_dim: int = 8  # number of heads (diffusers naming quirk)
+    cross_attention_dim: int = 768
+    norm_num_groups: int = 32
+    norm_eps: float = 1e-5
+    down_block_types: Tuple[str, ...] = ("CrossAttnDownBlock2D", "CrossAttnDownBlock2D",
+                                         "CrossAttnDownBlock2D", "DownBlock2D")
+    up_block_types: Tuple[str, ...] = ("UpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D",
+                                       "CrossAttnUpBlock2D")
+    mid_block_scale_factor: float = 1.0
+    conditioning_channels: int = 5       # BrushNet
+    controlnet_cond_channels: int = 3    # ControlNet
+    conditioning_embedding_out_channels: Tuple[int, ...] = (16, 32, 96, 256)
+
+
+class Plan:
+    """A recorded forward for fixed (batch, h, w): programs + the static buffers they touch."""
+
+    def __init__(self):
+        self.program: Optional[ops.Program] = None       # per-step forward
+        self.ctx_program: Optional[ops.Program] = None   # per-prompt cross-attention K / V^T
+        self.cond_program: Optional[ops.Program] = None  # ControlNet: per-control-image embedding
+        self.inputs: Dict[str, torch.Tensor] = {}
+        self.outputs: Dict[str, object] = {}
+        self.bytes = 0
+        self.buffers: List[torch.Tensor] = []  # every activation buffer, in recording order
+
+
+class NetEngine:
+    KINDS = ("unet", "brushnet", "controlnet")
+
+    def __init__(self, cfg: NetConfig, state_dict: Dict[str, torch.Tensor], kind: str = "unet",
+                 device: Optional[torch.device] = None):
+        if kind not in self.KINDS:
+            raise ValueError(f"kind must be one of {self.KINDS}")
+        self.cfg = cfg
+        self.kind = kind
+        self.device = torch.device(device or "cuda")
+        if self.device.type != "cuda":
+            raise RuntimeError("NetEngine needs a CUDA device: the hot path has no CPU fallback")
+        N.lib()  # fail loudly if the extension is missing
+        self._sd = state_dict
+        self._w: Dict[str, torch.Tensor] = {}
+        self._plans: Dict[tuple, Plan] = {}
+        for t in cfg.down_block_types:
+            if t not in ("CrossAttnDownBlock2D", "DownBlock2D"):
+                raise NotImplementedError(f"down block type {t} is outside the SD-1.5 hot path")
+        for t in cfg.up_block_types:
+            if t not in ("CrossAttnUpBlock2D", "UpBlock2D"):
+                raise NotImplementedError(f"up block type {t} is outside the SD-1.5 hot path")
+        if cfg.block_out_channels[0] % 8 or any(c % 8 for c in cfg.block_out_channels):
+            raise ValueError("block_out_channels must be multiples of 8")
+        self._pack_time_proj()
+
+    # ------------------------------------------------------------------ weights
+    def _raw(self, name: str) -> torch.Tensor:
+        if name not in self._sd:
+            raise KeyError(f"missing weight '{name}' in state dict")
+        return self._sd[name].detach().to(self.device, torch.float32)
+
+    def _cached(self, key: str, fn):
+        t = self._w.get(key)
+        if t is None:
+            t = fn()
+            self._w[key] = t
+        return t
+
+    def w_linear(self, name: str) -> torch.Tensor:
+        return self._cached("lin:" + name, lambda: ops.pack_linear_weight(self._raw(name + ".weight")))
+
+    def w_conv3(self, name: str, split: Optional[int] = None, pad_in: Optional[int] = None) -> torch.Tensor:
+        def make():
+            w = self._raw(name + ".weight")
+            if pad_in is not None and pad_in > w.shape[1]:
+                wp = torch.zeros(w.shape[0], pad_in, 3, 3, device=w.device)
+                wp[:, : w.shape[1]] = w
+                w = wp
+            return ops.pack_conv3x3_weight(w, split)
+        return self._cached(f"c3:{name}:{split}:{pad_in}", make)
+
+    def w_concat_linear(self, name: str, split: int) -> torch.Tensor:
+        return self._cached(f"cl:{name}:{split}",
+                            lambda: ops.pack_concat_linear_weight(self._raw(name + ".weight"), split))
+
+    def w_qk(self, prefix: str) -> torch.Tensor:
+        return self._cached("qk:" + prefix, lambda: torch.cat(
+            [self._raw(prefix + ".to_q.weight"), self._raw(prefix + ".to_k.weight")], 0).to(BF16).contiguous())
+
+    GEGLU_BLOCK_N = 128
+
+    def w_geglu(self, name: str):
+        def make():
+            return ops.pack_geglu_weight(self._raw(name + ".weight"), self._raw(name + ".bias"), self.GEGLU_BLOCK_N)
+        return self._cached("gg:" + name, make)
+
+    def vec(self, name: str) -> torch.Tensor:
+        return self._cached("v:" + name, lambda: self._raw(name).contiguous())
+
+    def _resnet_names(self) -> List[str]:
+        cfg = self.cfg
+        names = []
+        for i in range(len(cfg.down_block_types)):
+            for j in range(cfg.layers_per_block):
+                names.append(f"down_blocks.{i}.resnets.{j}")
+        names += ["mid_block.resnets.0", "mid_block.resnets.1"]
+        if self.kind != "controlnet":
+            for i in range(len(cfg.up_block_types)):
+                for j in range(cfg.layers_per_block + 1):
+                    names.append(f"up_blocks.{i}.resnets.{j}")
+        return names
+
+    def _pack_time_proj(self):
+        """stack every resnet's time_emb_proj into one [sum(Cout), 4*C0] matrix"""
+        ws, bs, self._tp_off = [], [], {}
+        off = 0
+        for n in self._resnet_names():
+            w = self._raw(n + ".time_emb_proj.weight")
+            self._tp_off[n] = (off, w.shape[0])
+            off += w.shape[0]
+            ws.append(w)
+            bs.append(self._raw(n + ".time_emb_proj.bias"))
+        self._tp_total = off
+        self._w["tp:w"] = torch.cat(ws, 0).to(BF16).contiguous()
+        self._w["tp:b"] = torch.cat(bs, 0).contiguous()
+
+    # ------------------------------------------------------------------ planning helpers
+    def _buf(self, plan: Plan, *shape, dtype=BF16) -> torch.Tensor:
+        t = torch.empty(*shape, dtype=dtype, device=self.device)
+        plan.bytes += t.numel() * t.element_size()
+        plan.buffers.append(t)
+        return t
+
+    def _gn(self, plan, prog, x0, x1, nb, hw, name, eps, silu):
+        c0 = x0.shape[-1]
+        c1 = x1.shape[-1] if x1 is not None else 0
+        groups = self.cfg.norm_num_groups
+        y = self._buf(plan, nb, hw, c0 + c1)
+        stats = self._buf(plan, nb, groups, 2, dtype=torch.float32)
+        prog.add(ops.gn_desc(x0=x0, x1=x1, c0=c0, c1=c1, batch=nb, hw=hw, groups=groups,
+                             gamma=self.vec(name + ".weight"), beta=self.vec(name + ".bias"), eps=eps, silu=silu,
+                             stats=stats, y=y))
+        return y
+
+    def _conv3(self, plan, prog, x, nb, h, w, name, cout, *, stride2=False, rowvec=None, res1=None, res2=None,
+               alpha=1.0, out_fp32=False, pad_in=None, out=None):
+        cin = x.shape[-1]
+        ho, wo = (h // 2, w // 2) if stride2 else (h, w)
+        if out is None:
+            out = self._buf(plan, nb, ho * wo, cout, dtype=torch.float32 if out_fp32 else BF16)
+        rv, rv_ld = (None, 0) if rowvec is None else rowvec
+        prog.add(ops.gemm_desc(a0=x, w=self.w_conv3(name, pad_in=pad_in), out=out, N_=cout,
+                               a_mode=N.PP_A_CONV3X3_S2 if stride2 else N.PP_A_CONV3X3, c0=cin, nb=nb, h=h, w_=w,
+                               bias=self.vec(name + ".bias"), rowvec=rv, rowvec_ld=rv_ld, res1=res1, res2=res2,
+                               alpha=alpha, out_fp32=out_fp32))
+        return out
+
+    def _linear(self, plan, prog, x, M, wname, n_out, *, w=None, bias=None, res1=None, res2=None, alpha=1.0,
+                act=N.PP_ACT_NONE, out=None, out_fp32=False, a1=None, c1=0, ldc=0, lda0=0):
+        if out is None:
+            out = self._buf(plan, M, n_out, dtype=torch.float32 if out_fp32 else BF16)
+        prog.add(ops.gemm_desc(a0=x, a1=a1, c1=c1, w=w if w is not None else self.w_linear(wname), out=out, N_=n_out,
+                               M=M, bias=bias, res1=res1, res2=res2, alpha=alpha, act=act, out_fp32=out_fp32,
+                               ldc=ldc, lda0=lda0))
+        return out
+
+    def _resnet(self, plan, prog, name, x0, x1, nb, h, w, cout, tproj, *, out_scale=1.0, add=None):
+        """ResnetBlock2D on the (virtual) concat of x0 and x1."""
+        hw = h * w
+        c0 = x0.shape[-1]
+        c1 = x1.shape[-1] if x1 is not None else 0
+        cin = c0 + c1
+        eps = self.cfg.norm_eps
+        n1 = self._gn(plan, prog, x0, x1, nb, hw, name + ".norm1", eps, True)
+        off, tc = self._tp_off[name]
+        assert tc == cout
+        t1 = self._conv3(plan, prog, n1, nb, h, w, name + ".conv1", cout, rowvec=(tproj[:, off:off + cout], self._tp_total))
+        n2 = self._gn(plan, prog, t1, None, nb, hw, name + ".norm2", eps, True)
+        if cin != cout or x1 is not None:
+            # 1x1 conv_shortcut over the concat: two A sources walked along K
+            if (name + ".conv_shortcut.weight") not in self._sd:
+                raise KeyError(f"{name}: in != out channels but no conv_shortcut weight")
+            if x1 is not None:
+                wsc = self.w_concat_linear(name + ".conv_shortcut", c0)
+                sc = self._buf(plan, nb * hw, cout)
+                prog.add(ops.gemm_desc(a0=x0, a1=x1, c0=c0, c1=c1, w=wsc, out=sc, N_=cout, M=nb * hw,
+                                       bias=self.vec(name + ".conv_shortcut.bias")))
+            else:
+                sc = self._linear(plan, prog, x0, nb * hw, name + ".conv_shortcut", cout,
+                                  bias=self.vec(name + ".conv_shortcut.bias"))
+        else:
+            sc = x0
+        return self._conv3(plan, prog, n2, nb, h, w, name + ".conv2", cout, res1=sc, res2=add, alpha=1.0 / out_scale)
+
+    def _transformer(self, plan, ctxprog, prog, name, x, nb, h, w, heads, ctx, *, add=None):
+        """Transformer2DModel with one BasicTransformerBlock."""
+        cfg = self.cfg
+        hw = h * w
+        M = nb * hw
+        C = x.shape[-1]
+        d = C // heads
+        scale = 1.0 / math.sqrt(d)
+        g = self._gn(plan, prog, x, None, nb, hw, name + ".norm", 1e-6, False)
+        t0 = self._linear(plan, prog, g, M, name + ".proj_in", C, bias=self.vec(name + ".proj_in.bias"))
+        b = name + ".transformer_blocks.0"
+        # --- self attention
+        l1 = self._buf(plan, M, C)
+        prog.add_layer_norm(t0, l1, self.vec(b + ".norm1.weight"), self.vec(b + ".norm1.bias"), M, C, 1e-5)
+        qk = self._linear(plan, prog, l1, M, None, 2 * C, w=self.w_qk(b + ".attn1"))
+        hw_ld = _ceil(hw, 8)
+        vt = self._buf(plan, nb, C, hw_ld)
+        prog.add(ops.gemm_desc(a0=l1, w=self.w_linear(b + ".attn1.to_v"), out=vt, N_=C, M=M,
+                               epilogue=N.PP_EPI_TRANSPOSED, t_rows=hw, t_ld=hw_ld))
+        a1 = self._buf(plan, M, C)
+        prog.add(ops.attn_desc(q=qk, k=qk[:, C:], vt=vt, out=a1, batch=nb, heads=heads, d=d, nq=hw, nk=hw,
+                               q_ld=2 * C, k_ld=2 * C, vt_ld=hw_ld, o_ld=C, q_batch_stride=hw * 2 * C,
+                               k_batch_stride=hw * 2 * C, scale=scale))
+        t1 = self._linear(plan, prog, a1, M, b + ".attn1.to_out.0", C, bias=self.vec(b + ".attn1.to_out.0.bias"), res1=t0)
+        # --- cross attention (K / V^T of the prompt are projected once per prompt)
+        l2 = self._buf(plan, M, C)
+        prog.add_layer_norm(t1, l2, self.vec(b + ".norm2.weight"), self.vec(b + ".norm2.bias"), M, C, 1e-5)
+        q2 = self._linear(plan, prog, l2, M, b + ".attn2.to_q", C)
+        nk = ctx.shape[1]
+        nk_ld = _ceil(nk, 8)
+        k2 = self._linear(plan, ctxprog, ctx, nb * nk, b + ".attn2.to_k", C)
+        v2t = self._buf(plan, nb, C, nk_ld)
+        ctxprog.add(ops.gemm_desc(a0=ctx, w=self.w_linear(b + ".attn2.to_v"), out=v2t, N_=C, M=nb * nk,
+                                  epilogue=N.PP_EPI_TRANSPOSED, t_rows=nk, t_ld=nk_ld))
+        a2 = self._buf(plan, M, C)
+        prog.add(ops.attn_desc(q=q2, k=k2, vt=v2t, out=a2, batch=nb, heads=heads, d=d, nq=hw, nk=nk, q_ld=C, k_ld=C,
+                               vt_ld=nk_ld, o_ld=C, q_batch_stride=hw * C, k_batch_stride=nk * C, scale=scale))
+        t2 = self._linear(plan, prog, a2, M, b + ".attn2.to_out.0", C, bias=self.vec(b + ".attn2.to_out.0.bias"), res1=t1)
+        # --- feed-forward (GEGLU)
+        l3 = self._buf(plan, M, C)
+        prog.add_layer_norm(t2, l3, self.vec(b + ".norm3.weight"), self.vec(b + ".norm3.bias"), M, C, 1e-5)
+        wg, bg = self.w_geglu(b + ".ff.net.0.proj")
+        F_ = wg.shape[0] // 2
+        ffh = self._buf(plan, M, F_)
+        prog.add(ops.gemm_desc(a0=l3, w=wg, out=ffh, N_=2 * F_, M=M, bias=bg, epilogue=N.PP_EPI_GEGLU,
+                               block_n=self.GEGLU_BLOCK_N))
+        t3 = self._linear(plan, prog, ffh, M, b + ".ff.net.2", C, bias=self.vec(b + ".ff.net.2.bias"), res1=t2)
+        # --- proj_out + the Transformer2DModel residual (+ BrushNet add)
+        return self._linear(plan, prog, t3, M, name + ".proj_out", C, bias=self.vec(name + ".proj_out.bias"),
+                            res1=x, res2=add)
+
+    # ------------------------------------------------------------------ plan
+    def plan(self, nb: int, h: int, w: int, ctx_len: int = 77, *, with_brushnet_adds: bool = False,
+             with_controlnet_res: bool = False, use_step_table: bool = False, n_steps: int = 0) -> Plan:
+        key = (nb, h, w, ctx_len, with_brushnet_adds, with_controlnet_res, use_step_table, n_steps)
+        p = self._plans.get(key)
+        if p is None:
+            p = self._build_plan(nb, h, w, ctx_len, with_brushnet_adds, with_controlnet_res, use_step_table, n_steps)
+            self._plans[key] = p
+        return p
+
+    def _state_shapes(self, nb, h, w):
+        """(channels, h, w) of the 12 down states, the mid state and the 15 up states"""
+        cfg = self.cfg
+        boc = cfg.block_out_channels
+        down = [(boc[0], h, w)]
+        ch, cw = h, w
+        for i, c in enumerate(boc):
+            for _ in range(cfg.layers_per_block):
+                down.append((c, ch, cw))
+            if i != len(boc) - 1:
+                ch, cw = ch // 2, cw // 2
+                down.append((c, ch, cw))
+        mid = (boc[-1], ch, cw)
+        up = []
+        for i, c in enumerate(reversed(boc)):
+            for _ in range(cfg.layers_per_block + 1):
+                up.append((c, ch, cw))
+            if i != len(boc) - 1:
+                ch, cw = ch * 2, cw * 2
+                up.append((c, ch, cw))
+        return down, mid, up
+
+    def _build_plan(self, nb, h, w, ctx_len, with_adds, with_cn, use_step_table, n_steps,
+                    shared: Optional[dict] = None) -> Plan:
+        """`shared` lets several nets record into ONE program over common inputs (the fused
+        per-step pipeline): keys `program`, `ctx_program`, `x_in` (a [nb, h*w, C] buffer whose
+        first channels are this net's input; extra channels meet zero weights), `timesteps`,
+        `step_idx`, and for the UNet `adds` = (down, mid, up) / `cn` = (down, mid) buffers
+        produced by the side net."""
+        shared = shared or {}
+        cfg = self.cfg
+        boc = cfg.block_out_channels
+        n_down = len(boc) - 1
+        if h % (1 << n_down) or w % (1 << n_down):
+            raise ValueError(f"latent size {h}x{w} must be divisible by {1 << n_down} "
+                             "(odd intermediate sizes are not implemented in this build)")
+        heads = cfg.attention_head_dim
+        plan = Plan()
+        prog = shared.get("program") or ops.Program()
+        ctxprog = shared.get("ctx_program") or ops.Program()
+        plan.program, plan.ctx_program = prog, ctxprog
+        C0 = boc[0]
+        temb_c = 4 * C0
+
+        # ---------------- inputs
+        if self.kind == "brushnet":
+            cin = cfg.in_channels + cfg.conditioning_channels
+            conv_in_name = "conv_in_condition"
+        else:
+            cin = cfg.in_channels
+            conv_in_name = "conv_in"
+        if shared.get("x_in") is not None:
+            x_in = shared["x_in"]
+            cin_pad = x_in.shape[-1]
+            if cin_pad < cin or tuple(x_in.shape[:2]) != (nb, h * w):
+                raise ValueError("shared x_in has the wrong shape")
+        else:
+            cin_pad = _ceil(cin, 8)
+            x_in = self._buf(plan, nb, h * w, cin_pad)
+            x_in.zero_()
+        ctx = self._buf(plan, nb, ctx_len, cfg.cross_attention_dim)
+        ctx.zero_()
+        plan.inputs["x_in"] = x_in
+        plan.inputs["ctx"] = ctx
+        if shared.get("timesteps") is not None:
+            plan.inputs["timesteps"] = shared["timesteps"]
+            plan.inputs["step_idx"] = shared["step_idx"]
+        elif use_step_table:
+            plan.inputs["timesteps"] = torch.zeros(max(n_steps, 1), dtype=torch.float32, device=self.device)
+            plan.inputs["step_idx"] = torch.zeros(1, dtype=torch.int32, device=self.device)
+        else:
+            plan.inputs["timesteps"] = torch.zeros(nb, dtype=torch.float32, device=self.device)
+        down_shapes, mid_shape, up_shapes = self._state_shapes(nb, h, w)
+        adds_down = adds_up = None
+        add_mid = None
+        if with_adds:
+            if shared.get("adds") is not None:
+                adds_down, add_mid, adds_up = shared["adds"]
+            else:
+                adds_down = [self._buf(plan, nb, hh * ww, c) for (c, hh, ww) in down_shapes]
+                add_mid = self._buf(plan, nb, mid_shape[1] * mid_shape[2], mid_shape[0])
+                adds_up = [self._buf(plan, nb, hh * ww, c) for (c, hh, ww) in up_shapes]
+                for t in adds_down + [add_mid] + adds_up:
+                    t.zero_()
+            plan.inputs["adds_down"], plan.inputs["add_mid"], plan.inputs["adds_up"] = adds_down, add_mid, adds_up
+        cn_down = cn_mid = None
+        if with_cn:
+            if shared.get("cn") is not None:
+                cn_down, cn_mid = shared["cn"]
+            else:
+                cn_down = [self._buf(plan, nb, hh * ww, c) for (c, hh, ww) in down_shapes]
+                cn_mid = self._buf(plan, nb, mid_shape[1] * mid_shape[2], mid_shape[0])
+                for t in cn_down + [cn_mid]:
+                    t.zero_()
+            plan.inputs["cn_down"], plan.inputs["cn_mid"] = cn_down, cn_mid
+
+        # ---------------- time embedding (unet_2d_condition.py:1155-1156) + stacked time_emb_proj
+        tsin = self._buf(plan, nb, C0)
+        prog.add_time_embed(plan.inputs["timesteps"], plan.inputs.get("step_idx"), tsin, nb, C0)
+        e1 = self._linear(plan, prog, tsin, nb, "time_embedding.linear_1", temb_c,
+                          bias=self.vec("time_embedding.linear_1.bias"), act=N.PP_ACT_SILU)
+        # resnets consume silu(emb); emb itself is not used elsewhere on the SD-1.5 path
+        e2 = self._linear(plan, prog, e1, nb, "time_embedding.linear_2", temb_c,
+                          bias=self.vec("time_embedding.linear_2.bias"), act=N.PP_ACT_SILU)
+        tproj = self._buf(plan, nb, self._tp_total, dtype=torch.float32)
+        prog.add(ops.gemm_desc(a0=e2, w=self._w["tp:w"], out=tproj, N_=self._tp_total, M=nb, bias=self._w["tp:b"],
+                               out_fp32=True))
+
+        # ---------------- conv_in
+        hcur = self._conv3(plan, prog, x_in.view(nb, h * w, cin_pad), nb, h, w, conv_in_name, C0, pad_in=cin_pad)
+        if self.kind == "controlnet":
+            cond_in = self._buf(plan, nb, (8 * h) * (8 * w), _ceil(cfg.controlnet_cond_channels, 8))
+            cond_in.zero_()
+            plan.inputs["cond_in"] = cond_in
+            cond_emb = self._buf(plan, nb, h * w, C0)
+            plan.outputs["cond_emb"] = cond_emb
+            plan.cond_program = self._build_cond_embedding(plan, cond_in, cond_emb, nb, 8 * h, 8 * w)
+            h_sum = self._buf(plan, nb, h * w, C0)
+            prog.add_add(hcur, cond_emb, h_sum, hcur.numel())
+            hcur = h_sum
+        skips = [hcur]  # pre-add (unet_2d_condition.py:1220 before :1223)
+        states_down = [hcur]
+        ai = 0
+        if with_adds:
+            hsum = self._buf(plan, nb, h * w, C0)
+            prog.add_add(hcur, adds_down[0], hsum, hcur.numel())
+            hcur = hsum
+            ai = 1
+
+        def next_add(lst, idx):
+            return lst[idx] if lst is not None else None
+
+        # ---------------- down
+        ch, cw = h, w
+        for i, btype in enumerate(cfg.down_block_types):
+            cout = boc[i]
+            for j in range(cfg.layers_per_block):
+                rn = f"down_blocks.{i}.resnets.{j}"
+                has_attn = btype == "CrossAttnDownBlock2D"
+                add = next_add(adds_down, ai) if with_adds else None
+                hcur = self._resnet(plan, prog, rn, hcur, None, nb, ch, cw, cout, tproj,
+                                    add=None if has_attn else add)
+                if has_attn:
+                    hcur = self._transformer(plan, ctxprog, prog, f"down_blocks.{i}.attentions.{j}", hcur, nb, ch, cw,
+                                             heads, ctx, add=add)
+                ai += 1 if with_adds else 0
+                skips.append(hcur)
+                states_down.append(hcur)
+            if i != len(boc) - 1:
+                add = next_add(adds_down, ai) if with_adds else None
+                hcur = self._conv3(plan, prog, hcur, nb, ch, cw, f"down_blocks.{i}.downsamplers.0.conv", cout,
+                                   stride2=True, res2=add)
+                ai += 1 if with_adds else 0
+                ch, cw = ch // 2, cw // 2
+                skips.append(hcur)
+                states_down.append(hcur)
+        if with_cn:
+            # ControlNet: skip_i += residual_i after the whole down path (:1263-1272); h itself is unchanged
+            new_skips = []
+            for sk, r in zip(skips, cn_down):
+                o = self._buf(plan, *sk.shape)
+                prog.add_add(sk, r, o, sk.numel())
+                new_skips.append(o)
+            skips = new_skips
+
+        # ---------------- mid (UNetMidBlock2DCrossAttn)
+        cm = boc[-1]
+        hcur = self._resnet(plan, prog, "mid_block.resnets.0", hcur, None, nb, ch, cw, cm, tproj,
+                            out_scale=cfg.mid_block_scale_factor)
+        hcur = self._transformer(plan, ctxprog, prog, "mid_block.attentions.0", hcur, nb, ch, cw, heads, ctx)
+        mid_add = cn_mid if with_cn else (add_mid if with_adds else None)
+        hcur = self._resnet(plan, prog, "mid_block.resnets.1", hcur, None, nb, ch, cw, cm, tproj,
+                            out_scale=cfg.mid_block_scale_factor,
+                            add=mid_add if self.kind == "unet" else None)
+        if with_cn and with_adds:
+            hs = self._buf(plan, *hcur.shape)
+            prog.add_add(hcur, add_mid, hs, hcur.numel())
+            hcur = hs
+        state_mid = hcur
+
+        if self.kind == "controlnet":
+            cn_scale = float(shared.get("cn_scale", 1.0))  # conditioning_scale baked in on the fused path
+            outs_down = []
+            for k, st in enumerate(states_down):
+                c = st.shape[-1]
+                outs_down.append(self._linear(plan, prog, st, st.numel() // c, f"controlnet_down_blocks.{k}", c,
+                                              bias=self.vec(f"controlnet_down_blocks.{k}.bias"), alpha=cn_scale))
+            out_mid = self._linear(plan, prog, state_mid, state_mid.numel() // cm, "controlnet_mid_block",
+                                   cm, bias=self.vec("controlnet_mid_block.bias"), alpha=cn_scale)
+            plan.outputs["down"], plan.outputs["mid"] = outs_down, out_mid
+            return plan
+
+        # ---------------- up
+        states_up = []
+        ui = 0
+        for i, btype in enumerate(cfg.up_block_types):
+            cout = list(reversed(boc))[i]
+            has_attn = btype == "CrossAttnUpBlock2D"
+            for j in range(cfg.layers_per_block + 1):
+                skip = skips.pop()
+                rn = f"up_blocks.{i}.resnets.{j}"
+                add = next_add(adds_up, ui) if with_adds else None
+                hcur = self._resnet(plan, prog, rn, hcur, skip.view(nb, ch * cw, skip.shape[-1]), nb, ch, cw, cout,
+                                    tproj, add=None if has_attn else add)
+                if has_attn:
+                    hcur = self._transformer(plan, ctxprog, prog, f"up_blocks.{i}.attentions.{j}", hcur, nb, ch, cw,
+                                             heads, ctx, add=add)
+                ui += 1 if with_adds else 0
+                # BrushNet captures the state BEFORE the add; BrushNet itself has no adds, so for
+                # kind == "brushnet" hcur is exactly the captured tensor
+                states_up.append(hcur)
+            if i != len(boc) - 1:
+                up = self._buf(plan, nb, 4 * ch * cw, cout)
+                prog.add_upsample2x(hcur, up, nb, ch, cw, cout)
+                ch, cw = ch * 2, cw * 2
+                add = next_add(adds_up, ui) if with_adds else None
+                hcur = self._conv3(plan, prog, up, nb, ch, cw, f"up_blocks.{i}.upsamplers.0.conv", cout, res2=add)
+                ui += 1 if with_adds else 0
+                states_up.append(hcur)
+
+        if self.kind == "brushnet":
+            plan.outputs["states"] = (states_down, state_mid, states_up)
+            return plan  # zero-convs are appended by `append_brushnet_outputs` (they need the scale)
+
+        # ---------------- out
+        gno = self._gn(plan, prog, hcur, None, nb, h * w, "conv_norm_out", cfg.norm_eps, True)
+        eps = self._conv3(plan, prog, gno, nb, h, w, "conv_out", cfg.out_channels, out_fp32=True)
+        plan.outputs["eps"] = eps  # fp32 NHWC [nb, h*w, out_channels]
+        return plan
+
+    # ------------------------------------------------------------------ BrushNet zero-convs
+    def append_brushnet_outputs(self, plan: Plan, conditioning_scale: float, targets=None):
+        """1x1 zero-convs x conditioning_scale on the 12 + 1 + 15 captured states
+        (BrushNet_CA.py:843-845, :861, :900-902, :930-934). `targets` = (down, mid, up) buffer
+        lists of a UNet plan (`with_brushnet_adds=True`) to write straight into."""
+        states_down, state_mid, states_up = plan.outputs["states"]
+        prog = plan.program
+        nb = states_down[0].shape[0]
+
+        def zc(st, wname, out):
+            c = st.shape[-1]
+            M = st.numel() // c
+            return self._linear(plan, prog, st, M, wname, c, bias=self.vec(wname + ".bias"), alpha=conditioning_scale,
+                                out=out)
+        t_down, t_mid, t_up = targets if targets is not None else (None, None, None)
+        outs_down = [zc(st, f"brushnet_down_blocks.{k}", t_down[k] if t_down else None) for k, st in enumerate(states_down)]
+        out_mid = zc(state_mid, "brushnet_mid_block", t_mid)
+        outs_up = [zc(st, f"brushnet_up_blocks.{k}", t_up[k] if t_up else None) for k, st in enumerate(states_up)]
+        plan.outputs["down"], plan.outputs["mid"], plan.outputs["up"] = outs_down, out_mid, outs_up
+        plan.outputs["conditioning_scale"] = conditioning_scale
+
+    # ------------------------------------------------------------------ ControlNet cond embedding
+    def _build_cond_embedding(self, plan, cond_in, cond_emb, nb, H, W):
+        """controlnet_cond_embedding: conv3x3(3->16)+SiLU, [conv+SiLU, conv s2+SiLU] x3, zero conv
+        (SURVEY.md App. A.9); independent of t, so it runs once per call, not per step."""
+        prog = ops.Program()
+        ce = self.cfg.conditioning_embedding_out_channels
+        pre = "controlnet_cond_embedding"
+        cpad = cond_in.shape[-1]
+
+        def conv(x, name, cout, hh, ww, stride2=False, act=True, out=None, pad_in=None):
+            cin = x.shape[-1]
+            ho, wo = (hh // 2, ww // 2) if stride2 else (hh, ww)
+            cout_pad = _ceil(cout, 8)
+            o = out if out is not None else self._buf(plan, nb, ho * wo, cout_pad)
+            if cout_pad != cout:
+                o.zero_()
+            prog.add(ops.gemm_desc(a0=x, w=self.w_conv3(name, pad_in=pad_in or cin), out=o, N_=cout,
+                                   a_mode=N.PP_A_CONV3X3_S2 if stride2 else N.PP_A_CONV3X3, c0=cin, nb=nb, h=hh, w_=ww,
+                                   bias=self.vec(name + ".bias"), act=N.PP_ACT_SILU if act else N.PP_ACT_NONE,
+                                   ldc=cout_pad))
+            return o
+        x = conv(cond_in, pre + ".conv_in", ce[0], H, W, pad_in=cpad)
+        hh, ww = H, W
+        for i in range(len(ce) - 1):
+            x = conv(x, f"{pre}.blocks.{2 * i}", ce[i], hh, ww)
+            x = conv(x, f"{pre}.blocks.{2 * i + 1}", ce[i + 1], hh, ww, stride2=True)
+            hh, ww = hh // 2, ww // 2
+        conv(x, pre + ".conv_out", self.cfg.block_out_channels[0], hh, ww, act=False, out=cond_emb)
+        return prog

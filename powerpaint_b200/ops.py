@@ -93,7 +93,7 @@ def gemm_desc(*, a0: torch.Tensor, w: torch.Tensor, out: torch.Tensor, N_: int,
               c0: Optional[int] = None, c1: int = 0, M: int = 0, lda0: int = 0, lda1: int = 0,
               nb: int = 0, h: int = 0, w_: int = 0, ldb: int = 0,
               bias: Optional[torch.Tensor] = None, rowvec: Optional[torch.Tensor] = None,
-              rows_per_group: int = 0, res1: Optional[torch.Tensor] = None, ldr1: int = 0,
+              rows_per_group: int = 0, rowvec_ld: int = 0, res1: Optional[torch.Tensor] = None, ldr1: int = 0,
               res2: Optional[torch.Tensor] = None, ldr2: int = 0, alpha: float = 1.0,
               act: int = N.PP_ACT_NONE, epilogue: int = N.PP_EPI_PLAIN, ldc: int = 0,
               out_fp32: bool = False, t_rows: int = 0, t_ld: int = 0, block_n: int = 0) -> Desc:
@@ -109,6 +109,7 @@ def gemm_desc(*, a0: torch.Tensor, w: torch.Tensor, out: torch.Tensor, N_: int,
     d.b = N.ptr(w)
     d.ldb = ldb or w.shape[-1]
     d.bias, d.rowvec, d.rows_per_group = N.ptr(bias), N.ptr(rowvec), rows_per_group
+    d.rowvec_ld = rowvec_ld
     d.res1, d.ldr1 = N.ptr(res1), (ldr1 or N_)
     d.res2, d.ldr2 = N.ptr(res2), (ldr2 or N_)
     d.alpha, d.act = alpha, act
@@ -142,7 +143,7 @@ def gn_desc(*, x0, x1, c0, c1, batch, hw, groups, gamma, beta, eps, silu, stats,
 
 def cfg_ddim_desc(*, eps, eps_fp32, eps_ld, latents, coef, step_idx, advance_step, noise,
                   guidance_scale, do_cfg, batch, hw, next_in=None, next_c=0, n_copies=0,
-                  extra=None, extra_c=0) -> Desc:
+                  extra=None, extra_c=0, guidance_from_coef=False) -> Desc:
     d = N.CfgDdimDesc()
     d.eps, d.eps_fp32, d.eps_ld = N.ptr(eps), 1 if eps_fp32 else 0, eps_ld
     d.latents, d.coef, d.step_idx = N.ptr(latents), N.ptr(coef), N.ptr(step_idx)
@@ -152,6 +153,7 @@ def cfg_ddim_desc(*, eps, eps_fp32, eps_ld, latents, coef, step_idx, advance_ste
     d.batch, d.hw = batch, hw
     d.next_in, d.next_c, d.n_copies = N.ptr(next_in), next_c, n_copies
     d.extra, d.extra_c = N.ptr(extra), extra_c
+    d.guidance_from_coef = 1 if guidance_from_coef else 0
     return Desc("cfg_ddim", d, (eps, latents, coef, step_idx, noise, next_in, extra))
 
 
@@ -211,6 +213,17 @@ def nhwc_to_nchw(x: torch.Tensor, c: Optional[int] = None) -> torch.Tensor:
     N.check(N.lib().pp_nhwc_to_nchw(N.ptr(x), 1 if x.dtype == torch.float32 else 0, N.ptr(y), nb, c,
                                     h * w, c_ld, N.current_stream()), "pp_nhwc_to_nchw")
     return y
+
+
+def nhwc_fp32_from_nchw(x: torch.Tensor) -> torch.Tensor:
+    """4-channel latents NCHW -> fp32 NHWC [nb, h*w, c] (boundary plumbing; 64 KB per image)"""
+    nb, c, h, w = x.shape
+    return x.float().permute(0, 2, 3, 1).contiguous().view(nb, h * w, c)
+
+
+def nchw_from_nhwc_fp32(x: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    nb, hw, c = x.shape
+    return x.view(nb, h, w, c).permute(0, 3, 1, 2).contiguous()
 
 
 # --------------------------------------------------------------------------- programs

@@ -1,0 +1,169 @@
+"""DDIMScheduler with the diffusers surface the reference pipelines duck-type
+(`.config`, `.set_timesteps`, `.timesteps`, `.order`, `.init_noise_sigma`, `.scale_model_input`,
+`.step(..., eta=, generator=, return_dict=False)[0]`, `.add_noise`, `from_config`),
+restating diffusers==0.27.0 DDIMScheduler as called by
+powerpaint/pipelines/pipeline_PowerPaint.py:906 (set_timesteps), :993 (scale_model_input),
+:1023 (step), :642 (init_noise_sigma).
+
+Host side only computes the schedule (numpy / CPU tensors). The arithmetic of `step` on CUDA
+tensors runs in the fused CFG+DDIM kernel (`pp_cfg_ddim_step`); there is no CPU `step`.
+`step_coefficients()` exports the per-step scalar table the captured CUDA graph indexes.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+from typing import List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+
+class _SchedConfig(SimpleNamespace):
+    def __getitem__(self, k):
+        return getattr(self, k)
+
+    def __contains__(self, k):
+        return hasattr(self, k)
+
+    def get(self, k, default=None):
+        return getattr(self, k, default)
+
+    def keys(self):
+        return self.__dict__.keys()
+
+
+class DDIMSchedulerOutput(SimpleNamespace):
+    pass
+
+
+class DDIMScheduler:
+    order = 1
+    _compatibles: List[str] = []
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012,
+                 beta_schedule: str = "scaled_linear", trained_betas=None, clip_sample: bool = False,
+                 set_alpha_to_one: bool = False, steps_offset: int = 1, prediction_type: str = "epsilon",
+                 thresholding: bool = False, dynamic_thresholding_ratio: float = 0.995, clip_sample_range: float = 1.0,
+                 sample_max_value: float = 1.0, timestep_spacing: str = "leading", rescale_betas_zero_snr: bool = False,
+                 **unused):
+        if prediction_type != "epsilon":
+            raise NotImplementedError("only prediction_type='epsilon' is on the PowerPaint hot path")
+        if clip_sample or thresholding or rescale_betas_zero_snr:
+            raise NotImplementedError("clip_sample / thresholding / zero-SNR rescale are off in the SD config")
+        self.config = _SchedConfig(
+            num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
+            beta_schedule=beta_schedule, trained_betas=trained_betas, clip_sample=clip_sample,
+            set_alpha_to_one=set_alpha_to_one, steps_offset=steps_offset, prediction_type=prediction_type,
+            thresholding=thresholding, dynamic_thresholding_ratio=dynamic_thresholding_ratio,
+            clip_sample_range=clip_sample_range, sample_max_value=sample_max_value,
+            timestep_spacing=timestep_spacing, rescale_betas_zero_snr=rescale_betas_zero_snr)
+        if trained_betas is not None:
+            betas = torch.tensor(trained_betas, dtype=torch.float32)
+        elif beta_schedule == "linear":
+            betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+        elif beta_schedule == "scaled_linear":
+            betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        else:
+            raise NotImplementedError(f"beta_schedule {beta_schedule}")
+        self.betas = betas
+        self.alphas = 1.0 - betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
+        self.init_noise_sigma = 1.0
+        self.num_inference_steps: Optional[int] = None
+        self.timesteps = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy().astype(np.int64))
+
+    @classmethod
+    def from_config(cls, config, **kwargs):
+        d = dict(config.__dict__) if hasattr(config, "__dict__") else dict(config)
+        d = {k: v for k, v in d.items() if not k.startswith("_")}
+        d.update(kwargs)
+        return cls(**d)
+
+    def scale_model_input(self, sample: torch.Tensor, timestep=None) -> torch.Tensor:
+        return sample
+
+    def set_timesteps(self, num_inference_steps: int, device: Union[str, torch.device, None] = None):
+        c = self.config
+        if num_inference_steps > c.num_train_timesteps:
+            raise ValueError(f"`num_inference_steps`: {num_inference_steps} cannot be larger than "
+                             f"`self.config.train_timesteps`: {c.num_train_timesteps}")
+        self.num_inference_steps = num_inference_steps
+        if c.timestep_spacing == "linspace":
+            ts = np.linspace(0, c.num_train_timesteps - 1, num_inference_steps).round()[::-1].copy().astype(np.int64)
+        elif c.timestep_spacing == "leading":
+            ratio = c.num_train_timesteps // num_inference_steps
+            ts = (np.arange(0, num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64)
+            ts += c.steps_offset
+        elif c.timestep_spacing == "trailing":
+            ratio = c.num_train_timesteps / num_inference_steps
+            ts = np.round(np.arange(c.num_train_timesteps, 0, -ratio)).astype(np.int64) - 1
+        else:
+            raise ValueError(f"{c.timestep_spacing} is not supported")
+        self.timesteps = torch.from_numpy(ts).to(device)
+
+    # ---- schedule scalars
+    def _alphas(self, timestep: int) -> Tuple[float, float]:
+        prev = timestep - self.config.num_train_timesteps // self.num_inference_steps
+        a_t = float(self.alphas_cumprod[timestep])
+        a_prev = float(self.alphas_cumprod[prev]) if prev >= 0 else float(self.final_alpha_cumprod)
+        return a_t, a_prev
+
+    def step_coefficients(self, timesteps=None, eta: float = 0.0) -> torch.Tensor:
+        """[n_steps, 8] fp32 rows {sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma,
+        0, 0, 0} consumed by pp_cfg_ddim_step (include/powerpaint_b200.h)."""
+        if self.num_inference_steps is None:
+            raise ValueError("call set_timesteps first")
+        ts = self.timesteps if timesteps is None else timesteps
+        rows = []
+        for t in [int(x) for x in ts]:
+            a_t, a_prev = self._alphas(t)
+            var = (1 - a_prev) / (1 - a_t) * (1 - a_t / a_prev)
+            sigma = eta * math.sqrt(max(var, 0.0))
+            rows.append([math.sqrt(a_t), math.sqrt(1 - a_t), math.sqrt(a_prev),
+                         math.sqrt(max(1 - a_prev - sigma * sigma, 0.0)), sigma, 0.0, 0.0, 0.0])
+        return torch.tensor(rows, dtype=torch.float32)
+
+    def step(self, model_output: torch.Tensor, timestep: int, sample: torch.Tensor, eta: float = 0.0,
+             use_clipped_model_output: bool = False, generator=None, variance_noise: Optional[torch.Tensor] = None,
+             return_dict: bool = True):
+        """x_t -> x_{t-1} on CUDA tensors through the fused kernel (no CFG: model_output is used as is)."""
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after "
+                             "creating the scheduler")
+        if not sample.is_cuda:
+            raise RuntimeError("DDIMScheduler.step runs in the CUDA kernel pp_cfg_ddim_step; "
+                               "CPU tensors are not supported (no CPU fallback on the hot path)")
+        from . import ops
+
+        nb, c, h, w = sample.shape
+        if c != 4:
+            raise ValueError("the fused step kernel handles 4-channel latents")
+        coef = self.step_coefficients([int(timestep)], eta).to(sample.device)
+        lat = ops.nhwc_fp32_from_nchw(sample)
+        eps = ops.nhwc_fp32_from_nchw(model_output)
+        noise = None
+        if eta > 0:
+            if variance_noise is None:
+                variance_noise = torch.randn(model_output.shape, generator=generator,
+                                             device=generator.device if generator is not None else sample.device,
+                                             dtype=torch.float32).to(sample.device)
+            noise = ops.nhwc_fp32_from_nchw(variance_noise)
+        ops.run(ops.cfg_ddim_desc(eps=eps, eps_fp32=True, eps_ld=4, latents=lat, coef=coef, step_idx=None,
+                                  advance_step=False, noise=noise, guidance_scale=1.0, do_cfg=False, batch=nb,
+                                  hw=h * w))
+        prev = lat.view(nb, h, w, 4).permute(0, 3, 1, 2).contiguous().to(sample.dtype)
+        if not return_dict:
+            return (prev,)
+        return DDIMSchedulerOutput(prev_sample=prev, pred_original_sample=None)
+
+    def add_noise(self, original_samples: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
+        a = self.alphas_cumprod.to(original_samples.device)[timesteps.to(original_samples.device)]
+        a = a.to(original_samples.dtype)
+        while a.dim() < original_samples.dim():
+            a = a.unsqueeze(-1)
+        return a ** 0.5 * original_samples + (1 - a) ** 0.5 * noise
+
+    def __len__(self):
+        return self.config.num_train_timesteps

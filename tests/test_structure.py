@@ -1,0 +1,55 @@
+"""CPU tests: parameter layout of the product models equals the oracle's (diffusers names)."""
+import torch
+
+from oracle.unet import BrushNetOracle, ControlNetOracle, UNet2DConditionOracle, UNetConfig
+from powerpaint_b200.engine import NetConfig
+from powerpaint_b200.models.spec import param_shapes, synthetic_state_dict
+
+
+def _cfgs(tiny: bool, in_channels: int):
+    o = UNetConfig.tiny(in_channels) if tiny else UNetConfig.sd15(in_channels)
+    n = NetConfig(in_channels=in_channels, block_out_channels=o.block_out_channels,
+                  attention_head_dim=o.attention_head_dim, cross_attention_dim=o.cross_attention_dim,
+                  norm_num_groups=o.norm_num_groups)
+    return o, n
+
+
+def _check(oracle_module, cfg, kind):
+    want = {k: tuple(v.shape) for k, v in oracle_module.state_dict().items()}
+    got = dict(param_shapes(cfg, kind))
+    assert set(got) == set(want), (sorted(set(got) ^ set(want))[:10])
+    for k in want:
+        assert got[k] == want[k], (k, got[k], want[k])
+
+
+def test_param_layout_tiny():
+    o, n = _cfgs(True, 9)
+    _check(UNet2DConditionOracle(o), n, "unet")
+    o4, n4 = _cfgs(True, 4)
+    _check(BrushNetOracle(o4), n4, "brushnet")
+    _check(ControlNetOracle(o4), n4, "controlnet")
+
+
+def test_param_layout_sd15_counts():
+    """SD-1.5 UNet has 859.5 M parameters with 9 input channels (857 M + conv_in) — SURVEY.md §6"""
+    _, n = _cfgs(False, 9)
+    total = 0
+    for shape in param_shapes(n, "unet").values():
+        k = 1
+        for s in shape:
+            k *= s
+        total += k
+    assert 855e6 < total < 865e6, total
+    _, n4 = _cfgs(False, 4)
+    sd = param_shapes(n4, "brushnet")
+    assert len([k for k in sd if k.startswith("brushnet_down_blocks") and k.endswith("weight")]) == 12
+    assert len([k for k in sd if k.startswith("brushnet_up_blocks") and k.endswith("weight")]) == 15
+
+
+def test_synthetic_state_dict_loads_into_oracle():
+    o, n = _cfgs(True, 9)
+    sd = synthetic_state_dict(n, "unet", seed=7)
+    m = UNet2DConditionOracle(o)
+    m.load_state_dict(sd, strict=True)
+    sd2 = synthetic_state_dict(n, "unet", seed=7)
+    assert all(torch.equal(sd[k], sd2[k]) for k in sd)
