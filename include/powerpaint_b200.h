@@ -185,6 +185,7 @@ typedef struct pp_cfg_ddim_desc {
     const float* extra;
     int32_t extra_c;
     int32_t guidance_from_coef; /* != 0: guidance scale = coef[row][5] (graph-replay friendly) */
+    int32_t extra_per_copy;     /* != 0: extra is [n_copies*batch, hw, extra_c] (one set per CFG half) */
 } pp_cfg_ddim_desc;
 pp_status pp_cfg_ddim_step(const pp_cfg_ddim_desc* d, pp_stream stream);
 

@@ -68,7 +68,7 @@ class CfgDdimDesc(C.Structure):
         ("noise", vp), ("guidance_scale", f32), ("do_cfg", i32),
         ("batch", i32), ("hw", i32),
         ("next_in", vp), ("next_c", i32), ("n_copies", i32),
-        ("extra", vp), ("extra_c", i32), ("guidance_from_coef", i32),
+        ("extra", vp), ("extra_c", i32), ("guidance_from_coef", i32), ("extra_per_copy", i32),
     ]
 
 

@@ -66,7 +66,8 @@ __global__ void cfg_ddim_kernel(pp_cfg_ddim_desc d) {
                 for (int c = 0; c < d.next_c; ++c) {
                     float v = 0.f;
                     if (c < 4) v = xp[c];
-                    else if (c - 4 < d.extra_c) v = d.extra[i * d.extra_c + (c - 4)];
+                    else if (c - 4 < d.extra_c)
+                        v = d.extra[((d.extra_per_copy ? (int64_t)cpy * total : 0) + i) * d.extra_c + (c - 4)];
                     o[c] = __float2bfloat16_rn(v);
                 }
             }

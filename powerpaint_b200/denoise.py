@@ -23,7 +23,7 @@ for it (weights are zero-padded at pack time), so no per-net concat exists.
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Optional
+from typing import Callable, Dict, Optional
 
 import torch
 
@@ -46,10 +46,12 @@ class FusedDenoiser:
         self.side = side
         self.mode = mode
         self._cache: Dict[tuple, dict] = {}
+        self._stream: Optional[torch.cuda.Stream] = None
 
     # ------------------------------------------------------------------ plan
-    def _get(self, B: int, h: int, w: int, do_cfg: bool, ctx_len: int, side_scale: float) -> dict:
-        key = (B, h, w, do_cfg, ctx_len, float(side_scale), id(self.unet.engine()),
+    def _get(self, B: int, h: int, w: int, do_cfg: bool, ctx_len: int, side_scale: float, with_noise: bool,
+             extra_per_copy: bool) -> dict:
+        key = (B, h, w, do_cfg, ctx_len, float(side_scale), with_noise, extra_per_copy, id(self.unet.engine()),
                id(self.side.engine()) if self.side is not None else 0)
         st = self._cache.get(key)
         if st is not None:
@@ -64,7 +66,8 @@ class FusedDenoiser:
         coef = torch.zeros(MAX_STEPS, 8, dtype=torch.float32, device=dev)
         shared = dict(program=prog, ctx_program=ctxprog, x_in=x_in, timesteps=timesteps, step_idx=step_idx)
         st = dict(B=B, nb=nb, h=h, w=w, do_cfg=do_cfg, x_in=x_in, timesteps=timesteps, step_idx=step_idx, coef=coef,
-                  program=prog, ctx_program=ctxprog, graph=False)
+                  program=prog, ctx_program=ctxprog, graph=False, with_noise=with_noise,
+                  extra_per_copy=extra_per_copy)
         side_plan: Optional[Plan] = None
         if self.mode == "brushnet":
             se: NetEngine = self.side.engine()
@@ -82,29 +85,34 @@ class FusedDenoiser:
             uplan = ue._build_plan(nb, h, w, ctx_len, False, False, True, 0, shared=shared)
         st["uplan"], st["side_plan"] = uplan, side_plan
         # fp32 master latents and the constant channels (channels-last)
+        n_extra = nb if extra_per_copy else B
         st["latents"] = torch.zeros(B, h * w, 4, dtype=torch.float32, device=dev)
-        st["extra"] = torch.zeros(B, h * w, 5, dtype=torch.float32, device=dev)
+        st["extra"] = torch.zeros(n_extra, h * w, 5, dtype=torch.float32, device=dev)
         st["noise"] = torch.zeros(B, h * w, 4, dtype=torch.float32, device=dev)
-        self._add_step_tail(st, with_noise=False)
+        prog.add(ops.cfg_ddim_desc(eps=uplan.outputs["eps"], eps_fp32=True, eps_ld=4, latents=st["latents"],
+                                   coef=coef, step_idx=step_idx, advance_step=True,
+                                   noise=st["noise"] if with_noise else None, guidance_scale=0.0,
+                                   guidance_from_coef=True, do_cfg=do_cfg, batch=B, hw=h * w, next_in=x_in,
+                                   next_c=X_IN_C, n_copies=2 if do_cfg else 1, extra=st["extra"], extra_c=5,
+                                   extra_per_copy=extra_per_copy))
         st["bytes"] = uplan.bytes + (side_plan.bytes if side_plan else 0)
         self._cache[key] = st
         return st
-
-    def _add_step_tail(self, st: dict, with_noise: bool):
-        d = ops.cfg_ddim_desc(eps=st["uplan"].outputs["eps"], eps_fp32=True, eps_ld=4, latents=st["latents"],
-                              coef=st["coef"], step_idx=st["step_idx"], advance_step=True,
-                              noise=st["noise"] if with_noise else None, guidance_scale=0.0,
-                              guidance_from_coef=True, do_cfg=st["do_cfg"], batch=st["B"], hw=st["h"] * st["w"],
-                              next_in=st["x_in"], next_c=X_IN_C, n_copies=2 if st["do_cfg"] else 1,
-                              extra=st["extra"], extra_c=5)
-        st["program"].add(d)
-        st["with_noise"] = with_noise
 
     @property
     def launches_per_step(self) -> int:
         return max((s["program"].num_launches for s in self._cache.values()), default=0)
 
     # ------------------------------------------------------------------ run
+    def _fill_x_in(self, st: dict, latents_only: bool = False):
+        B, do_cfg, x_in = st["B"], st["do_cfg"], st["x_in"]
+        lat16 = st["latents"].to(torch.bfloat16)
+        for cpy in range(2 if do_cfg else 1):
+            x_in[cpy * B:(cpy + 1) * B, :, :4] = lat16
+            if not latents_only:
+                ex = st["extra"][cpy * B:(cpy + 1) * B] if st["extra_per_copy"] else st["extra"]
+                x_in[cpy * B:(cpy + 1) * B, :, 4:9] = ex.to(torch.bfloat16)
+
     @torch.no_grad()
     def run(self, *, latents: torch.Tensor, prompt_embeds: torch.Tensor, timesteps, coef: torch.Tensor,
             guidance_scale: float, extra: Optional[torch.Tensor] = None,
@@ -113,10 +121,11 @@ class FusedDenoiser:
             callback: Optional[Callable[[int, int, torch.Tensor], Optional[torch.Tensor]]] = None,
             use_graph: bool = True) -> torch.Tensor:
         """latents [B,4,h,w]; prompt_embeds [nb,77,768] for the UNet (negative half first when CFG);
-        extra [B,5,h,w] = constant channels (v1/controlnet: mask + masked-image latents; brushnet:
-        conditioning latents + mask); side_prompt_embeds for the side net; coef [n,8] from
-        `DDIMScheduler.step_coefficients`. `callback(i, t, latents_nchw)` may return replacement
-        latents. Returns final latents [B,4,h,w] fp32."""
+        extra [B or nb,5,h,w] = constant channels (v1/controlnet: mask + masked-image latents;
+        brushnet: conditioning latents + mask; nb rows = one set per CFG half); side_prompt_embeds
+        for the side net; coef [n,8] from `DDIMScheduler.step_coefficients`; `noise_fn(i)` supplies
+        the eta > 0 variance noise of step i. `callback(i, t, latents_nchw)` may return replacement
+        latents. Returns the final latents [B,4,h,w] fp32."""
         B, _, h, w = latents.shape
         nb = prompt_embeds.shape[0]
         do_cfg = nb == 2 * B
@@ -125,60 +134,61 @@ class FusedDenoiser:
         n_steps = len(timesteps)
         if n_steps > MAX_STEPS:
             raise ValueError(f"at most {MAX_STEPS} steps")
-        st = self._get(B, h, w, do_cfg, prompt_embeds.shape[1], side_scale)
-        dev = st["x_in"].device
-        eta_noise = noise_fn is not None
-        if eta_noise != st["with_noise"]:
-            raise NotImplementedError("eta > 0 needs a plan recorded with noise; use FusedDenoiser(..., ) per eta mode")
-        # ---- per-call inputs (all outside the loop)
-        st["latents"].copy_(ops.nhwc_fp32_from_nchw(latents.to(dev)))
-        if extra is not None:
-            st["extra"].copy_(ops.nhwc_fp32_from_nchw(extra.to(dev)))
-        else:
-            st["extra"].zero_()
-        lat16 = st["latents"].to(torch.bfloat16)
-        ex16 = st["extra"].to(torch.bfloat16)
-        x_in = st["x_in"]
-        for cpy in range(2 if do_cfg else 1):
-            x_in[cpy * B:(cpy + 1) * B, :, :4] = lat16
-            x_in[cpy * B:(cpy + 1) * B, :, 4:9] = ex16
-        ts = torch.as_tensor([float(t) for t in timesteps], dtype=torch.float32)
-        st["timesteps"][:n_steps].copy_(ts.to(dev))
-        cf = coef.clone().float()
-        cf[:, 5] = float(guidance_scale)
-        st["coef"][:n_steps].copy_(cf.to(dev))
-        st["step_idx"].zero_()
-        st["uplan"].inputs["ctx"].copy_(prompt_embeds.to(dev, torch.bfloat16))
-        if st["side_plan"] is not None:
-            if side_prompt_embeds is None:
-                raise ValueError("side_prompt_embeds required")
-            st["side_plan"].inputs["ctx"].copy_(side_prompt_embeds.to(dev, torch.bfloat16))
-            if self.mode == "controlnet":
-                if control_image is None:
-                    raise ValueError("control_image required")
-                ci = st["side_plan"].inputs["cond_in"]
-                ci.copy_(ops.nchw_to_nhwc(control_image.to(dev).float().contiguous(), ci.shape[-1]).view_as(ci))
-                st["side_plan"].cond_program.run()
-        st["ctx_program"].run()
-        # ---- the loop
-        prog = st["program"]
-        if use_graph and callback is None and not eta_noise:
-            if not st["graph"]:
-                prog.build_graph()  # capture does not execute: device state is untouched
-                st["graph"] = True
-            for _ in range(n_steps):
-                prog.launch()
-        else:
-            for i in range(n_steps):
-                if eta_noise:
-                    st["noise"].copy_(ops.nhwc_fp32_from_nchw(noise_fn(i).to(dev)))
-                prog.run()
-                if callback is not None:
-                    cur = ops.nchw_from_nhwc_fp32(st["latents"], h, w)
-                    new = callback(i, timesteps[i], cur)
-                    if new is not None and new is not cur:
-                        st["latents"].copy_(ops.nhwc_fp32_from_nchw(new.to(dev)))
-                        l16 = st["latents"].to(torch.bfloat16)
-                        for cpy in range(2 if do_cfg else 1):
-                            x_in[cpy * B:(cpy + 1) * B, :, :4] = l16
-        return ops.nchw_from_nhwc_fp32(st["latents"], h, w).clone()
+        extra_per_copy = extra is not None and do_cfg and extra.shape[0] == nb
+        if extra is not None and extra.shape[0] not in (B, nb):
+            raise ValueError("extra batch must be B or 2B")
+        dev = self.unet.device
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        self._stream.wait_stream(cur)
+        with torch.cuda.stream(self._stream):
+            st = self._get(B, h, w, do_cfg, prompt_embeds.shape[1], side_scale, noise_fn is not None, extra_per_copy)
+            # ---- per-call inputs (all outside the loop)
+            st["latents"].copy_(ops.nhwc_fp32_from_nchw(latents.to(dev)))
+            if extra is not None:
+                st["extra"].copy_(ops.nhwc_fp32_from_nchw(extra.to(dev)))
+            else:
+                st["extra"].zero_()
+            self._fill_x_in(st)
+            ts = torch.as_tensor([float(t) for t in timesteps], dtype=torch.float32)
+            st["timesteps"][:n_steps].copy_(ts.to(dev))
+            cf = coef.clone().float()
+            cf[:, 5] = float(guidance_scale)
+            st["coef"][:n_steps].copy_(cf.to(dev))
+            st["step_idx"].zero_()
+            st["uplan"].inputs["ctx"].copy_(prompt_embeds.to(dev, torch.bfloat16))
+            if st["side_plan"] is not None:
+                if side_prompt_embeds is None:
+                    raise ValueError("side_prompt_embeds required")
+                st["side_plan"].inputs["ctx"].copy_(side_prompt_embeds.to(dev, torch.bfloat16))
+                if self.mode == "controlnet":
+                    if control_image is None:
+                        raise ValueError("control_image required")
+                    ci = st["side_plan"].inputs["cond_in"]
+                    ci.copy_(ops.nchw_to_nhwc(control_image.to(dev).float().contiguous(), ci.shape[-1]).view_as(ci))
+                    st["side_plan"].cond_program.run()
+            st["ctx_program"].run()
+            # ---- the loop
+            prog = st["program"]
+            if use_graph and callback is None and noise_fn is None:
+                if not st["graph"]:
+                    prog.build_graph()  # capture does not execute: device state is untouched
+                    st["graph"] = True
+                for _ in range(n_steps):
+                    prog.launch()
+            else:
+                for i in range(n_steps):
+                    if noise_fn is not None:
+                        st["noise"].copy_(ops.nhwc_fp32_from_nchw(noise_fn(i).to(dev)))
+                    prog.run()
+                    if callback is not None:
+                        cur_lat = ops.nchw_from_nhwc_fp32(st["latents"], h, w)
+                        new = callback(i, timesteps[i], cur_lat)
+                        if new is not None and new is not cur_lat:
+                            st["latents"].copy_(ops.nhwc_fp32_from_nchw(new.to(dev)))
+                            self._fill_x_in(st, latents_only=True)
+            out = ops.nchw_from_nhwc_fp32(st["latents"], h, w).clone()
+        cur.wait_stream(self._stream)
+        out.record_stream(cur)
+        return out

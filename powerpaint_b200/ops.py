@@ -143,7 +143,7 @@ def gn_desc(*, x0, x1, c0, c1, batch, hw, groups, gamma, beta, eps, silu, stats,
 
 def cfg_ddim_desc(*, eps, eps_fp32, eps_ld, latents, coef, step_idx, advance_step, noise,
                   guidance_scale, do_cfg, batch, hw, next_in=None, next_c=0, n_copies=0,
-                  extra=None, extra_c=0, guidance_from_coef=False) -> Desc:
+                  extra=None, extra_c=0, guidance_from_coef=False, extra_per_copy=False) -> Desc:
     d = N.CfgDdimDesc()
     d.eps, d.eps_fp32, d.eps_ld = N.ptr(eps), 1 if eps_fp32 else 0, eps_ld
     d.latents, d.coef, d.step_idx = N.ptr(latents), N.ptr(coef), N.ptr(step_idx)
@@ -154,6 +154,7 @@ def cfg_ddim_desc(*, eps, eps_fp32, eps_ld, latents, coef, step_idx, advance_ste
     d.next_in, d.next_c, d.n_copies = N.ptr(next_in), next_c, n_copies
     d.extra, d.extra_c = N.ptr(extra), extra_c
     d.guidance_from_coef = 1 if guidance_from_coef else 0
+    d.extra_per_copy = 1 if extra_per_copy else 0
     return Desc("cfg_ddim", d, (eps, latents, coef, step_idx, noise, next_in, extra))
 
 

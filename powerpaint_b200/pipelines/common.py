@@ -1,0 +1,161 @@
+"""Host-side helpers shared by the three pipelines (pre/post-processing = SURVEY.md §8f "next"
+rows; they run once per call outside the denoising loop and stay on PIL / torch for now).
+
+Restated from the reference: `prepare_mask_and_masked_image`
+(powerpaint/pipelines/pipeline_PowerPaint.py:39-153), diffusers `randn_tensor` and
+`VaeImageProcessor` pre/post-processing.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Union
+
+import numpy as np
+import PIL.Image
+import torch
+
+
+@dataclass
+class StableDiffusionPipelineOutput:
+    images: Union[List[PIL.Image.Image], np.ndarray, torch.Tensor]
+    nsfw_content_detected: Optional[List[bool]]
+
+
+def randn_tensor(shape, generator=None, device=None, dtype=None):
+    """diffusers.utils.torch_utils.randn_tensor: a CPU generator with a CUDA target samples on the
+    CPU and moves (so seeds are device independent); a list of generators samples per batch item."""
+    device = torch.device(device) if device is not None else torch.device("cpu")
+    batch = shape[0]
+    rand_device = device
+    if generator is not None:
+        gen_dev = generator[0].device.type if isinstance(generator, list) else generator.device.type
+        if gen_dev != device.type and gen_dev == "cpu":
+            rand_device = torch.device("cpu")
+        elif gen_dev != device.type and gen_dev == "cuda":
+            raise ValueError(f"Cannot generate a {device} tensor from a generator of type {gen_dev}.")
+    if isinstance(generator, list) and len(generator) == 1:
+        generator = generator[0]
+    if isinstance(generator, list):
+        s = (1,) + tuple(shape[1:])
+        lat = [torch.randn(s, generator=generator[i], device=rand_device, dtype=dtype) for i in range(batch)]
+        return torch.cat(lat, dim=0).to(device)
+    return torch.randn(shape, generator=generator, device=rand_device, dtype=dtype).to(device)
+
+
+def prepare_mask_and_masked_image(image, mask, height, width, return_image: bool = False):
+    """(mask [B,1,H,W] in {0,1}, masked_image [B,3,H,W] in [-1,1]) from PIL / numpy / tensor inputs;
+    same accepted types, range checks and exceptions as the reference (:39-153)."""
+    if image is None:
+        raise ValueError("`image` input cannot be undefined.")
+    if mask is None:
+        raise ValueError("`mask_image` input cannot be undefined.")
+    if isinstance(image, torch.Tensor):
+        if not isinstance(mask, torch.Tensor):
+            raise TypeError(f"`image` is a torch.Tensor but `mask` (type: {type(mask)} is not")
+        if image.ndim == 3:
+            assert image.shape[0] == 3, "Image outside a batch should be of shape (3, H, W)"
+            image = image.unsqueeze(0)
+        if mask.ndim == 2:
+            mask = mask.unsqueeze(0).unsqueeze(0)
+        if mask.ndim == 3:
+            mask = mask.unsqueeze(0) if mask.shape[0] == 1 else mask.unsqueeze(1)
+        assert image.ndim == 4 and mask.ndim == 4, "Image and Mask must have 4 dimensions"
+        assert image.shape[-2:] == mask.shape[-2:], "Image and Mask must have the same spatial dimensions"
+        assert image.shape[0] == mask.shape[0], "Image and Mask must have the same batch size"
+        if image.min() < -1 or image.max() > 1:
+            raise ValueError("Image should be in [-1, 1] range")
+        if mask.min() < 0 or mask.max() > 1:
+            raise ValueError("Mask should be in [0, 1] range")
+        mask = mask.clone()
+        mask[mask < 0.5] = 0
+        mask[mask >= 0.5] = 1
+        image = image.to(dtype=torch.float32)
+    elif isinstance(mask, torch.Tensor):
+        raise TypeError(f"`mask` is a torch.Tensor but `image` (type: {type(image)} is not")
+    else:
+        if isinstance(image, (PIL.Image.Image, np.ndarray)):
+            image = [image]
+        if isinstance(image, list) and isinstance(image[0], PIL.Image.Image):
+            image = [i.resize((width, height), resample=PIL.Image.LANCZOS) for i in image]
+            image = np.concatenate([np.array(i.convert("RGB"))[None, :] for i in image], axis=0)
+        elif isinstance(image, list) and isinstance(image[0], np.ndarray):
+            image = np.concatenate([i[None, :] for i in image], axis=0)
+        image = torch.from_numpy(image.transpose(0, 3, 1, 2)).to(dtype=torch.float32) / 127.5 - 1.0
+        if isinstance(mask, (PIL.Image.Image, np.ndarray)):
+            mask = [mask]
+        if isinstance(mask, list) and isinstance(mask[0], PIL.Image.Image):
+            mask = [i.resize((width, height), resample=PIL.Image.LANCZOS) for i in mask]
+            mask = np.concatenate([np.array(m.convert("L"))[None, None, :] for m in mask], axis=0)
+            mask = mask.astype(np.float32) / 255.0
+        elif isinstance(mask, list) and isinstance(mask[0], np.ndarray):
+            mask = np.concatenate([m[None, None, :] for m in mask], axis=0)
+        mask = mask.copy()
+        mask[mask < 0.5] = 0
+        mask[mask >= 0.5] = 1
+        mask = torch.from_numpy(mask)
+    masked_image = image * (mask < 0.5)
+    if return_image:
+        return mask, masked_image, image
+    return mask, masked_image
+
+
+def preprocess_image(image, height=None, width=None, do_normalize=True) -> torch.Tensor:
+    """VaeImageProcessor.preprocess: PIL/np/tensor -> float32 NCHW, resized (lanczos), [-1,1] if
+    do_normalize (the control-image processor uses do_normalize=False,
+    pipeline_PowerPaint_ControlNet.py:320-322)."""
+    if isinstance(image, torch.Tensor):
+        t = image if image.ndim == 4 else image.unsqueeze(0)
+        t = t.to(torch.float32)
+        if do_normalize and t.min() >= 0:
+            t = 2.0 * t - 1.0
+        return t
+    if isinstance(image, (PIL.Image.Image, np.ndarray)):
+        image = [image]
+    if isinstance(image[0], PIL.Image.Image):
+        if height is not None and width is not None:
+            image = [i.resize((width, height), resample=PIL.Image.LANCZOS) for i in image]
+        arr = np.stack([np.array(i.convert("RGB")).astype(np.float32) / 255.0 for i in image], axis=0)
+    else:
+        arr = np.stack([i.astype(np.float32) for i in image], axis=0)
+        if arr.max() > 1.0:
+            arr = arr / 255.0
+    t = torch.from_numpy(arr.transpose(0, 3, 1, 2))
+    return 2.0 * t - 1.0 if do_normalize else t
+
+
+def postprocess_image(image: torch.Tensor, output_type: str = "pil", do_denormalize=None):
+    """VaeImageProcessor.postprocess: (x/2+0.5).clamp(0,1) -> pt / np / pil"""
+    if output_type == "latent":
+        return image
+    if do_denormalize is None:
+        do_denormalize = [True] * image.shape[0]
+    image = torch.stack([(image[i] / 2 + 0.5).clamp(0, 1) if do_denormalize[i] else image[i]
+                         for i in range(image.shape[0])])
+    if output_type == "pt":
+        return image
+    arr = image.detach().cpu().permute(0, 2, 3, 1).float().numpy()
+    if output_type == "np":
+        return arr
+    if output_type == "pil":
+        arr = (arr * 255).round().astype("uint8")
+        return [PIL.Image.fromarray(a) for a in arr]
+    raise ValueError(f"unsupported output_type {output_type}")
+
+
+def encode_text(tokenizer, text_encoder, prompts, device, max_length=None) -> torch.Tensor:
+    """tokenize (max_length padding, truncation) + text encoder last hidden state"""
+    max_length = max_length or tokenizer.model_max_length
+    ids = tokenizer(prompts, padding="max_length", max_length=max_length, truncation=True,
+                    return_tensors="pt").input_ids
+    return text_encoder(ids.to(device))[0]
+
+
+def vae_encode(vae, image: torch.Tensor, generator=None) -> torch.Tensor:
+    """reference `_encode_vae_image` (pipeline_PowerPaint.py:657-669)"""
+    image = image.to(getattr(vae, "dtype", image.dtype))
+    if isinstance(generator, list):
+        lat = [vae.encode(image[i:i + 1]).latent_dist.sample(generator=generator[i]) for i in range(image.shape[0])]
+        lat = torch.cat(lat, dim=0)
+    else:
+        lat = vae.encode(image).latent_dist.sample(generator=generator)
+    return vae.config.scaling_factor * lat.float()

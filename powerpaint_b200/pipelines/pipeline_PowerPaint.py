@@ -1,0 +1,302 @@
+"""`StableDiffusionInpaintPipeline` of PowerPaint v1 — drop-in for the reference class
+(powerpaint/pipelines/pipeline_PowerPaint.py:156; `__call__` :722-1071) with the denoising loop
+(:988-1035) replaced by the fused CUDA program of `powerpaint_b200.denoise.FusedDenoiser`.
+
+Kept verbatim from the reference API: constructor argument names, plain settable
+attributes `.tokenizer/.text_encoder/.unet/.vae/.scheduler` (the app re-assigns them,
+app.py:94,111-112,130), the `__call__` signature including the `tradoff` / `tradoff_nag` spelling,
+the task-prompt blend `E = t*E_A + (1-t)*E_B` (:423,:499) with negative embeddings first (:516),
+`check_inputs` exceptions (:553-602), callback cadence (:1038-1041), return types (:1068-1071).
+Everything outside the loop (PIL pre-processing, CLIP, VAE) is the reference's host dataflow
+on torch; the VAE / text encoder / tokenizer are injected dependencies exactly as upstream.
+"""
+from __future__ import annotations
+
+import inspect
+from typing import Callable, List, Optional, Union
+
+import torch
+
+from ..denoise import FusedDenoiser
+from ..models.unet_2d_condition import UNet2DConditionModel
+from .common import (StableDiffusionPipelineOutput, encode_text, postprocess_image, prepare_mask_and_masked_image,
+                     randn_tensor, vae_encode)
+
+
+class StableDiffusionInpaintPipeline:
+    _optional_components = ["safety_checker", "feature_extractor"]
+
+    def __init__(self, vae, text_encoder, tokenizer, unet, scheduler, safety_checker=None, feature_extractor=None,
+                 requires_safety_checker: bool = False):
+        if safety_checker is not None:
+            raise NotImplementedError("safety_checker must be None (the reference app passes None, app.py:131-132)")
+        self.vae = vae
+        self.text_encoder = text_encoder
+        self.tokenizer = tokenizer
+        self.unet = unet
+        self.scheduler = scheduler
+        self.safety_checker = None
+        self.feature_extractor = feature_extractor
+        # the reference force-sets steps_offset=1 / clip_sample=False on the scheduler config (:205-231)
+        cfg = getattr(scheduler, "config", None)
+        if cfg is not None:
+            if getattr(cfg, "steps_offset", 1) != 1:
+                cfg.steps_offset = 1
+            if getattr(cfg, "clip_sample", False):
+                cfg.clip_sample = False
+        boc = getattr(getattr(vae, "config", None), "block_out_channels", (0, 0, 0, 0))
+        self.vae_scale_factor = 2 ** (len(boc) - 1)
+        self._denoiser: Optional[FusedDenoiser] = None
+        self._denoiser_unet = None
+        self._progress_bar_config = {}
+
+    # ------------------------------------------------------------------ small diffusers surface
+    @property
+    def _execution_device(self) -> torch.device:
+        return self.unet.device
+
+    @property
+    def device(self) -> torch.device:
+        return self.unet.device
+
+    def to(self, device=None, dtype=None):
+        for name in ("vae", "text_encoder", "unet"):
+            m = getattr(self, name, None)
+            if m is not None and device is not None:
+                m.to(device)
+        if dtype is not None:
+            self.unet.to(dtype=dtype)
+        return self
+
+    def set_progress_bar_config(self, **kwargs):
+        self._progress_bar_config = kwargs
+
+    def enable_model_cpu_offload(self, gpu_id=0):
+        raise NotImplementedError("CPU offload is not supported: the hot path has no CPU fallback (SURVEY.md §5)")
+
+    def denoiser(self) -> FusedDenoiser:
+        if not isinstance(self.unet, UNet2DConditionModel):
+            raise TypeError("`unet` must be a powerpaint_b200 UNet2DConditionModel: the denoising loop runs as a "
+                            "recorded CUDA program and has no eager fallback")
+        if self._denoiser is None or self._denoiser_unet is not self.unet:
+            self._denoiser = FusedDenoiser(self.unet, mode="v1")
+            self._denoiser_unet = self.unet
+        return self._denoiser
+
+    # ------------------------------------------------------------------ prompt encoding (:317-518)
+    def _encode_prompt(self, promptA, promptB, t, device, num_images_per_prompt, do_classifier_free_guidance,
+                       negative_promptA=None, negative_promptB=None, t_nag=None, prompt_embeds=None,
+                       negative_prompt_embeds=None, lora_scale=None):
+        prompt, negative_prompt = promptA, negative_promptA
+        if promptA is not None and isinstance(promptA, str):
+            batch_size = 1
+        elif promptA is not None and isinstance(promptA, list):
+            batch_size = len(promptA)
+        else:
+            batch_size = prompt_embeds.shape[0]
+        if prompt_embeds is None:
+            eA = encode_text(self.tokenizer, self.text_encoder, promptA, device)
+            eB = encode_text(self.tokenizer, self.text_encoder, promptB, device)
+            prompt_embeds = eA * t + (1 - t) * eB
+        prompt_embeds = prompt_embeds.to(device=device, dtype=torch.float32)
+        bs, seq, _ = prompt_embeds.shape
+        prompt_embeds = prompt_embeds.repeat(1, num_images_per_prompt, 1).view(bs * num_images_per_prompt, seq, -1)
+        if do_classifier_free_guidance and negative_prompt_embeds is None:
+            if negative_prompt is None:
+                uA, uB = [""] * batch_size, [""] * batch_size
+            elif prompt is not None and type(prompt) is not type(negative_prompt):
+                raise TypeError(f"`negative_prompt` should be the same type to `prompt`, but got "
+                                f"{type(negative_prompt)} != {type(prompt)}.")
+            elif isinstance(negative_prompt, str):
+                uA, uB = [negative_promptA], [negative_promptB]
+            elif batch_size != len(negative_prompt):
+                raise ValueError(f"`negative_prompt`: {negative_prompt} has batch size {len(negative_prompt)}, but "
+                                 f"`prompt`: {prompt} has batch size {batch_size}. Please make sure that passed "
+                                 "`negative_prompt` matches the batch size of `prompt`.")
+            else:
+                uA, uB = negative_promptA, negative_promptB
+            nA = encode_text(self.tokenizer, self.text_encoder, uA, device, max_length=seq)
+            nB = encode_text(self.tokenizer, self.text_encoder, uB, device, max_length=seq)
+            negative_prompt_embeds = nA * t_nag + (1 - t_nag) * nB
+        if do_classifier_free_guidance:
+            seq = negative_prompt_embeds.shape[1]
+            negative_prompt_embeds = negative_prompt_embeds.to(dtype=torch.float32, device=device)
+            negative_prompt_embeds = negative_prompt_embeds.repeat(1, num_images_per_prompt, 1)
+            negative_prompt_embeds = negative_prompt_embeds.view(batch_size * num_images_per_prompt, seq, -1)
+            prompt_embeds = torch.cat([negative_prompt_embeds, prompt_embeds])
+        return prompt_embeds
+
+    # ------------------------------------------------------------------ checks / helpers
+    def check_inputs(self, prompt, height, width, strength, callback_steps, negative_prompt=None, prompt_embeds=None,
+                     negative_prompt_embeds=None):
+        if strength < 0 or strength > 1:
+            raise ValueError(f"The value of strength should in [0.0, 1.0] but is {strength}")
+        if height % 8 != 0 or width % 8 != 0:
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+        if callback_steps is None or not isinstance(callback_steps, int) or callback_steps <= 0:
+            raise ValueError(f"`callback_steps` has to be a positive integer but is {callback_steps} of type"
+                             f" {type(callback_steps)}.")
+        if prompt is not None and prompt_embeds is not None:
+            raise ValueError(f"Cannot forward both `prompt`: {prompt} and `prompt_embeds`: {prompt_embeds}. Please "
+                             "make sure to only forward one of the two.")
+        elif prompt is None and prompt_embeds is None:
+            raise ValueError("Provide either `prompt` or `prompt_embeds`. Cannot leave both `prompt` and "
+                             "`prompt_embeds` undefined.")
+        elif prompt is not None and not isinstance(prompt, (str, list)):
+            raise ValueError(f"`prompt` has to be of type `str` or `list` but is {type(prompt)}")
+        if negative_prompt is not None and negative_prompt_embeds is not None:
+            raise ValueError(f"Cannot forward both `negative_prompt`: {negative_prompt} and `negative_prompt_embeds`:"
+                             f" {negative_prompt_embeds}. Please make sure to only forward one of the two.")
+        if prompt_embeds is not None and negative_prompt_embeds is not None:
+            if prompt_embeds.shape != negative_prompt_embeds.shape:
+                raise ValueError("`prompt_embeds` and `negative_prompt_embeds` must have the same shape when passed "
+                                 f"directly, but got: `prompt_embeds` {prompt_embeds.shape} != "
+                                 f"`negative_prompt_embeds` {negative_prompt_embeds.shape}.")
+
+    def prepare_extra_step_kwargs(self, generator, eta):
+        kw = {}
+        params = set(inspect.signature(self.scheduler.step).parameters.keys())
+        if "eta" in params:
+            kw["eta"] = eta
+        if "generator" in params:
+            kw["generator"] = generator
+        return kw
+
+    def get_timesteps(self, num_inference_steps, strength, device):
+        init_timestep = min(int(num_inference_steps * strength), num_inference_steps)
+        t_start = max(num_inference_steps - init_timestep, 0)
+        timesteps = self.scheduler.timesteps[t_start * self.scheduler.order:]
+        return timesteps, num_inference_steps - t_start
+
+    def prepare_latents(self, batch_size, num_channels_latents, height, width, dtype, device, generator, latents=None,
+                        image=None, timestep=None, is_strength_max=True, return_noise=False,
+                        return_image_latents=False):
+        shape = (batch_size, num_channels_latents, height // self.vae_scale_factor, width // self.vae_scale_factor)
+        if isinstance(generator, list) and len(generator) != batch_size:
+            raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an "
+                             f"effective batch size of {batch_size}. Make sure the batch size matches the length of "
+                             "the generators.")
+        if (image is None or timestep is None) and not is_strength_max:
+            raise ValueError("Since strength < 1. initial latents are to be initialised as a combination of Image + "
+                             "Noise.However, either the image or the noise timestep has not been provided.")
+        image_latents = None
+        if return_image_latents or (latents is None and not is_strength_max):
+            image_latents = vae_encode(self.vae, image.to(device=device, dtype=dtype), generator)
+        if latents is None:
+            noise = randn_tensor(shape, generator=generator, device=device, dtype=dtype)
+            latents = noise if is_strength_max else self.scheduler.add_noise(image_latents, noise, timestep)
+            latents = latents * self.scheduler.init_noise_sigma if is_strength_max else latents
+        else:
+            noise = latents.to(device)
+            latents = noise * self.scheduler.init_noise_sigma
+        outputs = (latents,)
+        if return_noise:
+            outputs += (noise,)
+        if return_image_latents:
+            outputs += (image_latents,)
+        return outputs
+
+    def prepare_mask_latents(self, mask, masked_image, batch_size, height, width, dtype, device, generator,
+                             do_classifier_free_guidance):
+        """nearest-resize the mask to latent resolution, VAE-encode the masked image (:671-710).
+        Unlike the reference this returns ONE copy per image even under CFG: the duplication
+        (`torch.cat([mask] * 2)`, :703-706) happens inside the fused step kernel."""
+        mask = torch.nn.functional.interpolate(mask, size=(height // self.vae_scale_factor,
+                                                           width // self.vae_scale_factor))
+        mask = mask.to(device=device, dtype=dtype)
+        masked_image = masked_image.to(device=device, dtype=dtype)
+        masked_image_latents = vae_encode(self.vae, masked_image, generator)
+        for name, t in (("masks", mask), ("images", masked_image_latents)):
+            if t.shape[0] < batch_size and batch_size % t.shape[0] != 0:
+                raise ValueError(f"The passed {name} and the required batch size don't match: {t.shape[0]} {name} "
+                                 f"were passed for a total batch size of {batch_size}.")
+        if mask.shape[0] < batch_size:
+            mask = mask.repeat(batch_size // mask.shape[0], 1, 1, 1)
+        if masked_image_latents.shape[0] < batch_size:
+            masked_image_latents = masked_image_latents.repeat(batch_size // masked_image_latents.shape[0], 1, 1, 1)
+        return mask, masked_image_latents.to(device=device, dtype=dtype)
+
+    # ------------------------------------------------------------------ __call__ (:722-1071)
+    @torch.no_grad()
+    def __call__(self, promptA: Union[str, List[str]] = None, promptB: Union[str, List[str]] = None, image=None,
+                 mask=None, height: Optional[int] = None, width: Optional[int] = None, strength: float = 1.0,
+                 tradoff: float = 1.0, tradoff_nag: float = 1.0, num_inference_steps: int = 50,
+                 guidance_scale: float = 7.5, negative_promptA: Optional[Union[str, List[str]]] = None,
+                 negative_promptB: Optional[Union[str, List[str]]] = None, num_images_per_prompt: Optional[int] = 1,
+                 eta: float = 0.0, generator: Optional[Union[torch.Generator, List[torch.Generator]]] = None,
+                 latents: Optional[torch.FloatTensor] = None, prompt_embeds: Optional[torch.FloatTensor] = None,
+                 negative_prompt_embeds: Optional[torch.FloatTensor] = None, output_type: Optional[str] = "pil",
+                 return_dict: bool = True, callback: Optional[Callable[[int, int, torch.FloatTensor], None]] = None,
+                 callback_steps: int = 1, cross_attention_kwargs=None, task_class=None):
+        height = height or self.unet.config.sample_size * self.vae_scale_factor
+        width = width or self.unet.config.sample_size * self.vae_scale_factor
+        prompt, negative_prompt = promptA, negative_promptA
+        self.check_inputs(prompt, height, width, strength, callback_steps, negative_prompt, prompt_embeds,
+                          negative_prompt_embeds)
+        if cross_attention_kwargs:
+            raise NotImplementedError("cross_attention_kwargs (LoRA scale) is outside the PowerPaint hot path")
+        if task_class is not None:
+            raise NotImplementedError("task_class needs the class-conditioned UNet, not part of the released models")
+        if strength != 1.0:
+            raise NotImplementedError("strength < 1 (SURVEY.md §8f rank 4) is not built yet")
+        if prompt is not None and isinstance(prompt, str):
+            batch_size = 1
+        elif prompt is not None and isinstance(prompt, list):
+            batch_size = len(prompt)
+        else:
+            batch_size = prompt_embeds.shape[0]
+        device = self._execution_device
+        do_cfg = guidance_scale > 1.0
+        prompt_embeds = self._encode_prompt(promptA, promptB, tradoff, device, num_images_per_prompt, do_cfg,
+                                            negative_promptA, negative_promptB, tradoff_nag,
+                                            prompt_embeds=prompt_embeds, negative_prompt_embeds=negative_prompt_embeds)
+        self.scheduler.set_timesteps(num_inference_steps, device="cpu")
+        timesteps, num_inference_steps = self.get_timesteps(num_inference_steps, strength, device)
+        if num_inference_steps < 1:
+            raise ValueError(f"After adjusting the num_inference_steps by strength parameter: {strength}, the number "
+                             f"of pipeline steps is {num_inference_steps} which is < 1 and not appropriate for this "
+                             "pipeline.")
+        mask, masked_image, init_image = prepare_mask_and_masked_image(image, mask, height, width, return_image=True)
+        num_channels_latents = self.vae.config.latent_channels
+        num_channels_unet = self.unet.config.in_channels
+        if num_channels_unet != 9:
+            raise ValueError(f"The unet {self.unet.__class__} should have 9 input channels (inpainting checkpoint), "
+                             f"not {num_channels_unet}; the 4-channel blend path (:1025-1035) is not built")
+        total = batch_size * num_images_per_prompt
+        latents, noise = self.prepare_latents(total, num_channels_latents, height, width, torch.float32, device,
+                                              generator, latents, image=init_image, timestep=None,
+                                              is_strength_max=True, return_noise=True, return_image_latents=False)
+        mask, masked_image_latents = self.prepare_mask_latents(mask, masked_image, total, height, width, torch.float32,
+                                                               device, generator, do_cfg)
+        if num_channels_latents + mask.shape[1] + masked_image_latents.shape[1] != num_channels_unet:
+            raise ValueError("Incorrect configuration settings! The config of `pipeline.unet` expects "
+                             f"{num_channels_unet} input channels but received {num_channels_latents} + "
+                             f"{mask.shape[1]} + {masked_image_latents.shape[1]}.")
+        extra_step_kwargs = self.prepare_extra_step_kwargs(generator, eta)
+        if not hasattr(self.scheduler, "step_coefficients"):
+            raise TypeError("the fused loop needs powerpaint_b200.schedulers.DDIMScheduler (step_coefficients)")
+        coef = self.scheduler.step_coefficients(timesteps, eta=extra_step_kwargs.get("eta", 0.0))
+        noise_fn = None
+        if eta > 0:
+            shape = latents.shape
+
+            def noise_fn(i):
+                return randn_tensor(shape, generator=generator, device=device, dtype=torch.float32)
+        cb = None
+        if callback is not None:
+            def cb(i, t, lat):
+                if i % callback_steps == 0:
+                    callback(i, t, lat)
+                return None
+        latents = self.denoiser().run(latents=latents, prompt_embeds=prompt_embeds, timesteps=timesteps, coef=coef,
+                                      guidance_scale=guidance_scale,
+                                      extra=torch.cat([mask, masked_image_latents], dim=1), noise_fn=noise_fn,
+                                      callback=cb)
+        if output_type != "latent":
+            image = self.vae.decode((latents / self.vae.config.scaling_factor).to(self.vae.dtype), return_dict=False)[0]
+        else:
+            image = latents
+        image = postprocess_image(image.float(), output_type=output_type)
+        if not return_dict:
+            return (image, None)
+        return StableDiffusionPipelineOutput(images=image, nsfw_content_detected=None)

@@ -1,0 +1,141 @@
+"""`StableDiffusionControlNetInpaintPipeline` (PowerPaint v1 + ControlNet) — drop-in for the
+reference class (powerpaint/pipelines/pipeline_PowerPaint_ControlNet.py:225; `__call__` :1347-1771).
+The loop (:1663-1735: ControlNet on the 4-channel latents + control image, 9-channel UNet with the
+12 down residuals + mid residual, CFG, scheduler.step) runs as one recorded CUDA program per step
+(`FusedDenoiser(mode="controlnet")`); the t-independent `controlnet_cond_embedding(control_image)`
+is evaluated once per call instead of once per step.
+
+Out of scope like upstream's dead code: `predict_woControl` (:996-1345, a buggy copy of the v1
+`__call__`), MultiControlNet, guess_mode.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Union
+
+import torch
+
+from ..denoise import FusedDenoiser
+from ..models.unet_2d_condition import ControlNetModel, UNet2DConditionModel
+from .common import (StableDiffusionPipelineOutput, postprocess_image, prepare_mask_and_masked_image,
+                     preprocess_image, randn_tensor)
+from .pipeline_PowerPaint import StableDiffusionInpaintPipeline
+
+
+class StableDiffusionControlNetInpaintPipeline(StableDiffusionInpaintPipeline):
+    def __init__(self, vae, text_encoder, tokenizer, unet, controlnet, scheduler, safety_checker=None,
+                 feature_extractor=None, requires_safety_checker: bool = False):
+        super().__init__(vae, text_encoder, tokenizer, unet, scheduler, safety_checker, feature_extractor,
+                         requires_safety_checker)
+        if isinstance(controlnet, (list, tuple)):
+            raise NotImplementedError("MultiControlNet is outside the hot path")
+        self.controlnet = controlnet
+        self._denoiser_side = None
+
+    def denoiser(self) -> FusedDenoiser:
+        if not isinstance(self.unet, UNet2DConditionModel) or not isinstance(self.controlnet, ControlNetModel):
+            assert False, "unet / controlnet must be powerpaint_b200 UNet2DConditionModel / ControlNetModel"
+        if self._denoiser is None or self._denoiser_unet is not self.unet or self._denoiser_side is not self.controlnet:
+            self._denoiser = FusedDenoiser(self.unet, self.controlnet, mode="controlnet")
+            self._denoiser_unet, self._denoiser_side = self.unet, self.controlnet
+        return self._denoiser
+
+    def prepare_control_image(self, image, width, height, batch_size, num_images_per_prompt, device, dtype,
+                              do_classifier_free_guidance=False, guess_mode=False):
+        """control images are NOT normalised to [-1, 1] (do_normalize=False, :320-322)"""
+        image = preprocess_image(image, height=height, width=width, do_normalize=False).to(dtype=torch.float32)
+        repeat_by = batch_size if image.shape[0] == 1 else num_images_per_prompt
+        image = image.repeat_interleave(repeat_by, dim=0).to(device=device, dtype=dtype)
+        if do_classifier_free_guidance and not guess_mode:
+            image = torch.cat([image] * 2)
+        return image
+
+    @torch.no_grad()
+    def __call__(self, promptA: Union[str, List[str]] = None, promptB: Union[str, List[str]] = None, image=None,
+                 mask=None, control_image=None, height: Optional[int] = None, width: Optional[int] = None,
+                 strength: float = 1.0, tradoff: float = 1.0, tradoff_nag: float = 1.0, num_inference_steps: int = 50,
+                 guidance_scale: float = 7.5, negative_promptA: Optional[Union[str, List[str]]] = None,
+                 negative_promptB: Optional[Union[str, List[str]]] = None, num_images_per_prompt: Optional[int] = 1,
+                 eta: float = 0.0, generator: Optional[Union[torch.Generator, List[torch.Generator]]] = None,
+                 latents: Optional[torch.FloatTensor] = None, prompt_embeds: Optional[torch.FloatTensor] = None,
+                 negative_prompt_embeds: Optional[torch.FloatTensor] = None, output_type: Optional[str] = "pil",
+                 return_dict: bool = True, callback: Optional[Callable[[int, int, torch.FloatTensor], None]] = None,
+                 callback_steps: int = 1, cross_attention_kwargs=None,
+                 controlnet_conditioning_scale: Union[float, List[float]] = 0.5, guess_mode: bool = False,
+                 control_guidance_start: Union[float, List[float]] = 0.0,
+                 control_guidance_end: Union[float, List[float]] = 1.0):
+        if guess_mode:
+            raise NotImplementedError("guess_mode is outside the hot path")
+        if cross_attention_kwargs:
+            raise NotImplementedError("cross_attention_kwargs (LoRA scale) is outside the hot path")
+        if strength != 1.0:
+            raise NotImplementedError("strength < 1 is not built yet")
+        if isinstance(controlnet_conditioning_scale, list):
+            controlnet_conditioning_scale = controlnet_conditioning_scale[0]
+        if not isinstance(control_guidance_start, list):
+            control_guidance_start = [control_guidance_start]
+        if not isinstance(control_guidance_end, list):
+            control_guidance_end = [control_guidance_end]
+        height = height or self.unet.config.sample_size * self.vae_scale_factor
+        width = width or self.unet.config.sample_size * self.vae_scale_factor
+        prompt, negative_prompt = promptA, negative_promptA
+        self.check_inputs(prompt, height, width, strength, callback_steps, negative_prompt, prompt_embeds,
+                          negative_prompt_embeds)
+        if control_image is None:
+            raise ValueError("`control_image` input cannot be undefined.")
+        if prompt is not None and isinstance(prompt, str):
+            batch_size = 1
+        elif prompt is not None and isinstance(prompt, list):
+            batch_size = len(prompt)
+        else:
+            batch_size = prompt_embeds.shape[0]
+        device = self._execution_device
+        do_cfg = guidance_scale > 1.0
+        prompt_embeds = self._encode_prompt(promptA, promptB, tradoff, device, num_images_per_prompt, do_cfg,
+                                            negative_promptA, negative_promptB, tradoff_nag,
+                                            prompt_embeds=prompt_embeds, negative_prompt_embeds=negative_prompt_embeds)
+        total = batch_size * num_images_per_prompt
+        control = self.prepare_control_image(control_image, width, height, total, num_images_per_prompt, device,
+                                             torch.float32, do_cfg)
+        mask, masked_image, init_image = prepare_mask_and_masked_image(image, mask, height, width, return_image=True)
+        self.scheduler.set_timesteps(num_inference_steps, device="cpu")
+        timesteps, num_inference_steps = self.get_timesteps(num_inference_steps, strength, device)
+        if self.unet.config.in_channels != 9:
+            raise ValueError("the ControlNet inpainting path expects the 9-channel inpainting UNet")
+        latents, noise = self.prepare_latents(total, self.vae.config.latent_channels, height, width, torch.float32,
+                                              device, generator, latents, image=init_image, timestep=None,
+                                              is_strength_max=True, return_noise=True, return_image_latents=False)
+        mask, masked_image_latents = self.prepare_mask_latents(mask, masked_image, total, height, width, torch.float32,
+                                                               device, generator, do_cfg)
+        extra_step_kwargs = self.prepare_extra_step_kwargs(generator, eta)
+        keep = [1.0 - float(i / len(timesteps) < control_guidance_start[0]
+                            or (i + 1) / len(timesteps) > control_guidance_end[0]) for i in range(len(timesteps))]
+        if any(k != 1.0 for k in keep):
+            raise NotImplementedError("control_guidance_start/end other than (0, 1) are not supported by the fused "
+                                      "program (one ControlNet scale is baked in)")
+        coef = self.scheduler.step_coefficients(timesteps, eta=extra_step_kwargs.get("eta", 0.0))
+        noise_fn = None
+        if eta > 0:
+            shape = latents.shape
+
+            def noise_fn(i):
+                return randn_tensor(shape, generator=generator, device=device, dtype=torch.float32)
+        cb = None
+        if callback is not None:
+            def cb(i, t, lat):
+                if i % callback_steps == 0:
+                    callback(i, t, lat)
+                return None
+        latents = self.denoiser().run(latents=latents, prompt_embeds=prompt_embeds, side_prompt_embeds=prompt_embeds,
+                                      control_image=control, timesteps=timesteps, coef=coef,
+                                      guidance_scale=guidance_scale,
+                                      extra=torch.cat([mask, masked_image_latents], dim=1),
+                                      side_scale=float(controlnet_conditioning_scale), noise_fn=noise_fn, callback=cb)
+        if output_type != "latent":
+            image_o = self.vae.decode((latents / self.vae.config.scaling_factor).to(self.vae.dtype),
+                                      return_dict=False)[0]
+        else:
+            image_o = latents
+        image_o = postprocess_image(image_o.float(), output_type=output_type)
+        if not return_dict:
+            return (image_o, None)
+        return StableDiffusionPipelineOutput(images=image_o, nsfw_content_detected=None)

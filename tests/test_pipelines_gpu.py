@@ -1,0 +1,258 @@
+"""GPU parity of the fused denoising loops and of the pipeline `__call__`s against the fp32 oracle
+loops (oracle/pipelines.py) on identical seeded weights / inputs.
+
+Stated tolerance (bf16 storage vs fp32 oracle): final latents rel-L2 <= 5e-2 and
+cosine >= 0.998 for the step counts used here. The synthetic randomly-initialised nets amplify
+rounding noise strongly (a single forward already differs by ~1.2e-2 from fp32 for BOTH this
+implementation and torch-bf16 eager), so long trajectories are compared over 10 steps for the
+tiny config; the per-step kernels are pinned much tighter in test_kernels_gpu.py."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+def _cos(a, b):
+    return torch.nn.functional.cosine_similarity(a.float().flatten(), b.float().flatten(), dim=0).item()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _fp32_exact():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+def _nets(in_channels, kinds, tiny=True):
+    from oracle.unet import BrushNetOracle, ControlNetOracle, UNet2DConditionOracle, UNetConfig
+    from powerpaint_b200.engine import NetConfig
+    from powerpaint_b200.models import BrushNetModel, ControlNetModel, UNet2DConditionModel, synthetic_state_dict
+
+    out = {}
+    for kind, cin, seed in kinds:
+        o = UNetConfig.tiny(cin) if tiny else UNetConfig.sd15(cin)
+        n = NetConfig(in_channels=cin, block_out_channels=o.block_out_channels, attention_head_dim=o.attention_head_dim,
+                      cross_attention_dim=o.cross_attention_dim, norm_num_groups=o.norm_num_groups)
+        sd = synthetic_state_dict(n, kind, seed)
+        ocls = {"unet": UNet2DConditionOracle, "brushnet": BrushNetOracle, "controlnet": ControlNetOracle}[kind]
+        pcls = {"unet": UNet2DConditionModel, "brushnet": BrushNetModel, "controlnet": ControlNetModel}[kind]
+        om = ocls(o)
+        om.load_state_dict(sd)
+        out[kind] = (om.to(DEV).eval(), pcls.from_state_dict(n, sd).to(DEV), o)
+    return out
+
+
+def _scheds(steps, total=50):
+    from oracle.ddim import DDIMOracle
+    from powerpaint_b200.schedulers import DDIMScheduler
+
+    so, sp = DDIMOracle(), DDIMScheduler()
+    so.set_timesteps(total)
+    sp.set_timesteps(total)
+    so.timesteps = so.timesteps[:steps]
+    return so, sp, sp.timesteps[:steps]
+
+
+def test_loop_v1_tiny_and_callback_and_eta():
+    from oracle.pipelines import loop_v1
+    from powerpaint_b200.denoise import FusedDenoiser
+
+    nets = _nets(9, [("unet", 9, 1234)])
+    om, pm, o = nets["unet"]
+    g = torch.Generator(device=DEV).manual_seed(0)
+    B, h, w = 2, 16, 8
+    lat = torch.randn(B, 4, h, w, device=DEV, generator=g)
+    emb = torch.randn(2 * B, 77, o.cross_attention_dim, device=DEV, generator=g) * 0.5
+    mask = (torch.rand(B, 1, h, w, device=DEV, generator=g) > 0.5).float()
+    ml = torch.randn(B, 4, h, w, device=DEV, generator=g)
+    so, sp, ts = _scheds(10)
+    rec = []
+    ref = loop_v1(om, so, lat, emb, mask, ml, 7.5, record=rec)
+    den = FusedDenoiser(pm)
+    extra = torch.cat([mask, ml], 1)
+    got = den.run(latents=lat, prompt_embeds=emb, timesteps=ts, coef=sp.step_coefficients(ts), guidance_scale=7.5,
+                  extra=extra)
+    assert _rel(got, ref) < 5e-2 and _cos(got, ref) > 0.998, (_rel(got, ref), _cos(got, ref))
+    # graph replay == plain launches == per-step callback path (all observe the same trajectory)
+    seen = []
+    got_cb = den.run(latents=lat, prompt_embeds=emb, timesteps=ts, coef=sp.step_coefficients(ts), guidance_scale=7.5,
+                     extra=extra, callback=lambda i, t, x: seen.append((i, int(t), x.clone())) or None)
+    assert len(seen) == 10 and [s[1] for s in seen] == [int(t) for t in ts]
+    assert _rel(got_cb, ref) < 5e-2
+    assert _rel(seen[0][2], rec[0]) < 2e-2, "first step latents"
+    # inputs are not mutated
+    assert torch.equal(lat, torch.randn(B, 4, h, w, device=DEV, generator=torch.Generator(device=DEV).manual_seed(0)))
+    # guidance_scale <= 1: no CFG, eps is the conditional prediction (B-row embeddings)
+    ref1 = loop_v1(om, so, lat, emb[B:], mask, ml, 1.0)
+    got1 = den.run(latents=lat, prompt_embeds=emb[B:], timesteps=ts, coef=sp.step_coefficients(ts),
+                   guidance_scale=1.0, extra=extra)
+    assert _rel(got1, ref1) < 5e-2
+    # eta > 0 with supplied variance noise
+    noises = [torch.randn(B, 4, h, w, device=DEV, generator=g) for _ in range(10)]
+    ref_e = loop_v1(om, so, lat, emb, mask, ml, 7.5, eta=0.7, noise_fn=lambda i: noises[i])
+    got_e = den.run(latents=lat, prompt_embeds=emb, timesteps=ts, coef=sp.step_coefficients(ts, eta=0.7),
+                    guidance_scale=7.5, extra=extra, noise_fn=lambda i: noises[i])
+    assert _rel(got_e, ref_e) < 5e-2
+
+
+def test_loop_brushnet_tiny():
+    from oracle.pipelines import loop_brushnet
+    from powerpaint_b200.denoise import FusedDenoiser
+
+    nets = _nets(4, [("unet", 4, 1234), ("brushnet", 4, 99)])
+    (om_u, pm_u, o), (om_b, pm_b, _) = nets["unet"], nets["brushnet"]
+    g = torch.Generator(device=DEV).manual_seed(1)
+    B, h = 2, 8
+    lat = torch.randn(B, 4, h, h, device=DEV, generator=g)
+    emb_t = torch.randn(2 * B, 77, o.cross_attention_dim, device=DEV, generator=g) * 0.5
+    emb_u = torch.randn(2 * B, 77, o.cross_attention_dim, device=DEV, generator=g) * 0.5
+    cond = torch.randn(2 * B, 5, h, h, device=DEV, generator=g)  # one set per CFG half, like the reference
+    so, sp, ts = _scheds(8)
+    ref = loop_brushnet(om_u, om_b, so, lat, emb_t, emb_u, cond, 7.5, 0.9)
+    got = FusedDenoiser(pm_u, pm_b, "brushnet").run(latents=lat, prompt_embeds=emb_u, side_prompt_embeds=emb_t,
+                                                    timesteps=ts, coef=sp.step_coefficients(ts), guidance_scale=7.5,
+                                                    extra=cond, side_scale=0.9)
+    assert _rel(got, ref) < 5e-2 and _cos(got, ref) > 0.998, (_rel(got, ref), _cos(got, ref))
+
+
+def test_loop_controlnet_tiny():
+    from oracle.pipelines import loop_controlnet
+    from powerpaint_b200.denoise import FusedDenoiser
+
+    nets = _nets(9, [("unet", 9, 1234), ("controlnet", 4, 77)])
+    (om_u, pm_u, o), (om_c, pm_c, _) = nets["unet"], nets["controlnet"]
+    g = torch.Generator(device=DEV).manual_seed(2)
+    B, h = 2, 8
+    lat = torch.randn(B, 4, h, h, device=DEV, generator=g)
+    emb = torch.randn(2 * B, 77, o.cross_attention_dim, device=DEV, generator=g) * 0.5
+    mask = (torch.rand(B, 1, h, h, device=DEV, generator=g) > 0.5).float()
+    ml = torch.randn(B, 4, h, h, device=DEV, generator=g)
+    ctrl = torch.rand(B, 3, 8 * h, 8 * h, device=DEV, generator=g)
+    ctrl2 = torch.cat([ctrl] * 2)
+    so, sp, ts = _scheds(8)
+    ref = loop_controlnet(om_u, om_c, so, lat, emb, mask, ml, ctrl2, 7.5, 0.5)
+    got = FusedDenoiser(pm_u, pm_c, "controlnet").run(latents=lat, prompt_embeds=emb, side_prompt_embeds=emb,
+                                                      control_image=ctrl2, timesteps=ts,
+                                                      coef=sp.step_coefficients(ts), guidance_scale=7.5,
+                                                      extra=torch.cat([mask, ml], 1), side_scale=0.5)
+    assert _rel(got, ref) < 5e-2 and _cos(got, ref) > 0.998, (_rel(got, ref), _cos(got, ref))
+
+
+def test_pipeline_v1_call_tiny():
+    """the public `__call__`: host tensors in, latents out, against the oracle fed the same prepared tensors"""
+    from oracle.pipelines import loop_v1
+    from powerpaint_b200.models.autoencoder_kl import AutoencoderKL
+    from powerpaint_b200.pipelines import StableDiffusionInpaintPipeline
+    from powerpaint_b200.pipelines.common import prepare_mask_and_masked_image, randn_tensor, vae_encode
+    from powerpaint_b200.schedulers import DDIMScheduler
+
+    nets = _nets(9, [("unet", 9, 1234)])
+    om, pm, o = nets["unet"]
+    vae = AutoencoderKL.synthetic(tiny=True).to(DEV)
+    pipe = StableDiffusionInpaintPipeline(vae=vae, text_encoder=None, tokenizer=None, unet=pm,
+                                          scheduler=DDIMScheduler(), safety_checker=None)
+    B, H = 2, 128
+    g = torch.Generator().manual_seed(3)
+    img = torch.rand(B, 3, H, H, generator=g) * 2 - 1
+    mask = torch.zeros(B, 1, H, H)
+    mask[:, :, 32:96, 32:96] = 1
+    pe = torch.randn(B, 77, o.cross_attention_dim, generator=g) * 0.5
+    ne = torch.randn(B, 77, o.cross_attention_dim, generator=g) * 0.5
+    steps = 6
+    out = pipe(image=img, mask=mask, prompt_embeds=pe, negative_prompt_embeds=ne, height=H, width=H,
+               num_inference_steps=steps, guidance_scale=7.5, generator=torch.Generator().manual_seed(11),
+               output_type="latent", return_dict=False)[0]
+    assert out.shape == (B, 4, H // 8, H // 8)
+    # the same host-side preparation, then the oracle loop
+    gen = torch.Generator().manual_seed(11)
+    m, mi = prepare_mask_and_masked_image(img, mask, H, H)
+    lat = randn_tensor((B, 4, H // 8, H // 8), generator=gen, device=DEV, dtype=torch.float32)
+    m_l = torch.nn.functional.interpolate(m, size=(H // 8, H // 8)).to(DEV)
+    ml = vae_encode(vae, mi.to(DEV), gen)
+    from oracle.ddim import DDIMOracle
+
+    so = DDIMOracle()
+    so.set_timesteps(steps)
+    ref = loop_v1(om, so, lat, torch.cat([ne, pe]).to(DEV), m_l, ml, 7.5)
+    assert _rel(out, ref) < 5e-2 and _cos(out, ref) > 0.998, (_rel(out, ref), _cos(out, ref))
+    # decoded output types
+    res = pipe(image=img, mask=mask, prompt_embeds=pe, negative_prompt_embeds=ne, height=H, width=H,
+               num_inference_steps=2, generator=torch.Generator().manual_seed(11), output_type="pil")
+    assert len(res.images) == B and res.images[0].size == (H, H) and res.nsfw_content_detected is None
+    # reference error behaviour
+    with pytest.raises(ValueError):
+        pipe(image=img, mask=mask, prompt_embeds=pe, negative_prompt_embeds=ne, height=H + 4, width=H)
+    with pytest.raises(ValueError):
+        pipe(image=img, mask=mask, height=H, width=H)
+
+
+def test_pipeline_brushnet_call_tiny():
+    from oracle.ddim import DDIMOracle
+    from oracle.pipelines import loop_brushnet
+    from powerpaint_b200.models.autoencoder_kl import AutoencoderKL
+    from powerpaint_b200.pipelines import StableDiffusionPowerPaintBrushNetPipeline
+    from powerpaint_b200.pipelines.common import preprocess_image, randn_tensor
+    from powerpaint_b200.schedulers import DDIMScheduler
+
+    nets = _nets(4, [("unet", 4, 1234), ("brushnet", 4, 99)])
+    (om_u, pm_u, o), (om_b, pm_b, _) = nets["unet"], nets["brushnet"]
+    vae = AutoencoderKL.synthetic(tiny=True).to(DEV)
+    pipe = StableDiffusionPowerPaintBrushNetPipeline(vae=vae, text_encoder=None, text_encoder_brushnet=None,
+                                                     tokenizer=None, unet=pm_u, brushnet=pm_b,
+                                                     scheduler=DDIMScheduler(), safety_checker=None)
+    B, H = 1, 64
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(B, 3, H, H, generator=g) * 2 - 1
+    mask = torch.ones(B, 3, H, H)
+    mask[:, :, 16:48, 16:48] = -1.0  # preprocessed mask: sum over channels < 0 -> 1
+    pe = torch.randn(B, 77, o.cross_attention_dim, generator=g) * 0.5
+    ne = torch.randn(B, 77, o.cross_attention_dim, generator=g) * 0.5
+    peU = torch.randn(2 * B, 77, o.cross_attention_dim, generator=g) * 0.5
+    steps = 5
+    with pytest.raises(TypeError):
+        pipe(image=img, mask=mask, prompt_embeds=pe, negative_prompt_embeds=ne, prompt_embedsU=peU,
+             brushnet_conditioning_scale=1)
+    torch.manual_seed(123)  # the conditioning latents use the GLOBAL RNG like the reference
+    out = pipe(image=img, mask=mask, prompt_embeds=pe, negative_prompt_embeds=ne, prompt_embedsU=peU, height=H,
+               width=H, num_inference_steps=steps, guidance_scale=7.5, brushnet_conditioning_scale=1.0,
+               generator=torch.Generator().manual_seed(9), output_type="latent", return_dict=False)[0]
+    # same preparation for the oracle
+    image_t = torch.cat([img.to(DEV)] * 2)
+    om_mask = torch.cat([mask.to(DEV)] * 2)
+    original_mask = (om_mask.sum(1)[:, None] < 0).float()
+    lat = randn_tensor((B, 4, H // 8, H // 8), generator=torch.Generator().manual_seed(9), device=DEV,
+                       dtype=torch.float32)
+    torch.manual_seed(123)
+    cl = vae.encode(image_t).latent_dist.sample() * vae.config.scaling_factor
+    cond = torch.cat([cl, torch.nn.functional.interpolate(original_mask, size=cl.shape[-2:])], 1)
+    so = DDIMOracle()
+    so.set_timesteps(steps)
+    ref = loop_brushnet(om_u, om_b, so, lat, torch.cat([ne, pe]).to(DEV), peU.to(DEV), cond, 7.5, 1.0)
+    assert _rel(out, ref) < 5e-2 and _cos(out, ref) > 0.998, (_rel(out, ref), _cos(out, ref))
+
+
+def test_loop_v1_sd15_5steps():
+    """SD-1.5-size UNet, one image x CFG, 5 DDIM steps at 512^2"""
+    from oracle.pipelines import loop_v1
+    from powerpaint_b200.denoise import FusedDenoiser
+
+    nets = _nets(9, [("unet", 9, 1234)], tiny=False)
+    om, pm, o = nets["unet"]
+    g = torch.Generator(device=DEV).manual_seed(0)
+    B, h = 1, 64
+    lat = torch.randn(B, 4, h, h, device=DEV, generator=g)
+    emb = torch.randn(2 * B, 77, 768, device=DEV, generator=g) * 0.5
+    mask = (torch.rand(B, 1, h, h, device=DEV, generator=g) > 0.75).float()
+    ml = torch.randn(B, 4, h, h, device=DEV, generator=g)
+    so, sp, ts = _scheds(5)
+    ref = loop_v1(om, so, lat, emb, mask, ml, 7.5)
+    got = FusedDenoiser(pm).run(latents=lat, prompt_embeds=emb, timesteps=ts, coef=sp.step_coefficients(ts),
+                                guidance_scale=7.5, extra=torch.cat([mask, ml], 1))
+    print(f"sd15 5-step loop: rel-L2 {_rel(got, ref):.3e} cos {_cos(got, ref):.5f}")
+    assert _rel(got, ref) < 5e-2 and _cos(got, ref) > 0.998
