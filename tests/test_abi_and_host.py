@@ -1,0 +1,138 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/powerpaint_b200.h declares (no
+compute calls without a GPU); host-side logic (weight packing, pre-processing, sharding, checks)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import PIL.Image
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from powerpaint_b200 import _native, build
+
+    path = build.build()
+    lib = ctypes.CDLL(str(path))
+    hdr = open(os.path.join(ROOT, "include", "powerpaint_b200.h")).read()
+    declared = set(re.findall(r"\b(pp_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in the header but not exported"
+    assert declared == set(_native.EXPORTED_SYMBOLS), declared ^ set(_native.EXPORTED_SYMBOLS)
+    assert _native.lib().pp_abi_version() == 1
+    assert _native.lib().pp_device_supported() in (0, 1)
+
+
+def test_ctypes_struct_sizes_match_header_layout():
+    from powerpaint_b200 import _native as N
+
+    # pointer-heavy structs: sizes must be multiples of 8 and stable (guards accidental field drift)
+    assert ctypes.sizeof(N.GemmDesc) % 8 == 0 and ctypes.sizeof(N.AttnDesc) % 8 == 0
+    assert N.GemmDesc.rowvec_ld.offset > N.GemmDesc.rows_per_group.offset
+    assert N.CfgDdimDesc.extra_per_copy.offset > N.CfgDdimDesc.guidance_from_coef.offset
+
+
+def test_invalid_descriptors_fail_loudly_without_gpu():
+    from powerpaint_b200 import _native as N
+
+    L = N.lib()
+    d = N.GemmDesc()  # all zeros
+    assert L.pp_gemm_conv(ctypes.byref(d), None) != 0
+    assert b"gemm" in L.pp_last_error()
+    a = N.AttnDesc()
+    assert L.pp_attention(ctypes.byref(a), None) != 0
+    with pytest.raises(RuntimeError):
+        N.check(1, "x")
+
+
+def test_weight_packing():
+    from powerpaint_b200 import ops
+
+    w = torch.arange(2 * 5 * 9, dtype=torch.float32).reshape(2, 5, 3, 3)
+    p = ops.pack_conv3x3_weight(w)
+    assert p.shape == (2, 9 * 64) and p.dtype == torch.bfloat16
+    p3 = p.reshape(2, 9, 64).float()
+    for tap in range(9):
+        assert torch.equal(p3[:, tap, :5], w[:, :, tap // 3, tap % 3].to(torch.bfloat16).float())
+    assert (p3[:, :, 5:] == 0).all()
+    ps = ops.pack_conv3x3_weight(torch.randn(4, 72, 3, 3), split=64)  # 64 + 8 channels
+    assert ps.shape == (4, 9 * 128)
+    wl = torch.randn(6, 72)
+    pl = ops.pack_concat_linear_weight(wl, 64)
+    assert pl.shape == (6, 128) and torch.equal(pl[:, 64:72].float(), wl[:, 64:].to(torch.bfloat16).float())
+    wg, bg = torch.arange(256 * 4, dtype=torch.float32).reshape(256, 4), torch.arange(256, dtype=torch.float32)
+    wi, bi = ops.pack_geglu_weight(wg, bg, 128)
+    assert torch.equal(bi[:64], bg[:64]) and torch.equal(bi[64:128], bg[128:192]) and torch.equal(bi[128:192], bg[64:128])
+    assert torch.equal(wi[64:128].float(), wg[128:192].to(torch.bfloat16).float())
+
+
+def test_prepare_mask_and_masked_image_like_reference():
+    from powerpaint_b200.pipelines.common import postprocess_image, prepare_mask_and_masked_image, randn_tensor
+
+    img = PIL.Image.fromarray((np.random.RandomState(0).rand(40, 48, 3) * 255).astype("uint8"))
+    m = np.zeros((40, 48), "uint8")
+    m[10:30, 10:30] = 255
+    mask, masked = prepare_mask_and_masked_image(img, PIL.Image.fromarray(m), 32, 32)
+    assert mask.shape == (1, 1, 32, 32) and masked.shape == (1, 3, 32, 32)
+    assert set(mask.unique().tolist()) <= {0.0, 1.0}
+    assert (masked[:, :, mask[0, 0] == 1] == 0).all() and masked.abs().max() <= 1
+    t_img, t_mask = torch.rand(2, 3, 16, 16) * 2 - 1, torch.rand(2, 16, 16)
+    mk, ms, im = prepare_mask_and_masked_image(t_img, t_mask, 16, 16, return_image=True)
+    assert mk.shape == (2, 1, 16, 16) and torch.equal(im, t_img) and torch.equal(ms, t_img * (mk < 0.5))
+    with pytest.raises(ValueError):
+        prepare_mask_and_masked_image(t_img * 3, t_mask, 16, 16)
+    with pytest.raises(TypeError):
+        prepare_mask_and_masked_image(t_img, m, 16, 16)
+    with pytest.raises(ValueError):
+        prepare_mask_and_masked_image(None, t_mask, 16, 16)
+    a = randn_tensor((2, 4, 8, 8), generator=torch.Generator().manual_seed(1), device="cpu", dtype=torch.float32)
+    b = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(1))
+    assert torch.equal(a, b)
+    gl = [torch.Generator().manual_seed(i) for i in range(2)]
+    c = randn_tensor((2, 4, 8, 8), generator=gl, device="cpu", dtype=torch.float32)
+    assert torch.equal(c[1], torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(1))[0])
+    pil = postprocess_image(torch.zeros(1, 3, 8, 8), "pil")
+    assert pil[0].size == (8, 8) and np.array(pil[0]).max() == 128
+
+
+def test_pipeline_check_inputs_errors_cpu():
+    from powerpaint_b200.engine import NetConfig
+    from powerpaint_b200.models import UNet2DConditionModel
+    from powerpaint_b200.models.autoencoder_kl import AutoencoderKL
+    from powerpaint_b200.pipelines import StableDiffusionInpaintPipeline
+    from powerpaint_b200.schedulers import DDIMScheduler
+
+    n = NetConfig(in_channels=9, block_out_channels=(32, 64, 128, 128), attention_head_dim=4, cross_attention_dim=64,
+                  norm_num_groups=8)
+    pipe = StableDiffusionInpaintPipeline(vae=AutoencoderKL.synthetic(tiny=True), text_encoder=None, tokenizer=None,
+                                          unet=UNet2DConditionModel.synthetic(n), scheduler=DDIMScheduler())
+    assert pipe.vae_scale_factor == 8
+    with pytest.raises(ValueError):
+        pipe.check_inputs("a", 100, 64, 1.0, 1)           # not divisible by 8
+    with pytest.raises(ValueError):
+        pipe.check_inputs("a", 64, 64, 1.5, 1)            # strength out of range
+    with pytest.raises(ValueError):
+        pipe.check_inputs("a", 64, 64, 1.0, 0)            # callback_steps
+    with pytest.raises(ValueError):
+        pipe.check_inputs(None, 64, 64, 1.0, 1)           # neither prompt nor embeds
+    with pytest.raises(ValueError):
+        pipe.check_inputs("a", 64, 64, 1.0, 1, prompt_embeds=torch.zeros(1, 77, 64))
+    with pytest.raises(NotImplementedError):
+        pipe.enable_model_cpu_offload()
+    with pytest.raises(NotImplementedError):
+        StableDiffusionInpaintPipeline(vae=pipe.vae, text_encoder=None, tokenizer=None, unet=pipe.unet,
+                                       scheduler=DDIMScheduler(), safety_checker=object())
+
+
+def test_shard_ranges():
+    from powerpaint_b200.parallel import shard_ranges
+
+    assert shard_ranges(32, 8) == [(4 * i, 4 * i + 4) for i in range(8)]
+    assert shard_ranges(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert shard_ranges(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    with pytest.raises(ValueError):
+        shard_ranges(4, 0)
