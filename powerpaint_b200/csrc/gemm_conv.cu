@@ -37,7 +37,8 @@ static constexpr int BLOCK_M = 128;
 static constexpr int BLOCK_K = 64;
 static constexpr int UMMA_K = 16;
 static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
-static constexpr int GEMM_THREADS = 192;
+static constexpr int GEMM_EPI_WARPS = 8;
+static constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 
 __host__ __device__ constexpr int tmem_cols_for(int n) {
     return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512;
@@ -47,22 +48,15 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return act == PP_ACT_SILU ? silu_f(v) : v;
 }
 
-// Epilogue for 8 consecutive output columns of one row. v[] holds acc (+ nothing yet).
+// Epilogue for 8 consecutive output columns of one row. v[] holds the accumulators; `sbias` points
+// at this tile's bias staged in shared memory (column n0 - n_base), r1/r2 hold the 8 bf16 residual
+// values that were loaded ahead of time (vector path only).
 template <bool kVec>
-__device__ __forceinline__ void epilogue_store8(const GemmKParams& p, float (&v)[8], int64_t row,
-                                                int grp, int n0) {
-    // bias
+__device__ __forceinline__ void epilogue_store8(const GemmKParams& p, float (&v)[8], int64_t row, int grp, int n0,
+                                                const float* sbias, uint4 r1, uint4 r2) {
     if (p.bias) {
-        if (kVec) {
-            float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0));
-            float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4));
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-        } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
-        }
+        for (int j = 0; j < 8; ++j) v[j] += sbias[j];
     }
     if (p.rowvec) {
         const float* rv = p.rowvec + (int64_t)grp * p.rowvec_ld + n0;
@@ -71,12 +65,11 @@ __device__ __forceinline__ void epilogue_store8(const GemmKParams& p, float (&v)
             if (kVec || n0 + j < p.N) v[j] += __ldg(rv + j);
     }
     if (p.res1) {
-        const __nv_bfloat16* r = p.res1 + row * p.ldr1 + n0;
         if (kVec) {
-            uint4 q = __ldg(reinterpret_cast<const uint4*>(r));
-            v[0] += bf16_lo(q.x); v[1] += bf16_hi(q.x); v[2] += bf16_lo(q.y); v[3] += bf16_hi(q.y);
-            v[4] += bf16_lo(q.z); v[5] += bf16_hi(q.z); v[6] += bf16_lo(q.w); v[7] += bf16_hi(q.w);
+            v[0] += bf16_lo(r1.x); v[1] += bf16_hi(r1.x); v[2] += bf16_lo(r1.y); v[3] += bf16_hi(r1.y);
+            v[4] += bf16_lo(r1.z); v[5] += bf16_hi(r1.z); v[6] += bf16_lo(r1.w); v[7] += bf16_hi(r1.w);
         } else {
+            const __nv_bfloat16* r = p.res1 + row * p.ldr1 + n0;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 if (n0 + j < p.N) v[j] += __bfloat162float(r[j]);
@@ -85,12 +78,11 @@ __device__ __forceinline__ void epilogue_store8(const GemmKParams& p, float (&v)
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] *= p.alpha;
     if (p.res2) {
-        const __nv_bfloat16* r = p.res2 + row * p.ldr2 + n0;
         if (kVec) {
-            uint4 q = __ldg(reinterpret_cast<const uint4*>(r));
-            v[0] += bf16_lo(q.x); v[1] += bf16_hi(q.x); v[2] += bf16_lo(q.y); v[3] += bf16_hi(q.y);
-            v[4] += bf16_lo(q.z); v[5] += bf16_hi(q.z); v[6] += bf16_lo(q.w); v[7] += bf16_hi(q.w);
+            v[0] += bf16_lo(r2.x); v[1] += bf16_hi(r2.x); v[2] += bf16_lo(r2.y); v[3] += bf16_hi(r2.y);
+            v[4] += bf16_lo(r2.z); v[5] += bf16_hi(r2.z); v[6] += bf16_lo(r2.w); v[7] += bf16_hi(r2.w);
         } else {
+            const __nv_bfloat16* r = p.res2 + row * p.ldr2 + n0;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 if (n0 + j < p.N) v[j] += __bfloat162float(r[j]);
@@ -138,10 +130,23 @@ __device__ __forceinline__ void epilogue_store8(const GemmKParams& p, float (&v)
     }
 }
 
-template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_conv_kernel(const __grid_constant__ GemmKParams p) {
+// number of smem ring stages per tile width (one persistent CTA per SM owns the whole smem)
+__host__ __device__ constexpr int stages_for(int block_n) {
+    return block_n <= 64 ? 8 : block_n <= 128 ? 6 : block_n <= 160 ? 6 : 4;
+}
+
+// Persistent, warp-specialised kernel: grid = min(#tiles, #SMs); each CTA walks tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, so CTAs running concurrently share A tiles
+// through L2 and the weights stay L2-resident).
+//   warp 0      TMA producer  (smem ring continues across tile boundaries)
+//   warp 1      tcgen05.mma issuer + TMEM owner; two accumulator stages in TMEM
+//   warps 2..9  epilogue: 2 warps per TMEM lane quarter, alternating 32-column chunks, so the
+//               epilogue of tile i overlaps the main loop of tile i+1
+template <int BLOCK_N>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid_constant__ GemmKParams p) {
+    constexpr int STAGES = stages_for(BLOCK_N);
     constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
-    constexpr int TMEM_COLS = tmem_cols_for(BLOCK_N);
+    constexpr int TMEM_COLS = tmem_cols_for(2 * BLOCK_N);
     constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M, BLOCK_N);
 
     extern __shared__ uint8_t smem_raw[];
@@ -149,28 +154,20 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_conv_kernel(const __grid_co
     const uint32_t sA = smem_base;
     const uint32_t sB = sA + STAGES * A_STAGE_BYTES;
     const uint32_t bar_base = sB + STAGES * B_STAGE_BYTES;
-    // barriers: full[STAGES], empty[STAGES], tmem_full; then the TMEM base address slot
+    // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
-    uint32_t* tmem_slot_ptr =
-        reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    // bias of the current / next tile, staged by the epilogue warps: [2][BLOCK_N] floats
+    float* sbias_all = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
-    const int m_tile = blockIdx.x;
-    const int n_tile = blockIdx.y;
-
-    // tile origin
-    int x0 = 0, y0 = 0, nb0 = 0;
-    if (p.a_mode != PP_A_MATRIX) {
-        const int tx = m_tile % p.tiles_x;
-        const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-        const int tn = m_tile / (p.tiles_x * p.tiles_y);
-        x0 = tx * p.bw;
-        y0 = ty * p.bh;
-        nb0 = tn * p.bn;
-    }
+    const int n_tiles = p.n_tiles;
+    const int num_tiles = p.m_tiles * n_tiles;
+    const int num_k_iters = p.num_k_iters;
 
     if (warp == 0 && elect_one()) {
         prefetch_tmap(&p.tmA[0]);
@@ -179,7 +176,10 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_conv_kernel(const __grid_co
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full_bar(a), 1);
+            mbar_init(tmem_empty_bar(a), GEMM_EPI_WARPS);
+        }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -191,142 +191,217 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_conv_kernel(const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int num_k_iters = p.num_k_iters;
+    // conv tile origin of an m-tile index
+    auto tile_origin = [&](int m_tile, int& x0, int& y0, int& nb0) {
+        const int tx = m_tile % p.tiles_x;
+        const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+        const int tn = m_tile / (p.tiles_x * p.tiles_y);
+        x0 = tx * p.bw;
+        y0 = ty * p.bh;
+        nb0 = tn * p.bn;
+    };
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
             const int cpt = p.chunks0 + p.chunks1;  // chunks per tap
-            for (int it = 0; it < num_k_iters; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                mbar_arrive_expect_tx(full_bar(s), p.a_bytes + B_STAGE_BYTES);
-                const uint32_t dstA = sA + s * A_STAGE_BYTES;
-                const uint32_t dstB = sB + s * B_STAGE_BYTES;
-                const int tap = it / cpt;
-                const int ch = it - tap * cpt;
-                const int src = ch >= p.chunks0 ? 1 : 0;
-                const int cc = (src ? ch - p.chunks0 : ch) * BLOCK_K;
-                if (p.a_mode == PP_A_MATRIX) {
-                    tma_load_2d(dstA, &p.tmA[src], full_bar(s), cc, m_tile * BLOCK_M);
-                } else if (p.a_mode == PP_A_CONV3X3) {
-                    const int ky = tap / 3, kx = tap - ky * 3;
-                    tma_load_4d(dstA, &p.tmA[src], full_bar(s), cc, x0 + kx - 1, y0 + ky - 1, nb0);
-                } else {
-                    // stride 2: input (2*oy + ky - 1, 2*ox + kx - 1) = parity plane (py, px) at
-                    // (oy + dy, ox + dx) with d = -1 for k == 0 else 0, parity = (k != 1)
-                    const int ky = tap / 3, kx = tap - ky * 3;
-                    const int py = (ky != 1), px = (kx != 1);
-                    const int dy = (ky == 0) ? -1 : 0, dx = (kx == 0) ? -1 : 0;
-                    tma_load_4d(dstA, &p.tmA[py * 2 + px], full_bar(s), cc, x0 + dx, y0 + dy, nb0);
+            uint32_t git = 0;                       // global k-iteration counter (ring position)
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int n_tile = tile % n_tiles, m_tile = tile / n_tiles;
+                int x0 = 0, y0 = 0, nb0 = 0;
+                if (p.a_mode != PP_A_MATRIX) tile_origin(m_tile, x0, y0, nb0);
+                for (int it = 0; it < num_k_iters; ++it, ++git) {
+                    const int s = git % STAGES;
+                    const uint32_t ph = (git / STAGES) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_arrive_expect_tx(full_bar(s), p.a_bytes + B_STAGE_BYTES);
+                    const uint32_t dstA = sA + s * A_STAGE_BYTES;
+                    const uint32_t dstB = sB + s * B_STAGE_BYTES;
+                    const int tap = it / cpt;
+                    const int ch = it - tap * cpt;
+                    const int src = ch >= p.chunks0 ? 1 : 0;
+                    const int cc = (src ? ch - p.chunks0 : ch) * BLOCK_K;
+                    if (p.a_mode == PP_A_MATRIX) {
+                        tma_load_2d(dstA, &p.tmA[src], full_bar(s), cc, m_tile * BLOCK_M);
+                    } else if (p.a_mode == PP_A_CONV3X3) {
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        tma_load_4d(dstA, &p.tmA[src], full_bar(s), cc, x0 + kx - 1, y0 + ky - 1, nb0);
+                    } else {
+                        // stride 2: input (2*oy + ky - 1, 2*ox + kx - 1) = parity plane (py, px) at
+                        // (oy + dy, ox + dx) with d = -1 for k == 0 else 0, parity = (k != 1)
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        const int py = (ky != 1), px = (kx != 1);
+                        const int dy = (ky == 0) ? -1 : 0, dx = (kx == 0) ? -1 : 0;
+                        tma_load_4d(dstA, &p.tmA[py * 2 + px], full_bar(s), cc, x0 + dx, y0 + dy, nb0);
+                    }
+                    tma_load_2d(dstB, &p.tmB, full_bar(s), it * BLOCK_K, n_tile * BLOCK_N);
                 }
-                tma_load_2d(dstB, &p.tmB, full_bar(s), it * BLOCK_K, n_tile * BLOCK_N);
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
-            for (int it = 0; it < num_k_iters; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(full_bar(s), ph);
+            uint32_t git = 0;
+            uint32_t lt = 0;  // local tile counter
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+                const uint32_t acc = lt & 1u;
+                const uint32_t acc_ph = (lt >> 1) & 1u;
+                mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u);  // epilogue drained this accumulator
                 tc_fence_after();
-                const uint64_t da = umma_desc_kmajor_sw128(sA + s * A_STAGE_BYTES);
-                const uint64_t db = umma_desc_kmajor_sw128(sB + s * B_STAGE_BYTES);
+                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                for (int it = 0; it < num_k_iters; ++it, ++git) {
+                    const int s = git % STAGES;
+                    const uint32_t ph = (git / STAGES) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_kmajor_sw128(sA + s * A_STAGE_BYTES);
+                    const uint64_t db = umma_desc_kmajor_sw128(sB + s * B_STAGE_BYTES);
 #pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                    umma_bf16_ss(tmem_base, umma_desc_advance_k(da, k * UMMA_K),
-                                 umma_desc_advance_k(db, k * UMMA_K), IDESC, (it | k) != 0);
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        umma_bf16_ss(tmem_d, umma_desc_advance_k(da, k * UMMA_K),
+                                     umma_desc_advance_k(db, k * UMMA_K), IDESC, (it | k) != 0);
+                    }
+                    umma_commit(empty_bar(s));  // frees the smem slot once these MMAs retire
                 }
-                umma_commit(empty_bar(s));  // frees the smem slot once these MMAs retire
+                umma_commit(tmem_full_bar(acc));  // accumulator complete
             }
-            umma_commit(tmem_full_bar);  // accumulator complete
         }
         __syncwarp();
     } else {
         // ===================== epilogue warps =====================
-        const int quarter = warp & 3;  // TMEM lanes this warp may read: [32*quarter, +32)
-        const int r = quarter * 32 + lane_id();  // accumulator row handled by this thread
-        // output row for this thread
-        bool valid;
-        int64_t row;
-        int grp;
-        if (p.a_mode == PP_A_MATRIX) {
-            row = (int64_t)m_tile * BLOCK_M + r;
-            valid = row < p.M;
-            grp = p.rowvec ? (int)(row / p.rows_per_group) : 0;
-        } else {
-            const int ix = r % p.bw;
-            const int iy = (r / p.bw) % p.bh;
-            const int in = r / (p.bw * p.bh);
-            const int ox = x0 + ix, oy = y0 + iy, on = nb0 + in;
-            valid = in < p.bn && ox < p.wo && oy < p.ho && on < p.nb;
-            row = ((int64_t)on * p.ho + oy) * p.wo + ox;
-            grp = on;
+        const int ew = warp - 2;             // 0..7
+        const int quarter = warp & 3;        // TMEM lanes this warp may read: [32*quarter, +32)
+        const int half = ew >> 2;            // which of the two warps sharing the quarter
+        const int etid = threadIdx.x - 64;   // 0..255 among the epilogue threads
+        const int r = quarter * 32 + (int)lane_id();
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        const bool vec_ok = (p.N % 8 == 0);
+        auto epi_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory"); };
+        auto load_bias = [&](int tile) -> float {
+            const int n = (tile % n_tiles) * BLOCK_N + etid;
+            return (p.bias && etid < BLOCK_N && n < p.N) ? __ldg(p.bias + n) : 0.f;
+        };
+        // stage the first tile's bias
+        if (blockIdx.x < num_tiles) {
+            const float b0 = load_bias(blockIdx.x);
+            if (etid < BLOCK_N) sbias_all[etid] = b0;
         }
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const int n_base = n_tile * BLOCK_N;
-        if (p.epilogue == PP_EPI_GEGLU) {
-            constexpr int HALF = BLOCK_N / 2;
-            const int o_base = n_tile * HALF;  // output column of this tile
-            const int n_out = p.N / 2;
+        epi_sync();
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            const int n_tile = tile % n_tiles, m_tile = tile / n_tiles;
+            const uint32_t acc = lt & 1u;
+            const uint32_t acc_ph = (lt >> 1) & 1u;
+            const float* sbias = sbias_all + acc * BLOCK_N;
+            // bias of the next tile: issue the load now, park it in smem at the end of this tile
+            const int next_tile = tile + gridDim.x;
+            const float bias_next = next_tile < num_tiles ? load_bias(next_tile) : 0.f;
+            // output row of this thread
+            bool valid;
+            int64_t row;
+            int grp;
+            if (p.a_mode == PP_A_MATRIX) {
+                row = (int64_t)m_tile * BLOCK_M + r;
+                valid = row < p.M;
+                grp = p.rowvec ? (int)(row / p.rows_per_group) : 0;
+            } else {
+                int x0, y0, nb0;
+                tile_origin(m_tile, x0, y0, nb0);
+                const int ix = r % p.bw;
+                const int iy = (r / p.bw) % p.bh;
+                const int in = r / (p.bw * p.bh);
+                const int ox = x0 + ix, oy = y0 + iy, on = nb0 + in;
+                valid = in < p.bn && ox < p.wo && oy < p.ho && on < p.nb;
+                row = ((int64_t)on * p.ho + oy) * p.wo + ox;
+                grp = on;
+            }
+            const int n_base = n_tile * BLOCK_N;
+            const uint32_t taddr = tmem_base + lane_addr + acc * BLOCK_N;
+            if (p.epilogue == PP_EPI_GEGLU) {
+                constexpr int HALF = BLOCK_N / 2;
+                const int o_base = n_tile * HALF;  // output column of this tile
+                const int n_out = p.N / 2;
+                mbar_wait(tmem_full_bar(acc), acc_ph);
+                tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < HALF; c0 += 16) {
-                uint32_t ra[16], rg[16];
-                tmem_ld16(taddr + c0, ra);
-                tmem_ld16(taddr + HALF + c0, rg);
-                tmem_wait_ld();
-                if (valid && o_base + c0 < n_out) {
+                for (int c0 = half * 16; c0 < HALF; c0 += 32) {
+                    uint32_t ra[16], rg[16];
+                    tmem_ld16(taddr + c0, ra);
+                    tmem_ld16(taddr + HALF + c0, rg);
+                    tmem_wait_ld();
+                    if (valid && o_base + c0 < n_out) {
 #pragma unroll
-                    for (int h8 = 0; h8 < 16; h8 += 8) {
-                        float v[8];
+                        for (int h8 = 0; h8 < 16; h8 += 8) {
+                            float v[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float a = __uint_as_float(ra[h8 + j]);
-                            float g = __uint_as_float(rg[h8 + j]);
-                            if (p.bias) {
-                                a += __ldg(p.bias + n_base + c0 + h8 + j);
-                                g += __ldg(p.bias + n_base + HALF + c0 + h8 + j);
+                            for (int j = 0; j < 8; ++j) {
+                                const float a = __uint_as_float(ra[h8 + j]) + sbias[c0 + h8 + j];
+                                const float g = __uint_as_float(rg[h8 + j]) + sbias[HALF + c0 + h8 + j];
+                                v[j] = a * gelu_erf_f(g);
                             }
-                            v[j] = a * gelu_erf_f(g);
+                            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + o_base + c0 + h8;
+                            uint4 q;
+                            q.x = pack_bf16x2(v[0], v[1]);
+                            q.y = pack_bf16x2(v[2], v[3]);
+                            q.z = pack_bf16x2(v[4], v[5]);
+                            q.w = pack_bf16x2(v[6], v[7]);
+                            *reinterpret_cast<uint4*>(o) = q;
                         }
-                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + o_base + c0 + h8;
-                        uint4 q;
-                        q.x = pack_bf16x2(v[0], v[1]);
-                        q.y = pack_bf16x2(v[2], v[3]);
-                        q.z = pack_bf16x2(v[4], v[5]);
-                        q.w = pack_bf16x2(v[6], v[7]);
-                        *reinterpret_cast<uint4*>(o) = q;
                     }
                 }
-            }
-        } else {
-            const bool vec_ok = (p.N % 8 == 0);
+            } else {
+                // residuals of a 32-column chunk are fetched one chunk ahead (the first chunk's
+                // before the accumulator is even ready), so their latency hides behind TMEM
+                // reads and the previous chunk's stores
+                uint4 c1[4], c2[4], x1[4], x2[4];
+                auto fetch = [&](int c0, uint4 (&a)[4], uint4 (&b)[4]) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int n0 = n_base + c0 + g * 8;
+                        const bool ok = valid && vec_ok && c0 < BLOCK_N && n0 + 8 <= p.N;
+                        a[g] = (ok && p.res1) ? __ldg(reinterpret_cast<const uint4*>(p.res1 + row * p.ldr1 + n0))
+                                              : make_uint4(0, 0, 0, 0);
+                        b[g] = (ok && p.res2) ? __ldg(reinterpret_cast<const uint4*>(p.res2 + row * p.ldr2 + n0))
+                                              : make_uint4(0, 0, 0, 0);
+                    }
+                };
+                fetch(half * 32, c1, c2);
+                mbar_wait(tmem_full_bar(acc), acc_ph);
+                tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                uint32_t acc[32];
-                tmem_ld32(taddr + c0, acc);
-                tmem_wait_ld();
-                if (valid) {
+                for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
+                    fetch(c0 + 64, x1, x2);
+                    uint32_t accv[32];
+                    tmem_ld32(taddr + c0, accv);
+                    tmem_wait_ld();
+                    if (valid) {
 #pragma unroll
-                    for (int g8 = 0; g8 < 32; g8 += 8) {
-                        const int n0 = n_base + c0 + g8;
-                        if (n0 >= p.N) break;
-                        float v[8];
+                        for (int g = 0; g < 4; ++g) {
+                            const int n0 = n_base + c0 + g * 8;
+                            if (n0 < p.N) {
+                                float v[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g8 + j]);
-                        if (vec_ok && n0 + 8 <= p.N)
-                            epilogue_store8<true>(p, v, row, grp, n0);
-                        else
-                            epilogue_store8<false>(p, v, row, grp, n0);
+                                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(accv[g * 8 + j]);
+                                if (vec_ok && n0 + 8 <= p.N)
+                                    epilogue_store8<true>(p, v, row, grp, n0, sbias + c0 + g * 8, c1[g], c2[g]);
+                                else
+                                    epilogue_store8<false>(p, v, row, grp, n0, sbias + c0 + g * 8, c1[g], c2[g]);
+                            }
+                        }
                     }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) { c1[g] = x1[g]; c2[g] = x2[g]; }
                 }
             }
+            // all TMEM reads of this accumulator stage are complete (wait::ld above)
+            tc_fence_before();
+            __syncwarp();
+            if (lane_id() == 0) mbar_arrive(tmem_empty_bar(acc));
+            // park the next tile's bias in the other staging buffer; everyone has finished reading
+            // the buffer of tile lt-1 (same slot) long ago, the barrier orders this tile's writes
+            if (etid < BLOCK_N) sbias_all[(acc ^ 1u) * BLOCK_N + etid] = bias_next;
+            epi_sync();
         }
-        tc_fence_before();
     }
 
     __syncthreads();
@@ -342,27 +417,36 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_conv_kernel(const __grid_co
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int pad64(int c) { return ceil_div(c, 64) * 64; }
 
-template <int BLOCK_N, int STAGES>
-static size_t gemm_smem_bytes() {
-    return (size_t)STAGES * (A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2) + 8 * (2 * STAGES + 2) + 1024;
+static size_t smem_for_block_n(int bn) {
+    return (size_t)stages_for(bn) * (A_STAGE_BYTES + bn * BLOCK_K * 2) + 8 * (2 * stages_for(bn) + 6) + 2 * bn * 4 + 1024;
 }
 
-template <int BLOCK_N, int STAGES>
+static int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+template <int BLOCK_N>
 static int launch_variant(const GemmLaunch& l, cudaStream_t s) {
-    gemm_conv_kernel<BLOCK_N, STAGES><<<l.grid, GEMM_THREADS, l.smem, s>>>(l.p);
+    gemm_conv_kernel<BLOCK_N><<<l.grid, GEMM_THREADS, l.smem, s>>>(l.p);
     PP_CUDA_CHECK(cudaGetLastError());
     return PP_OK;
 }
 
 // opt the kernel variant into its dynamic shared memory size (done at prepare time so that
 // launches are pure and can be stream-captured)
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N>
 static int ensure_attr() {
     static bool done = false;
     if (!done) {
-        PP_CUDA_CHECK(cudaFuncSetAttribute(gemm_conv_kernel<BLOCK_N, STAGES>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)gemm_smem_bytes<BLOCK_N, STAGES>()));
+        PP_CUDA_CHECK(cudaFuncSetAttribute(gemm_conv_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem_for_block_n(BLOCK_N)));
         done = true;
     }
     return PP_OK;
@@ -370,62 +454,44 @@ static int ensure_attr() {
 
 static int ensure_attr_for(int block_n) {
     switch (block_n) {
-        case 64: return ensure_attr<64, 4>();
-        case 128: return ensure_attr<128, 3>();
-        case 160: return ensure_attr<160, 3>();
-        case 256: return ensure_attr<256, 4>();
+        case 64: return ensure_attr<64>();
+        case 128: return ensure_attr<128>();
+        case 160: return ensure_attr<160>();
+        case 256: return ensure_attr<256>();
     }
     return PP_ERR_INVALID;
 }
 
 int gemm_launch(const GemmLaunch& l, cudaStream_t s) {
     switch (l.block_n) {
-        case 64: return launch_variant<64, 4>(l, s);
-        case 128: return launch_variant<128, 3>(l, s);
-        case 160: return launch_variant<160, 3>(l, s);
-        case 256: return launch_variant<256, 4>(l, s);
+        case 64: return launch_variant<64>(l, s);
+        case 128: return launch_variant<128>(l, s);
+        case 160: return launch_variant<160>(l, s);
+        case 256: return launch_variant<256>(l, s);
     }
     set_last_error("gemm_launch: unsupported block_n %d", l.block_n);
     return PP_ERR_INVALID;
 }
 
-static size_t smem_for_block_n(int bn) {
-    switch (bn) {
-        case 64: return gemm_smem_bytes<64, 4>();
-        case 128: return gemm_smem_bytes<128, 3>();
-        case 160: return gemm_smem_bytes<160, 3>();
-        case 256: return gemm_smem_bytes<256, 4>();
-    }
-    return 0;
-}
-
+// Tile width: minimise (rounds over the SMs) x (per-tile cost ~ width + fixed overhead), where
+// padding beyond N is paid as well; ties go to the wider tile (fewer A re-reads).
 static int pick_block_n(int N, int m_tiles, bool geglu) {
     const int cands[4] = {256, 160, 128, 64};
-    if (N <= 64) return 64;
-    // smallest padded N first, then the widest tile that still fills the machine
-    int best = 0, best_pad = 1 << 30;
+    const int sms = num_sms();
+    int best = 0;
+    double best_cost = 1e30;
     for (int c : cands) {
-        if (geglu && c == 64) continue;
-        int padn = ceil_div(N, c) * c;
-        if (padn < best_pad) best_pad = padn;
+        if (geglu && (c == 64 || N % c != 0)) continue;
+        const int nt = ceil_div(N, c);
+        const long tiles = (long)m_tiles * nt;
+        const long rounds = (tiles + sms - 1) / sms;
+        const double cost = (double)rounds * (c + 24);
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best = c;
+        }
     }
-    for (int c : cands) {
-        if (geglu && c == 64) continue;
-        int padn = ceil_div(N, c) * c;
-        if (padn != best_pad) continue;
-        if (!best) best = c;  // widest with minimal padding
-        if (m_tiles * (padn / c) >= 148) return c;
-    }
-    // cannot fill the machine: prefer the most tiles among minimal-padding candidates
-    int most = best, most_tiles = 0;
-    for (int c : cands) {
-        if (geglu && c == 64) continue;
-        int padn = ceil_div(N, c) * c;
-        if (padn > best_pad + best_pad / 8) continue;
-        int t = m_tiles * (padn / c);
-        if (t > most_tiles) { most_tiles = t; most = c; }
-    }
-    return most;
+    return best ? best : 128;
 }
 
 int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
@@ -570,7 +636,12 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
         if (d.res2) PP_REQUIRE(d.ldr2 % 8 == 0 && (reinterpret_cast<uintptr_t>(d.res2) & 15) == 0, "gemm: res2 alignment");
         if (d.bias) PP_REQUIRE((reinterpret_cast<uintptr_t>(d.bias) & 15) == 0, "gemm: bias alignment");
     }
-    l.grid = dim3((unsigned)m_tiles, (unsigned)ceil_div(d.N, bn), 1);
+    p.m_tiles = m_tiles;
+    p.n_tiles = ceil_div(d.N, bn);
+    {
+        const long tiles = (long)p.m_tiles * p.n_tiles;
+        l.grid = dim3((unsigned)std::min<long>(tiles, num_sms()), 1, 1);
+    }
     l.smem = smem_for_block_n(bn);
     {
         int rc = ensure_attr_for(bn);

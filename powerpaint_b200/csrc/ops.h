@@ -24,6 +24,7 @@ struct GemmKParams {
     int32_t nb, ho, wo;
     int32_t bw, bh, bn;
     int32_t tiles_x, tiles_y;
+    int32_t m_tiles, n_tiles;  // persistent tile walk: tile = m_tile * n_tiles + n_tile
     uint32_t a_bytes;  // bytes one A stage receives (box volume * 128)
     // epilogue
     int32_t epilogue, act, out_fp32;

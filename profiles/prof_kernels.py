@@ -1,0 +1,85 @@
+"""Isolated launches of the hot kernels at C2 shapes, for `ncu --set full` captures:
+
+    ncu --set full --clock-control none --import-source on -k regex:'gemm_conv|attn_fwd' -c 12 \
+        -o gpurun_out/prof python profiles/prof_kernels.py
+"""
+import math
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from powerpaint_b200 import _native as nat  # noqa: E402
+from powerpaint_b200 import ops  # noqa: E402
+
+dev = "cuda"
+BF = torch.bfloat16
+g = torch.Generator(device=dev).manual_seed(0)
+
+
+def conv(nb, h, w, cin, cout, bn=0):
+    x = torch.randn(nb, h * w, cin, device=dev, generator=g).to(BF)
+    wt = ops.pack_conv3x3_weight(torch.randn(cout, cin, 3, 3, device=dev, generator=g) / math.sqrt(9 * cin))
+    bias = torch.zeros(cout, device=dev)
+    out = torch.empty(nb, h * w, cout, device=dev, dtype=BF)
+    d = ops.gemm_desc(a0=x, w=wt, out=out, N_=cout, a_mode=nat.PP_A_CONV3X3, c0=cin, nb=nb, h=h, w_=w, bias=bias,
+                      block_n=bn)
+    return lambda: ops.run(d)
+
+
+def linear(M, K, N, geglu=False, bn=0):
+    a = torch.randn(M, K, device=dev, generator=g).to(BF)
+    if geglu:
+        w, b = ops.pack_geglu_weight(torch.randn(N, K, device=dev, generator=g) / math.sqrt(K),
+                                     torch.zeros(N, device=dev), 128)
+        out = torch.empty(M, N // 2, device=dev, dtype=BF)
+        d = ops.gemm_desc(a0=a, w=w, out=out, N_=N, M=M, bias=b, epilogue=nat.PP_EPI_GEGLU, block_n=128)
+    else:
+        w = (torch.randn(N, K, device=dev, generator=g) / math.sqrt(K)).to(BF)
+        out = torch.empty(M, N, device=dev, dtype=BF)
+        d = ops.gemm_desc(a0=a, w=w, out=out, N_=N, M=M, bias=torch.zeros(N, device=dev), block_n=bn)
+    return lambda: ops.run(d)
+
+
+def attn(B, H, d, nq, nk):
+    C = H * d
+    q = torch.randn(B, nq, C, device=dev, generator=g).to(BF)
+    k = torch.randn(B, nk, C, device=dev, generator=g).to(BF)
+    ld = (nk + 7) // 8 * 8
+    vt = torch.randn(B, C, ld, device=dev, generator=g).to(BF)
+    out = torch.empty(B, nq, C, device=dev, dtype=BF)
+    dd = ops.attn_desc(q=q, k=k, vt=vt, out=out, batch=B, heads=H, d=d, nq=nq, nk=nk, q_ld=C, k_ld=C, vt_ld=ld,
+                       o_ld=C, q_batch_stride=nq * C, k_batch_stride=nk * C, scale=1 / math.sqrt(d))
+    return lambda: ops.run(dd)
+
+
+cases = [
+    ("conv 320->320 @64x64 b16", conv(16, 64, 64, 320, 320), 2 * 16 * 4096 * 320 * 2880),
+    ("conv 640->640 @32x32 b16", conv(16, 32, 32, 640, 640), 2 * 16 * 1024 * 640 * 5760),
+    ("conv 1280->1280 @16x16 b16", conv(16, 16, 16, 1280, 1280), 2 * 16 * 256 * 1280 * 11520),
+    ("conv 1280->1280 @8x8 b16", conv(16, 8, 8, 1280, 1280), 2 * 16 * 64 * 1280 * 11520),
+    ("conv 2560->1280 @16x16 b16", conv(16, 16, 16, 2560, 1280), 2 * 16 * 256 * 1280 * 23040),
+    ("linear 320->320 M=65536", linear(65536, 320, 320), 2 * 65536 * 320 * 320),
+    ("geglu 320->2560 M=65536", linear(65536, 320, 2560, geglu=True), 2 * 65536 * 320 * 2560),
+    ("linear 1280->320 M=65536", linear(65536, 1280, 320), 2 * 65536 * 1280 * 320),
+    ("geglu 640->5120 M=16384", linear(16384, 640, 5120, geglu=True), 2 * 16384 * 640 * 5120),
+    ("self-attn d40 N=4096 b16", attn(16, 8, 40, 4096, 4096), 4 * 16 * 8 * 4096 * 4096 * 40),
+    ("cross-attn d40 N=4096x77 b16", attn(16, 8, 40, 4096, 77), 4 * 16 * 8 * 4096 * 77 * 40),
+    ("self-attn d80 N=1024 b16", attn(16, 8, 80, 1024, 1024), 4 * 16 * 8 * 1024 * 1024 * 80),
+]
+only = sys.argv[1] if len(sys.argv) > 1 else None
+for name, fn, flops in cases:
+    if only and only not in name:
+        continue
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n = 5
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / n * 1e3
+    print(f"{name:36s} {us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s")
