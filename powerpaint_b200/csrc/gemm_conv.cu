@@ -142,7 +142,10 @@ __host__ __device__ constexpr int stages_for(int block_n) {
 //   warp 1      tcgen05.mma issuer + TMEM owner; two accumulator stages in TMEM
 //   warps 2..9  epilogue: 2 warps per TMEM lane quarter, alternating 32-column chunks, so the
 //               epilogue of tile i overlaps the main loop of tile i+1
-template <int BLOCK_N>
+// MODE selects the epilogue flavour at compile time (keeps the hot epilogue short and the
+// instruction footprint small): 0 = bf16 row-major output, N % 8 == 0 (bias, rowvec, two residuals,
+// alpha, SiLU), 1 = generic (fp32 / transposed / ragged N), 2 = GEGLU.
+template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid_constant__ GemmKParams p) {
     constexpr int STAGES = stages_for(BLOCK_N);
     constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
@@ -317,7 +320,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
             }
             const int n_base = n_tile * BLOCK_N;
             const uint32_t taddr = tmem_base + lane_addr + acc * BLOCK_N;
-            if (p.epilogue == PP_EPI_GEGLU) {
+            if constexpr (MODE == 2) {
                 constexpr int HALF = BLOCK_N / 2;
                 const int o_base = n_tile * HALF;  // output column of this tile
                 const int n_out = p.N / 2;
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                             for (int j = 0; j < 8; ++j) {
                                 const float a = __uint_as_float(ra[h8 + j]) + sbias[c0 + h8 + j];
                                 const float g = __uint_as_float(rg[h8 + j]) + sbias[HALF + c0 + h8 + j];
-                                v[j] = a * gelu_erf_f(g);
+                                v[j] = a * gelu_fast_f(g);
                             }
                             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + o_base + c0 + h8;
                             uint4 q;
@@ -348,6 +351,74 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                             *reinterpret_cast<uint4*>(o) = q;
                         }
                     }
+                }
+            } else if constexpr (MODE == 0) {
+                // lean path: per-row base pointers, 32-bit column offsets, uniform flags hoisted
+                const float alpha = p.alpha;
+                const bool has_r1 = p.res1 != nullptr, has_r2 = p.res2 != nullptr, has_rv = p.rowvec != nullptr;
+                const bool silu = p.act == PP_ACT_SILU;
+                const __nv_bfloat16* r1row = p.res1 + row * p.ldr1 + n_base;
+                const __nv_bfloat16* r2row = p.res2 + row * p.ldr2 + n_base;
+                const float* rvrow = p.rowvec + (int64_t)grp * p.rowvec_ld + n_base;
+                __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + n_base;
+                const int ncols = min(BLOCK_N, p.N - n_base);  // multiple of 8
+                uint4 c1[4], c2[4], x1[4], x2[4];
+                auto fetch = [&](int c0, uint4 (&ra)[4], uint4 (&rb)[4]) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int col = c0 + g * 8;
+                        const bool ok = valid && col < ncols;
+                        ra[g] = (ok && has_r1) ? __ldg(reinterpret_cast<const uint4*>(r1row + col)) : make_uint4(0, 0, 0, 0);
+                        rb[g] = (ok && has_r2) ? __ldg(reinterpret_cast<const uint4*>(r2row + col)) : make_uint4(0, 0, 0, 0);
+                    }
+                };
+                fetch(half * 32, c1, c2);
+                mbar_wait(tmem_full_bar(acc), acc_ph);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
+                    fetch(c0 + 64, x1, x2);
+                    uint32_t accv[32];
+                    tmem_ld32(taddr + c0, accv);
+                    tmem_wait_ld();
+                    if (valid) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const int col = c0 + g * 8;
+                            if (col < ncols) {
+                                const float4 b0 = *reinterpret_cast<const float4*>(sbias + col);
+                                const float4 b1 = *reinterpret_cast<const float4*>(sbias + col + 4);
+                                float v[8];
+                                v[0] = __uint_as_float(accv[g * 8 + 0]) + b0.x; v[1] = __uint_as_float(accv[g * 8 + 1]) + b0.y;
+                                v[2] = __uint_as_float(accv[g * 8 + 2]) + b0.z; v[3] = __uint_as_float(accv[g * 8 + 3]) + b0.w;
+                                v[4] = __uint_as_float(accv[g * 8 + 4]) + b1.x; v[5] = __uint_as_float(accv[g * 8 + 5]) + b1.y;
+                                v[6] = __uint_as_float(accv[g * 8 + 6]) + b1.z; v[7] = __uint_as_float(accv[g * 8 + 7]) + b1.w;
+                                if (has_rv) {
+                                    const float4 t0 = __ldg(reinterpret_cast<const float4*>(rvrow + col));
+                                    const float4 t1 = __ldg(reinterpret_cast<const float4*>(rvrow + col + 4));
+                                    v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
+                                    v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
+                                }
+                                const uint4 q1 = c1[g], q2 = c2[g];  // zeros when the residual is absent
+                                v[0] = (v[0] + bf16_lo(q1.x)) * alpha + bf16_lo(q2.x); v[1] = (v[1] + bf16_hi(q1.x)) * alpha + bf16_hi(q2.x);
+                                v[2] = (v[2] + bf16_lo(q1.y)) * alpha + bf16_lo(q2.y); v[3] = (v[3] + bf16_hi(q1.y)) * alpha + bf16_hi(q2.y);
+                                v[4] = (v[4] + bf16_lo(q1.z)) * alpha + bf16_lo(q2.z); v[5] = (v[5] + bf16_hi(q1.z)) * alpha + bf16_hi(q2.z);
+                                v[6] = (v[6] + bf16_lo(q1.w)) * alpha + bf16_lo(q2.w); v[7] = (v[7] + bf16_hi(q1.w)) * alpha + bf16_hi(q2.w);
+                                if (silu) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+                                }
+                                uint4 q;
+                                q.x = pack_bf16x2(v[0], v[1]);
+                                q.y = pack_bf16x2(v[2], v[3]);
+                                q.z = pack_bf16x2(v[4], v[5]);
+                                q.w = pack_bf16x2(v[6], v[7]);
+                                *reinterpret_cast<uint4*>(orow + col) = q;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) { c1[g] = x1[g]; c2[g] = x2[g]; }
                 }
             } else {
                 // residuals of a 32-column chunk are fetched one chunk ahead (the first chunk's
@@ -432,44 +503,50 @@ static int num_sms() {
     return n;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MODE>
 static int launch_variant(const GemmLaunch& l, cudaStream_t s) {
-    gemm_conv_kernel<BLOCK_N><<<l.grid, GEMM_THREADS, l.smem, s>>>(l.p);
+    gemm_conv_kernel<BLOCK_N, MODE><<<l.grid, GEMM_THREADS, l.smem, s>>>(l.p);
     PP_CUDA_CHECK(cudaGetLastError());
     return PP_OK;
 }
 
 // opt the kernel variant into its dynamic shared memory size (done at prepare time so that
 // launches are pure and can be stream-captured)
-template <int BLOCK_N>
+template <int BLOCK_N, int MODE>
 static int ensure_attr() {
     static bool done = false;
     if (!done) {
-        PP_CUDA_CHECK(cudaFuncSetAttribute(gemm_conv_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PP_CUDA_CHECK(cudaFuncSetAttribute(gemm_conv_kernel<BLOCK_N, MODE>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem_for_block_n(BLOCK_N)));
         done = true;
     }
     return PP_OK;
 }
 
-static int ensure_attr_for(int block_n) {
-    switch (block_n) {
-        case 64: return ensure_attr<64>();
-        case 128: return ensure_attr<128>();
-        case 160: return ensure_attr<160>();
-        case 256: return ensure_attr<256>();
+#define PP_GEMM_DISPATCH(FN, bn, mode, ...)                                      \
+    switch ((bn) * 4 + (mode)) {                                                 \
+        case 64 * 4 + 0: return FN<64, 0>(__VA_ARGS__);                          \
+        case 64 * 4 + 1: return FN<64, 1>(__VA_ARGS__);                          \
+        case 128 * 4 + 0: return FN<128, 0>(__VA_ARGS__);                        \
+        case 128 * 4 + 1: return FN<128, 1>(__VA_ARGS__);                        \
+        case 128 * 4 + 2: return FN<128, 2>(__VA_ARGS__);                        \
+        case 160 * 4 + 0: return FN<160, 0>(__VA_ARGS__);                        \
+        case 160 * 4 + 1: return FN<160, 1>(__VA_ARGS__);                        \
+        case 160 * 4 + 2: return FN<160, 2>(__VA_ARGS__);                        \
+        case 256 * 4 + 0: return FN<256, 0>(__VA_ARGS__);                        \
+        case 256 * 4 + 1: return FN<256, 1>(__VA_ARGS__);                        \
+        case 256 * 4 + 2: return FN<256, 2>(__VA_ARGS__);                        \
     }
+
+static int ensure_attr_for(int block_n, int mode) {
+    PP_GEMM_DISPATCH(ensure_attr, block_n, mode)
     return PP_ERR_INVALID;
 }
 
 int gemm_launch(const GemmLaunch& l, cudaStream_t s) {
-    switch (l.block_n) {
-        case 64: return launch_variant<64>(l, s);
-        case 128: return launch_variant<128>(l, s);
-        case 160: return launch_variant<160>(l, s);
-        case 256: return launch_variant<256>(l, s);
-    }
-    set_last_error("gemm_launch: unsupported block_n %d", l.block_n);
+    PP_GEMM_DISPATCH(launch_variant, l.block_n, l.mode, l, s)
+    set_last_error("gemm_launch: unsupported block_n %d / mode %d", l.block_n, l.mode);
     return PP_ERR_INVALID;
 }
 
@@ -643,8 +720,15 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
         l.grid = dim3((unsigned)std::min<long>(tiles, num_sms()), 1, 1);
     }
     l.smem = smem_for_block_n(bn);
+    if (geglu) {
+        l.mode = 2;
+    } else {
+        const bool fast = d.epilogue == PP_EPI_PLAIN && !d.out_fp32 && d.N % 8 == 0 &&
+                          (!d.rowvec || (p.rowvec_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d.rowvec) & 15) == 0));
+        l.mode = fast ? 0 : 1;
+    }
     {
-        int rc = ensure_attr_for(bn);
+        int rc = ensure_attr_for(bn, l.mode);
         if (rc) return rc;
     }
     *out = l;

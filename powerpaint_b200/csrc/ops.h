@@ -46,6 +46,7 @@ struct GemmKParams {
 struct GemmLaunch {
     GemmKParams p;
     int block_n;
+    int mode;  // epilogue flavour: 0 fast bf16, 1 generic, 2 GEGLU
     dim3 grid;
     size_t smem;
 };
