@@ -101,6 +101,7 @@ typedef struct pp_gemm_desc {
     int32_t t_rows;   /* PP_EPI_TRANSPOSED */
     int64_t t_ld;
     int32_t block_n;  /* 0 = auto, else one of 64/128/160/256 */
+    int32_t t_fp16;   /* PP_EPI_TRANSPOSED: store fp16 instead of bf16 (V^T for pp_attention) */
 } pp_gemm_desc;
 
 pp_status pp_gemm_conv(const pp_gemm_desc* d, pp_stream stream);
@@ -108,7 +109,7 @@ pp_status pp_gemm_conv(const pp_gemm_desc* d, pp_stream stream);
 /* ------------------------------------------------------------------ attention */
 typedef struct pp_attn_desc {
     /* q: [batch, nq, heads, d] with token pitch q_ld (elements); k likewise with nk, k_ld.
-       vt: V transposed, [batch, heads*d, vt_ld] (keys contiguous, vt_ld >= nk, vt_ld % 8 == 0).
+       vt: V transposed, [batch, heads*d, vt_ld] (keys contiguous, vt_ld >= nk, vt_ld % 8 == 0), bf16 or fp16.
        out: [batch, nq, heads*d] row pitch o_ld. softmax(q k^T * scale) v, no mask. */
     const void* q;
     const void* k;
@@ -118,6 +119,7 @@ typedef struct pp_attn_desc {
     int64_t q_ld, k_ld, vt_ld, o_ld;
     int64_t q_batch_stride, k_batch_stride; /* elements between batches */
     float scale;
+    int32_t vt_fp16; /* != 0: vt holds fp16 (P is then computed in fp16 too); 0: bf16 */
 } pp_attn_desc;
 
 pp_status pp_attention(const pp_attn_desc* d, pp_stream stream);

@@ -38,7 +38,7 @@ class GemmDesc(C.Structure):
         ("alpha", f32), ("act", i32),
         ("out", vp), ("ldc", i64),
         ("out_fp32", i32), ("t_rows", i32), ("t_ld", i64),
-        ("block_n", i32),
+        ("block_n", i32), ("t_fp16", i32),
     ]
 
 
@@ -48,7 +48,7 @@ class AttnDesc(C.Structure):
         ("batch", i32), ("heads", i32), ("d", i32), ("nq", i32), ("nk", i32),
         ("q_ld", i64), ("k_ld", i64), ("vt_ld", i64), ("o_ld", i64),
         ("q_batch_stride", i64), ("k_batch_stride", i64),
-        ("scale", f32),
+        ("scale", f32), ("vt_fp16", i32),
     ]
 
 

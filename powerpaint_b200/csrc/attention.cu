@@ -22,6 +22,8 @@
 
 #include <algorithm>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "ops.h"
 
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __grid_cons
         // ===================== MMA issuer =====================
         if (elect_one()) {
             const uint32_t idesc_s = umma_idesc_bf16(ATT_BM, ATT_BN);
-            const uint32_t idesc_o = umma_idesc_bf16(ATT_BM, (uint32_t)p.dv);
+            const uint32_t idesc_o = p.vt_fp16 ? umma_idesc_f16(ATT_BM, (uint32_t)p.dv) : umma_idesc_bf16(ATT_BM, (uint32_t)p.dv);
             auto issue_s = [&](int j) {
                 const int s = j % S;
                 mbar_wait(bar_kv_full(s), (j / S) & 1);
@@ -221,9 +223,16 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __grid_cons
                 for (int i = 0; i < 32; i += 2) {
                     float p0 = (c * 32 + i < nvalid) ? fast_exp2(fmaf(__uint_as_float(sv[i]), p.scale_log2, -m_ref)) : 0.f;
                     float p1 = (c * 32 + i + 1 < nvalid) ? fast_exp2(fmaf(__uint_as_float(sv[i + 1]), p.scale_log2, -m_ref)) : 0.f;
-                    const uint32_t q = pack_bf16x2(p0, p1);
+                    uint32_t q;
+                    if (p.vt_fp16) {
+                        q = pack_f16x2(p0, p1);
+                        const __half2 h = *reinterpret_cast<const __half2*>(&q);
+                        lsum += __low2float(h) + __high2float(h);
+                    } else {
+                        q = pack_bf16x2(p0, p1);
+                        lsum += bf16_lo(q) + bf16_hi(q);
+                    }
                     pk[c * 16 + i / 2] = q;
-                    lsum += bf16_lo(q) + bf16_hi(q);
                 }
             }
             l = l * alpha + lsum;
@@ -288,9 +297,25 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __grid_cons
     }
 }
 
+}  // namespace pp
+
+#include "attention2.cuh"
+
+namespace pp {
+
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
+static int attn2_ensure_attr() {
+    static bool done = false;
+    if (!done) {
+        PP_CUDA_CHECK(cudaFuncSetAttribute(attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)att2_smem_bytes(80)));
+        done = true;
+    }
+    return PP_OK;
+}
+
 template <int DCH>
 static int attn_ensure_attr() {
     static bool done = false;
@@ -317,8 +342,12 @@ int attn_prepare(const pp_attn_desc& d, AttnLaunch* out) {
     p.batch = d.batch; p.heads = d.heads; p.d = d.d; p.nq = d.nq; p.nk = d.nk;
     p.d_chunks = (d.d + 63) / 64;
     p.k_steps = (d.d + 15) / 16;
-    p.dv = ((d.d + 15) / 16) * 16;
+    // dual-tile kernel for d <= 64 when there are at least two query tiles; it keeps the row sums
+    // in column d of O, so its V^T tile has one extra (ones) row
+    const bool dual = p.d_chunks == 1 && d.nq > ATT_BM && d.vt_fp16;
+    p.dv = dual ? ((d.d + 1 + 15) / 16) * 16 : ((d.d + 15) / 16) * 16;
     p.scale_log2 = d.scale * 1.4426950408889634f;
+    p.vt_fp16 = d.vt_fp16;
     p.out = reinterpret_cast<__nv_bfloat16*>(d.out);
     p.o_ld = d.o_ld;
     {
@@ -342,6 +371,16 @@ int attn_prepare(const pp_attn_desc& d, AttnLaunch* out) {
         int rc = make_tmap_bf16(&p.tmV, d.vt, 3, dims, str, box, true);
         if (rc) return rc;
     }
+    if (dual) {
+        l.variant = 10;
+        l.grid = dim3((unsigned)((d.nq + 2 * ATT_BM - 1) / (2 * ATT_BM)), (unsigned)d.heads, (unsigned)d.batch);
+        l.smem = att2_smem_bytes((uint32_t)p.dv);
+        l.kv_stages = ATT2_KV_STAGES;
+        int rc2 = attn2_ensure_attr();
+        if (rc2) return rc2;
+        *out = l;
+        return PP_OK;
+    }
     l.variant = p.d_chunks;
     l.grid = dim3((unsigned)((d.nq + ATT_BM - 1) / ATT_BM), (unsigned)d.heads, (unsigned)d.batch);
     int rc;
@@ -357,6 +396,7 @@ int attn_prepare(const pp_attn_desc& d, AttnLaunch* out) {
 
 int attn_launch(const AttnLaunch& l, cudaStream_t s) {
     switch (l.variant) {
+        case 10: attn2_kernel<<<l.grid, ATT2_THREADS, l.smem, s>>>(l.p); break;
         case 1: attn_fwd_kernel<1><<<l.grid, ATT_THREADS, l.smem, s>>>(l.p); break;
         case 2: attn_fwd_kernel<2><<<l.grid, ATT_THREADS, l.smem, s>>>(l.p); break;
         default: attn_fwd_kernel<3><<<l.grid, ATT_THREADS, l.smem, s>>>(l.p); break;

@@ -1,0 +1,309 @@
+// Dual-tile ("ping-pong") attention kernel for head dims <= 64 with fp16 P / V^T — the d = 40
+// self-attention over 4096 tokens that dominates the 512^2 step. Included by attention.cu.
+//
+// One CTA (one per SM, 320 threads) owns TWO 128-query tiles of one (sample, head) and streams the
+// keys once for both, 128 keys per block:
+//   warp 0        TMA producer: Q0, Q1, then K / V^T blocks through a 3-stage ring
+//   warp 1        tcgen05.mma issuer, alternating between the tiles:
+//                 ... PV0(j), S0(j+1), PV1(j), S1(j+1) ... so while softmax group 0 works on S0(j+1)
+//                 the tensor core runs tile 1, and vice versa
+//   warps 2..5    softmax group 0 (tile 0), warps 6..9 softmax group 1 (tile 1): one thread per query row
+// TMEM: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512).
+// Softmax is single-pass in the steady state: exponentials use the running reference max m_ref
+// (exp2 domain); only if a row's new max exceeds m_ref by more than 2^8 is the block redone with the
+// new reference and O rescaled. The row sum costs no ALU work: row d of the V^T tile (zero-filled by
+// TMA since d < dv) is overwritten with ones in shared memory, so column d of O accumulates sum_j p_ij
+// on the tensor core, consistent with the fp16-rounded P the MMA actually sees.
+// Measured on B200 (d = 40, 4096 x 4096, 16 x 8 heads): 985 us = 349 TFLOP/s; the kernel is bound by
+// the exponential throughput of the SM (16 ex2 / clk / SM: 2.15 G exps -> 477 us floor), not by the
+// tensor core (profiles/r01_attn2_notes.md).
+#pragma once
+
+namespace pp {
+
+static constexpr int ATT2_THREADS = 320;
+static constexpr int ATT2_KV_STAGES = 3;
+
+__host__ __device__ constexpr uint32_t att2_smem_bytes(uint32_t dv) {
+    return 2 * ATT_CHUNK_BYTES                                   // Q0, Q1
+           + ATT2_KV_STAGES * (ATT_CHUNK_BYTES + dv * 256u)      // K + V^T ring
+           + 2 * 2 * ATT_CHUNK_BYTES                             // P0, P1
+           + 256 + 1024;
+}
+
+__global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_constant__ AttnKParams p) {
+    constexpr int S = ATT2_KV_STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t v_chunk_bytes = (uint32_t)p.dv * 128u;
+    const uint32_t v_stage_bytes = 2u * v_chunk_bytes;
+    const uint32_t sQ = base;                                    // [2][16 KB]
+    const uint32_t sK0 = sQ + 2 * ATT_CHUNK_BYTES;               // [S][16 KB]
+    const uint32_t sV0 = sK0 + S * ATT_CHUNK_BYTES;              // [S][v_stage_bytes]
+    const uint32_t sP = sV0 + S * v_stage_bytes;                 // [2][32 KB]
+    const uint32_t bars = sP + 4 * ATT_CHUNK_BYTES;
+    const uint32_t bar_q = bars;
+    auto bar_kv_full = [&](int s) { return bars + 8u * (1 + s); };
+    auto bar_kv_empty = [&](int s) { return bars + 8u * (1 + S + s); };
+    auto bar_s_full = [&](int t) { return bars + 8u * (1 + 2 * S + t); };
+    auto bar_p_full = [&](int t) { return bars + 8u * (3 + 2 * S + t); };
+    auto bar_pv_done = [&](int t) { return bars + 8u * (5 + 2 * S + t); };
+    const uint32_t tmem_slot = bars + 8u * (7 + 2 * S);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+    const int warp = threadIdx.x >> 5;
+    const int q0 = blockIdx.x * 2 * ATT_BM;
+    const int head = blockIdx.y;
+    const int b = blockIdx.z;
+    const int nkv = (p.nk + ATT_BN - 1) / ATT_BN;
+
+    if (warp == 0 && elect_one()) {
+        prefetch_tmap(&p.tmQ);
+        prefetch_tmap(&p.tmK);
+        prefetch_tmap(&p.tmV);
+        mbar_init(bar_q, 1);
+        for (int s = 0; s < S; ++s) {
+            mbar_init(bar_kv_full(s), 1);
+            mbar_init(bar_kv_empty(s), 1);
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(bar_s_full(t), 1);
+            mbar_init(bar_p_full(t), 128);
+            mbar_init(bar_pv_done(t), 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            mbar_arrive_expect_tx(bar_q, 2 * ATT_CHUNK_BYTES);
+            tma_load_4d(sQ, &p.tmQ, bar_q, 0, head, q0, b);
+            tma_load_4d(sQ + ATT_CHUNK_BYTES, &p.tmQ, bar_q, 0, head, q0 + ATT_BM, b);
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j % S;
+                const uint32_t ph = (j / S) & 1;
+                mbar_wait(bar_kv_empty(s), ph ^ 1u);
+                mbar_arrive_expect_tx(bar_kv_full(s), ATT_CHUNK_BYTES + v_stage_bytes);
+                tma_load_4d(sK0 + s * ATT_CHUNK_BYTES, &p.tmK, bar_kv_full(s), 0, head, j * ATT_BN, b);
+                const uint32_t dV = sV0 + s * v_stage_bytes;
+                tma_load_3d(dV, &p.tmV, bar_kv_full(s), j * ATT_BN, 0, b * p.heads + head);
+                tma_load_3d(dV + v_chunk_bytes, &p.tmV, bar_kv_full(s), j * ATT_BN + 64, 0, b * p.heads + head);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            const uint32_t idesc_s = umma_idesc_bf16(ATT_BM, ATT_BN);
+            const uint32_t idesc_o = umma_idesc_f16(ATT_BM, (uint32_t)p.dv);  // P and V^T are fp16 here
+            auto issue_s = [&](int t, int j) {
+                const uint32_t kb = sK0 + (j % S) * ATT_CHUNK_BYTES;
+                const uint64_t da0 = umma_desc_kmajor_sw128(sQ + t * ATT_CHUNK_BYTES);
+                const uint64_t db0 = umma_desc_kmajor_sw128(kb);
+                for (int ks = 0; ks < p.k_steps; ++ks)
+                    umma_bf16_ss(tmem_base + t * 128, umma_desc_advance_k(da0, ks * 16),
+                                 umma_desc_advance_k(db0, ks * 16), idesc_s, ks != 0);
+                umma_commit(bar_s_full(t));
+            };
+            auto issue_pv = [&](int t, int j) {
+                const uint32_t vb = sV0 + (j % S) * v_stage_bytes;
+                const uint32_t pb = sP + t * 2 * ATT_CHUNK_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const int c = ks >> 2, kk = (ks & 3) * 16;
+                    umma_bf16_ss(tmem_base + 256 + t * 128,
+                                 umma_desc_advance_k(umma_desc_kmajor_sw128(pb + c * ATT_CHUNK_BYTES), kk),
+                                 umma_desc_advance_k(umma_desc_kmajor_sw128(vb + c * v_chunk_bytes), kk), idesc_o,
+                                 (j | ks) != 0);
+                }
+                umma_commit(bar_pv_done(t));
+            };
+            mbar_wait(bar_q, 0);
+            mbar_wait(bar_kv_full(0), 0);
+            tc_fence_after();
+            issue_s(0, 0);
+            issue_s(1, 0);
+            for (int j = 0; j < nkv; ++j) {
+                for (int t = 0; t < 2; ++t) {
+                    mbar_wait(bar_p_full(t), j & 1);
+                    tc_fence_after();
+                    issue_pv(t, j);
+                    if (t == 1) umma_commit(bar_kv_empty(j % S));  // both tiles' PV(j) precede this commit
+                    if (j + 1 < nkv) {
+                        if (t == 0) {
+                            mbar_wait(bar_kv_full((j + 1) % S), ((j + 1) / S) & 1);
+                            tc_fence_after();
+                        }
+                        issue_s(t, j + 1);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== softmax groups =====================
+        const int t = (warp - 2) >> 2;          // tile / group index
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + (int)lane_id();
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        const uint32_t tS = tmem_base + t * 128 + lane_addr;
+        const uint32_t tO = tmem_base + 256 + t * 128 + lane_addr;
+        uint8_t* prow = smem_raw + (sP + t * 2 * ATT_CHUNK_BYTES - raw) + r * 128;
+        float c;  // pinned in a register (otherwise re-fetched from the constant bank per element)
+        asm volatile("mov.f32 %0, %1;" : "=f"(c) : "f"(p.scale_log2));
+        float m_ref = 0.f;
+        for (int j = 0; j < nkv; ++j) {
+            mbar_wait(bar_s_full(t), j & 1);
+            tc_fence_after();
+            const int nvalid = min(ATT_BN, p.nk - j * ATT_BN);
+            if (j == 0) {
+                // the first block has no reference yet: one extra pass for the row max
+                float mx = -INFINITY;
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t sv[32];
+                    tmem_ld32(tS + ch * 32, sv);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (ch * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(sv[i]));
+                }
+                m_ref = mx * c;
+            }
+            uint32_t pk[64];
+            float alpha = 1.f;
+            bool redo;
+            do {
+                // four independent running maxima break the 128-long fmax dependency chain; the
+                // TMEM load of chunk ch+1 is in flight while chunk ch is exponentiated
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+                uint32_t sa[32], sb[32];
+                tmem_ld32(tS, sa);
+                tmem_wait_ld();
+                auto process = [&](const uint32_t (&sv)[32], int ch) {
+                    if (nvalid == ATT_BN) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float s0 = __uint_as_float(sv[i]), s1 = __uint_as_float(sv[i + 1]);
+                            const float s2 = __uint_as_float(sv[i + 2]), s3 = __uint_as_float(sv[i + 3]);
+                            mx0 = fmaxf(mx0, s0); mx1 = fmaxf(mx1, s1); mx2 = fmaxf(mx2, s2); mx3 = fmaxf(mx3, s3);
+                            pk[ch * 16 + i / 2] = ex2_f16x2(pack_f16x2(fmaf(s0, c, -m_ref), fmaf(s1, c, -m_ref)));
+                            pk[ch * 16 + i / 2 + 1] = ex2_f16x2(pack_f16x2(fmaf(s2, c, -m_ref), fmaf(s3, c, -m_ref)));
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const float s0 = __uint_as_float(sv[i]), s1 = __uint_as_float(sv[i + 1]);
+                            const bool v0 = ch * 32 + i < nvalid, v1 = ch * 32 + i + 1 < nvalid;
+                            if (v0) mx0 = fmaxf(mx0, s0);
+                            if (v1) mx1 = fmaxf(mx1, s1);
+                            const float p0 = v0 ? fast_exp2(fmaf(s0, c, -m_ref)) : 0.f;
+                            const float p1 = v1 ? fast_exp2(fmaf(s1, c, -m_ref)) : 0.f;
+                            pk[ch * 16 + i / 2] = pack_f16x2(p0, p1);
+                        }
+                    }
+                };
+                tmem_ld32(tS + 32, sb);
+                process(sa, 0);
+                tmem_wait_ld();
+                tmem_ld32(tS + 64, sa);
+                process(sb, 1);
+                tmem_wait_ld();
+                tmem_ld32(tS + 96, sb);
+                process(sa, 2);
+                tmem_wait_ld();
+                process(sb, 3);
+                const float mnew = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
+                const bool need = mnew > m_ref + 8.0f;
+                redo = __any_sync(0xffffffffu, need);
+                if (need) {
+                    alpha *= fast_exp2(m_ref - mnew);
+                    m_ref = mnew;
+                }
+            } while (redo);
+            if (j > 0) {
+                mbar_wait(bar_pv_done(t), (j - 1) & 1);  // P buffer free, O holds blocks < j
+                tc_fence_after();
+            }
+            if (__any_sync(0xffffffffu, alpha != 1.f)) {
+                for (int col = 0; col < p.dv; col += 16) {
+                    uint32_t ov[16];
+                    tmem_ld16(tO + col, ov);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+                    tmem_st16(tO + col, ov);
+                }
+                tmem_wait_st();
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int ch = q >> 3, i = q & 7;
+                *reinterpret_cast<uint4*>(prow + ch * ATT_CHUNK_BYTES + ((i ^ (r & 7)) << 4)) =
+                    make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+            }
+            if (t == 0 && warp == 2 && lane_id() < 16) {
+                // row d of the V^T tile := 1.0 (fp16 0x3C00) so O[:, d] accumulates the row sums
+                const int ch = lane_id() >> 3, piece = lane_id() & 7;
+                uint8_t* vrow = smem_raw + (sV0 + (j % S) * v_stage_bytes + ch * v_chunk_bytes - raw) + p.d * 128;
+                *reinterpret_cast<uint4*>(vrow + piece * 16) =
+                    make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_p_full(t));
+        }
+        // epilogue: O[:, :d] / O[:, d]
+        mbar_wait(bar_pv_done(t), (nkv - 1) & 1);
+        tc_fence_after();
+        const int qi = q0 + t * ATT_BM + r;
+        __nv_bfloat16* orow = p.out + ((int64_t)b * p.nq + qi) * p.o_ld + head * p.d;
+        float inv_l = 1.f;
+        {
+            uint32_t lv[16];
+            tmem_ld16(tO + (p.d & ~15), lv);
+            tmem_wait_ld();
+            float l = 1.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i == (p.d & 15)) l = __uint_as_float(lv[i]);
+            inv_l = 1.0f / l;
+        }
+        for (int col = 0; col < p.d; col += 16) {
+            uint32_t ov[16];
+            tmem_ld16(tO + col, ov);
+            tmem_wait_ld();
+            if (qi < p.nq) {
+#pragma unroll
+                for (int g = 0; g < 16; g += 8) {
+                    if (col + g < p.d) {
+                        uint4 o;
+                        o.x = pack_bf16x2(__uint_as_float(ov[g + 0]) * inv_l, __uint_as_float(ov[g + 1]) * inv_l);
+                        o.y = pack_bf16x2(__uint_as_float(ov[g + 2]) * inv_l, __uint_as_float(ov[g + 3]) * inv_l);
+                        o.z = pack_bf16x2(__uint_as_float(ov[g + 4]) * inv_l, __uint_as_float(ov[g + 5]) * inv_l);
+                        o.w = pack_bf16x2(__uint_as_float(ov[g + 6]) * inv_l, __uint_as_float(ov[g + 7]) * inv_l);
+                        *reinterpret_cast<uint4*>(orow + col + g) = o;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace pp

@@ -238,6 +238,10 @@ __device__ __forceinline__ uint64_t umma_desc_advance_k(uint64_t desc, uint32_t 
     return desc + static_cast<uint64_t>((k_elems * 2u) >> 4);
 }
 // Instruction descriptor: D=f32, A=B=bf16, both K-major, shape M x N (K=16 implied)
+// same with A = B = fp16 (format code 0)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
+    return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4)            // D format f32
            | (1u << 7)          // A format bf16
@@ -252,6 +256,17 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %2, %1;" : "=r"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+// two exponentials per MUFU op: packed fp16 in, packed fp16 out
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
+    uint32_t r;
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }

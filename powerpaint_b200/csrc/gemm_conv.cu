@@ -28,6 +28,8 @@
 //    GEGLU gate → bf16 or fp32 store, optionally transposed (V^T for the attention kernel).
 #include <algorithm>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "ops.h"
 
@@ -97,6 +99,13 @@ __device__ __forceinline__ void epilogue_store8(const GemmKParams& p, float (&v)
         // so each per-column store is a 64-byte contiguous run across the warp.
         const int64_t b = row / p.t_rows;
         const int64_t t = row - b * p.t_rows;
+        if (p.t_fp16) {
+            __half* o = reinterpret_cast<__half*>(p.out) + (b * p.N + n0) * p.t_ld + t;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (kVec || n0 + j < p.N) o[(int64_t)j * p.t_ld] = __float2half_rn(v[j]);
+            return;
+        }
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (b * p.N + n0) * p.t_ld + t;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -698,6 +707,7 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
     p.ldc = d.ldc;
     p.t_rows = d.t_rows;
     p.t_ld = d.t_ld;
+    p.t_fp16 = d.t_fp16;
     if (d.epilogue == PP_EPI_TRANSPOSED) {
         PP_REQUIRE(d.t_rows > 0 && d.t_ld >= d.t_rows, "gemm: transposed store needs t_rows/t_ld");
         PP_REQUIRE(!d.out_fp32, "gemm: transposed store is bf16 only");

@@ -77,47 +77,50 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, const __nv
 }
 
 // GroupNorm pass 2: y = (x - mean) * rstd * gamma + beta, optional SiLU; writes the concat.
+// grid = (pixel chunks, batch); like pass 1 every thread owns one 8-channel vector (so gamma / beta /
+// mean / rstd live in registers for the whole kernel) and strides over pixels: 32-bit index math only.
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, const __nv_bfloat16* __restrict__ x1,
                                 int c0, int c1, int hw, int groups, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int silu,
                                 const float* __restrict__ stats, __nv_bfloat16* __restrict__ y,
-                                int64_t total_vec) {
+                                int pix_per_block) {
     const int C = c0 + c1;
     const int CV = C / 8;
     const int cpg = C / groups;
+    const int n = blockIdx.y;
+    const int lanes = blockDim.x / CV;
+    const int cv = threadIdx.x % CV;
+    const int pl = threadIdx.x / CV;
+    if (pl >= lanes) return;
+    const int c = cv * 8;
+    const __nv_bfloat16* src;
+    int cs, co;
+    if (c < c0) { src = x0; cs = c0; co = c; } else { src = x1; cs = c1; co = c - c0; }
+    // per-channel scale / shift: y = x * a + b with a = rstd * gamma, b = beta - mean * a
     const float inv_cnt = 1.0f / ((float)cpg * (float)hw);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        const int cv = (int)(i % CV);
-        const int64_t pix = i / CV;  // n*hw + p
-        const int n = (int)(pix / hw);
-        const int c = cv * 8;
-        const __nv_bfloat16* src;
-        int cs, co;
-        if (c < c0) { src = x0; cs = c0; co = c; } else { src = x1; cs = c1; co = c - c0; }
-        uint4 q = __ldg(reinterpret_cast<const uint4*>(src + pix * cs + co));
+    float a[8], bsh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int g = (c + j) / cpg;
+        const float s = __ldg(&stats[((int64_t)n * groups + g) * 2]);
+        const float ss = __ldg(&stats[((int64_t)n * groups + g) * 2 + 1]);
+        const float mean = s * inv_cnt;
+        const float var = fmaxf(ss * inv_cnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        a[j] = rstd * __ldg(gamma + c + j);
+        bsh[j] = __ldg(beta + c + j) - mean * a[j];
+    }
+    const int p_begin = blockIdx.x * pix_per_block;
+    const int p_end = min(hw, p_begin + pix_per_block);
+    const __nv_bfloat16* sp = src + ((int64_t)n * hw) * cs + co;
+    __nv_bfloat16* yp = y + ((int64_t)n * hw) * C + c;
+    for (int p = p_begin + pl; p < p_end; p += lanes) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(sp + (int64_t)p * cs));
         float v[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
                       bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
-        float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
-        float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
-        float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c));
-        float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
-        const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        int g_prev = -1;
-        float mean = 0.f, rstd = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int g = (c + j) / cpg;
-            if (g != g_prev) {
-                const float s = __ldg(&stats[((int64_t)n * groups + g) * 2]);
-                const float ss = __ldg(&stats[((int64_t)n * groups + g) * 2 + 1]);
-                mean = s * inv_cnt;
-                const float var = fmaxf(ss * inv_cnt - mean * mean, 0.f);
-                rstd = rsqrtf(var + eps);
-                g_prev = g;
-            }
-            float o = (v[j] - mean) * rstd * ga[j] + be[j];
+            const float o = fmaf(v[j], a[j], bsh[j]);
             v[j] = silu ? silu_f(o) : o;
         }
         uint4 o;
@@ -125,7 +128,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, const __nv
         o.y = pack_bf16x2(v[2], v[3]);
         o.z = pack_bf16x2(v[4], v[5]);
         o.w = pack_bf16x2(v[6], v[7]);
-        *reinterpret_cast<uint4*>(y + pix * C + c) = o;
+        *reinterpret_cast<uint4*>(yp + (int64_t)p * C) = o;
     }
 }
 
@@ -158,12 +161,10 @@ int group_norm_launch(const pp_gn_desc& d, cudaStream_t s) {
         reinterpret_cast<const __nv_bfloat16*>(d.x0), reinterpret_cast<const __nv_bfloat16*>(d.x1), d.c0,
         d.c1, d.hw, d.groups, ppb, d.stats);
     PP_CUDA_CHECK(cudaGetLastError());
-    const int64_t total_vec = (int64_t)d.batch * d.hw * CV;
-    int blocks = (int)std::min<int64_t>((total_vec + 255) / 256, 148 * 16);
-    gn_apply_kernel<<<blocks, 256, 0, s>>>(
+    gn_apply_kernel<<<dim3(chunks, d.batch), threads, 0, s>>>(
         reinterpret_cast<const __nv_bfloat16*>(d.x0), reinterpret_cast<const __nv_bfloat16*>(d.x1), d.c0,
         d.c1, d.hw, d.groups, d.gamma, d.beta, d.eps, d.silu, d.stats,
-        reinterpret_cast<__nv_bfloat16*>(d.y), total_vec);
+        reinterpret_cast<__nv_bfloat16*>(d.y), ppb);
     PP_CUDA_CHECK(cudaGetLastError());
     return PP_OK;
 }

@@ -41,6 +41,7 @@ struct GemmKParams {
     int64_t ldc;
     int32_t t_rows;
     int64_t t_ld;
+    int32_t t_fp16;
 };
 
 struct GemmLaunch {
@@ -62,6 +63,7 @@ struct AttnKParams {
     int32_t k_steps;   // ceil(d / 16)
     int32_t dv;        // ceil16(d): UMMA N of the PV product
     float scale_log2;  // scale * log2(e)
+    int32_t vt_fp16;   // V^T (and P) in fp16 instead of bf16
     __nv_bfloat16* out;
     int64_t o_ld;
 };

@@ -256,9 +256,9 @@ class NetEngine:
         prog.add_layer_norm(t0, l1, self.vec(b + ".norm1.weight"), self.vec(b + ".norm1.bias"), M, C, 1e-5)
         qk = self._linear(plan, prog, l1, M, None, 2 * C, w=self.w_qk(b + ".attn1"))
         hw_ld = _ceil(hw, 8)
-        vt = self._buf(plan, nb, C, hw_ld)
+        vt = self._buf(plan, nb, C, hw_ld, dtype=torch.float16)  # fp16 V^T: P is fp16 in pp_attention
         prog.add(ops.gemm_desc(a0=l1, w=self.w_linear(b + ".attn1.to_v"), out=vt, N_=C, M=M,
-                               epilogue=N.PP_EPI_TRANSPOSED, t_rows=hw, t_ld=hw_ld))
+                               epilogue=N.PP_EPI_TRANSPOSED, t_rows=hw, t_ld=hw_ld, t_fp16=True))
         a1 = self._buf(plan, M, C)
         prog.add(ops.attn_desc(q=qk, k=qk[:, C:], vt=vt, out=a1, batch=nb, heads=heads, d=d, nq=hw, nk=hw,
                                q_ld=2 * C, k_ld=2 * C, vt_ld=hw_ld, o_ld=C, q_batch_stride=hw * 2 * C,
@@ -271,9 +271,9 @@ class NetEngine:
         nk = ctx.shape[1]
         nk_ld = _ceil(nk, 8)
         k2 = self._linear(plan, ctxprog, ctx, nb * nk, b + ".attn2.to_k", C)
-        v2t = self._buf(plan, nb, C, nk_ld)
+        v2t = self._buf(plan, nb, C, nk_ld, dtype=torch.float16)
         ctxprog.add(ops.gemm_desc(a0=ctx, w=self.w_linear(b + ".attn2.to_v"), out=v2t, N_=C, M=nb * nk,
-                                  epilogue=N.PP_EPI_TRANSPOSED, t_rows=nk, t_ld=nk_ld))
+                                  epilogue=N.PP_EPI_TRANSPOSED, t_rows=nk, t_ld=nk_ld, t_fp16=True))
         a2 = self._buf(plan, M, C)
         prog.add(ops.attn_desc(q=q2, k=k2, vt=v2t, out=a2, batch=nb, heads=heads, d=d, nq=hw, nk=nk, q_ld=C, k_ld=C,
                                vt_ld=nk_ld, o_ld=C, q_batch_stride=hw * C, k_batch_stride=nk * C, scale=scale))

@@ -96,7 +96,7 @@ def gemm_desc(*, a0: torch.Tensor, w: torch.Tensor, out: torch.Tensor, N_: int,
               rows_per_group: int = 0, rowvec_ld: int = 0, res1: Optional[torch.Tensor] = None, ldr1: int = 0,
               res2: Optional[torch.Tensor] = None, ldr2: int = 0, alpha: float = 1.0,
               act: int = N.PP_ACT_NONE, epilogue: int = N.PP_EPI_PLAIN, ldc: int = 0,
-              out_fp32: bool = False, t_rows: int = 0, t_ld: int = 0, block_n: int = 0) -> Desc:
+              out_fp32: bool = False, t_rows: int = 0, t_ld: int = 0, block_n: int = 0, t_fp16: bool = False) -> Desc:
     d = N.GemmDesc()
     d.a_mode, d.epilogue = a_mode, epilogue
     d.a0, d.a1 = N.ptr(a0), N.ptr(a1)
@@ -118,6 +118,7 @@ def gemm_desc(*, a0: torch.Tensor, w: torch.Tensor, out: torch.Tensor, N_: int,
     d.out_fp32 = 1 if out_fp32 else 0
     d.t_rows, d.t_ld = t_rows, t_ld
     d.block_n = block_n
+    d.t_fp16 = 1 if t_fp16 else 0
     return Desc("gemm", d, (a0, a1, w, out, bias, rowvec, res1, res2))
 
 
@@ -129,6 +130,7 @@ def attn_desc(*, q, k, vt, out, batch, heads, d, nq, nk, q_ld, k_ld, vt_ld, o_ld
     a.q_ld, a.k_ld, a.vt_ld, a.o_ld = q_ld, k_ld, vt_ld, o_ld
     a.q_batch_stride, a.k_batch_stride = q_batch_stride, k_batch_stride
     a.scale = scale
+    a.vt_fp16 = 1 if vt.dtype == torch.float16 else 0
     return Desc("attn", a, (q, k, vt, out))
 
 

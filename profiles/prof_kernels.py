@@ -46,7 +46,7 @@ def attn(B, H, d, nq, nk):
     q = torch.randn(B, nq, C, device=dev, generator=g).to(BF)
     k = torch.randn(B, nk, C, device=dev, generator=g).to(BF)
     ld = (nk + 7) // 8 * 8
-    vt = torch.randn(B, C, ld, device=dev, generator=g).to(BF)
+    vt = torch.randn(B, C, ld, device=dev, generator=g).to(torch.float16)
     out = torch.empty(B, nq, C, device=dev, dtype=BF)
     dd = ops.attn_desc(q=q, k=k, vt=vt, out=out, batch=B, heads=H, d=d, nq=nq, nk=nk, q_ld=C, k_ld=C, vt_ld=ld,
                        o_ld=C, q_batch_stride=nq * C, k_batch_stride=nk * C, scale=1 / math.sqrt(d))

@@ -175,15 +175,16 @@ def test_conv3x3_stride2(ops, nb, h, w, c):
                                           (2, 8, 160, 64, 64), (2, 8, 40, 4096, 77), (2, 8, 80, 1024, 77),
                                           (2, 8, 160, 64, 77), (2, 4, 8, 64, 64), (2, 4, 16, 16, 77),
                                           (3, 4, 32, 4, 4), (2, 4, 32, 1, 77), (1, 2, 64, 300, 333)])
-def test_attention(ops, B, H, d, nq, nk):
+@pytest.mark.parametrize("vdt", [torch.bfloat16, torch.float16])
+def test_attention(ops, B, H, d, nq, nk, vdt):
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + d + nq)
     C_ = H * d
     q = (torch.randn(B, nq, C_, device=_dev(), generator=g)).to(BF16)
     k = (torch.randn(B, nk, C_, device=_dev(), generator=g)).to(BF16)
     v = (torch.randn(B, nk, C_, device=_dev(), generator=g)).to(BF16)
     vt_ld = (nk + 7) // 8 * 8
-    vt = torch.full((B, C_, vt_ld), float("nan"), device=_dev(), dtype=BF16)
-    vt[:, :, :nk] = v.permute(0, 2, 1)
+    vt = torch.full((B, C_, vt_ld), float("nan"), device=_dev(), dtype=vdt)
+    vt[:, :, :nk] = v.permute(0, 2, 1).to(vdt)
     out = torch.full((B, nq, C_), float("nan"), device=_dev(), dtype=BF16)
     scale = 1.0 / math.sqrt(d)
     ops.run(ops.attn_desc(q=q, k=k, vt=vt, out=out, batch=B, heads=H, d=d, nq=nq, nk=nk, q_ld=C_, k_ld=C_,
@@ -206,7 +207,7 @@ def test_attention_large_logits(ops):
     k = torch.randn(B, nk, C_, device=_dev(), generator=g)
     k = (k * torch.linspace(0.2, 6.0, nk, device=_dev())[None, :, None]).to(BF16)  # later keys dominate
     v = torch.randn(B, nk, C_, device=_dev(), generator=g).to(BF16)
-    vt = v.permute(0, 2, 1).contiguous()
+    vt = v.permute(0, 2, 1).contiguous().to(torch.float16)  # fp16 V^T -> dual-tile kernel
     out = torch.zeros(B, nq, C_, device=_dev(), dtype=BF16)
     ops.run(ops.attn_desc(q=q, k=k, vt=vt, out=out, batch=B, heads=H, d=d, nq=nq, nk=nk, q_ld=C_, k_ld=C_,
                           vt_ld=nk, o_ld=C_, q_batch_stride=nq * C_, k_batch_stride=nk * C_, scale=1 / math.sqrt(d)))
