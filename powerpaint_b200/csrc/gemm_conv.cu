@@ -181,7 +181,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
     const int num_tiles = p.m_tiles * n_tiles;
     const int num_k_iters = p.num_k_iters;
 
-    if (warp == 0 && elect_one()) {
+    // the two single-thread roles take the HIGHEST warp ids: the SM's issue arbiter favours higher
+    // warp ids, and a starved producer / MMA issuer stalls the whole pipeline
+    constexpr int W_PROD = GEMM_EPI_WARPS, W_MMA = GEMM_EPI_WARPS + 1;
+    if (warp == W_PROD && elect_one()) {
         prefetch_tmap(&p.tmA[0]);
         prefetch_tmap(&p.tmB);
         for (int s = 0; s < STAGES; ++s) {
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
         }
         fence_mbar_init();
     }
-    if (warp == 1) {
+    if (warp == W_MMA) {
         tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
     }
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
         nb0 = tn * p.bn;
     };
 
-    if (warp == 0) {
+    if (warp == W_PROD) {
         // ===================== TMA producer =====================
         if (elect_one()) {
             const int cpt = p.chunks0 + p.chunks1;  // chunks per tap
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == W_MMA) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
             uint32_t git = 0;
@@ -281,17 +284,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
         __syncwarp();
     } else {
         // ===================== epilogue warps =====================
-        const int ew = warp - 2;             // 0..7
+        const int ew = warp;                 // 0..7
         const int quarter = warp & 3;        // TMEM lanes this warp may read: [32*quarter, +32)
         const int half = ew >> 2;            // which of the two warps sharing the quarter
-        const int etid = threadIdx.x - 64;   // 0..255 among the epilogue threads
+        const int etid = threadIdx.x;        // 0..255 among the epilogue threads
         const int r = quarter * 32 + (int)lane_id();
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         const bool vec_ok = (p.N % 8 == 0);
         auto epi_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory"); };
         auto load_bias = [&](int tile) -> float {
             const int n = (tile % n_tiles) * BLOCK_N + etid;
-            return (p.bias && etid < BLOCK_N && n < p.N) ? __ldg(p.bias + n) : 0.f;
+            // volatile asm: the load must be issued HERE (a tile ahead of its use); a plain __ldg gets
+            // sunk by the compiler to just before the shared-memory store at the end of the tile, which
+            // exposes a full global-memory latency per tile right in front of the epilogue barrier
+            float v = 0.f;
+            if (p.bias && etid < BLOCK_N && n < p.N)
+                asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p.bias + n));
+            return v;
         };
         // stage the first tile's bias
         if (blockIdx.x < num_tiles) {
@@ -362,7 +371,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                     }
                 }
             } else if constexpr (MODE == 0) {
-                // lean path: per-row base pointers, 32-bit column offsets, uniform flags hoisted
+                // lean path: per-row base pointers, 32-bit column offsets, uniform flags hoisted.
+                // The epilogue runs with only two warps per scheduler, so it is latency-bound unless
+                // the four 8-column groups of a chunk are independent straight-line code: the common
+                // case (tile fully inside the matrix, all 32 rows of the warp valid) has no per-group
+                // branches at all, and launches without residual / row-vector terms skip those adds.
                 const float alpha = p.alpha;
                 const bool has_r1 = p.res1 != nullptr, has_r2 = p.res2 != nullptr, has_rv = p.rowvec != nullptr;
                 const bool silu = p.act == PP_ACT_SILU;
@@ -371,63 +384,85 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 const float* rvrow = p.rowvec + (int64_t)grp * p.rowvec_ld + n_base;
                 __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + n_base;
                 const int ncols = min(BLOCK_N, p.N - n_base);  // multiple of 8
-                uint4 c1[4], c2[4], x1[4], x2[4];
-                auto fetch = [&](int c0, uint4 (&ra)[4], uint4 (&rb)[4]) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int col = c0 + g * 8;
-                        const bool ok = valid && col < ncols;
-                        ra[g] = (ok && has_r1) ? __ldg(reinterpret_cast<const uint4*>(r1row + col)) : make_uint4(0, 0, 0, 0);
-                        rb[g] = (ok && has_r2) ? __ldg(reinterpret_cast<const uint4*>(r2row + col)) : make_uint4(0, 0, 0, 0);
-                    }
-                };
-                fetch(half * 32, c1, c2);
+                const bool full = ncols == BLOCK_N && __all_sync(0xffffffffu, valid);
+                const bool plain = !has_r1 && !has_r2 && !has_rv;
                 mbar_wait(tmem_full_bar(acc), acc_ph);
                 tc_fence_after();
-#pragma unroll 1
-                for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
-                    fetch(c0 + 64, x1, x2);
-                    uint32_t accv[32];
-                    tmem_ld32(taddr + c0, accv);
-                    tmem_wait_ld();
-                    if (valid) {
+                uint32_t accA[32], accB[32];
+                tmem_ld32(taddr + half * 32, accA);
+                // ---- store helper: 8 fp32 -> (silu) -> bf16 -> 16-byte store
+                auto store8 = [&](float (&v)[8], int col) {
+                    if (silu) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+                    }
+                    uint4 q;
+                    q.x = pack_bf16x2(v[0], v[1]);
+                    q.y = pack_bf16x2(v[2], v[3]);
+                    q.z = pack_bf16x2(v[4], v[5]);
+                    q.w = pack_bf16x2(v[6], v[7]);
+                    *reinterpret_cast<uint4*>(orow + col) = q;
+                };
+                // ---- one 32-column chunk
+                auto process = [&](const uint32_t (&accv)[32], int c0) {
+                    if (full && plain) {
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             const int col = c0 + g * 8;
-                            if (col < ncols) {
-                                const float4 b0 = *reinterpret_cast<const float4*>(sbias + col);
-                                const float4 b1 = *reinterpret_cast<const float4*>(sbias + col + 4);
-                                float v[8];
-                                v[0] = __uint_as_float(accv[g * 8 + 0]) + b0.x; v[1] = __uint_as_float(accv[g * 8 + 1]) + b0.y;
-                                v[2] = __uint_as_float(accv[g * 8 + 2]) + b0.z; v[3] = __uint_as_float(accv[g * 8 + 3]) + b0.w;
-                                v[4] = __uint_as_float(accv[g * 8 + 4]) + b1.x; v[5] = __uint_as_float(accv[g * 8 + 5]) + b1.y;
-                                v[6] = __uint_as_float(accv[g * 8 + 6]) + b1.z; v[7] = __uint_as_float(accv[g * 8 + 7]) + b1.w;
-                                if (has_rv) {
-                                    const float4 t0 = __ldg(reinterpret_cast<const float4*>(rvrow + col));
-                                    const float4 t1 = __ldg(reinterpret_cast<const float4*>(rvrow + col + 4));
-                                    v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
-                                    v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
-                                }
-                                const uint4 q1 = c1[g], q2 = c2[g];  // zeros when the residual is absent
-                                v[0] = (v[0] + bf16_lo(q1.x)) * alpha + bf16_lo(q2.x); v[1] = (v[1] + bf16_hi(q1.x)) * alpha + bf16_hi(q2.x);
-                                v[2] = (v[2] + bf16_lo(q1.y)) * alpha + bf16_lo(q2.y); v[3] = (v[3] + bf16_hi(q1.y)) * alpha + bf16_hi(q2.y);
-                                v[4] = (v[4] + bf16_lo(q1.z)) * alpha + bf16_lo(q2.z); v[5] = (v[5] + bf16_hi(q1.z)) * alpha + bf16_hi(q2.z);
-                                v[6] = (v[6] + bf16_lo(q1.w)) * alpha + bf16_lo(q2.w); v[7] = (v[7] + bf16_hi(q1.w)) * alpha + bf16_hi(q2.w);
-                                if (silu) {
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
-                                }
-                                uint4 q;
-                                q.x = pack_bf16x2(v[0], v[1]);
-                                q.y = pack_bf16x2(v[2], v[3]);
-                                q.z = pack_bf16x2(v[4], v[5]);
-                                q.w = pack_bf16x2(v[6], v[7]);
-                                *reinterpret_cast<uint4*>(orow + col) = q;
-                            }
+                            const float4 b0 = *reinterpret_cast<const float4*>(sbias + col);
+                            const float4 b1 = *reinterpret_cast<const float4*>(sbias + col + 4);
+                            float v[8];
+                            v[0] = (__uint_as_float(accv[g * 8 + 0]) + b0.x) * alpha; v[1] = (__uint_as_float(accv[g * 8 + 1]) + b0.y) * alpha;
+                            v[2] = (__uint_as_float(accv[g * 8 + 2]) + b0.z) * alpha; v[3] = (__uint_as_float(accv[g * 8 + 3]) + b0.w) * alpha;
+                            v[4] = (__uint_as_float(accv[g * 8 + 4]) + b1.x) * alpha; v[5] = (__uint_as_float(accv[g * 8 + 5]) + b1.y) * alpha;
+                            v[6] = (__uint_as_float(accv[g * 8 + 6]) + b1.z) * alpha; v[7] = (__uint_as_float(accv[g * 8 + 7]) + b1.w) * alpha;
+                            store8(v, col);
                         }
+                        return;
+                    }
+                    // general: residuals / row vector / ragged tile. All loads of the chunk are issued
+                    // before any arithmetic so their latencies overlap.
+                    uint4 q1[4], q2[4];
+                    float4 t0[4], t1[4];
+                    bool ok[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int col = c0 + g * 8;
+                        ok[g] = valid && col < ncols;
+                        q1[g] = (ok[g] && has_r1) ? __ldg(reinterpret_cast<const uint4*>(r1row + col)) : make_uint4(0, 0, 0, 0);
+                        q2[g] = (ok[g] && has_r2) ? __ldg(reinterpret_cast<const uint4*>(r2row + col)) : make_uint4(0, 0, 0, 0);
+                        t0[g] = (ok[g] && has_rv) ? __ldg(reinterpret_cast<const float4*>(rvrow + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        t1[g] = (ok[g] && has_rv) ? __ldg(reinterpret_cast<const float4*>(rvrow + col + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) { c1[g] = x1[g]; c2[g] = x2[g]; }
+                    for (int g = 0; g < 4; ++g) {
+                        const int col = c0 + g * 8;
+                        if (ok[g]) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(sbias + col);
+                            const float4 b1 = *reinterpret_cast<const float4*>(sbias + col + 4);
+                            float v[8];
+                            v[0] = __uint_as_float(accv[g * 8 + 0]) + b0.x + t0[g].x; v[1] = __uint_as_float(accv[g * 8 + 1]) + b0.y + t0[g].y;
+                            v[2] = __uint_as_float(accv[g * 8 + 2]) + b0.z + t0[g].z; v[3] = __uint_as_float(accv[g * 8 + 3]) + b0.w + t0[g].w;
+                            v[4] = __uint_as_float(accv[g * 8 + 4]) + b1.x + t1[g].x; v[5] = __uint_as_float(accv[g * 8 + 5]) + b1.y + t1[g].y;
+                            v[6] = __uint_as_float(accv[g * 8 + 6]) + b1.z + t1[g].z; v[7] = __uint_as_float(accv[g * 8 + 7]) + b1.w + t1[g].w;
+                            v[0] = (v[0] + bf16_lo(q1[g].x)) * alpha + bf16_lo(q2[g].x); v[1] = (v[1] + bf16_hi(q1[g].x)) * alpha + bf16_hi(q2[g].x);
+                            v[2] = (v[2] + bf16_lo(q1[g].y)) * alpha + bf16_lo(q2[g].y); v[3] = (v[3] + bf16_hi(q1[g].y)) * alpha + bf16_hi(q2[g].y);
+                            v[4] = (v[4] + bf16_lo(q1[g].z)) * alpha + bf16_lo(q2[g].z); v[5] = (v[5] + bf16_hi(q1[g].z)) * alpha + bf16_hi(q2[g].z);
+                            v[6] = (v[6] + bf16_lo(q1[g].w)) * alpha + bf16_lo(q2[g].w); v[7] = (v[7] + bf16_hi(q1[g].w)) * alpha + bf16_hi(q2[g].w);
+                            store8(v, col);
+                        }
+                    }
+                };
+#pragma unroll 1
+                for (int c0 = half * 32; c0 < BLOCK_N; c0 += 128) {
+                    tmem_wait_ld();
+                    if (c0 + 64 < BLOCK_N) tmem_ld32(taddr + c0 + 64, accB);
+                    process(accA, c0);
+                    if (c0 + 64 < BLOCK_N) {
+                        tmem_wait_ld();
+                        if (c0 + 128 < BLOCK_N) tmem_ld32(taddr + c0 + 128, accA);
+                        process(accB, c0 + 64);
+                    }
                 }
             } else {
                 // residuals of a 32-column chunk are fetched one chunk ahead (the first chunk's
@@ -485,7 +520,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
     }
 
     __syncthreads();
-    if (warp == 1) {
+    if (warp == W_MMA) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
