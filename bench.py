@@ -108,6 +108,31 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------- CPU arm (oracle port)
 _CPU_UNET = None
+_CPU_THREADS = None
+
+
+def best_cpu_threads():
+    """torch's fp32 conv/GEMM throughput on a many-core host is not monotonic in the thread count
+    (oversubscription, NUMA): probe a few counts on a representative conv and keep the fastest."""
+    global _CPU_THREADS
+    if _CPU_THREADS is not None:
+        return _CPU_THREADS
+    n = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, n) if c <= n})
+    x = torch.randn(2, 320, 64, 64)
+    w = torch.randn(320, 320, 3, 3)
+    best, best_t = n, None
+    for c in cands:
+        torch.set_num_threads(c)
+        torch.nn.functional.conv2d(x, w, padding=1)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            torch.nn.functional.conv2d(x, w, padding=1)
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = c, dt
+    _CPU_THREADS = best
+    return best
 
 
 def cpu_oracle_rate(threads: int, ddim_steps_sample: int = 2, repeats: int = 1):
@@ -145,7 +170,7 @@ def run_reference_arm(args):
     rank, world, _ = _dist_env()
     if rank != 0:
         return 0
-    threads = os.cpu_count() or 1
+    threads = best_cpu_threads()
     vals = []
     for i in range(args.warmup + args.steps):
         v, per = cpu_oracle_rate(threads, ddim_steps_sample=1)
@@ -285,14 +310,13 @@ def run_gpu_arm(args):
     def e2e_once():
         if dist is not None and world > 1:
             # rank 0 owns every request: H2D there, NCCL scatter, ..., NCCL gather, D2H on rank 0
-            bufs = []
-            for k, shape in enumerate([(B, 3, 8 * LATENT, 8 * LATENT), (B, 1, 8 * LATENT, 8 * LATENT),
-                                       (B, 77, 768), (B, 77, 768)]):
-                dst = torch.empty(shape, device=dev)
-                src = [a[k].to(dev, non_blocking=True) for a in all_in] if rank == 0 else None
-                dist.scatter(dst, src, src=0)
-                bufs.append(dst)
-            i_d, m_d, p_d, n_d = bufs
+            from powerpaint_b200.parallel import scatter_requests
+
+            full = [torch.cat([a[k] for a in all_in]).pin_memory().to(dev, non_blocking=True) for k in range(4)] \
+                if rank == 0 else None
+            i_d, m_d, p_d, n_d = scatter_requests(
+                full, [(B, 3, 8 * LATENT, 8 * LATENT), (B, 1, 8 * LATENT, 8 * LATENT), (B, 77, 768), (B, 77, 768)],
+                [torch.float32] * 4, dev)
         else:
             i_d, m_d = img_h.to(dev, non_blocking=True), mask_h.to(dev, non_blocking=True)
             p_d, n_d = pe_h.to(dev, non_blocking=True), ne_h.to(dev, non_blocking=True)
@@ -301,11 +325,10 @@ def run_gpu_arm(args):
                    generator=torch.Generator().manual_seed(rank), output_type="pt").images
         res = (res * 255).round().to(torch.uint8)
         if dist is not None and world > 1:
-            outs = [torch.empty_like(res) for _ in range(world)] if rank == 0 else None
-            dist.gather(res, outs, dst=0)
-            if rank == 0:
-                return torch.stack(outs).cpu()
-            return None
+            from powerpaint_b200.parallel import gather_images
+
+            allimg = gather_images(res)
+            return allimg.cpu() if rank == 0 else None
         return res.cpu()
 
     e2e_once()
@@ -325,7 +348,7 @@ def run_gpu_arm(args):
 
     line = None
     if rank == 0:
-        cpu_v, cpu_per = cpu_oracle_rate(os.cpu_count() or 1, ddim_steps_sample=2) if world == 1 else (None, None)
+        cpu_v, cpu_per = cpu_oracle_rate(best_cpu_threads(), ddim_steps_sample=2) if world == 1 else (None, None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 1), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -348,7 +371,8 @@ def run_gpu_arm(args):
                          "flops_per_launch": flops_step, "ms_per_launch": step_mean},
         }
         if cpu_v is not None:
-            line["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+            line["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": best_cpu_threads(), "kind": "port",
+                                    "host_cpus": os.cpu_count(),
                                     "sample": "fp32 oracle port, 1 image (UNet batch 2), 2 of 50 DDIM steps, "
                                               f"{cpu_per:.2f} s per DDIM step, extrapolated x50"}
         print(json.dumps(line))
