@@ -306,11 +306,12 @@ namespace pp {
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
+template <int NBUF>
 static int attn2_ensure_attr() {
     static bool done = false;
     if (!done) {
-        PP_CUDA_CHECK(cudaFuncSetAttribute(attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)att2_smem_bytes(80)));
+        PP_CUDA_CHECK(cudaFuncSetAttribute(attn2_kernel<NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)std::max(att2_smem_bytes(48), att2_smem_bytes(NBUF == 3 ? 64 : 80))));
         done = true;
     }
     return PP_OK;
@@ -372,11 +373,12 @@ int attn_prepare(const pp_attn_desc& d, AttnLaunch* out) {
         if (rc) return rc;
     }
     if (dual) {
-        l.variant = 10;
+        l.variant = p.dv <= 64 ? 10 : 11;  // three rotating score buffers need dv <= 64 TMEM columns per O
         l.grid = dim3((unsigned)((d.nq + 2 * ATT_BM - 1) / (2 * ATT_BM)), (unsigned)d.heads, (unsigned)d.batch);
         l.smem = att2_smem_bytes((uint32_t)p.dv);
-        l.kv_stages = ATT2_KV_STAGES;
-        int rc2 = attn2_ensure_attr();
+        l.kv_stages = (int)att2_kv_stages((uint32_t)p.dv);
+        p.kv_stages = l.kv_stages;
+        int rc2 = l.variant == 10 ? attn2_ensure_attr<3>() : attn2_ensure_attr<2>();
         if (rc2) return rc2;
         *out = l;
         return PP_OK;
@@ -396,7 +398,8 @@ int attn_prepare(const pp_attn_desc& d, AttnLaunch* out) {
 
 int attn_launch(const AttnLaunch& l, cudaStream_t s) {
     switch (l.variant) {
-        case 10: attn2_kernel<<<l.grid, ATT2_THREADS, l.smem, s>>>(l.p); break;
+        case 10: attn2_kernel<3><<<l.grid, ATT2_THREADS, l.smem, s>>>(l.p); break;
+        case 11: attn2_kernel<2><<<l.grid, ATT2_THREADS, l.smem, s>>>(l.p); break;
         case 1: attn_fwd_kernel<1><<<l.grid, ATT_THREADS, l.smem, s>>>(l.p); break;
         case 2: attn_fwd_kernel<2><<<l.grid, ATT_THREADS, l.smem, s>>>(l.p); break;
         default: attn_fwd_kernel<3><<<l.grid, ATT_THREADS, l.smem, s>>>(l.p); break;

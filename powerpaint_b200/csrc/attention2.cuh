@@ -4,11 +4,15 @@
 // One CTA (one per SM, 320 threads) owns TWO 128-query tiles of one (sample, head) and streams the
 // keys once for both, 128 keys per block:
 //   warp 0        TMA producer: Q0, Q1, then K / V^T blocks through a 3-stage ring
-//   warp 1        tcgen05.mma issuer, alternating between the tiles:
-//                 ... PV0(j), S0(j+1), PV1(j), S1(j+1) ... so while softmax group 0 works on S0(j+1)
-//                 the tensor core runs tile 1, and vice versa
+//   warp 1        tcgen05.mma issuer. The score products are numbered k = 2 j + t (key block j, tile t)
+//                 and rotate through NBUF TMEM score buffers; the issuer runs NBUF products ahead of
+//                 the PV products: ... PV(k), S(k + NBUF), PV(k + 1), S(k + NBUF + 1) ...
+//                 With NBUF = 3 (dv <= 64) the scores of a group's next block are already in TMEM when
+//                 it finishes the current one, so the tensor-core round trip is off the softmax
+//                 critical path and both groups keep the exponential pipe busy back to back. NBUF = 2
+//                 (dv = 80) degenerates to one score buffer per tile.
 //   warps 2..5    softmax group 0 (tile 0), warps 6..9 softmax group 1 (tile 1): one thread per query row
-// TMEM: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512).
+// TMEM: NBUF = 3: S [0,384) O0 [384,448) O1 [448,512); NBUF = 2: S [0,256) O0 [256,384) O1 [384,512).
 // Softmax is single-pass in the steady state: exponentials use the running reference max m_ref
 // (exp2 domain); only if a row's new max exceeds m_ref by more than 2^8 is the block redone with the
 // new reference and O rescaled. The row sum costs no ALU work: row d of the V^T tile (zero-filled by
@@ -22,17 +26,20 @@
 namespace pp {
 
 static constexpr int ATT2_THREADS = 320;
-static constexpr int ATT2_KV_STAGES = 3;
 
+__host__ __device__ constexpr uint32_t att2_kv_stages(uint32_t dv) { return dv <= 48 ? 4 : 3; }
 __host__ __device__ constexpr uint32_t att2_smem_bytes(uint32_t dv) {
     return 2 * ATT_CHUNK_BYTES                                   // Q0, Q1
-           + ATT2_KV_STAGES * (ATT_CHUNK_BYTES + dv * 256u)      // K + V^T ring
+           + att2_kv_stages(dv) * (ATT_CHUNK_BYTES + dv * 256u)  // K + V^T ring
            + 2 * 2 * ATT_CHUNK_BYTES                             // P0, P1
            + 256 + 1024;
 }
 
+template <int NBUF>
 __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_constant__ AttnKParams p) {
-    constexpr int S = ATT2_KV_STAGES;
+    constexpr int MAXS = 4;
+    constexpr uint32_t O_BASE = NBUF * 128, O_STRIDE = NBUF == 3 ? 64 : 128;
+    const int S = p.kv_stages;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -45,11 +52,12 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
     const uint32_t bars = sP + 4 * ATT_CHUNK_BYTES;
     const uint32_t bar_q = bars;
     auto bar_kv_full = [&](int s) { return bars + 8u * (1 + s); };
-    auto bar_kv_empty = [&](int s) { return bars + 8u * (1 + S + s); };
-    auto bar_s_full = [&](int t) { return bars + 8u * (1 + 2 * S + t); };
-    auto bar_p_full = [&](int t) { return bars + 8u * (3 + 2 * S + t); };
-    auto bar_pv_done = [&](int t) { return bars + 8u * (5 + 2 * S + t); };
-    const uint32_t tmem_slot = bars + 8u * (7 + 2 * S);
+    auto bar_kv_empty = [&](int s) { return bars + 8u * (1 + MAXS + s); };
+    auto bar_s_full = [&](int i) { return bars + 8u * (1 + 2 * MAXS + i); };
+    auto bar_s_free = [&](int i) { return bars + 8u * (4 + 2 * MAXS + i); };
+    auto bar_p_full = [&](int t) { return bars + 8u * (7 + 2 * MAXS + t); };
+    auto bar_pv_done = [&](int t) { return bars + 8u * (9 + 2 * MAXS + t); };
+    const uint32_t tmem_slot = bars + 8u * (11 + 2 * MAXS);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
 
     const int warp = threadIdx.x >> 5;
@@ -67,8 +75,11 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
             mbar_init(bar_kv_full(s), 1);
             mbar_init(bar_kv_empty(s), 1);
         }
+        for (int i = 0; i < NBUF; ++i) {
+            mbar_init(bar_s_full(i), 1);
+            mbar_init(bar_s_free(i), 4);
+        }
         for (int t = 0; t < 2; ++t) {
-            mbar_init(bar_s_full(t), 1);
             mbar_init(bar_p_full(t), 128);
             mbar_init(bar_pv_done(t), 1);
         }
@@ -105,14 +116,19 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
         if (elect_one()) {
             const uint32_t idesc_s = umma_idesc_bf16(ATT_BM, ATT_BN);
             const uint32_t idesc_o = umma_idesc_f16(ATT_BM, (uint32_t)p.dv);  // P and V^T are fp16 here
-            auto issue_s = [&](int t, int j) {
+            // score product k = 2 j + t into buffer k % NBUF
+            auto issue_s = [&](int k) {
+                const int j = k >> 1, t = k & 1, buf = k % NBUF;
+                if (t == 0) mbar_wait(bar_kv_full(j % S), (j / S) & 1);       // first use of key block j
+                mbar_wait(bar_s_free(buf), ((k / NBUF) & 1) ^ 1u);           // softmax drained product k - NBUF
+                tc_fence_after();
                 const uint32_t kb = sK0 + (j % S) * ATT_CHUNK_BYTES;
                 const uint64_t da0 = umma_desc_kmajor_sw128(sQ + t * ATT_CHUNK_BYTES);
                 const uint64_t db0 = umma_desc_kmajor_sw128(kb);
                 for (int ks = 0; ks < p.k_steps; ++ks)
-                    umma_bf16_ss(tmem_base + t * 128, umma_desc_advance_k(da0, ks * 16),
+                    umma_bf16_ss(tmem_base + buf * 128, umma_desc_advance_k(da0, ks * 16),
                                  umma_desc_advance_k(db0, ks * 16), idesc_s, ks != 0);
-                umma_commit(bar_s_full(t));
+                umma_commit(bar_s_full(buf));
             };
             auto issue_pv = [&](int t, int j) {
                 const uint32_t vb = sV0 + (j % S) * v_stage_bytes;
@@ -120,32 +136,23 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
                     const int c = ks >> 2, kk = (ks & 3) * 16;
-                    umma_bf16_ss(tmem_base + 256 + t * 128,
+                    umma_bf16_ss(tmem_base + O_BASE + t * O_STRIDE,
                                  umma_desc_advance_k(umma_desc_kmajor_sw128(pb + c * ATT_CHUNK_BYTES), kk),
                                  umma_desc_advance_k(umma_desc_kmajor_sw128(vb + c * v_chunk_bytes), kk), idesc_o,
                                  (j | ks) != 0);
                 }
                 umma_commit(bar_pv_done(t));
             };
+            const int nprod = 2 * nkv;
             mbar_wait(bar_q, 0);
-            mbar_wait(bar_kv_full(0), 0);
-            tc_fence_after();
-            issue_s(0, 0);
-            issue_s(1, 0);
-            for (int j = 0; j < nkv; ++j) {
-                for (int t = 0; t < 2; ++t) {
-                    mbar_wait(bar_p_full(t), j & 1);
-                    tc_fence_after();
-                    issue_pv(t, j);
-                    if (t == 1) umma_commit(bar_kv_empty(j % S));  // both tiles' PV(j) precede this commit
-                    if (j + 1 < nkv) {
-                        if (t == 0) {
-                            mbar_wait(bar_kv_full((j + 1) % S), ((j + 1) / S) & 1);
-                            tc_fence_after();
-                        }
-                        issue_s(t, j + 1);
-                    }
-                }
+            for (int k = 0; k < NBUF && k < nprod; ++k) issue_s(k);
+            for (int k = 0; k < nprod; ++k) {
+                const int j = k >> 1, t = k & 1;
+                mbar_wait(bar_p_full(t), j & 1);
+                tc_fence_after();
+                issue_pv(t, j);
+                if (t == 1) umma_commit(bar_kv_empty(j % S));  // both tiles' PV(j) precede this commit
+                if (k + NBUF < nprod) issue_s(k + NBUF);
             }
         }
         __syncwarp();
@@ -155,14 +162,15 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
         const int quarter = warp & 3;
         const int r = quarter * 32 + (int)lane_id();
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-        const uint32_t tS = tmem_base + t * 128 + lane_addr;
-        const uint32_t tO = tmem_base + 256 + t * 128 + lane_addr;
+        const uint32_t tO = tmem_base + O_BASE + t * O_STRIDE + lane_addr;
         uint8_t* prow = smem_raw + (sP + t * 2 * ATT_CHUNK_BYTES - raw) + r * 128;
         float c;  // pinned in a register (otherwise re-fetched from the constant bank per element)
         asm volatile("mov.f32 %0, %1;" : "=f"(c) : "f"(p.scale_log2));
         float m_ref = 0.f;
         for (int j = 0; j < nkv; ++j) {
-            mbar_wait(bar_s_full(t), j & 1);
+            const int k = 2 * j + t, buf = k % NBUF;
+            const uint32_t tS = tmem_base + buf * 128 + lane_addr;
+            mbar_wait(bar_s_full(buf), (k / NBUF) & 1);
             tc_fence_after();
             const int nvalid = min(ATT_BN, p.nk - j * ATT_BN);
             if (j == 0) {
@@ -230,6 +238,10 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
                     m_ref = mnew;
                 }
             } while (redo);
+            // the scores are in registers: hand the buffer back so product k + NBUF can be issued
+            tc_fence_before();
+            __syncwarp();
+            if (lane_id() == 0) mbar_arrive(bar_s_free(buf));
             if (j > 0) {
                 mbar_wait(bar_pv_done(t), (j - 1) & 1);  // P buffer free, O holds blocks < j
                 tc_fence_after();

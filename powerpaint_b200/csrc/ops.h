@@ -64,6 +64,7 @@ struct AttnKParams {
     int32_t dv;        // ceil16(d): UMMA N of the PV product
     float scale_log2;  // scale * log2(e)
     int32_t vt_fp16;   // V^T (and P) in fp16 instead of bf16
+    int32_t kv_stages; // K / V^T ring depth (dual-tile kernel)
     __nv_bfloat16* out;
     int64_t o_ld;
 };
