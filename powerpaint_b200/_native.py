@@ -9,7 +9,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "libpowerpaint_b200.so"
+import os
+
+# PP_B200_LIB points at an alternative build of the same library (kernel experiments)
+_LIB_PATH = Path(os.environ.get("PP_B200_LIB") or Path(__file__).resolve().parent / "libpowerpaint_b200.so")
 _lib = None
 
 # enums (mirror include/powerpaint_b200.h)

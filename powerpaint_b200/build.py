@@ -25,6 +25,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
+    *os.environ.get("PP_EXTRA_NVCC_FLAGS", "").split(),  # developer switches, e.g. -DATT2_PROFILE
 ]
 
 

@@ -3,35 +3,34 @@
 //
 // One CTA (one per SM, 320 threads) owns TWO 128-query tiles of one (sample, head) and streams the
 // keys once for both, 128 keys per block:
-//   warp 0        TMA producer: Q0, Q1, then K / V^T blocks through a 3-stage ring
+//   warp 0        TMA producer: Q0, Q1, then K / V^T blocks through a 4-stage ring
 //   warp 1        tcgen05.mma issuer. The score products are numbered k = 2 j + t (key block j, tile t)
-//                 and rotate through NBUF TMEM score buffers; the issuer runs NBUF products ahead of
-//                 the PV products: ... PV(k), S(k + NBUF), PV(k + 1), S(k + NBUF + 1) ...
+//                 and rotate through NBUF TMEM score buffers, NBUF products ahead of the PV products:
+//                 ... PV(k), S(k + NBUF), PV(k + 1), S(k + NBUF + 1) ...
 //                 With NBUF = 3 (dv <= 64) the scores of a group's next block are already in TMEM when
-//                 it finishes the current one, so the tensor-core round trip is off the softmax
-//                 critical path and both groups keep the exponential pipe busy back to back. NBUF = 2
-//                 (dv = 80) degenerates to one score buffer per tile.
+//                 it finishes the current one. NBUF = 2 (dv = 80) is one score buffer per tile.
 //   warps 2..5    softmax group 0 (tile 0), warps 6..9 softmax group 1 (tile 1): one thread per query row
-// TMEM: NBUF = 3: S [0,384) O0 [384,448) O1 [448,512); NBUF = 2: S [0,256) O0 [256,384) O1 [384,512).
+// P never touches shared memory: the fp16 probabilities are written back over the first 64 columns of
+// their own score buffer (tcgen05.st) and the PV product reads its A operand from tensor memory. With
+// P in shared memory the kernel was bound by shared-memory bandwidth (per block and tile: 32 KB of P
+// stores + 32 KB of P reads by the SS-mode MMA, next to 24 KB for Q K^T and 12 KB of V^T), measured as
+// ~350 cycles per PV product instead of the 8 x 24-cycle tensor-core floor.
+// TMEM: NBUF = 3: S/P [0,384) O0 [384,448) O1 [448,512); NBUF = 2: S/P [0,256) O0 [256,384) O1 [384,512).
 // Softmax is single-pass in the steady state: exponentials use the running reference max m_ref
 // (exp2 domain); only if a row's new max exceeds m_ref by more than 2^8 is the block redone with the
 // new reference and O rescaled. The row sum costs no ALU work: row d of the V^T tile (zero-filled by
 // TMA since d < dv) is overwritten with ones in shared memory, so column d of O accumulates sum_j p_ij
 // on the tensor core, consistent with the fp16-rounded P the MMA actually sees.
-// Measured on B200 (d = 40, 4096 x 4096, 16 x 8 heads): 985 us = 349 TFLOP/s; the kernel is bound by
-// the exponential throughput of the SM (16 ex2 / clk / SM: 2.15 G exps -> 477 us floor), not by the
-// tensor core (profiles/r01_attn2_notes.md).
 #pragma once
 
 namespace pp {
 
 static constexpr int ATT2_THREADS = 320;
 
-__host__ __device__ constexpr uint32_t att2_kv_stages(uint32_t dv) { return dv <= 48 ? 4 : 3; }
+__host__ __device__ constexpr uint32_t att2_kv_stages(uint32_t) { return 4; }
 __host__ __device__ constexpr uint32_t att2_smem_bytes(uint32_t dv) {
     return 2 * ATT_CHUNK_BYTES                                   // Q0, Q1
            + att2_kv_stages(dv) * (ATT_CHUNK_BYTES + dv * 256u)  // K + V^T ring
-           + 2 * 2 * ATT_CHUNK_BYTES                             // P0, P1
            + 256 + 1024;
 }
 
@@ -39,7 +38,7 @@ template <int NBUF>
 __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_constant__ AttnKParams p) {
     constexpr int MAXS = 4;
     constexpr uint32_t O_BASE = NBUF * 128, O_STRIDE = NBUF == 3 ? 64 : 128;
-    const int S = p.kv_stages;
+    constexpr int S = MAXS;  // compile-time ring depth: j % S and j / S sit on the issuer's critical path
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -48,13 +47,11 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
     const uint32_t sQ = base;                                    // [2][16 KB]
     const uint32_t sK0 = sQ + 2 * ATT_CHUNK_BYTES;               // [S][16 KB]
     const uint32_t sV0 = sK0 + S * ATT_CHUNK_BYTES;              // [S][v_stage_bytes]
-    const uint32_t sP = sV0 + S * v_stage_bytes;                 // [2][32 KB]
-    const uint32_t bars = sP + 4 * ATT_CHUNK_BYTES;
+    const uint32_t bars = sV0 + S * v_stage_bytes;
     const uint32_t bar_q = bars;
     auto bar_kv_full = [&](int s) { return bars + 8u * (1 + s); };
     auto bar_kv_empty = [&](int s) { return bars + 8u * (1 + MAXS + s); };
     auto bar_s_full = [&](int i) { return bars + 8u * (1 + 2 * MAXS + i); };
-    auto bar_s_free = [&](int i) { return bars + 8u * (4 + 2 * MAXS + i); };
     auto bar_p_full = [&](int t) { return bars + 8u * (7 + 2 * MAXS + t); };
     auto bar_pv_done = [&](int t) { return bars + 8u * (9 + 2 * MAXS + t); };
     const uint32_t tmem_slot = bars + 8u * (11 + 2 * MAXS);
@@ -77,10 +74,9 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
         }
         for (int i = 0; i < NBUF; ++i) {
             mbar_init(bar_s_full(i), 1);
-            mbar_init(bar_s_free(i), 4);
         }
         for (int t = 0; t < 2; ++t) {
-            mbar_init(bar_p_full(t), 128);
+            mbar_init(bar_p_full(t), 4);
             mbar_init(bar_pv_done(t), 1);
         }
         fence_mbar_init();
@@ -116,12 +112,13 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
         if (elect_one()) {
             const uint32_t idesc_s = umma_idesc_bf16(ATT_BM, ATT_BN);
             const uint32_t idesc_o = umma_idesc_f16(ATT_BM, (uint32_t)p.dv);  // P and V^T are fp16 here
-            // score product k = 2 j + t into buffer k % NBUF
+            // score product k = 2 j + t into buffer k % NBUF (free: PV(k - NBUF) has retired, see below)
             auto issue_s = [&](int k) {
                 const int j = k >> 1, t = k & 1, buf = k % NBUF;
-                if (t == 0) mbar_wait(bar_kv_full(j % S), (j / S) & 1);       // first use of key block j
-                mbar_wait(bar_s_free(buf), ((k / NBUF) & 1) ^ 1u);           // softmax drained product k - NBUF
-                tc_fence_after();
+                if (t == 0) {
+                    mbar_wait(bar_kv_full(j % S), (j / S) & 1);  // first use of key block j
+                    tc_fence_after();
+                }
                 const uint32_t kb = sK0 + (j % S) * ATT_CHUNK_BYTES;
                 const uint64_t da0 = umma_desc_kmajor_sw128(sQ + t * ATT_CHUNK_BYTES);
                 const uint64_t db0 = umma_desc_kmajor_sw128(kb);
@@ -130,16 +127,17 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
                                  umma_desc_advance_k(db0, ks * 16), idesc_s, ks != 0);
                 umma_commit(bar_s_full(buf));
             };
-            auto issue_pv = [&](int t, int j) {
+            // O(t) += P(k) V(j): P is read straight from tensor memory (the fp16 probabilities overwrite
+            // the first 64 columns of their own score buffer), V^T from shared memory
+            auto issue_pv = [&](int k) {
+                const int j = k >> 1, t = k & 1, buf = k % NBUF;
                 const uint32_t vb = sV0 + (j % S) * v_stage_bytes;
-                const uint32_t pb = sP + t * 2 * ATT_CHUNK_BYTES;
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
                     const int c = ks >> 2, kk = (ks & 3) * 16;
-                    umma_bf16_ss(tmem_base + O_BASE + t * O_STRIDE,
-                                 umma_desc_advance_k(umma_desc_kmajor_sw128(pb + c * ATT_CHUNK_BYTES), kk),
-                                 umma_desc_advance_k(umma_desc_kmajor_sw128(vb + c * v_chunk_bytes), kk), idesc_o,
-                                 (j | ks) != 0);
+                    umma_f16_ts(tmem_base + O_BASE + t * O_STRIDE, tmem_base + buf * 128 + ks * 8,
+                                umma_desc_advance_k(umma_desc_kmajor_sw128(vb + c * v_chunk_bytes), kk), idesc_o,
+                                (j | ks) != 0);
                 }
                 umma_commit(bar_pv_done(t));
             };
@@ -150,9 +148,14 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
                 const int j = k >> 1, t = k & 1;
                 mbar_wait(bar_p_full(t), j & 1);
                 tc_fence_after();
-                issue_pv(t, j);
+                issue_pv(k);
                 if (t == 1) umma_commit(bar_kv_empty(j % S));  // both tiles' PV(j) precede this commit
-                if (k + NBUF < nprod) issue_s(k + NBUF);
+                if (k + NBUF < nprod) {
+                    // the next scores for this buffer overwrite P(k): wait until PV(k) has read it
+                    mbar_wait(bar_pv_done(t), j & 1);
+                    tc_fence_after();
+                    issue_s(k + NBUF);
+                }
             }
         }
         __syncwarp();
@@ -163,7 +166,6 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
         const int r = quarter * 32 + (int)lane_id();
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         const uint32_t tO = tmem_base + O_BASE + t * O_STRIDE + lane_addr;
-        uint8_t* prow = smem_raw + (sP + t * 2 * ATT_CHUNK_BYTES - raw) + r * 128;
         float c;  // pinned in a register (otherwise re-fetched from the constant bank per element)
         asm volatile("mov.f32 %0, %1;" : "=f"(c) : "f"(p.scale_log2));
         float m_ref = 0.f;
@@ -238,15 +240,11 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
                     m_ref = mnew;
                 }
             } while (redo);
-            // the scores are in registers: hand the buffer back so product k + NBUF can be issued
-            tc_fence_before();
-            __syncwarp();
-            if (lane_id() == 0) mbar_arrive(bar_s_free(buf));
-            if (j > 0) {
-                mbar_wait(bar_pv_done(t), (j - 1) & 1);  // P buffer free, O holds blocks < j
-                tc_fence_after();
-            }
             if (__any_sync(0xffffffffu, alpha != 1.f)) {
+                if (j > 0) {
+                    mbar_wait(bar_pv_done(t), (j - 1) & 1);  // O holds blocks < j
+                    tc_fence_after();
+                }
                 for (int col = 0; col < p.dv; col += 16) {
                     uint32_t ov[16];
                     tmem_ld16(tO + col, ov);
@@ -255,14 +253,12 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
                     for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
                     tmem_st16(tO + col, ov);
                 }
-                tmem_wait_st();
             }
+            // P(k) (fp16 pairs, one 32-bit column per key pair) replaces the first 64 columns of S(k);
+            // every thread owns its TMEM lane, and its own score reads have completed (wait::ld above)
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const int ch = q >> 3, i = q & 7;
-                *reinterpret_cast<uint4*>(prow + ch * ATT_CHUNK_BYTES + ((i ^ (r & 7)) << 4)) =
-                    make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-            }
+            for (int q = 0; q < 4; ++q) tmem_st16_from(tS + q * 16, &pk[q * 16]);
+            tmem_wait_st();
             if (t == 0 && warp == 2 && lane_id() < 16) {
                 // row d of the V^T tile := 1.0 (fp16 0x3C00) so O[:, d] accumulates the row sums
                 const int ch = lane_id() >> 3, piece = lane_id() & 7;
@@ -270,9 +266,10 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
                 *reinterpret_cast<uint4*>(vrow + piece * 16) =
                     make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
             }
-            fence_proxy_async_smem();
+            fence_proxy_async_smem();  // the ones row above is read by the tensor core (async proxy)
             tc_fence_before();
-            mbar_arrive(bar_p_full(t));
+            __syncwarp();
+            if (lane_id() == 0) mbar_arrive(bar_p_full(t));
         }
         // epilogue: O[:, :d] / O[:, d]
         mbar_wait(bar_pv_done(t), (nkv - 1) & 1);
