@@ -23,6 +23,12 @@
 // on the tensor core, consistent with the fp16-rounded P the MMA actually sees.
 #pragma once
 
+// share of the softmax exponentials evaluated by exp2_poly3 instead of MUFU.EX2:
+// 0 = none, 1 = 1/4, 2 = 3/8, 3 = 1/2
+#ifndef ATT2_POLY
+#define ATT2_POLY 0
+#endif
+
 namespace pp {
 
 static constexpr int ATT2_THREADS = 320;
@@ -206,8 +212,21 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
                             const float s0 = __uint_as_float(sv[i]), s1 = __uint_as_float(sv[i + 1]);
                             const float s2 = __uint_as_float(sv[i + 2]), s3 = __uint_as_float(sv[i + 3]);
                             mx0 = fmaxf(mx0, s0); mx1 = fmaxf(mx1, s1); mx2 = fmaxf(mx2, s2); mx3 = fmaxf(mx3, s3);
+#if ATT2_POLY == 0
                             pk[ch * 16 + i / 2] = ex2_f16x2(pack_f16x2(fmaf(s0, c, -m_ref), fmaf(s1, c, -m_ref)));
                             pk[ch * 16 + i / 2 + 1] = ex2_f16x2(pack_f16x2(fmaf(s2, c, -m_ref), fmaf(s3, c, -m_ref)));
+#else
+                            // a fixed share of the keys takes the polynomial path: the block is bound by
+                            // the MUFU pipe (2 warps x 128 keys x 8 cycles per scheduler), while the FMA
+                            // and integer pipes idle
+                            const bool poly1 = ATT2_POLY == 3 || (ATT2_POLY == 2 && (i & 4));
+                            const float e0 = fast_exp2(fmaf(s0, c, -m_ref));
+                            const float e1 = poly1 ? exp2_poly3(fmaf(s1, c, -m_ref)) : fast_exp2(fmaf(s1, c, -m_ref));
+                            const float e2 = fast_exp2(fmaf(s2, c, -m_ref));
+                            const float e3 = exp2_poly3(fmaf(s3, c, -m_ref));
+                            pk[ch * 16 + i / 2] = pack_f16x2(e0, e1);
+                            pk[ch * 16 + i / 2 + 1] = pack_f16x2(e2, e3);
+#endif
                         }
                     } else {
 #pragma unroll

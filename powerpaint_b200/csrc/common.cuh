@@ -296,6 +296,19 @@ __device__ __forceinline__ uint32_t pack_f16x2_ordered(float lo, float hi) {
     asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo));
     return y;
 }
+// 2^x on the FMA / integer pipes (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5];
+// 2^f by a degree-3 minimax polynomial (max relative error 7.5e-5, below fp16 half-ulp), 2^n by
+// adding n to the exponent field. Valid for x in [-120, 120]; smaller inputs are clamped (result ~ 0).
+// Used to take a share of the softmax exponentials off the 16 / clk / SM MUFU pipe.
+__device__ __forceinline__ float exp2_poly3(float x) {
+    x = fmaxf(x, -120.f);
+    const float xr = x + 12582912.f;  // 1.5 * 2^23: round(x) lands in the low mantissa bits
+    const float f = x - (xr - 12582912.f);
+    float p = fmaf(f, 0.0551716648f, 0.2426111251f);
+    p = fmaf(p, f, 0.6932609677f);
+    p = fmaf(p, f, 0.9999280572f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
 __device__ __forceinline__ float fmax3_f(float a, float b, float c) {
     float y;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));

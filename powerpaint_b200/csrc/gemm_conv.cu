@@ -50,6 +50,27 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return act == PP_ACT_SILU ? silu_f(v) : v;
 }
 
+// (m_tile, n_tile) of the tiles one persistent CTA walks: tile = blockIdx.x + i * gridDim.x, n fastest.
+// Kept incrementally — a runtime integer division costs ~40 dependent instructions, and the producer,
+// the MMA issuer and every epilogue thread would otherwise pay two of them per tile.
+struct TileWalk {
+    int m, n, step_m, step_n, n_tiles;
+    __device__ __forceinline__ TileWalk(int first, int stride, int n_tiles_) : n_tiles(n_tiles_) {
+        m = first / n_tiles_;
+        n = first - m * n_tiles_;
+        step_m = stride / n_tiles_;
+        step_n = stride - step_m * n_tiles_;
+    }
+    __device__ __forceinline__ void next() {
+        m += step_m;
+        n += step_n;
+        if (n >= n_tiles) {
+            n -= n_tiles;
+            ++m;
+        }
+    }
+};
+
 // Epilogue for 8 consecutive output columns of one row. v[] holds the accumulators; `sbias` points
 // at this tile's bias staged in shared memory (column n0 - n_base), r1/r2 hold the 8 bf16 residual
 // values that were loaded ahead of time (vector path only).
@@ -231,43 +252,46 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
         // ===================== TMA producer =====================
         if (elect_one()) {
             const int cpt = p.chunks0 + p.chunks1;  // chunks per tap
-            uint32_t git = 0;                       // global k-iteration counter (ring position)
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int n_tile = tile % n_tiles, m_tile = tile / n_tiles;
+            int s = 0;                              // ring slot and its phase, carried across tiles
+            uint32_t ph = 0;
+            TileWalk tw(blockIdx.x, gridDim.x, n_tiles);
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tw.next()) {
+                const int n_tile = tw.n, m_tile = tw.m;
                 int x0 = 0, y0 = 0, nb0 = 0;
                 if (p.a_mode != PP_A_MATRIX) tile_origin(m_tile, x0, y0, nb0);
-                for (int it = 0; it < num_k_iters; ++it, ++git) {
-                    const int s = git % STAGES;
-                    const uint32_t ph = (git / STAGES) & 1;
+                int ky = 0, kx = 0, ch = 0;  // filter tap and 64-channel chunk of this k-iteration
+                for (int it = 0; it < num_k_iters; ++it) {
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     mbar_arrive_expect_tx(full_bar(s), p.a_bytes + B_STAGE_BYTES);
                     const uint32_t dstA = sA + s * A_STAGE_BYTES;
                     const uint32_t dstB = sB + s * B_STAGE_BYTES;
-                    const int tap = it / cpt;
-                    const int ch = it - tap * cpt;
                     const int src = ch >= p.chunks0 ? 1 : 0;
                     const int cc = (src ? ch - p.chunks0 : ch) * BLOCK_K;
                     if (p.a_mode == PP_A_MATRIX) {
                         tma_load_2d(dstA, &p.tmA[src], full_bar(s), cc, m_tile * BLOCK_M);
                     } else if (p.a_mode == PP_A_CONV3X3) {
-                        const int ky = tap / 3, kx = tap - ky * 3;
                         tma_load_4d(dstA, &p.tmA[src], full_bar(s), cc, x0 + kx - 1, y0 + ky - 1, nb0);
                     } else {
                         // stride 2: input (2*oy + ky - 1, 2*ox + kx - 1) = parity plane (py, px) at
                         // (oy + dy, ox + dx) with d = -1 for k == 0 else 0, parity = (k != 1)
-                        const int ky = tap / 3, kx = tap - ky * 3;
                         const int py = (ky != 1), px = (kx != 1);
                         const int dy = (ky == 0) ? -1 : 0, dx = (kx == 0) ? -1 : 0;
                         tma_load_4d(dstA, &p.tmA[py * 2 + px], full_bar(s), cc, x0 + dx, y0 + dy, nb0);
                     }
                     tma_load_2d(dstB, &p.tmB, full_bar(s), it * BLOCK_K, n_tile * BLOCK_N);
+                    if (++ch == cpt) {
+                        ch = 0;
+                        if (++kx == 3) { kx = 0; ++ky; }
+                    }
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == W_MMA) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
-            uint32_t git = 0;
+            int s = 0;
+            uint32_t ph = 0;
             uint32_t lt = 0;  // local tile counter
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
                 const uint32_t acc = lt & 1u;
@@ -275,9 +299,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u);  // epilogue drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-                for (int it = 0; it < num_k_iters; ++it, ++git) {
-                    const int s = git % STAGES;
-                    const uint32_t ph = (git / STAGES) & 1;
+                for (int it = 0; it < num_k_iters; ++it) {
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
                     const uint64_t da = umma_desc_kmajor_sw128(sA + s * A_STAGE_BYTES);
@@ -288,6 +310,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                                      umma_desc_advance_k(db, k * UMMA_K), IDESC, (it | k) != 0);
                     }
                     umma_commit(empty_bar(s));  // frees the smem slot once these MMAs retire
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
                 umma_commit(tmem_full_bar(acc));  // accumulator complete
             }
@@ -303,8 +326,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         const bool vec_ok = (p.N % 8 == 0);
         auto epi_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory"); };
-        auto load_bias = [&](int tile) -> float {
-            const int n = (tile % n_tiles) * BLOCK_N + etid;
+        auto load_bias = [&](int n_tile_of) -> float {
+            const int n = n_tile_of * BLOCK_N + etid;
             // volatile asm: the load must be issued HERE (a tile ahead of its use); a plain __ldg gets
             // sunk by the compiler to just before the shared-memory store at the end of the tile, which
             // exposes a full global-memory latency per tile right in front of the epilogue barrier
@@ -314,20 +337,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
             return v;
         };
         // stage the first tile's bias
+        TileWalk tw(blockIdx.x, gridDim.x, n_tiles);
         if (blockIdx.x < num_tiles) {
-            const float b0 = load_bias(blockIdx.x);
+            const float b0 = load_bias(tw.n);
             if (etid < BLOCK_N) sbias_all[etid] = b0;
         }
         epi_sync();
         uint32_t lt = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-            const int n_tile = tile % n_tiles, m_tile = tile / n_tiles;
+            const int n_tile = tw.n, m_tile = tw.m;
+            tw.next();  // now at the tile after this one
             const uint32_t acc = lt & 1u;
             const uint32_t acc_ph = (lt >> 1) & 1u;
             const float* sbias = sbias_all + acc * BLOCK_N;
             // bias of the next tile: issue the load now, park it in smem at the end of this tile
             const int next_tile = tile + gridDim.x;
-            const float bias_next = next_tile < num_tiles ? load_bias(next_tile) : 0.f;
+            const float bias_next = next_tile < num_tiles ? load_bias(tw.n) : 0.f;
             // output row of this thread
             bool valid;
             int64_t row;
@@ -339,9 +364,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
             } else {
                 int x0, y0, nb0;
                 tile_origin(m_tile, x0, y0, nb0);
-                const int ix = r % p.bw;
-                const int iy = (r / p.bw) % p.bh;
-                const int in = r / (p.bw * p.bh);
+                // bw, bh, bn are powers of two
+                const int ix = r & (p.bw - 1);
+                const int iy = (r >> p.bw_log2) & (p.bh - 1);
+                const int in = r >> (p.bw_log2 + p.bh_log2);
                 const int ox = x0 + ix, oy = y0 + iy, on = nb0 + in;
                 valid = in < p.bn && ox < p.wo && oy < p.ho && on < p.nb;
                 row = ((int64_t)on * p.ho + oy) * p.wo + ox;
@@ -707,6 +733,10 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
                 }
             }
         }
+        p.bw_log2 = 0;
+        while ((1 << p.bw_log2) < p.bw) ++p.bw_log2;
+        p.bh_log2 = 0;
+        while ((1 << p.bh_log2) < p.bh) ++p.bh_log2;
         p.tiles_x = ceil_div(p.wo, p.bw);
         p.tiles_y = ceil_div(p.ho, p.bh);
         m_tiles = p.tiles_x * p.tiles_y * ceil_div(p.nb, p.bn);

@@ -22,7 +22,8 @@ struct GemmKParams {
     int32_t chunks0, chunks1;  // per tap: chunks of src0 then src1
     // conv tiling
     int32_t nb, ho, wo;
-    int32_t bw, bh, bn;
+    int32_t bw, bh, bn;      // conv pixel box (powers of two, bw * bh * bn == 128)
+    int32_t bw_log2, bh_log2;
     int32_t tiles_x, tiles_y;
     int32_t m_tiles, n_tiles;  // persistent tile walk: tile = m_tile * n_tiles + n_tile
     uint32_t a_bytes;  // bytes one A stage receives (box volume * 128)
