@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                             for (int j = 0; j < 8; ++j) {
                                 const float a = __uint_as_float(ra[h8 + j]) + sbias[c0 + h8 + j];
                                 const float g = __uint_as_float(rg[h8 + j]) + sbias[HALF + c0 + h8 + j];
-                                v[j] = a * gelu_fast_f(g);
+                                v[j] = a * gelu_tanh_f(g);
                             }
                             uint4 q;
                             q.x = pack_bf16x2(v[0], v[1]);
