@@ -109,6 +109,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();  // Q / K / V^T come from the preceding kernels
+    pdl_launch_dependents();
     const uint32_t tS = tmem_base;
     const uint32_t tO = tmem_base + TMEM_O_COL;
 
@@ -398,13 +400,12 @@ int attn_prepare(const pp_attn_desc& d, AttnLaunch* out) {
 
 int attn_launch(const AttnLaunch& l, cudaStream_t s) {
     switch (l.variant) {
-        case 10: attn2_kernel<3><<<l.grid, ATT2_THREADS, l.smem, s>>>(l.p); break;
-        case 11: attn2_kernel<2><<<l.grid, ATT2_THREADS, l.smem, s>>>(l.p); break;
-        case 1: attn_fwd_kernel<1><<<l.grid, ATT_THREADS, l.smem, s>>>(l.p); break;
-        case 2: attn_fwd_kernel<2><<<l.grid, ATT_THREADS, l.smem, s>>>(l.p); break;
-        default: attn_fwd_kernel<3><<<l.grid, ATT_THREADS, l.smem, s>>>(l.p); break;
+        case 10: PP_CUDA_CHECK(launch(attn2_kernel<3>, l.grid, ATT2_THREADS, l.smem, s, l.p)); break;
+        case 11: PP_CUDA_CHECK(launch(attn2_kernel<2>, l.grid, ATT2_THREADS, l.smem, s, l.p)); break;
+        case 1: PP_CUDA_CHECK(launch(attn_fwd_kernel<1>, l.grid, ATT_THREADS, l.smem, s, l.p)); break;
+        case 2: PP_CUDA_CHECK(launch(attn_fwd_kernel<2>, l.grid, ATT_THREADS, l.smem, s, l.p)); break;
+        default: PP_CUDA_CHECK(launch(attn_fwd_kernel<3>, l.grid, ATT_THREADS, l.smem, s, l.p)); break;
     }
-    PP_CUDA_CHECK(cudaGetLastError());
     return PP_OK;
 }
 

@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();  // Q / K / V^T come from the preceding kernels
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ===================== TMA producer =====================

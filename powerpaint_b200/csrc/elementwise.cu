@@ -22,6 +22,8 @@ namespace pp {
 // Algorithmic bytes per pixel: eps 2*4*{2|4} + latents 2*16 (+ next_in n_copies*next_c*2).
 // ------------------------------------------------------------------------------------
 __global__ void cfg_ddim_kernel(pp_cfg_ddim_desc d) {
+    pdl_wait();  // inputs come from the preceding kernel
+    pdl_launch_dependents();
     const int64_t total = (int64_t)d.batch * d.hw;
     const int step = d.step_idx ? *d.step_idx : 0;
     const float* cf = d.coef + (int64_t)step * 8;
@@ -77,7 +79,11 @@ __global__ void cfg_ddim_kernel(pp_cfg_ddim_desc d) {
     // single-thread launch (cfg_ddim_advance_kernel) enqueued right after this kernel.
 }
 
-__global__ void cfg_ddim_advance_kernel(int32_t* step_idx) { *step_idx += 1; }
+__global__ void cfg_ddim_advance_kernel(int32_t* step_idx) {
+    pdl_wait();
+    pdl_launch_dependents();
+    *step_idx += 1;
+}
 
 int cfg_ddim_validate(const pp_cfg_ddim_desc& d) {
     PP_REQUIRE(d.eps && d.latents && d.coef, "cfg_ddim: null pointer");
@@ -98,10 +104,10 @@ int cfg_ddim_launch(const pp_cfg_ddim_desc& d, cudaStream_t s) {
     const int64_t total = (int64_t)d.batch * d.hw;
     const int threads = 128;
     const int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, 148 * 8);
-    cfg_ddim_kernel<<<blocks, threads, 0, s>>>(d);
+    PP_CUDA_CHECK(launch(cfg_ddim_kernel, blocks, threads, 0, s, d));
     PP_CUDA_CHECK(cudaGetLastError());
     if (d.advance_step) {
-        cfg_ddim_advance_kernel<<<1, 1, 0, s>>>(d.step_idx);
+        PP_CUDA_CHECK(launch(cfg_ddim_advance_kernel, 1, 1, 0, s, d.step_idx));
         PP_CUDA_CHECK(cudaGetLastError());
     }
     return PP_OK;
@@ -114,6 +120,8 @@ int cfg_ddim_launch(const pp_cfg_ddim_desc& d, cudaStream_t s) {
 // ------------------------------------------------------------------------------------
 __global__ void time_embed_kernel(const float* __restrict__ timesteps, const int32_t* __restrict__ step_idx,
                                   __nv_bfloat16* __restrict__ out, int batch, int dim) {
+    pdl_wait();  // inputs come from the preceding kernel
+    pdl_launch_dependents();
     const int half = dim / 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= batch * half) return;
@@ -130,8 +138,8 @@ int time_embed_launch(const float* timesteps, const int32_t* step_idx, void* out
     PP_REQUIRE(timesteps && out, "time_embed: null pointer");
     PP_REQUIRE(batch > 0 && dim > 0 && dim % 2 == 0, "time_embed: batch=%d dim=%d invalid", batch, dim);
     const int n = batch * dim / 2;
-    time_embed_kernel<<<(n + 127) / 128, 128, 0, s>>>(timesteps, step_idx,
-                                                       reinterpret_cast<__nv_bfloat16*>(out), batch, dim);
+    PP_CUDA_CHECK(launch(time_embed_kernel, (n + 127) / 128, 128, 0, s, timesteps, step_idx,
+                                                       reinterpret_cast<__nv_bfloat16*>(out), batch, dim));
     PP_CUDA_CHECK(cudaGetLastError());
     return PP_OK;
 }
@@ -141,6 +149,8 @@ int time_embed_launch(const float* timesteps, const int32_t* step_idx, void* out
 // ------------------------------------------------------------------------------------
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int nb, int h, int w,
                                   int cv) {
+    pdl_wait();  // inputs come from the preceding kernel
+    pdl_launch_dependents();
     const int64_t total = (int64_t)nb * (2 * h) * (2 * w) * cv;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -158,8 +168,8 @@ int upsample2x_launch(const void* x, void* y, int nb, int h, int w, int c, cudaS
     PP_REQUIRE(nb > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "upsample2x: bad shape");
     const int64_t total = (int64_t)nb * 4 * h * w * (c / 8);
     const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
-    upsample2x_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), nb,
-                                             h, w, c / 8);
+    PP_CUDA_CHECK(launch(upsample2x_kernel, blocks, 256, 0, s, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), nb,
+                                             h, w, c / 8));
     PP_CUDA_CHECK(cudaGetLastError());
     return PP_OK;
 }
@@ -168,6 +178,8 @@ int upsample2x_launch(const void* x, void* y, int nb, int h, int w, int c, cudaS
 // powerpaint/models/unet_2d_condition.py:1263-1272).
 __global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ y,
                            int64_t nvec) {
+    pdl_wait();  // inputs come from the preceding kernel
+    pdl_launch_dependents();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
          i += (int64_t)gridDim.x * blockDim.x) {
         uint4 p = __ldg(&a[i]), q = __ldg(&b[i]);
@@ -185,8 +197,8 @@ int add_launch(const void* a, const void* b, void* y, int64_t n, cudaStream_t s)
     PP_REQUIRE(n > 0 && n % 8 == 0, "add: n=%lld must be a positive multiple of 8", (long long)n);
     const int64_t nvec = n / 8;
     const int blocks = (int)std::min<int64_t>((nvec + 255) / 256, 148 * 16);
-    add_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
-                                      reinterpret_cast<uint4*>(y), nvec);
+    PP_CUDA_CHECK(launch(add_kernel, blocks, 256, 0, s, reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
+                                      reinterpret_cast<uint4*>(y), nvec));
     PP_CUDA_CHECK(cudaGetLastError());
     return PP_OK;
 }
@@ -197,6 +209,8 @@ int add_launch(const void* a, const void* b, void* y, int64_t n, cudaStream_t s)
 // ------------------------------------------------------------------------------------
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int c, int hw,
                                     int c_pad) {
+    pdl_wait();  // inputs come from the preceding kernel
+    pdl_launch_dependents();
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -215,13 +229,15 @@ int nchw_to_nhwc_launch(const float* x, void* y, int nb, int c, int hw, int c_pa
     PP_REQUIRE(x && y, "nchw_to_nhwc: null pointer");
     PP_REQUIRE(nb > 0 && c > 0 && hw > 0 && c_pad >= c, "nchw_to_nhwc: bad shape");
     dim3 grid((hw + 31) / 32, (c_pad + 31) / 32, nb);
-    nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, s>>>(x, reinterpret_cast<__nv_bfloat16*>(y), c, hw, c_pad);
+    PP_CUDA_CHECK(launch(nchw_to_nhwc_kernel, grid, dim3(32, 8), 0, s, x, reinterpret_cast<__nv_bfloat16*>(y), c, hw, c_pad));
     PP_CUDA_CHECK(cudaGetLastError());
     return PP_OK;
 }
 
 __global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int x_is_fp32, float* __restrict__ y, int c,
                                     int hw, int c_ld) {
+    pdl_wait();  // inputs come from the preceding kernel
+    pdl_launch_dependents();
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -247,7 +263,7 @@ int nhwc_to_nchw_launch(const void* x, int x_is_fp32, float* y, int nb, int c, i
     PP_REQUIRE(x && y, "nhwc_to_nchw: null pointer");
     PP_REQUIRE(nb > 0 && c > 0 && hw > 0 && c_ld >= c, "nhwc_to_nchw: bad shape");
     dim3 grid((hw + 31) / 32, (c + 31) / 32, nb);
-    nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, s>>>(x, x_is_fp32, y, c, hw, c_ld);
+    PP_CUDA_CHECK(launch(nhwc_to_nchw_kernel, grid, dim3(32, 8), 0, s, x, x_is_fp32, y, c, hw, c_ld));
     PP_CUDA_CHECK(cudaGetLastError());
     return PP_OK;
 }

@@ -237,6 +237,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // everything above touched only shared / tensor memory and kernel parameters; global memory
+    // written by the preceding kernel is read (and this kernel's output written) from here on
+    pdl_wait();
+    pdl_launch_dependents();
 
     // conv tile origin of an m-tile index
     auto tile_origin = [&](int m_tile, int& x0, int& y0, int& nb0) {
@@ -604,8 +608,7 @@ static int num_sms() {
 
 template <int BLOCK_N, int MODE>
 static int launch_variant(const GemmLaunch& l, cudaStream_t s) {
-    gemm_conv_kernel<BLOCK_N, MODE><<<l.grid, GEMM_THREADS, l.smem, s>>>(l.p);
-    PP_CUDA_CHECK(cudaGetLastError());
+    PP_CUDA_CHECK(launch(gemm_conv_kernel<BLOCK_N, MODE>, l.grid, GEMM_THREADS, l.smem, s, l.p));
     return PP_OK;
 }
 

@@ -28,6 +28,8 @@ namespace pp {
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, const __nv_bfloat16* __restrict__ x1,
                                 int c0, int c1, int hw, int groups, int pix_per_block,
                                 float* __restrict__ stats) {
+    pdl_wait();  // inputs come from the preceding kernel
+    pdl_launch_dependents();
     extern __shared__ float sh[];  // [groups][2]
     const int C = c0 + c1;
     const int CV = C / 8;
@@ -48,13 +50,24 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, const __nv
         float s[8], ss[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
-        for (int p = p_begin + pl; p < p_end; p += lanes) {
-            uint4 q = __ldg(reinterpret_cast<const uint4*>(src + ((int64_t)n * hw + p) * cs + co));
-            float v[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
-                          bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
+        const __nv_bfloat16* sp = src + ((int64_t)n * hw) * cs + co;
+        auto accumulate = [&](const uint4& q) {
+            const float v[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
+                                bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
 #pragma unroll
             for (int j = 0; j < 8; ++j) { s[j] += v[j]; ss[j] += v[j] * v[j]; }
+        };
+        // four independent 16-byte loads in flight per thread: with ~4 blocks per SM a single load per
+        // thread leaves the memory system at about a third of its bandwidth
+        int p = p_begin + pl;
+        for (; p + 3 * lanes < p_end; p += 4 * lanes) {
+            const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(sp + (int64_t)p * cs));
+            const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(sp + (int64_t)(p + lanes) * cs));
+            const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(sp + (int64_t)(p + 2 * lanes) * cs));
+            const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(sp + (int64_t)(p + 3 * lanes) * cs));
+            accumulate(q0); accumulate(q1); accumulate(q2); accumulate(q3);
         }
+        for (; p < p_end; p += lanes) accumulate(__ldg(reinterpret_cast<const uint4*>(sp + (int64_t)p * cs)));
         // fold the 8 channels into their groups (a vector may straddle a group boundary)
         int g_prev = c / cpg;
         float as = 0.f, ass = 0.f;
@@ -84,6 +97,8 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, const __nv
                                 const float* __restrict__ beta, float eps, int silu,
                                 const float* __restrict__ stats, __nv_bfloat16* __restrict__ y,
                                 int pix_per_block) {
+    pdl_wait();  // inputs come from the preceding kernel
+    pdl_launch_dependents();
     const int C = c0 + c1;
     const int CV = C / 8;
     const int cpg = C / groups;
@@ -114,8 +129,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, const __nv
     const int p_end = min(hw, p_begin + pix_per_block);
     const __nv_bfloat16* sp = src + ((int64_t)n * hw) * cs + co;
     __nv_bfloat16* yp = y + ((int64_t)n * hw) * C + c;
-    for (int p = p_begin + pl; p < p_end; p += lanes) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(sp + (int64_t)p * cs));
+    auto emit = [&](const uint4& q, int p) {
         float v[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
                       bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
 #pragma unroll
@@ -129,7 +143,16 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, const __nv
         o.z = pack_bf16x2(v[4], v[5]);
         o.w = pack_bf16x2(v[6], v[7]);
         *reinterpret_cast<uint4*>(yp + (int64_t)p * C) = o;
+    };
+    int p = p_begin + pl;
+    for (; p + 3 * lanes < p_end; p += 4 * lanes) {  // four loads in flight per thread (see pass 1)
+        const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(sp + (int64_t)p * cs));
+        const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(sp + (int64_t)(p + lanes) * cs));
+        const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(sp + (int64_t)(p + 2 * lanes) * cs));
+        const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(sp + (int64_t)(p + 3 * lanes) * cs));
+        emit(q0, p); emit(q1, p + lanes); emit(q2, p + 2 * lanes); emit(q3, p + 3 * lanes);
     }
+    for (; p < p_end; p += lanes) emit(__ldg(reinterpret_cast<const uint4*>(sp + (int64_t)p * cs)), p);
 }
 
 int group_norm_validate(const pp_gn_desc& d) {
@@ -152,19 +175,19 @@ int group_norm_launch(const pp_gn_desc& d, cudaStream_t s) {
     int k = 256 / CV;
     if (k < 1) k = 1;
     const int threads = CV * k;
-    // ~4 waves of blocks over the machine, at least 32 pixels per lane-stride
-    int chunks = (148 * 4 + d.batch - 1) / d.batch;
+    // ~8 blocks per SM over the machine, at least 32 pixels per lane-stride
+    int chunks = (148 * 8 + d.batch - 1) / d.batch;
     int ppb = (d.hw + chunks - 1) / chunks;
     if (ppb < k * 8) ppb = k * 8;
     chunks = (d.hw + ppb - 1) / ppb;
-    gn_stats_kernel<<<dim3(chunks, d.batch), threads, sizeof(float) * 2 * d.groups, s>>>(
+    PP_CUDA_CHECK(launch(gn_stats_kernel, dim3(chunks, d.batch), threads, sizeof(float) * 2 * d.groups, s, 
         reinterpret_cast<const __nv_bfloat16*>(d.x0), reinterpret_cast<const __nv_bfloat16*>(d.x1), d.c0,
-        d.c1, d.hw, d.groups, ppb, d.stats);
+        d.c1, d.hw, d.groups, ppb, d.stats));
     PP_CUDA_CHECK(cudaGetLastError());
-    gn_apply_kernel<<<dim3(chunks, d.batch), threads, 0, s>>>(
+    PP_CUDA_CHECK(launch(gn_apply_kernel, dim3(chunks, d.batch), threads, 0, s, 
         reinterpret_cast<const __nv_bfloat16*>(d.x0), reinterpret_cast<const __nv_bfloat16*>(d.x1), d.c0,
         d.c1, d.hw, d.groups, d.gamma, d.beta, d.eps, d.silu, d.stats,
-        reinterpret_cast<__nv_bfloat16*>(d.y), ppb);
+        reinterpret_cast<__nv_bfloat16*>(d.y), ppb));
     PP_CUDA_CHECK(cudaGetLastError());
     return PP_OK;
 }
@@ -176,6 +199,8 @@ template <int MAX_VEC>
 __global__ void layer_norm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                   int rows, int c, float eps) {
+    pdl_wait();  // inputs come from the preceding kernel
+    pdl_launch_dependents();
     const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
     const int CV = c / 8;
@@ -242,11 +267,11 @@ int layer_norm_launch(const void* x, void* y, const float* gamma, const float* b
     int blocks = std::min((rows + warps - 1) / warps, 148 * 8);
     auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
     auto yb = reinterpret_cast<__nv_bfloat16*>(y);
-    if (CV <= 32) layer_norm_kernel<1><<<blocks, warps * 32, 0, s>>>(xb, yb, gamma, beta, rows, c, eps);
-    else if (CV <= 64) layer_norm_kernel<2><<<blocks, warps * 32, 0, s>>>(xb, yb, gamma, beta, rows, c, eps);
-    else if (CV <= 96) layer_norm_kernel<3><<<blocks, warps * 32, 0, s>>>(xb, yb, gamma, beta, rows, c, eps);
-    else if (CV <= 160) layer_norm_kernel<5><<<blocks, warps * 32, 0, s>>>(xb, yb, gamma, beta, rows, c, eps);
-    else layer_norm_kernel<8><<<blocks, warps * 32, 0, s>>>(xb, yb, gamma, beta, rows, c, eps);
+    if (CV <= 32) PP_CUDA_CHECK(launch(layer_norm_kernel<1>, blocks, warps * 32, 0, s, xb, yb, gamma, beta, rows, c, eps));
+    else if (CV <= 64) PP_CUDA_CHECK(launch(layer_norm_kernel<2>, blocks, warps * 32, 0, s, xb, yb, gamma, beta, rows, c, eps));
+    else if (CV <= 96) PP_CUDA_CHECK(launch(layer_norm_kernel<3>, blocks, warps * 32, 0, s, xb, yb, gamma, beta, rows, c, eps));
+    else if (CV <= 160) PP_CUDA_CHECK(launch(layer_norm_kernel<5>, blocks, warps * 32, 0, s, xb, yb, gamma, beta, rows, c, eps));
+    else PP_CUDA_CHECK(launch(layer_norm_kernel<8>, blocks, warps * 32, 0, s, xb, yb, gamma, beta, rows, c, eps));
     PP_CUDA_CHECK(cudaGetLastError());
     return PP_OK;
 }

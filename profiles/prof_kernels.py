@@ -53,6 +53,23 @@ def attn(B, H, d, nq, nk):
     return lambda: ops.run(dd)
 
 
+def gnorm(nb, hw, c, silu=True):
+    x = torch.randn(nb, hw, c, device=dev, generator=g).to(BF)
+    y = torch.empty_like(x)
+    gamma = torch.ones(c, device=dev); beta = torch.zeros(c, device=dev)
+    stats = torch.empty(nb, 32, 2, device=dev)
+    d = ops.gn_desc(x0=x, x1=None, c0=c, c1=0, y=y, gamma=gamma, beta=beta, stats=stats, batch=nb, hw=hw, groups=32,
+                    eps=1e-5, silu=silu)
+    return lambda: ops.run(d)
+
+
+def lnorm(rows, c):
+    x = torch.randn(rows, c, device=dev, generator=g).to(BF)
+    y = torch.empty_like(x)
+    gamma = torch.ones(c, device=dev); beta = torch.zeros(c, device=dev)
+    return lambda: ops.layer_norm(x, y, gamma, beta, 1e-5)
+
+
 cases = [
     ("conv 320->320 @64x64 b16", conv(16, 64, 64, 320, 320), 2 * 16 * 4096 * 320 * 2880),
     ("conv 640->640 @32x32 b16", conv(16, 32, 32, 640, 640), 2 * 16 * 1024 * 640 * 5760),
@@ -66,6 +83,10 @@ cases = [
     ("self-attn d40 N=4096 b16", attn(16, 8, 40, 4096, 4096), 4 * 16 * 8 * 4096 * 4096 * 40),
     ("cross-attn d40 N=4096x77 b16", attn(16, 8, 40, 4096, 77), 4 * 16 * 8 * 4096 * 77 * 40),
     ("self-attn d80 N=1024 b16", attn(16, 8, 80, 1024, 1024), 4 * 16 * 8 * 1024 * 1024 * 80),
+    # bandwidth kernels: "flops" = bytes moved (stats read + apply read + write), so the last column is TB/s
+    ("groupnorm+silu 320ch @64x64 b16 [TB/s]", gnorm(16, 4096, 320), 3 * 16 * 4096 * 320 * 2),
+    ("groupnorm+silu 640ch @32x32 b16 [TB/s]", gnorm(16, 1024, 640), 3 * 16 * 1024 * 640 * 2),
+    ("layernorm 320ch M=65536 [TB/s]", lnorm(65536, 320), 2 * 65536 * 320 * 2),
 ]
 only = sys.argv[1] if len(sys.argv) > 1 else None
 for name, fn, flops in cases:
@@ -82,4 +103,4 @@ for name, fn, flops in cases:
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / n * 1e3
-    print(f"{name:36s} {us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s")
+    print(f"{name:40s} {us:9.1f} us  {flops / us / 1e6:8.2f} {'TB/s' if 'TB/s' in name else 'TFLOP/s'}")
