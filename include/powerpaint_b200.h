@@ -135,8 +135,10 @@ typedef struct pp_gn_desc {
     const float* beta;
     float eps;
     int32_t silu;
-    float* stats; /* scratch [batch, groups, 2] fp32; zeroed by the call */
+    float* stats; /* scratch [batch, groups, 2] fp32; zeroed by the call unless stats_prezeroed */
     void* y;
+    int32_t stats_prezeroed; /* 1: the caller zeroed `stats` (e.g. one memset over the scratch of every
+                                GroupNorm of a step) and the call enqueues no memset of its own */
 } pp_gn_desc;
 pp_status pp_group_norm(const pp_gn_desc* d, pp_stream stream);
 

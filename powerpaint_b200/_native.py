@@ -60,7 +60,7 @@ class GnDesc(C.Structure):
         ("x0", vp), ("x1", vp), ("c0", i32), ("c1", i32),
         ("batch", i32), ("hw", i32), ("groups", i32),
         ("gamma", vp), ("beta", vp), ("eps", f32), ("silu", i32),
-        ("stats", vp), ("y", vp),
+        ("stats", vp), ("y", vp), ("stats_prezeroed", i32),
     ]
 
 

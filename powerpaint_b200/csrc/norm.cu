@@ -171,7 +171,7 @@ int group_norm_launch(const pp_gn_desc& d, cudaStream_t s) {
     if (rc) return rc;
     const int C = d.c0 + d.c1;
     const int CV = C / 8;
-    PP_CUDA_CHECK(cudaMemsetAsync(d.stats, 0, sizeof(float) * 2 * d.groups * d.batch, s));
+    if (!d.stats_prezeroed) PP_CUDA_CHECK(cudaMemsetAsync(d.stats, 0, sizeof(float) * 2 * d.groups * d.batch, s));
     int k = 256 / CV;
     if (k < 1) k = 1;
     const int threads = CV * k;

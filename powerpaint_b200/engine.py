@@ -73,10 +73,12 @@ class Plan:
         self.outputs: Dict[str, object] = {}
         self.bytes = 0
         self.buffers: List[torch.Tensor] = []  # every activation buffer, in recording order
+        self.gn_arenas: Dict[int, list] = {}   # per program: [GroupNorm scratch arena, slots used]
 
 
 class NetEngine:
     KINDS = ("unet", "brushnet", "controlnet")
+    GN_ARENA_SLOTS = 96  # GroupNorm layers per program (SD-1.5 UNet: 61)
 
     def __init__(self, cfg: NetConfig, state_dict: Dict[str, torch.Tensor], kind: str = "unet",
                  device: Optional[torch.device] = None):
@@ -184,10 +186,21 @@ class NetEngine:
         c1 = x1.shape[-1] if x1 is not None else 0
         groups = self.cfg.norm_num_groups
         y = self._buf(plan, nb, hw, c0 + c1)
-        stats = self._buf(plan, nb, groups, 2, dtype=torch.float32)
+        # the sum / sum-of-squares scratch of every GroupNorm of this plan lives in one arena that a single
+        # memset at the head of the program clears (one graph node per step instead of one per GroupNorm)
+        key = id(prog)
+        if key not in plan.gn_arenas:
+            arena = self._buf(plan, self.GN_ARENA_SLOTS, nb, groups, 2, dtype=torch.float32)
+            prog.add_memset(arena)
+            plan.gn_arenas[key] = [arena, 0]
+        arena, used = plan.gn_arenas[key]
+        if used >= arena.shape[0]:
+            raise RuntimeError("GroupNorm scratch arena exhausted; raise NetEngine.GN_ARENA_SLOTS")
+        stats = arena[used]
+        plan.gn_arenas[key][1] = used + 1
         prog.add(ops.gn_desc(x0=x0, x1=x1, c0=c0, c1=c1, batch=nb, hw=hw, groups=groups,
                              gamma=self.vec(name + ".weight"), beta=self.vec(name + ".bias"), eps=eps, silu=silu,
-                             stats=stats, y=y))
+                             stats=stats, y=y, stats_prezeroed=True))
         return y
 
     def _conv3(self, plan, prog, x, nb, h, w, name, cout, *, stride2=False, rowvec=None, res1=None, res2=None,

@@ -134,12 +134,14 @@ def attn_desc(*, q, k, vt, out, batch, heads, d, nq, nk, q_ld, k_ld, vt_ld, o_ld
     return Desc("attn", a, (q, k, vt, out))
 
 
-def gn_desc(*, x0, x1, c0, c1, batch, hw, groups, gamma, beta, eps, silu, stats, y) -> Desc:
+def gn_desc(*, x0, x1, c0, c1, batch, hw, groups, gamma, beta, eps, silu, stats, y,
+            stats_prezeroed=False) -> Desc:
     g = N.GnDesc()
     g.x0, g.x1, g.c0, g.c1 = N.ptr(x0), N.ptr(x1), c0, c1
     g.batch, g.hw, g.groups = batch, hw, groups
     g.gamma, g.beta, g.eps, g.silu = N.ptr(gamma), N.ptr(beta), eps, 1 if silu else 0
     g.stats, g.y = N.ptr(stats), N.ptr(y)
+    g.stats_prezeroed = 1 if stats_prezeroed else 0
     return Desc("gn", g, (x0, x1, gamma, beta, stats, y))
 
 
