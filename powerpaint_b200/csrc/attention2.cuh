@@ -140,8 +140,10 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
             auto issue_pv = [&](int k) {
                 const int j = k >> 1, t = k & 1, buf = k % NBUF;
                 const uint32_t vb = sV0 + (j % S) * v_stage_bytes;
+                const int pv_steps = (min(ATT_BN, p.nk - j * ATT_BN) + 15) >> 4;  // 16 keys per MMA; 8 unless ragged
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
+                    if (ks >= pv_steps) break;
                     const int c = ks >> 2, kk = (ks & 3) * 16;
                     umma_f16_ts(tmem_base + O_BASE + t * O_STRIDE, tmem_base + buf * 128 + ks * 8,
                                 umma_desc_advance_k(umma_desc_kmajor_sw128(vb + c * v_chunk_bytes), kk), idesc_o,
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
                 // the first block has no reference yet: one extra pass for the row max
                 float mx = -INFINITY;
 #pragma unroll 1
-                for (int ch = 0; ch < 4; ++ch) {
+                for (int ch = 0; ch * 32 < nvalid; ++ch) {
                     uint32_t sv[32];
                     tmem_ld32(tS + ch * 32, sv);
                     tmem_wait_ld();
@@ -230,6 +232,10 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
                             pk[ch * 16 + i / 2 + 1] = pack_f16x2(e2, e3);
 #endif
                         }
+                    } else if (ch * 32 >= nvalid) {
+                        // chunk entirely past the last key (the 77-key cross-attention ends in chunk 2)
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) pk[ch * 16 + i] = 0u;
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; i += 2) {
@@ -286,8 +292,8 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
                 uint8_t* vrow = smem_raw + (sV0 + (j % S) * v_stage_bytes + ch * v_chunk_bytes - raw) + p.d * 128;
                 *reinterpret_cast<uint4*>(vrow + piece * 16) =
                     make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+                fence_proxy_async_smem();  // the tensor core reads this row through the async proxy
             }
-            fence_proxy_async_smem();  // the ones row above is read by the tensor core (async proxy)
             tc_fence_before();
             __syncwarp();
             if (lane_id() == 0) mbar_arrive(bar_p_full(t));
