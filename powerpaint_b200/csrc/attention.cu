@@ -308,12 +308,13 @@ namespace pp {
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
-template <int NBUF>
+template <int NBUF, int DCH, int S>
 static int attn2_ensure_attr() {
     static bool done = false;
     if (!done) {
-        PP_CUDA_CHECK(cudaFuncSetAttribute(attn2_kernel<NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)std::max(att2_smem_bytes(48), att2_smem_bytes(NBUF == 3 ? 64 : 80))));
+        // largest V^T tile the variant can meet: dv <= 64 with three score buffers, else <= 128
+        PP_CUDA_CHECK(cudaFuncSetAttribute(attn2_kernel<NBUF, DCH, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)att2_smem_bytes(NBUF == 3 ? 64 : 128, DCH, S)));
         done = true;
     }
     return PP_OK;
@@ -347,7 +348,7 @@ int attn_prepare(const pp_attn_desc& d, AttnLaunch* out) {
     p.k_steps = (d.d + 15) / 16;
     // dual-tile kernel for d <= 64 when there are at least two query tiles; it keeps the row sums
     // in column d of O, so its V^T tile has one extra (ones) row
-    const bool dual = p.d_chunks == 1 && d.nq > ATT_BM && d.vt_fp16;
+    const bool dual = d.d <= 112 && d.nq > ATT_BM && d.vt_fp16;  // dv = ceil16(d + 1) must fit 128 TMEM columns
     p.dv = dual ? ((d.d + 1 + 15) / 16) * 16 : ((d.d + 15) / 16) * 16;
     p.scale_log2 = d.scale * 1.4426950408889634f;
     p.vt_fp16 = d.vt_fp16;
@@ -375,12 +376,15 @@ int attn_prepare(const pp_attn_desc& d, AttnLaunch* out) {
         if (rc) return rc;
     }
     if (dual) {
-        l.variant = p.dv <= 64 ? 10 : 11;  // three rotating score buffers need dv <= 64 TMEM columns per O
+        // three rotating score buffers need dv <= 64 TMEM columns per O; two head-dim chunks leave room
+        // for a two-stage K / V^T ring only
+        l.variant = p.d_chunks == 2 ? 12 : p.dv <= 64 ? 10 : 11;
         l.grid = dim3((unsigned)((d.nq + 2 * ATT_BM - 1) / (2 * ATT_BM)), (unsigned)d.heads, (unsigned)d.batch);
-        l.smem = att2_smem_bytes((uint32_t)p.dv);
-        l.kv_stages = (int)att2_kv_stages((uint32_t)p.dv);
+        l.kv_stages = l.variant == 12 ? 2 : 4;
         p.kv_stages = l.kv_stages;
-        int rc2 = l.variant == 10 ? attn2_ensure_attr<3>() : attn2_ensure_attr<2>();
+        l.smem = att2_smem_bytes((uint32_t)p.dv, (uint32_t)p.d_chunks, (uint32_t)l.kv_stages);
+        int rc2 = l.variant == 10 ? attn2_ensure_attr<3, 1, 4>()
+                  : l.variant == 11 ? attn2_ensure_attr<2, 1, 4>() : attn2_ensure_attr<2, 2, 2>();
         if (rc2) return rc2;
         *out = l;
         return PP_OK;
@@ -400,8 +404,9 @@ int attn_prepare(const pp_attn_desc& d, AttnLaunch* out) {
 
 int attn_launch(const AttnLaunch& l, cudaStream_t s) {
     switch (l.variant) {
-        case 10: PP_CUDA_CHECK(launch(attn2_kernel<3>, l.grid, ATT2_THREADS, l.smem, s, l.p)); break;
-        case 11: PP_CUDA_CHECK(launch(attn2_kernel<2>, l.grid, ATT2_THREADS, l.smem, s, l.p)); break;
+        case 10: PP_CUDA_CHECK(launch(attn2_kernel<3, 1, 4>, l.grid, ATT2_THREADS, l.smem, s, l.p)); break;
+        case 11: PP_CUDA_CHECK(launch(attn2_kernel<2, 1, 4>, l.grid, ATT2_THREADS, l.smem, s, l.p)); break;
+        case 12: PP_CUDA_CHECK(launch(attn2_kernel<2, 2, 2>, l.grid, ATT2_THREADS, l.smem, s, l.p)); break;
         case 1: PP_CUDA_CHECK(launch(attn_fwd_kernel<1>, l.grid, ATT_THREADS, l.smem, s, l.p)); break;
         case 2: PP_CUDA_CHECK(launch(attn_fwd_kernel<2>, l.grid, ATT_THREADS, l.smem, s, l.p)); break;
         default: PP_CUDA_CHECK(launch(attn_fwd_kernel<3>, l.grid, ATT_THREADS, l.smem, s, l.p)); break;

@@ -1,5 +1,6 @@
-// Dual-tile ("ping-pong") attention kernel for head dims <= 64 with fp16 P / V^T — the d = 40
-// self-attention over 4096 tokens that dominates the 512^2 step. Included by attention.cu.
+// Dual-tile ("ping-pong") attention kernel for head dims <= 112 with fp16 P / V^T — the d = 40
+// self-attention over 4096 tokens that dominates the 512^2 step, and d = 80 over 1024 tokens.
+// Included by attention.cu.
 //
 // One CTA (one per SM, 320 threads) owns TWO 128-query tiles of one (sample, head) and streams the
 // keys once for both, 128 keys per block:
@@ -33,26 +34,29 @@ namespace pp {
 
 static constexpr int ATT2_THREADS = 320;
 
-__host__ __device__ constexpr uint32_t att2_kv_stages(uint32_t) { return 4; }
-__host__ __device__ constexpr uint32_t att2_smem_bytes(uint32_t dv) {
-    return 2 * ATT_CHUNK_BYTES                                   // Q0, Q1
-           + att2_kv_stages(dv) * (ATT_CHUNK_BYTES + dv * 256u)  // K + V^T ring
+// dch = 64-channel chunks of the head dim (1: d <= 64, 2: d <= 112), stages = K / V^T ring depth
+__host__ __device__ constexpr uint32_t att2_smem_bytes(uint32_t dv, uint32_t dch, uint32_t stages) {
+    return 2 * dch * ATT_CHUNK_BYTES                             // Q0, Q1
+           + stages * (dch * ATT_CHUNK_BYTES + dv * 256u)        // K + V^T ring
            + 256 + 1024;
 }
 
-template <int NBUF>
+// NBUF score buffers (3 needs dv <= 64), DCH head-dim chunks, S ring stages — all compile-time: j % S,
+// j / S and k % NBUF sit on the MMA issuer's critical path.
+// Instantiations: <3,1,4> d <= 48 (SD-1.5 d = 40), <2,1,4> d = 56/64, <2,2,2> d = 72..112 (SD-1.5 d = 80).
+template <int NBUF, int DCH, int S>
 __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_constant__ AttnKParams p) {
     constexpr int MAXS = 4;
+    static_assert(S <= MAXS, "barrier slots");
     constexpr uint32_t O_BASE = NBUF * 128, O_STRIDE = NBUF == 3 ? 64 : 128;
-    constexpr int S = MAXS;  // compile-time ring depth: j % S and j / S sit on the issuer's critical path
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     const uint32_t v_chunk_bytes = (uint32_t)p.dv * 128u;
     const uint32_t v_stage_bytes = 2u * v_chunk_bytes;
-    const uint32_t sQ = base;                                    // [2][16 KB]
-    const uint32_t sK0 = sQ + 2 * ATT_CHUNK_BYTES;               // [S][16 KB]
-    const uint32_t sV0 = sK0 + S * ATT_CHUNK_BYTES;              // [S][v_stage_bytes]
+    const uint32_t sQ = base;                                    // [2][DCH][16 KB]
+    const uint32_t sK0 = sQ + 2 * DCH * ATT_CHUNK_BYTES;         // [S][DCH][16 KB]
+    const uint32_t sV0 = sK0 + S * DCH * ATT_CHUNK_BYTES;        // [S][v_stage_bytes]
     const uint32_t bars = sV0 + S * v_stage_bytes;
     const uint32_t bar_q = bars;
     auto bar_kv_full = [&](int s) { return bars + 8u * (1 + s); };
@@ -101,15 +105,20 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
-            mbar_arrive_expect_tx(bar_q, 2 * ATT_CHUNK_BYTES);
-            tma_load_4d(sQ, &p.tmQ, bar_q, 0, head, q0, b);
-            tma_load_4d(sQ + ATT_CHUNK_BYTES, &p.tmQ, bar_q, 0, head, q0 + ATT_BM, b);
+            mbar_arrive_expect_tx(bar_q, 2 * DCH * ATT_CHUNK_BYTES);
+#pragma unroll
+            for (int tc = 0; tc < 2 * DCH; ++tc)  // tile tc / DCH, channel chunk tc % DCH (zero-filled past d)
+                tma_load_4d(sQ + tc * ATT_CHUNK_BYTES, &p.tmQ, bar_q, (tc % DCH) * 64, head,
+                            q0 + (tc / DCH) * ATT_BM, b);
             for (int j = 0; j < nkv; ++j) {
                 const int s = j % S;
                 const uint32_t ph = (j / S) & 1;
                 mbar_wait(bar_kv_empty(s), ph ^ 1u);
-                mbar_arrive_expect_tx(bar_kv_full(s), ATT_CHUNK_BYTES + v_stage_bytes);
-                tma_load_4d(sK0 + s * ATT_CHUNK_BYTES, &p.tmK, bar_kv_full(s), 0, head, j * ATT_BN, b);
+                mbar_arrive_expect_tx(bar_kv_full(s), DCH * ATT_CHUNK_BYTES + v_stage_bytes);
+#pragma unroll
+                for (int c = 0; c < DCH; ++c)
+                    tma_load_4d(sK0 + (s * DCH + c) * ATT_CHUNK_BYTES, &p.tmK, bar_kv_full(s), c * 64, head,
+                                j * ATT_BN, b);
                 const uint32_t dV = sV0 + s * v_stage_bytes;
                 tma_load_3d(dV, &p.tmV, bar_kv_full(s), j * ATT_BN, 0, b * p.heads + head);
                 tma_load_3d(dV + v_chunk_bytes, &p.tmV, bar_kv_full(s), j * ATT_BN + 64, 0, b * p.heads + head);
@@ -127,12 +136,15 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
                     mbar_wait(bar_kv_full(j % S), (j / S) & 1);  // first use of key block j
                     tc_fence_after();
                 }
-                const uint32_t kb = sK0 + (j % S) * ATT_CHUNK_BYTES;
-                const uint64_t da0 = umma_desc_kmajor_sw128(sQ + t * ATT_CHUNK_BYTES);
-                const uint64_t db0 = umma_desc_kmajor_sw128(kb);
-                for (int ks = 0; ks < p.k_steps; ++ks)
-                    umma_bf16_ss(tmem_base + buf * 128, umma_desc_advance_k(da0, ks * 16),
-                                 umma_desc_advance_k(db0, ks * 16), idesc_s, ks != 0);
+                const uint32_t qb = sQ + t * DCH * ATT_CHUNK_BYTES;
+                const uint32_t kb = sK0 + (j % S) * DCH * ATT_CHUNK_BYTES;
+                for (int ks = 0; ks < p.k_steps; ++ks) {
+                    const int c = ks >> 2, kk = (ks & 3) * 16;  // 64-channel chunk, offset inside it
+                    umma_bf16_ss(tmem_base + buf * 128,
+                                 umma_desc_advance_k(umma_desc_kmajor_sw128(qb + c * ATT_CHUNK_BYTES), kk),
+                                 umma_desc_advance_k(umma_desc_kmajor_sw128(kb + c * ATT_CHUNK_BYTES), kk), idesc_s,
+                                 ks != 0);
+                }
                 umma_commit(bar_s_full(buf));
             };
             // O(t) += P(k) V(j): P is read straight from tensor memory (the fp16 probabilities overwrite

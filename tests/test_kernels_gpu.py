@@ -174,7 +174,8 @@ def test_conv3x3_stride2(ops, nb, h, w, c):
 @pytest.mark.parametrize("B,H,d,nq,nk", [(2, 8, 40, 4096, 4096), (2, 8, 80, 1024, 1024), (3, 8, 160, 256, 256),
                                           (2, 8, 160, 64, 64), (2, 8, 40, 4096, 77), (2, 8, 80, 1024, 77),
                                           (2, 8, 160, 64, 77), (2, 4, 8, 64, 64), (2, 4, 16, 16, 77),
-                                          (3, 4, 32, 4, 4), (2, 4, 32, 1, 77), (1, 2, 64, 300, 333)])
+                                          (3, 4, 32, 4, 4), (2, 4, 32, 1, 77), (1, 2, 64, 300, 333),
+                                          (1, 3, 96, 384, 200), (1, 2, 112, 300, 333)])
 @pytest.mark.parametrize("vdt", [torch.bfloat16, torch.float16])
 def test_attention(ops, B, H, d, nq, nk, vdt):
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + d + nq)
