@@ -345,7 +345,10 @@ def test_program_and_graph(ops):
         prog.build_graph()
         prog.launch()
         s.synchronize()
-    assert torch.equal(z, z1)
+    # replay == plain launches. Not bit-for-bit: the GroupNorm statistics are accumulated with fp32 atomics,
+    # whose order differs from run to run, so the last bit of a statistic (and then of a few bf16 outputs)
+    # may differ between ANY two runs; everything downstream of the statistics is deterministic.
+    assert _rel(z, z1) < 2e-3
     ref = F.silu(F.group_norm(x.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)).to(BF16).float()
     ref = F.conv2d(ref, wt.float(), None, padding=1).to(BF16).float().permute(0, 2, 3, 1)
     ref = F.layer_norm(ref, (c,), gamma, beta, 1e-5)
