@@ -135,12 +135,17 @@ typedef struct pp_gn_desc {
     const float* beta;
     float eps;
     int32_t silu;
-    float* stats; /* scratch [batch, groups, 2] fp32; zeroed by the call unless stats_prezeroed */
+    float* stats; /* scratch of pp_group_norm_scratch_bytes() bytes, 16-byte aligned: the per-(sample, group)
+                     sum / sum of squares [batch, groups, 2] fp32, then the ticket counters and per-block
+                     partials of the deterministic reduction */
     void* y;
-    int32_t stats_prezeroed; /* 1: the caller zeroed `stats` (e.g. one memset over the scratch of every
-                                GroupNorm of a step) and the call enqueues no memset of its own */
+    int32_t stats_prezeroed; /* 1: the scratch was zeroed once when it was allocated (every call leaves its
+                                ticket counters zero again) or by one memset per step over all scratch;
+                                0: the call clears its ticket counters with a memset of its own */
 } pp_gn_desc;
 pp_status pp_group_norm(const pp_gn_desc* d, pp_stream stream);
+/* bytes of `stats` scratch a GroupNorm over [batch, hw, channels] with `groups` groups needs (0: invalid) */
+int64_t pp_group_norm_scratch_bytes(int32_t batch, int32_t hw, int32_t channels, int32_t groups);
 
 pp_status pp_layer_norm(const void* x, void* y, const float* gamma, const float* beta,
                         int32_t rows, int32_t c, float eps, pp_stream stream);

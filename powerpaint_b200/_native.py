@@ -83,6 +83,7 @@ _SIGNATURES = {
     "pp_gemm_conv": (C.c_int, [C.POINTER(GemmDesc), vp]),
     "pp_attention": (C.c_int, [C.POINTER(AttnDesc), vp]),
     "pp_group_norm": (C.c_int, [C.POINTER(GnDesc), vp]),
+    "pp_group_norm_scratch_bytes": (i64, [i32, i32, i32, i32]),
     "pp_layer_norm": (C.c_int, [vp, vp, vp, vp, i32, i32, f32, vp]),
     "pp_upsample2x": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
     "pp_add": (C.c_int, [vp, vp, vp, i64, vp]),

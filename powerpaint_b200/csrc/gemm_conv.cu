@@ -17,11 +17,12 @@
 //    Up to two A sources are walked back to back along K: the up-path skip concat
 //    (unet_2d_blocks.py:2589,2732) never materialises.
 //  * B operand: weights [N, K] K-major, K ordered (tap, source, channel) to match.
-//  * Pipeline: warp 0 = TMA producer, warp 1 = single-thread tcgen05.mma issuer,
-//    warps 2..5 = epilogue (tcgen05.ld -> registers -> global). STAGES-deep smem ring with
-//    full/empty mbarriers; tcgen05.commit releases ring slots and publishes the accumulator.
-//    Two CTAs co-reside per SM for the 128/160-wide tiles so one CTA's epilogue overlaps the
-//    other's main loop.
+//  * Pipeline: persistent kernel, one 320-thread CTA per SM. Warp 8 = TMA producer, warp 9 =
+//    single-thread tcgen05.mma issuer and TMEM owner, warps 0..7 = epilogue (tcgen05.ld -> registers ->
+//    shared-memory staging tile -> coalesced row stores). STAGES-deep smem ring with full/empty
+//    mbarriers that keeps running across tile boundaries; two TMEM accumulator stages, so the epilogue
+//    of one tile overlaps the main loop of the next. tcgen05.commit releases ring slots and publishes
+//    the accumulator.
 //  * Epilogue (fused): + bias[n] + time-embedding row vector + residual (skip / shortcut)
 //    → × alpha (1/output_scale_factor or BrushNet conditioning_scale) → + second residual
 //    (BrushNet / ControlNet feature injection, unet_2d_condition.py:1223,1300) → SiLU /

@@ -19,28 +19,63 @@
 namespace pp {
 
 // ------------------------------------------------------------------------------------
-// GroupNorm pass 1: per-(sample, group) sum and sum of squares.
+// GroupNorm pass 1: per-(sample, group) sum and sum of squares — deterministic (no atomics on data).
 // grid = (chunks, batch); block = CV * k threads where CV = C/8 channel vectors; each thread
 // owns one 8-channel vector and strides over pixels, so loads are 16-byte and coalesced along
-// channels. Per-thread partials are folded per group through shared-memory atomics, then one
-// global atomicAdd per (group, stat) per block.
+// channels. The per-thread per-channel partials go to shared memory, 2*groups threads fold them per
+// group in a fixed order and write the block's partial to `partials`; the last block of a sample to
+// finish (ticket counter) adds the blocks' partials in chunk order into `stats`. Every float addition
+// therefore happens in an order that depends only on the launch geometry: results are bit-identical
+// from run to run (the ticket decides WHO does the final sum, not in which order).
+// Scratch layout (pp_group_norm_scratch_bytes): stats [batch][groups][2] f32 | tickets [batch] u32
+// (zero before the call, left zero by it) | partials [batch][chunks][groups][2] f32.
 // ------------------------------------------------------------------------------------
+struct GnGeometry {
+    int threads, lanes, chunks, ppb;
+    size_t smem;           // dynamic shared memory of the statistics kernel
+    size_t ticket_offset;  // bytes from the scratch base
+    size_t partial_offset;
+    size_t scratch_bytes;
+};
+
+static GnGeometry gn_geometry(int batch, int hw, int C, int groups) {
+    GnGeometry g;
+    const int CV = C / 8;
+    int k = 256 / CV;
+    if (k < 1) k = 1;
+    g.threads = CV * k;
+    g.lanes = k;
+    // ~8 blocks per SM over the machine, at least 8 pixels per pixel lane
+    int chunks = (148 * 8 + batch - 1) / batch;
+    int ppb = (hw + chunks - 1) / chunks;
+    if (ppb < k * 8) ppb = k * 8;
+    g.ppb = ppb;
+    g.chunks = (hw + ppb - 1) / ppb;
+    g.smem = sizeof(float) * 2 * (size_t)k * C + 16;
+    const size_t stats_bytes = sizeof(float) * 2 * (size_t)groups * batch;
+    g.ticket_offset = (stats_bytes + 15) & ~(size_t)15;
+    g.partial_offset = g.ticket_offset + ((sizeof(uint32_t) * (size_t)batch + 15) & ~(size_t)15);
+    g.scratch_bytes = g.partial_offset + sizeof(float) * 2 * (size_t)groups * g.chunks * batch;
+    return g;
+}
+
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, const __nv_bfloat16* __restrict__ x1,
                                 int c0, int c1, int hw, int groups, int pix_per_block,
-                                float* __restrict__ stats) {
+                                float* __restrict__ stats, uint32_t* __restrict__ tickets,
+                                float* __restrict__ partials) {
     pdl_wait();  // inputs come from the preceding kernel
     pdl_launch_dependents();
-    extern __shared__ float sh[];  // [groups][2]
+    extern __shared__ float sh[];  // [lanes][C] sums, then [lanes][C] sums of squares, then the ticket
     const int C = c0 + c1;
     const int CV = C / 8;
     const int cpg = C / groups;
     const int n = blockIdx.y;
-    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sh[i] = 0.f;
-    __syncthreads();
     const int lanes = blockDim.x / CV;  // pixel lanes
     const int cv = threadIdx.x % CV;
     const int pl = threadIdx.x / CV;
-    if (pl < lanes) {
+    float* sh_s = sh;
+    float* sh_ss = sh + lanes * C;
+    {
         const int c = cv * 8;
         const __nv_bfloat16* src;
         int cs, co;
@@ -57,8 +92,7 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, const __nv
 #pragma unroll
             for (int j = 0; j < 8; ++j) { s[j] += v[j]; ss[j] += v[j] * v[j]; }
         };
-        // four independent 16-byte loads in flight per thread: with ~4 blocks per SM a single load per
-        // thread leaves the memory system at about a third of its bandwidth
+        // four independent 16-byte loads in flight per thread
         int p = p_begin + pl;
         for (; p + 3 * lanes < p_end; p += 4 * lanes) {
             const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(sp + (int64_t)p * cs));
@@ -68,25 +102,39 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, const __nv
             accumulate(q0); accumulate(q1); accumulate(q2); accumulate(q3);
         }
         for (; p < p_end; p += lanes) accumulate(__ldg(reinterpret_cast<const uint4*>(sp + (int64_t)p * cs)));
-        // fold the 8 channels into their groups (a vector may straddle a group boundary)
-        int g_prev = c / cpg;
-        float as = 0.f, ass = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int g = (c + j) / cpg;
-            if (g != g_prev) {
-                atomicAdd(&sh[g_prev * 2], as);
-                atomicAdd(&sh[g_prev * 2 + 1], ass);
-                as = 0.f; ass = 0.f; g_prev = g;
-            }
-            as += s[j]; ass += ss[j];
-        }
-        atomicAdd(&sh[g_prev * 2], as);
-        atomicAdd(&sh[g_prev * 2 + 1], ass);
+        float4* ds = reinterpret_cast<float4*>(sh_s + pl * C + c);
+        float4* dss = reinterpret_cast<float4*>(sh_ss + pl * C + c);
+        ds[0] = make_float4(s[0], s[1], s[2], s[3]);
+        ds[1] = make_float4(s[4], s[5], s[6], s[7]);
+        dss[0] = make_float4(ss[0], ss[1], ss[2], ss[3]);
+        dss[1] = make_float4(ss[4], ss[5], ss[6], ss[7]);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
-        atomicAdd(&stats[(int64_t)n * groups * 2 + i], sh[i]);
+    // fold: thread i < 2 * groups owns (group i / 2, statistic i % 2); fixed order: lanes outer, channels inner
+    const int chunks = gridDim.x;
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) {
+        const int g = i >> 1;
+        const float* srcv = (i & 1) ? sh_ss : sh_s;
+        float acc = 0.f;
+        for (int l = 0; l < lanes; ++l)
+            for (int cc = 0; cc < cpg; ++cc) acc += srcv[l * C + g * cpg + cc];
+        partials[(((int64_t)n * chunks + blockIdx.x) * groups) * 2 + i] = acc;
+    }
+    // ticket: the last block of this sample to arrive sums the partials of all its blocks in chunk order
+    __threadfence();
+    __syncthreads();
+    uint32_t* sh_ticket = reinterpret_cast<uint32_t*>(sh + 2 * lanes * C);
+    if (threadIdx.x == 0) *sh_ticket = atomicAdd(&tickets[n], 1u);
+    __syncthreads();
+    if (*sh_ticket != (uint32_t)(chunks - 1)) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) {
+        const float* pp_ = partials + ((int64_t)n * chunks * groups) * 2 + i;
+        float acc = 0.f;
+        for (int ch = 0; ch < chunks; ++ch) acc += __ldcg(pp_ + (int64_t)ch * groups * 2);
+        stats[(int64_t)n * groups * 2 + i] = acc;
+    }
+    if (threadIdx.x == 0) tickets[n] = 0u;  // ready for the next call
 }
 
 // GroupNorm pass 2: y = (x - mean) * rstd * gamma + beta, optional SiLU; writes the concat.
@@ -163,26 +211,30 @@ int group_norm_validate(const pp_gn_desc& d) {
     PP_REQUIRE(d.groups > 0 && C % d.groups == 0, "group_norm: C=%d not divisible by groups=%d", C, d.groups);
     PP_REQUIRE(C / 8 <= 1024, "group_norm: C=%d too large", C);
     PP_REQUIRE(d.batch > 0 && d.hw > 0, "group_norm: empty input");
+    PP_REQUIRE(gn_geometry(d.batch, d.hw, C, d.groups).smem <= 48 * 1024,
+               "group_norm: C=%d needs more than 48 KB of shared memory for the block reduction", C);
+    PP_REQUIRE((reinterpret_cast<uintptr_t>(d.stats) & 15) == 0, "group_norm: scratch not 16-byte aligned");
     return PP_OK;
+}
+
+int64_t group_norm_scratch_bytes(int batch, int hw, int channels, int groups) {
+    if (batch <= 0 || hw <= 0 || channels <= 0 || channels % 8 || groups <= 0) return 0;
+    return (int64_t)gn_geometry(batch, hw, channels, groups).scratch_bytes;
 }
 
 int group_norm_launch(const pp_gn_desc& d, cudaStream_t s) {
     int rc = group_norm_validate(d);
     if (rc) return rc;
     const int C = d.c0 + d.c1;
-    const int CV = C / 8;
-    if (!d.stats_prezeroed) PP_CUDA_CHECK(cudaMemsetAsync(d.stats, 0, sizeof(float) * 2 * d.groups * d.batch, s));
-    int k = 256 / CV;
-    if (k < 1) k = 1;
-    const int threads = CV * k;
-    // ~8 blocks per SM over the machine, at least 32 pixels per lane-stride
-    int chunks = (148 * 8 + d.batch - 1) / d.batch;
-    int ppb = (d.hw + chunks - 1) / chunks;
-    if (ppb < k * 8) ppb = k * 8;
-    chunks = (d.hw + ppb - 1) / ppb;
-    PP_CUDA_CHECK(launch(gn_stats_kernel, dim3(chunks, d.batch), threads, sizeof(float) * 2 * d.groups, s, 
+    const GnGeometry g = gn_geometry(d.batch, d.hw, C, d.groups);
+    uint8_t* scratch = reinterpret_cast<uint8_t*>(d.stats);
+    uint32_t* tickets = reinterpret_cast<uint32_t*>(scratch + g.ticket_offset);
+    float* partials = reinterpret_cast<float*>(scratch + g.partial_offset);
+    if (!d.stats_prezeroed) PP_CUDA_CHECK(cudaMemsetAsync(tickets, 0, sizeof(uint32_t) * d.batch, s));
+    const int threads = g.threads, chunks = g.chunks, ppb = g.ppb;
+    PP_CUDA_CHECK(launch(gn_stats_kernel, dim3(chunks, d.batch), threads, g.smem, s,
         reinterpret_cast<const __nv_bfloat16*>(d.x0), reinterpret_cast<const __nv_bfloat16*>(d.x1), d.c0,
-        d.c1, d.hw, d.groups, ppb, d.stats));
+        d.c1, d.hw, d.groups, ppb, d.stats, tickets, partials));
     PP_CUDA_CHECK(cudaGetLastError());
     PP_CUDA_CHECK(launch(gn_apply_kernel, dim3(chunks, d.batch), threads, 0, s, 
         reinterpret_cast<const __nv_bfloat16*>(d.x0), reinterpret_cast<const __nv_bfloat16*>(d.x1), d.c0,
@@ -277,6 +329,10 @@ int layer_norm_launch(const void* x, void* y, const float* gamma, const float* b
 }
 
 }  // namespace pp
+
+extern "C" int64_t pp_group_norm_scratch_bytes(int32_t batch, int32_t hw, int32_t channels, int32_t groups) {
+    return pp::group_norm_scratch_bytes(batch, hw, channels, groups);
+}
 
 extern "C" {
 pp_status pp_group_norm(const pp_gn_desc* d, pp_stream stream) {

@@ -82,6 +82,7 @@ int attn_launch(const AttnLaunch& l, cudaStream_t s);
 // ---------------------------------------------------------------- simple ops
 int group_norm_launch(const pp_gn_desc& d, cudaStream_t s);
 int group_norm_validate(const pp_gn_desc& d);
+int64_t group_norm_scratch_bytes(int batch, int hw, int channels, int groups);
 int layer_norm_launch(const void* x, void* y, const float* gamma, const float* beta, int rows,
                       int c, float eps, cudaStream_t s);
 int upsample2x_launch(const void* x, void* y, int nb, int h, int w, int c, cudaStream_t s);

@@ -73,12 +73,12 @@ class Plan:
         self.outputs: Dict[str, object] = {}
         self.bytes = 0
         self.buffers: List[torch.Tensor] = []  # every activation buffer, in recording order
-        self.gn_arenas: Dict[int, list] = {}   # per program: [GroupNorm scratch arena, slots used]
+        self.gn_arenas: Dict[int, list] = {}   # per program: [GroupNorm scratch arena, floats used]
 
 
 class NetEngine:
     KINDS = ("unet", "brushnet", "controlnet")
-    GN_ARENA_SLOTS = 96  # GroupNorm layers per program (SD-1.5 UNet: 61)
+    GN_ARENA_BYTES = 32 << 20  # GroupNorm scratch per program (SD-1.5 UNet: 61 layers x <= 320 KB)
 
     def __init__(self, cfg: NetConfig, state_dict: Dict[str, torch.Tensor], kind: str = "unet",
                  device: Optional[torch.device] = None):
@@ -190,14 +190,15 @@ class NetEngine:
         # memset at the head of the program clears (one graph node per step instead of one per GroupNorm)
         key = id(prog)
         if key not in plan.gn_arenas:
-            arena = self._buf(plan, self.GN_ARENA_SLOTS, nb, groups, 2, dtype=torch.float32)
+            arena = self._buf(plan, self.GN_ARENA_BYTES // 4, dtype=torch.float32)
             prog.add_memset(arena)
             plan.gn_arenas[key] = [arena, 0]
         arena, used = plan.gn_arenas[key]
-        if used >= arena.shape[0]:
-            raise RuntimeError("GroupNorm scratch arena exhausted; raise NetEngine.GN_ARENA_SLOTS")
-        stats = arena[used]
-        plan.gn_arenas[key][1] = used + 1
+        need = (ops.gn_scratch_bytes(nb, hw, c0 + c1, groups) + 255) // 256 * 64  # floats, 256-byte slots
+        if used + need > arena.numel():
+            raise RuntimeError("GroupNorm scratch arena exhausted; raise NetEngine.GN_ARENA_BYTES")
+        stats = arena[used:used + need]
+        plan.gn_arenas[key][1] = used + need
         prog.add(ops.gn_desc(x0=x0, x1=x1, c0=c0, c1=c1, batch=nb, hw=hw, groups=groups,
                              gamma=self.vec(name + ".weight"), beta=self.vec(name + ".bias"), eps=eps, silu=silu,
                              stats=stats, y=y, stats_prezeroed=True))

@@ -134,8 +134,21 @@ def attn_desc(*, q, k, vt, out, batch, heads, d, nq, nk, q_ld, k_ld, vt_ld, o_ld
     return Desc("attn", a, (q, k, vt, out))
 
 
-def gn_desc(*, x0, x1, c0, c1, batch, hw, groups, gamma, beta, eps, silu, stats, y,
+def gn_scratch_bytes(batch: int, hw: int, channels: int, groups: int) -> int:
+    n = N.lib().pp_group_norm_scratch_bytes(batch, hw, channels, groups)
+    if n <= 0:
+        raise ValueError(f"invalid GroupNorm shape batch={batch} hw={hw} channels={channels} groups={groups}")
+    return int(n)
+
+
+def gn_desc(*, x0, x1, c0, c1, batch, hw, groups, gamma, beta, eps, silu, y, stats=None,
             stats_prezeroed=False) -> Desc:
+    """`stats`: scratch of gn_scratch_bytes() bytes (fp32 tensor, 16-byte aligned); allocated (zeroed) here
+    when omitted."""
+    if stats is None:
+        stats = torch.zeros((gn_scratch_bytes(batch, hw, c0 + c1, groups) + 3) // 4, dtype=torch.float32,
+                            device=x0.device)
+        stats_prezeroed = True
     g = N.GnDesc()
     g.x0, g.x1, g.c0, g.c1 = N.ptr(x0), N.ptr(x1), c0, c1
     g.batch, g.hw, g.groups = batch, hw, groups

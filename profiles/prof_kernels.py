@@ -57,8 +57,7 @@ def gnorm(nb, hw, c, silu=True):
     x = torch.randn(nb, hw, c, device=dev, generator=g).to(BF)
     y = torch.empty_like(x)
     gamma = torch.ones(c, device=dev); beta = torch.zeros(c, device=dev)
-    stats = torch.empty(nb, 32, 2, device=dev)
-    d = ops.gn_desc(x0=x, x1=None, c0=c, c1=0, y=y, gamma=gamma, beta=beta, stats=stats, batch=nb, hw=hw, groups=32,
+    d = ops.gn_desc(x0=x, x1=None, c0=c, c1=0, y=y, gamma=gamma, beta=beta, batch=nb, hw=hw, groups=32,
                     eps=1e-5, silu=silu)
     return lambda: ops.run(d)
 

@@ -230,7 +230,8 @@ def test_group_norm(ops, B, hw, c0, c1, groups, silu):
     x1 = (torch.randn(B, hw, c1, device=_dev(), generator=g) - 0.3).to(BF16) if c1 else None
     gamma = torch.randn(C_, device=_dev(), generator=g)
     beta = torch.randn(C_, device=_dev(), generator=g)
-    stats = torch.empty(B, groups, 2, device=_dev())
+    # garbage-filled scratch + stats_prezeroed=False: the call has to clear its own ticket counters
+    stats = torch.full(((ops.gn_scratch_bytes(B, hw, c0 + c1, groups) + 3) // 4,), float("nan"), device=_dev())
     y = torch.zeros(B, hw, C_, device=_dev(), dtype=BF16)
     ops.run(ops.gn_desc(x0=x0, x1=x1, c0=c0, c1=c1, batch=B, hw=hw, groups=groups, gamma=gamma, beta=beta,
                         eps=1e-5, silu=silu, stats=stats, y=y))
@@ -240,6 +241,13 @@ def test_group_norm(ops, B, hw, c0, c1, groups, silu):
     if silu:
         ref = F.silu(ref)
     assert _rel(y.permute(0, 2, 1), ref) < 5e-3, _rel(y.permute(0, 2, 1), ref)
+    # second call on the same scratch without clearing it: the first call left the ticket counters at zero,
+    # and the statistics are reduced in a fixed order, so the result is bit-identical
+    y2 = torch.zeros_like(y)
+    ops.run(ops.gn_desc(x0=x0, x1=x1, c0=c0, c1=c1, batch=B, hw=hw, groups=groups, gamma=gamma, beta=beta,
+                        eps=1e-5, silu=silu, stats=stats, y=y2, stats_prezeroed=True))
+    torch.cuda.synchronize()
+    assert torch.equal(y, y2)
 
 
 @pytest.mark.parametrize("rows,c", [(4096, 320), (1000, 640), (77, 1280), (5, 32), (64, 128)])
@@ -324,7 +332,6 @@ def test_program_and_graph(ops):
     g = torch.Generator(device="cuda").manual_seed(2)
     x = torch.randn(nb, h, w, c, device=_dev(), generator=g).to(BF16)
     gamma = torch.ones(c, device=_dev()); beta = torch.zeros(c, device=_dev())
-    stats = torch.zeros(nb, 32, 2, device=_dev())
     xn = torch.zeros_like(x)
     wt = (torch.randn(c, c, 3, 3, device=_dev(), generator=g) / math.sqrt(9 * c)).to(BF16)
     wp = ops.pack_conv3x3_weight(wt.float())
@@ -334,7 +341,7 @@ def test_program_and_graph(ops):
     with torch.cuda.stream(s):
         prog = ops.Program()
         prog.add(ops.gn_desc(x0=x, x1=None, c0=c, c1=0, batch=nb, hw=h * w, groups=32, gamma=gamma, beta=beta,
-                             eps=1e-5, silu=True, stats=stats, y=xn))
+                             eps=1e-5, silu=True, y=xn))
         prog.add(ops.gemm_desc(a0=xn, w=wp, out=y, N_=c, a_mode=nat.PP_A_CONV3X3, c0=c, nb=nb, h=h, w_=w))
         prog.add_layer_norm(y, z, gamma, beta, nb * h * w, c, 1e-5)
         assert prog.num_ops == 3 and prog.num_launches == 4
@@ -345,10 +352,8 @@ def test_program_and_graph(ops):
         prog.build_graph()
         prog.launch()
         s.synchronize()
-    # replay == plain launches. Not bit-for-bit: the GroupNorm statistics are accumulated with fp32 atomics,
-    # whose order differs from run to run, so the last bit of a statistic (and then of a few bf16 outputs)
-    # may differ between ANY two runs; everything downstream of the statistics is deterministic.
-    assert _rel(z, z1) < 2e-3
+    # replay == plain launches, bit for bit (the GroupNorm statistics are reduced in a fixed order)
+    assert torch.equal(z, z1)
     ref = F.silu(F.group_norm(x.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)).to(BF16).float()
     ref = F.conv2d(ref, wt.float(), None, padding=1).to(BF16).float().permute(0, 2, 3, 1)
     ref = F.layer_norm(ref, (c,), gamma, beta, 1e-5)
