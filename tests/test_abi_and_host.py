@@ -49,6 +49,19 @@ def test_invalid_descriptors_fail_loudly_without_gpu():
         N.check(1, "x")
 
 
+def test_group_norm_scratch_size_is_a_pure_host_query():
+    from powerpaint_b200 import ops
+
+    # stats [batch, groups, 2] + ticket counters + one partial per (sample, block): always larger than the
+    # statistics alone, 16-byte granular offsets, bounded (~1200 blocks over the machine) for any shape
+    for batch, hw, c, groups in [(16, 4096, 320, 32), (16, 64, 1280, 32), (2, 4, 64, 8), (1, 16384, 2560, 32)]:
+        n = ops.gn_scratch_bytes(batch, hw, c, groups)
+        assert n > batch * groups * 2 * 4 and n % 4 == 0
+        assert n <= batch * groups * 8 + 64 + (148 * 8 + 2 * batch) * groups * 8
+    with pytest.raises(ValueError):
+        ops.gn_scratch_bytes(2, 64, 30, 5)  # channels not a multiple of 8
+
+
 def test_weight_packing():
     from powerpaint_b200 import ops
 
