@@ -237,8 +237,6 @@ class StableDiffusionInpaintPipeline:
             raise NotImplementedError("cross_attention_kwargs (LoRA scale) is outside the PowerPaint hot path")
         if task_class is not None:
             raise NotImplementedError("task_class needs the class-conditioned UNet, not part of the released models")
-        if strength != 1.0:
-            raise NotImplementedError("strength < 1 (SURVEY.md §8f rank 4) is not built yet")
         if prompt is not None and isinstance(prompt, str):
             batch_size = 1
         elif prompt is not None and isinstance(prompt, list):
@@ -263,9 +261,14 @@ class StableDiffusionInpaintPipeline:
             raise ValueError(f"The unet {self.unet.__class__} should have 9 input channels (inpainting checkpoint), "
                              f"not {num_channels_unet}; the 4-channel blend path (:1025-1035) is not built")
         total = batch_size * num_images_per_prompt
+        # strength < 1 (ref:pipeline_PowerPaint.py:916-941): start part-way down the schedule from the encoded
+        # image noised to the first kept timestep; the fused loop just sees a shorter timestep / coefficient table
+        latent_timestep = timesteps[:1].repeat(total)
+        is_strength_max = strength == 1.0
         latents, noise = self.prepare_latents(total, num_channels_latents, height, width, torch.float32, device,
-                                              generator, latents, image=init_image, timestep=None,
-                                              is_strength_max=True, return_noise=True, return_image_latents=False)
+                                              generator, latents, image=init_image, timestep=latent_timestep,
+                                              is_strength_max=is_strength_max, return_noise=True,
+                                              return_image_latents=False)
         mask, masked_image_latents = self.prepare_mask_latents(mask, masked_image, total, height, width, torch.float32,
                                                                device, generator, do_cfg)
         if num_channels_latents + mask.shape[1] + masked_image_latents.shape[1] != num_channels_unet:

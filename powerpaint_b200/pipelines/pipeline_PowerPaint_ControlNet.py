@@ -67,8 +67,6 @@ class StableDiffusionControlNetInpaintPipeline(StableDiffusionInpaintPipeline):
             raise NotImplementedError("guess_mode is outside the hot path")
         if cross_attention_kwargs:
             raise NotImplementedError("cross_attention_kwargs (LoRA scale) is outside the hot path")
-        if strength != 1.0:
-            raise NotImplementedError("strength < 1 is not built yet")
         if isinstance(controlnet_conditioning_scale, list):
             controlnet_conditioning_scale = controlnet_conditioning_scale[0]
         if not isinstance(control_guidance_start, list):
@@ -101,9 +99,17 @@ class StableDiffusionControlNetInpaintPipeline(StableDiffusionInpaintPipeline):
         timesteps, num_inference_steps = self.get_timesteps(num_inference_steps, strength, device)
         if self.unet.config.in_channels != 9:
             raise ValueError("the ControlNet inpainting path expects the 9-channel inpainting UNet")
+        if num_inference_steps < 1:
+            raise ValueError(f"After adjusting the num_inference_steps by strength parameter: {strength}, the number "
+                             f"of pipeline steps is {num_inference_steps} which is < 1 and not appropriate for this "
+                             "pipeline.")
+        # strength < 1 (ref:pipeline_PowerPaint_ControlNet.py:1603-1625): noised image latents, shorter schedule
+        latent_timestep = timesteps[:1].repeat(total)
+        is_strength_max = strength == 1.0
         latents, noise = self.prepare_latents(total, self.vae.config.latent_channels, height, width, torch.float32,
-                                              device, generator, latents, image=init_image, timestep=None,
-                                              is_strength_max=True, return_noise=True, return_image_latents=False)
+                                              device, generator, latents, image=init_image,
+                                              timestep=latent_timestep, is_strength_max=is_strength_max,
+                                              return_noise=True, return_image_latents=False)
         mask, masked_image_latents = self.prepare_mask_latents(mask, masked_image, total, height, width, torch.float32,
                                                                device, generator, do_cfg)
         extra_step_kwargs = self.prepare_extra_step_kwargs(generator, eta)

@@ -192,6 +192,55 @@ def test_pipeline_v1_call_tiny():
         pipe(image=img, mask=mask, height=H, width=H)
 
 
+def test_pipeline_v1_strength_below_one_tiny():
+    """strength < 1 (ref:pipeline_PowerPaint.py:713-720,916-941): the loop starts part-way down the schedule
+    from the VAE-encoded image noised to the first kept timestep"""
+    from oracle.ddim import DDIMOracle
+    from oracle.pipelines import loop_v1
+    from powerpaint_b200.models.autoencoder_kl import AutoencoderKL
+    from powerpaint_b200.pipelines import StableDiffusionInpaintPipeline
+    from powerpaint_b200.pipelines.common import prepare_mask_and_masked_image, randn_tensor, vae_encode
+    from powerpaint_b200.schedulers import DDIMScheduler
+
+    nets = _nets(9, [("unet", 9, 1234)])
+    om, pm, o = nets["unet"]
+    vae = AutoencoderKL.synthetic(tiny=True).to(DEV)
+    pipe = StableDiffusionInpaintPipeline(vae=vae, text_encoder=None, tokenizer=None, unet=pm,
+                                          scheduler=DDIMScheduler(), safety_checker=None)
+    B, H = 2, 128
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(B, 3, H, H, generator=g) * 2 - 1
+    mask = torch.zeros(B, 1, H, H)
+    mask[:, :, 16:80, 40:120] = 1
+    pe = torch.randn(B, 77, o.cross_attention_dim, generator=g) * 0.5
+    ne = torch.randn(B, 77, o.cross_attention_dim, generator=g) * 0.5
+    steps, strength = 10, 0.5
+    out = pipe(image=img, mask=mask, prompt_embeds=pe, negative_prompt_embeds=ne, height=H, width=H,
+               strength=strength, num_inference_steps=steps, guidance_scale=7.5,
+               generator=torch.Generator().manual_seed(21), output_type="latent", return_dict=False)[0]
+    assert out.shape == (B, 4, H // 8, H // 8)
+    # the same host-side preparation in the reference's order (image latents, noise, masked-image latents)
+    gen = torch.Generator().manual_seed(21)
+    m, mi, init = prepare_mask_and_masked_image(img, mask, H, H, return_image=True)
+    so, sp = DDIMOracle(), DDIMScheduler()
+    so.set_timesteps(steps)
+    sp.set_timesteps(steps)
+    t_start = steps - min(int(steps * strength), steps)
+    assert t_start == 5
+    so.timesteps = so.timesteps[t_start:]
+    image_latents = vae_encode(vae, init.to(DEV), gen)
+    noise = randn_tensor((B, 4, H // 8, H // 8), generator=gen, device=DEV, dtype=torch.float32)
+    lat = sp.add_noise(image_latents, noise, sp.timesteps[t_start:t_start + 1].repeat(B))
+    m_l = torch.nn.functional.interpolate(m, size=(H // 8, H // 8)).to(DEV)
+    ml = vae_encode(vae, mi.to(DEV), gen)
+    ref = loop_v1(om, so, lat, torch.cat([ne, pe]).to(DEV), m_l, ml, 7.5)
+    assert _rel(out, ref) < 5e-2 and _cos(out, ref) > 0.998, (_rel(out, ref), _cos(out, ref))
+    # strength so small that no step is left: reference error
+    with pytest.raises(ValueError):
+        pipe(image=img, mask=mask, prompt_embeds=pe, negative_prompt_embeds=ne, height=H, width=H, strength=0.05,
+             num_inference_steps=steps)
+
+
 def test_pipeline_brushnet_call_tiny():
     from oracle.ddim import DDIMOracle
     from oracle.pipelines import loop_brushnet

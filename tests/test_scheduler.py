@@ -63,3 +63,35 @@ def test_config_surface_and_errors():
     x0, n = torch.ones(2, 4, 2, 2), torch.zeros(2, 4, 2, 2)
     out = s.add_noise(x0, n, torch.tensor([0, 999]))
     assert torch.allclose(out[0], x0[0] * float(s.alphas_cumprod[0]) ** 0.5)
+
+
+def test_strength_subset_of_the_schedule_matches_oracle():
+    """strength < 1 keeps the LAST int(n * strength) timesteps (ref:pipeline_PowerPaint.py:713-720); the
+    coefficient rows for that suffix must drive the same trajectory as the oracle's DDIM step"""
+    from powerpaint_b200.pipelines.pipeline_PowerPaint import StableDiffusionInpaintPipeline as P
+
+    sp, so = DDIMScheduler(), DDIMOracle()
+    sp.set_timesteps(20)
+    so.set_timesteps(20)
+
+    class _Stub:  # get_timesteps only touches self.scheduler
+        scheduler = sp
+
+    ts, n = P.get_timesteps(_Stub(), 20, 0.35, "cpu")
+    assert n == 7 and ts.tolist() == sp.timesteps[13:].tolist() == list(range(301, 0, -50))
+    ts1, n1 = P.get_timesteps(_Stub(), 20, 1.0, "cpu")
+    assert n1 == 20 and ts1.tolist() == sp.timesteps.tolist()
+    ts0, n0 = P.get_timesteps(_Stub(), 20, 0.01, "cpu")
+    assert n0 == 0 and len(ts0) == 0
+    g = torch.Generator().manual_seed(1)
+    x0, nz, eps = (torch.randn(2, 4, 8, 8, generator=g, dtype=torch.float64) for _ in range(3))
+    # initial latents: image latents noised to the first kept timestep (scheduler.add_noise == oracle.add_noise)
+    x = sp.add_noise(x0, nz, ts[:1].repeat(2))
+    assert torch.allclose(x, so.add_noise(x0, nz, ts[:1].repeat(2)))
+    coef = sp.step_coefficients(ts).double()
+    ref = x.clone()
+    for i, t in enumerate(ts.tolist()):
+        sa, s1a, sap, dirc, _ = coef[i, :5]
+        x = sap * ((x - s1a * eps) / sa) + dirc * eps
+        ref = so.step(eps, t, ref)
+    assert torch.allclose(x, ref, atol=1e-5)
