@@ -90,3 +90,161 @@ def test_v1_call_host_side_matches_oracle_loop(strength, steps, kept):
     ml = vae_encode(vae, mi, gen)
     ref = loop_v1(om, so, lat, torch.cat([ne, pe]), m_l, ml, 7.5)
     assert torch.allclose(out, ref, atol=2e-4, rtol=1e-4), (out - ref).abs().max()
+
+
+class _ControlNetCoefficientDenoiser:
+    """stand-in for FusedDenoiser(mode="controlnet").run: oracle ControlNet + UNet, coefficient-row DDIM"""
+
+    def __init__(self, unet, controlnet):
+        self.unet, self.controlnet = unet, controlnet
+
+    @torch.no_grad()
+    def run(self, *, latents, prompt_embeds, side_prompt_embeds, control_image, timesteps, coef, guidance_scale,
+            extra, side_scale, noise_fn=None, callback=None):
+        do_cfg = guidance_scale > 1.0
+        for i, t in enumerate(timesteps):
+            x4 = torch.cat([latents] * 2) if do_cfg else latents
+            ex = torch.cat([extra] * 2) if do_cfg else extra
+            d, m = self.controlnet(x4, int(t), side_prompt_embeds, control_image, side_scale)
+            eps = self.unet(torch.cat([x4, ex], dim=1), int(t), prompt_embeds, down_block_additional_residuals=d,
+                            mid_block_additional_residual=m)
+            if do_cfg:
+                u, c = eps.chunk(2)
+                eps = u + guidance_scale * (c - u)
+            sa, s1a, sap, dirc, _ = [float(v) for v in coef[i, :5]]
+            latents = sap * ((latents - s1a * eps) / sa) + dirc * eps
+        return latents
+
+
+@pytest.mark.parametrize("strength,steps,kept", [(1.0, 3, 3), (0.5, 6, 3)])
+def test_controlnet_call_host_side_matches_oracle_loop(strength, steps, kept):
+    from oracle.pipelines import loop_controlnet
+    from oracle.unet import ControlNetOracle
+    from powerpaint_b200.engine import NetConfig
+    from powerpaint_b200.models import ControlNetModel, UNet2DConditionModel, synthetic_state_dict
+    from powerpaint_b200.models.autoencoder_kl import AutoencoderKL
+    from powerpaint_b200.pipelines import StableDiffusionControlNetInpaintPipeline
+    from powerpaint_b200.pipelines.common import prepare_mask_and_masked_image, randn_tensor, vae_encode
+    from powerpaint_b200.schedulers import DDIMScheduler
+
+    o9, o4 = UNetConfig.tiny(9), UNetConfig.tiny(4)
+
+    def cfg(o, cin):
+        return NetConfig(in_channels=cin, block_out_channels=o.block_out_channels,
+                         attention_head_dim=o.attention_head_dim, cross_attention_dim=o.cross_attention_dim,
+                         norm_num_groups=o.norm_num_groups)
+
+    sd_u, sd_c = synthetic_state_dict(cfg(o9, 9), "unet", 5), synthetic_state_dict(cfg(o4, 4), "controlnet", 6)
+    ou, oc = UNet2DConditionOracle(o9), ControlNetOracle(o4)
+    ou.load_state_dict(sd_u)
+    oc.load_state_dict(sd_c)
+    ou.eval()
+    oc.eval()
+    vae = AutoencoderKL.synthetic(tiny=True)
+    pipe = StableDiffusionControlNetInpaintPipeline(
+        vae=vae, text_encoder=None, tokenizer=None, unet=UNet2DConditionModel.from_state_dict(cfg(o9, 9), sd_u),
+        controlnet=ControlNetModel.from_state_dict(cfg(o4, 4), sd_c), scheduler=DDIMScheduler())
+    fake = _ControlNetCoefficientDenoiser(ou, oc)
+    pipe.denoiser = lambda: fake
+    B, H = 1, 64
+    g = torch.Generator().manual_seed(2)
+    img = torch.rand(B, 3, H, H, generator=g) * 2 - 1
+    ctl = torch.rand(B, 3, H, H, generator=g)
+    mask = torch.zeros(B, 1, H, H)
+    mask[:, :, 16:48, 8:40] = 1
+    pe = torch.randn(B, 77, o9.cross_attention_dim, generator=g) * 0.5
+    ne = torch.randn(B, 77, o9.cross_attention_dim, generator=g) * 0.5
+    out = pipe(image=img, mask=mask, control_image=ctl, prompt_embeds=pe, negative_prompt_embeds=ne, height=H, width=H,
+               strength=strength, num_inference_steps=steps, guidance_scale=5.0, controlnet_conditioning_scale=0.5,
+               generator=torch.Generator().manual_seed(8), output_type="latent", return_dict=False)[0]
+    gen = torch.Generator().manual_seed(8)
+    m, mi, init = prepare_mask_and_masked_image(img, mask, H, H, return_image=True)
+    so, sp = DDIMOracle(), DDIMScheduler()
+    so.set_timesteps(steps)
+    sp.set_timesteps(steps)
+    t_start = steps - kept
+    so.timesteps = so.timesteps[t_start:]
+    if strength == 1.0:
+        lat = randn_tensor((B, 4, H // 8, H // 8), generator=gen, device="cpu", dtype=torch.float32)
+    else:
+        image_latents = vae_encode(vae, init, gen)
+        noise = randn_tensor((B, 4, H // 8, H // 8), generator=gen, device="cpu", dtype=torch.float32)
+        lat = sp.add_noise(image_latents, noise, sp.timesteps[t_start:t_start + 1].repeat(B))
+    m_l = torch.nn.functional.interpolate(m, size=(H // 8, H // 8))
+    ml = vae_encode(vae, mi, gen)
+    ref = loop_controlnet(ou, oc, so, lat, torch.cat([ne, pe]), m_l, ml, torch.cat([ctl] * 2), 5.0, 0.5)
+    assert torch.allclose(out, ref, atol=2e-4, rtol=1e-4), (out - ref).abs().max()
+
+
+class _BrushNetCoefficientDenoiser:
+    """stand-in for FusedDenoiser(mode="brushnet").run: oracle BrushNet + UNet, coefficient-row DDIM"""
+
+    def __init__(self, unet, brushnet):
+        self.unet, self.brushnet = unet, brushnet
+
+    @torch.no_grad()
+    def run(self, *, latents, prompt_embeds, side_prompt_embeds, timesteps, coef, guidance_scale, extra, side_scale,
+            noise_fn=None, callback=None):
+        do_cfg = guidance_scale > 1.0
+        for i, t in enumerate(timesteps):
+            x = torch.cat([latents] * 2) if do_cfg else latents
+            d, m, u = self.brushnet(x, int(t), side_prompt_embeds, extra, side_scale)
+            eps = self.unet(x, int(t), prompt_embeds, down_block_add_samples=d, mid_block_add_sample=m,
+                            up_block_add_samples=u)
+            if do_cfg:
+                a, c = eps.chunk(2)
+                eps = a + guidance_scale * (c - a)
+            sa, s1a, sap, dirc, _ = [float(v) for v in coef[i, :5]]
+            latents = sap * ((latents - s1a * eps) / sa) + dirc * eps
+        return latents
+
+
+def test_brushnet_call_host_side_matches_oracle_loop():
+    from oracle.pipelines import loop_brushnet
+    from oracle.unet import BrushNetOracle
+    from powerpaint_b200.engine import NetConfig
+    from powerpaint_b200.models import BrushNetModel, UNet2DConditionModel, synthetic_state_dict
+    from powerpaint_b200.models.autoencoder_kl import AutoencoderKL
+    from powerpaint_b200.pipelines import StableDiffusionPowerPaintBrushNetPipeline
+    from powerpaint_b200.pipelines.common import randn_tensor
+    from powerpaint_b200.schedulers import DDIMScheduler
+
+    o = UNetConfig.tiny(4)
+    n = NetConfig(in_channels=4, block_out_channels=o.block_out_channels, attention_head_dim=o.attention_head_dim,
+                  cross_attention_dim=o.cross_attention_dim, norm_num_groups=o.norm_num_groups)
+    sd_u, sd_b = synthetic_state_dict(n, "unet", 11), synthetic_state_dict(n, "brushnet", 12)
+    ou, ob = UNet2DConditionOracle(o), BrushNetOracle(o)
+    ou.load_state_dict(sd_u)
+    ob.load_state_dict(sd_b)
+    ou.eval()
+    ob.eval()
+    vae = AutoencoderKL.synthetic(tiny=True)
+    pipe = StableDiffusionPowerPaintBrushNetPipeline(
+        vae=vae, text_encoder=None, text_encoder_brushnet=None, tokenizer=None,
+        unet=UNet2DConditionModel.from_state_dict(n, sd_u), brushnet=BrushNetModel.from_state_dict(n, sd_b),
+        scheduler=DDIMScheduler(), safety_checker=None)
+    fake = _BrushNetCoefficientDenoiser(ou, ob)
+    pipe.denoiser = lambda: fake
+    B, H, steps = 1, 64, 3
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(B, 3, H, H, generator=g) * 2 - 1
+    mask = torch.ones(B, 3, H, H)
+    mask[:, :, 16:48, 16:48] = -1.0  # preprocessed mask: sum over channels < 0 -> 1
+    pe = torch.randn(B, 77, o.cross_attention_dim, generator=g) * 0.5
+    ne = torch.randn(B, 77, o.cross_attention_dim, generator=g) * 0.5
+    peU = torch.randn(2 * B, 77, o.cross_attention_dim, generator=g) * 0.5
+    torch.manual_seed(123)  # the conditioning latents use the GLOBAL RNG like the reference
+    out = pipe(image=img, mask=mask, prompt_embeds=pe, negative_prompt_embeds=ne, prompt_embedsU=peU, height=H,
+               width=H, num_inference_steps=steps, guidance_scale=7.5, brushnet_conditioning_scale=1.0,
+               generator=torch.Generator().manual_seed(9), output_type="latent", return_dict=False)[0]
+    image_t = torch.cat([img] * 2)
+    original_mask = (torch.cat([mask] * 2).sum(1)[:, None] < 0).float()
+    lat = randn_tensor((B, 4, H // 8, H // 8), generator=torch.Generator().manual_seed(9), device="cpu",
+                       dtype=torch.float32)
+    torch.manual_seed(123)
+    cl = vae.encode(image_t).latent_dist.sample() * vae.config.scaling_factor
+    cond = torch.cat([cl, torch.nn.functional.interpolate(original_mask, size=cl.shape[-2:])], 1)
+    so = DDIMOracle()
+    so.set_timesteps(steps)
+    ref = loop_brushnet(ou, ob, so, lat, torch.cat([ne, pe]), peU, cond, 7.5, 1.0)
+    assert torch.allclose(out, ref, atol=2e-4, rtol=1e-4), (out - ref).abs().max()
