@@ -10,7 +10,7 @@ this path and the reference modules cannot be imported here (diffusers absent).
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
 import torch

@@ -11,7 +11,7 @@ diffusers ControlNetModel.
 from __future__ import annotations
 
 from collections import OrderedDict
-from typing import Dict, Tuple
+from typing import Dict
 
 import torch
 
