@@ -1,9 +1,9 @@
 """Per-step device time of the fused denoising program for the BASELINE.json configs on ONE GPU
-(per-GPU share of each config), plus the torch-eager bf16 restatement of the reference dataflow
-(oracle modules run on the GPU in bf16: cuDNN / cuBLAS / SDPA — the library path the reference reaches
-through diffusers) for C2. Developer/profile script, not the judged bench.
+(per-GPU share of each config). Developer/profile script, not the judged bench. The torch-eager bf16
+comparison point lives in tests/measure_torch_eager_bf16.py (it runs the oracle modules, which only test
+infrastructure may import).
 
-    python profiles/bench_configs.py [c2 c3 c4 c5 eager]
+    python profiles/bench_configs.py [c2 c3 c4 c5]
 """
 import sys
 import time
@@ -17,7 +17,7 @@ from powerpaint_b200.models import BrushNetModel, ControlNetModel, UNet2DConditi
 from powerpaint_b200.schedulers import DDIMScheduler  # noqa: E402
 
 dev = torch.device("cuda:0")
-which = set(sys.argv[1:]) or {"c2", "c3", "c4", "c5", "eager"}
+which = set(sys.argv[1:]) or {"c2", "c3", "c4", "c5"}
 sched = DDIMScheduler()
 sched.set_timesteps(50)
 coef = sched.step_coefficients()
@@ -69,22 +69,3 @@ if "c3" in which:
           dict(latents=lat, prompt_embeds=emb, side_prompt_embeds=emb, timesteps=sched.timesteps, coef=coef,
                guidance_scale=7.5, extra=torch.cat([extra, extra]), side_scale=1.0), 4,
           "C3 v2 BrushNet 4x512^2 per GPU (batch 8 + 8)", 8 * (FL[64] + 0.8262e12))
-if "eager" in which:
-    from oracle.unet import UNet2DConditionOracle, UNetConfig, init_synthetic_
-
-    om = init_synthetic_(UNet2DConditionOracle(UNetConfig.sd15(9))).to(dev).to(torch.bfloat16).eval()
-    x = torch.randn(16, 9, 64, 64, device=dev, dtype=torch.bfloat16)
-    ctx = torch.randn(16, 77, 768, device=dev, dtype=torch.bfloat16)
-    with torch.no_grad():
-        for _ in range(3):
-            om(x, 500, ctx)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10):
-            om(x, 500, ctx)
-        e1.record()
-        torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
-    print(f"torch_eager_restatement (oracle modules, bf16, cuDNN/cuBLAS/SDPA) C2 UNet forward batch 16: {ms:.2f} ms "
-          f"= {16 * FL[64] / (ms / 1e3) / 1e12:.0f} TFLOP/s", flush=True)
