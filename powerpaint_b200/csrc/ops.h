@@ -74,7 +74,8 @@ struct AttnLaunch {
     dim3 grid;
     size_t smem;
     int kv_stages;
-    int variant;  // d_chunks (1, 2 or 3)
+    int variant;  // 1..3: single-tile kernel with that many 64-channel chunks; 10 / 11 / 12: dual-tile
+                  // attn2_kernel<3,1,4> / <2,1,4> / <2,2,2> (attention2.cuh)
 };
 int attn_prepare(const pp_attn_desc& d, AttnLaunch* out);
 int attn_launch(const AttnLaunch& l, cudaStream_t s);
