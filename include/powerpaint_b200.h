@@ -59,14 +59,30 @@ int pp_device_supported(void);
 enum {
     PP_A_MATRIX = 0,    /* A is [M, K] row-major (a Linear or 1x1 conv over tokens) */
     PP_A_CONV3X3 = 1,   /* implicit GEMM, 3x3 stride 1 pad 1 over NHWC [nb, h, w, c] */
-    PP_A_CONV3X3_S2 = 2 /* implicit GEMM, 3x3 stride 2 pad 1 (Downsample2D); h, w even */
+    PP_A_CONV3X3_S2 = 2,  /* implicit GEMM, 3x3 stride 2 pad 1 (Downsample2D); output ceil(h/2) x ceil(w/2) */
+    PP_A_CONV3X3_S2P0 = 3 /* 3x3 stride 2 over F.pad(x, (0,1,0,1)) (the VAE encoder's Downsample2D(padding=0));
+                             output floor(h/2) x floor(w/2) */
 };
 enum {
     PP_EPI_PLAIN = 0,
     PP_EPI_GEGLU = 1,      /* out[:, j] = (acc_a + bias_a) * gelu(acc_g + bias_g); weights tile-interleaved */
     PP_EPI_TRANSPOSED = 2  /* out[(m / t_rows) * N + n][m % t_rows], row pitch t_ld (V^T for attention) */
 };
-enum { PP_ACT_NONE = 0, PP_ACT_SILU = 1 };
+enum { PP_ACT_NONE = 0, PP_ACT_SILU = 1, PP_ACT_QUICK_GELU = 2 /* x * sigmoid(1.702 x): CLIP text encoder MLP */ };
+
+/* Geometry of the per-channel GroupNorm partial sums a GEMM / conv can emit from its epilogue
+   (pp_gemm_desc.chan_stats) and pp_group_norm consumes (pp_gn_desc.part0 / part1): one {sum, sum of
+   squares} pair per (m-tile, sample segment of the tile, output channel), fp32,
+   laid out [m_tiles][segs][N][2]. Filled by pp_gemm_stats_geometry(). */
+typedef struct pp_stats_geom {
+    int32_t supported;   /* 0: this GEMM cannot emit statistics (the consumer runs its own statistics pass) */
+    int32_t channels;    /* N */
+    int32_t segs;        /* samples per m-tile */
+    int32_t seg_rows;    /* rows of one sample inside an m-tile */
+    int32_t tiles_per_group; /* m-tiles that cover one group of `segs` samples */
+    int32_t tiles_x, tiles_y, bw, bh, wo, ho; /* pixel-tile geometry (matrix mode: a 1-D strip) */
+    int64_t bytes;       /* size of the partials buffer */
+} pp_stats_geom;
 
 typedef struct pp_gemm_desc {
     int32_t a_mode;
@@ -102,9 +118,20 @@ typedef struct pp_gemm_desc {
     int64_t t_ld;
     int32_t block_n;  /* 0 = auto, else one of 64/128/160/256 */
     int32_t t_fp16;   /* PP_EPI_TRANSPOSED: store fp16 instead of bf16 (V^T for pp_attention) */
+    /* alpha is multiplied by alpha_dev[(alpha_step ? *alpha_step : 0) * alpha_stride] when alpha_dev != NULL:
+       the BrushNet / ControlNet conditioning scale x per-step keep flag lives in a device table, so one
+       recorded program serves every scale (Brushnet_CA.py:1369-1376,1403-1409; ControlNet.py:1652-1658) */
+    const float* alpha_dev;
+    const int32_t* alpha_step;
+    int32_t alpha_stride;
+    /* optional GroupNorm partial sums of the stored output (bf16 row-major outputs only), see pp_stats_geom;
+       rows_per_group must hold the rows per sample in PP_A_MATRIX mode */
+    float* chan_stats;
 } pp_gemm_desc;
 
 pp_status pp_gemm_conv(const pp_gemm_desc* d, pp_stream stream);
+/* host-only query: can this GEMM emit GroupNorm partial sums, and with which layout */
+pp_status pp_gemm_stats_geometry(const pp_gemm_desc* d, pp_stats_geom* out);
 
 /* ------------------------------------------------------------------ attention */
 typedef struct pp_attn_desc {
@@ -142,6 +169,14 @@ typedef struct pp_gn_desc {
     int32_t stats_prezeroed; /* 1: the scratch was zeroed once when it was allocated (every call leaves its
                                 ticket counters zero again) or by one memset per step over all scratch;
                                 0: the call clears its ticket counters with a memset of its own */
+    /* from_partials != 0: the statistics pass is replaced by a small finalize kernel that folds the
+       per-tile channel sums the producing GEMMs emitted (part0 for x0, part1 for x1) into
+       (mean, rstd) per (sample, group) — Chan's parallel combination in fp64, fixed order. `stats` then
+       only needs batch * groups * 2 floats. */
+    int32_t from_partials;
+    const float* part0;
+    const float* part1;
+    pp_stats_geom geom0, geom1;
 } pp_gn_desc;
 pp_status pp_group_norm(const pp_gn_desc* d, pp_stream stream);
 /* bytes of `stats` scratch a GroupNorm over [batch, hw, channels] with `groups` groups needs (0: invalid) */
@@ -154,6 +189,10 @@ pp_status pp_layer_norm(const void* x, void* y, const float* gamma, const float*
 /* nearest 2x upsample of NHWC bf16 [nb,h,w,c] -> [nb,2h,2w,c] */
 pp_status pp_upsample2x(const void* x, void* y, int32_t nb, int32_t h, int32_t w, int32_t c,
                         pp_stream stream);
+/* F.interpolate(x, size=(ho, wo), mode="nearest") on NHWC bf16 — Upsample2D with an explicit output size
+   (unet_2d_condition.py:1120-1126,1311-1312: latent sizes that are not multiples of 8) */
+pp_status pp_upsample_nearest(const void* x, void* y, int32_t nb, int32_t h, int32_t w, int32_t c,
+                              int32_t ho, int32_t wo, pp_stream stream);
 /* y = a + b (bf16, n elements, n % 8 == 0) — ControlNet skip residuals */
 pp_status pp_add(const void* a, const void* b, void* y, int64_t n, pp_stream stream);
 /* sinusoidal timestep embedding [batch, dim] bf16: cat(cos, sin) (flip_sin_to_cos=True, shift 0).
@@ -211,6 +250,8 @@ pp_status pp_program_add_layer_norm(pp_program* p, const void* x, void* y, const
                                     const float* beta, int32_t rows, int32_t c, float eps);
 pp_status pp_program_add_upsample2x(pp_program* p, const void* x, void* y, int32_t nb, int32_t h,
                                     int32_t w, int32_t c);
+pp_status pp_program_add_upsample_nearest(pp_program* p, const void* x, void* y, int32_t nb, int32_t h,
+                                          int32_t w, int32_t c, int32_t ho, int32_t wo);
 pp_status pp_program_add_add(pp_program* p, const void* a, const void* b, void* y, int64_t n);
 pp_status pp_program_add_time_embed(pp_program* p, const float* timesteps,
                                     const int32_t* step_idx, void* out, int32_t batch, int32_t dim);

@@ -41,12 +41,15 @@ def loop_v1(unet, sched: DDIMOracle, latents, prompt_embeds, mask, masked_image_
 
 @torch.no_grad()
 def loop_brushnet(unet, brushnet, sched: DDIMOracle, latents, prompt_embeds_task, prompt_embeds_u,
-                  conditioning_latents, guidance_scale: float, conditioning_scale: float = 1.0, record=None):
-    """conditioning_latents [2B,5,h,w] (already duplicated for CFG like the reference, :949-950)"""
+                  conditioning_latents, guidance_scale: float, conditioning_scale: float = 1.0, record=None,
+                  keep=None):
+    """conditioning_latents [2B,5,h,w] (already duplicated for CFG like the reference, :949-950);
+    keep[i] = `brushnet_keep[i]` of the control_guidance window (:1369-1376, :1403-1409)"""
     do_cfg = guidance_scale > 1.0
     for i, t in enumerate(sched.timesteps):
         x = torch.cat([latents] * 2) if do_cfg else latents
-        d, m, u = brushnet(x, int(t), prompt_embeds_task, conditioning_latents, conditioning_scale)
+        cs = conditioning_scale * (keep[i] if keep is not None else 1.0)
+        d, m, u = brushnet(x, int(t), prompt_embeds_task, conditioning_latents, cs)
         eps = unet(x, int(t), prompt_embeds_u, down_block_add_samples=d, mid_block_add_sample=m,
                    up_block_add_samples=u)
         if do_cfg:
@@ -60,15 +63,17 @@ def loop_brushnet(unet, brushnet, sched: DDIMOracle, latents, prompt_embeds_task
 
 @torch.no_grad()
 def loop_controlnet(unet, controlnet, sched: DDIMOracle, latents, prompt_embeds, mask, masked_image_latents,
-                    control_image, guidance_scale: float, conditioning_scale: float = 0.5, record=None):
-    """control_image [2B,3,H,W] in [0,1] (duplicated for CFG, :855-856)"""
+                    control_image, guidance_scale: float, conditioning_scale: float = 0.5, record=None, keep=None):
+    """control_image [2B,3,H,W] in [0,1] (duplicated for CFG, :855-856); keep[i] = `controlnet_keep[i]`
+    (:1652-1658, :1682-1684)"""
     do_cfg = guidance_scale > 1.0
     if do_cfg:
         mask = torch.cat([mask] * 2)
         masked_image_latents = torch.cat([masked_image_latents] * 2)
     for i, t in enumerate(sched.timesteps):
         x4 = torch.cat([latents] * 2) if do_cfg else latents
-        d, m = controlnet(x4, int(t), prompt_embeds, control_image, conditioning_scale)
+        d, m = controlnet(x4, int(t), prompt_embeds, control_image,
+                          conditioning_scale * (keep[i] if keep is not None else 1.0))
         x9 = torch.cat([x4, mask, masked_image_latents], dim=1)
         eps = unet(x9, int(t), prompt_embeds, down_block_additional_residuals=d, mid_block_additional_residual=m)
         if do_cfg:

@@ -16,14 +16,23 @@ _LIB_PATH = Path(os.environ.get("PP_B200_LIB") or Path(__file__).resolve().paren
 _lib = None
 
 # enums (mirror include/powerpaint_b200.h)
-PP_A_MATRIX, PP_A_CONV3X3, PP_A_CONV3X3_S2 = 0, 1, 2
+PP_A_MATRIX, PP_A_CONV3X3, PP_A_CONV3X3_S2, PP_A_CONV3X3_S2P0 = 0, 1, 2, 3
 PP_EPI_PLAIN, PP_EPI_GEGLU, PP_EPI_TRANSPOSED = 0, 1, 2
-PP_ACT_NONE, PP_ACT_SILU = 0, 1
+PP_ACT_NONE, PP_ACT_SILU, PP_ACT_QUICK_GELU = 0, 1, 2
+ABI_VERSION = 2
 
 vp = C.c_void_p
 i32 = C.c_int32
 i64 = C.c_int64
 f32 = C.c_float
+
+
+class StatsGeom(C.Structure):
+    _fields_ = [
+        ("supported", i32), ("channels", i32), ("segs", i32), ("seg_rows", i32), ("tiles_per_group", i32),
+        ("tiles_x", i32), ("tiles_y", i32), ("bw", i32), ("bh", i32), ("wo", i32), ("ho", i32),
+        ("bytes", i64),
+    ]
 
 
 class GemmDesc(C.Structure):
@@ -42,6 +51,8 @@ class GemmDesc(C.Structure):
         ("out", vp), ("ldc", i64),
         ("out_fp32", i32), ("t_rows", i32), ("t_ld", i64),
         ("block_n", i32), ("t_fp16", i32),
+        ("alpha_dev", vp), ("alpha_step", vp), ("alpha_stride", i32),
+        ("chan_stats", vp),
     ]
 
 
@@ -61,6 +72,7 @@ class GnDesc(C.Structure):
         ("batch", i32), ("hw", i32), ("groups", i32),
         ("gamma", vp), ("beta", vp), ("eps", f32), ("silu", i32),
         ("stats", vp), ("y", vp), ("stats_prezeroed", i32),
+        ("from_partials", i32), ("part0", vp), ("part1", vp), ("geom0", StatsGeom), ("geom1", StatsGeom),
     ]
 
 
@@ -81,11 +93,13 @@ _SIGNATURES = {
     "pp_abi_version": (C.c_int, []),
     "pp_device_supported": (C.c_int, []),
     "pp_gemm_conv": (C.c_int, [C.POINTER(GemmDesc), vp]),
+    "pp_gemm_stats_geometry": (C.c_int, [C.POINTER(GemmDesc), C.POINTER(StatsGeom)]),
     "pp_attention": (C.c_int, [C.POINTER(AttnDesc), vp]),
     "pp_group_norm": (C.c_int, [C.POINTER(GnDesc), vp]),
     "pp_group_norm_scratch_bytes": (i64, [i32, i32, i32, i32]),
     "pp_layer_norm": (C.c_int, [vp, vp, vp, vp, i32, i32, f32, vp]),
     "pp_upsample2x": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
+    "pp_upsample_nearest": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "pp_add": (C.c_int, [vp, vp, vp, i64, vp]),
     "pp_time_embed": (C.c_int, [vp, vp, vp, i32, i32, vp]),
     "pp_nchw_to_nhwc": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
@@ -98,6 +112,7 @@ _SIGNATURES = {
     "pp_program_add_group_norm": (C.c_int, [vp, C.POINTER(GnDesc)]),
     "pp_program_add_layer_norm": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, f32]),
     "pp_program_add_upsample2x": (C.c_int, [vp, vp, vp, i32, i32, i32, i32]),
+    "pp_program_add_upsample_nearest": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, i32, i32]),
     "pp_program_add_add": (C.c_int, [vp, vp, vp, vp, i64]),
     "pp_program_add_time_embed": (C.c_int, [vp, vp, vp, vp, i32, i32]),
     "pp_program_add_cfg_ddim": (C.c_int, [vp, C.POINTER(CfgDdimDesc)]),
@@ -130,6 +145,9 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
+        if L.pp_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"{_LIB_PATH} has ABI version {L.pp_abi_version()}, this binding needs {ABI_VERSION}: "
+                               "rebuild with `python -m powerpaint_b200.build`")
         _lib = L
     return _lib
 
@@ -146,7 +164,8 @@ def ptr(t) -> int | None:
     return None if t is None else t.data_ptr()
 
 
-def current_stream() -> int:
+def current_stream(device=None) -> int:
+    """raw handle of torch's current stream on `device` (default: the current device)"""
     import torch
 
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream

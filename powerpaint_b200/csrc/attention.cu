@@ -310,23 +310,27 @@ namespace pp {
 // ---------------------------------------------------------------------------------
 template <int NBUF, int DCH, int S>
 static int attn2_ensure_attr() {
-    static bool done = false;
-    if (!done) {
+    static bool done[PP_MAX_DEVICES] = {};  // the attribute is per device
+    int dev = 0;
+    PP_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= PP_MAX_DEVICES || !done[dev]) {
         // largest V^T tile the variant can meet: dv <= 64 with three score buffers, else <= 128
         PP_CUDA_CHECK(cudaFuncSetAttribute(attn2_kernel<NBUF, DCH, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)att2_smem_bytes(NBUF == 3 ? 64 : 128, DCH, S)));
-        done = true;
+        if (dev >= 0 && dev < PP_MAX_DEVICES) done[dev] = true;
     }
     return PP_OK;
 }
 
 template <int DCH>
 static int attn_ensure_attr() {
-    static bool done = false;
-    if (!done) {
+    static bool done[PP_MAX_DEVICES] = {};  // the attribute is per device
+    int dev = 0;
+    PP_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= PP_MAX_DEVICES || !done[dev]) {
         PP_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)AttSmem<DCH>::TOTAL_MAX));
-        done = true;
+        if (dev >= 0 && dev < PP_MAX_DEVICES) done[dev] = true;
     }
     return PP_OK;
 }

@@ -338,6 +338,13 @@ __device__ __forceinline__ float silu_f(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
     return fmaf(h, t, h);
 }
+// CLIP's quick_gelu: x * sigmoid(1.702 x) = h + h * tanh(0.851 x), h = x / 2
+__device__ __forceinline__ float quick_gelu_f(float x) {
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+    return fmaf(h, t, h);
+}
 // exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below bf16
 // output resolution): 1 rcp + 1 ex2 + a degree-5 polynomial instead of libdevice erff.
 __device__ __forceinline__ float gelu_fast_f(float x) {
@@ -374,6 +381,8 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
 // host side
 // ----------------------------------------------------------------------------
 namespace pp {
+
+static constexpr int PP_MAX_DEVICES = 64;  // per-device "kernel attribute set" flags
 
 // status codes of the C ABI (see include/powerpaint_b200.h)
 enum : int { PP_OK = 0, PP_ERR_INVALID = 1, PP_ERR_CUDA = 2, PP_ERR_UNSUPPORTED = 3 };

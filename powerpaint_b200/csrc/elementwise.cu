@@ -18,8 +18,9 @@ namespace pp {
 //            masked_image_latents], dim=1)` (:990,:996).
 // The reference rounds to the model dtype after every elementwise op; here everything is
 // fp32 in registers and rounded once when the bf16 UNet input is written.
-// One thread per pixel: reads 2x4 eps + 4 latent values, writes 4 latents (+ n_copies*next_c).
-// Algorithmic bytes per pixel: eps 2*4*{2|4} + latents 2*16 (+ next_in n_copies*next_c*2).
+// One thread per pixel, everything as 16-byte (eps halves, latents) / 8-byte (next input) accesses, so a
+// warp touches contiguous 512 / 256-byte runs. Algorithmic bytes per pixel (CFG, fp32 eps): eps 2*16 +
+// latents read 16 + write 16 + next input 2*8 = 80 B (C2: 8 x 4096 px -> 2.6 MB per step).
 // ------------------------------------------------------------------------------------
 __global__ void cfg_ddim_kernel(pp_cfg_ddim_desc d) {
     pdl_wait();  // inputs come from the preceding kernel
@@ -30,10 +31,17 @@ __global__ void cfg_ddim_kernel(pp_cfg_ddim_desc d) {
     const float sa_t = cf[0], s1a_t = cf[1], sa_p = cf[2], dir_c = cf[3], sigma = cf[4];
     const float inv_sa_t = 1.0f / sa_t;
     const float gscale = d.guidance_from_coef ? cf[5] : d.guidance_scale;
+    const bool eps_vec = d.eps_fp32 && d.eps_ld == 4;  // the UNet's fp32 conv_out: one 16-byte load per half
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         float eu[4], ec[4];
-        if (d.eps_fp32) {
+        if (eps_vec) {
+            const float4* e = reinterpret_cast<const float4*>(d.eps);
+            const float4 u = __ldg(e + i);
+            const float4 c = __ldg(e + i + (d.do_cfg ? total : 0));
+            eu[0] = u.x; eu[1] = u.y; eu[2] = u.z; eu[3] = u.w;
+            ec[0] = c.x; ec[1] = c.y; ec[2] = c.z; ec[3] = c.w;
+        } else if (d.eps_fp32) {
             const float* e = reinterpret_cast<const float*>(d.eps);
             const float* pu = e + i * d.eps_ld;
             const float* pc = e + (i + (d.do_cfg ? total : 0)) * d.eps_ld;
@@ -63,20 +71,28 @@ __global__ void cfg_ddim_kernel(pp_cfg_ddim_desc d) {
         *reinterpret_cast<float4*>(d.latents + i * 4) = make_float4(xp[0], xp[1], xp[2], xp[3]);
         if (d.next_in) {
             __nv_bfloat16* ni = reinterpret_cast<__nv_bfloat16*>(d.next_in);
-            for (int cpy = 0; cpy < d.n_copies; ++cpy) {
-                __nv_bfloat16* o = ni + ((int64_t)cpy * total + i) * d.next_c;
-                for (int c = 0; c < d.next_c; ++c) {
-                    float v = 0.f;
-                    if (c < 4) v = xp[c];
-                    else if (c - 4 < d.extra_c)
-                        v = d.extra[((d.extra_per_copy ? (int64_t)cpy * total : 0) + i) * d.extra_c + (c - 4)];
-                    o[c] = __float2bfloat16_rn(v);
+            if (d.extra_c == 0) {
+                // the constant channels (mask, masked-image latents, ...) were written once before the loop
+                // and never change: only the 4 latent channels are refreshed, one 8-byte store per CFG half
+                const uint2 v = make_uint2(pack_bf16x2(xp[0], xp[1]), pack_bf16x2(xp[2], xp[3]));
+                for (int cpy = 0; cpy < d.n_copies; ++cpy)
+                    *reinterpret_cast<uint2*>(ni + ((int64_t)cpy * total + i) * d.next_c) = v;
+            } else {
+                for (int cpy = 0; cpy < d.n_copies; ++cpy) {
+                    __nv_bfloat16* o = ni + ((int64_t)cpy * total + i) * d.next_c;
+                    for (int c = 0; c < d.next_c; ++c) {
+                        float v = 0.f;
+                        if (c < 4) v = xp[c];
+                        else if (c - 4 < d.extra_c)
+                            v = d.extra[((d.extra_per_copy ? (int64_t)cpy * total : 0) + i) * d.extra_c + (c - 4)];
+                        o[c] = __float2bfloat16_rn(v);
+                    }
                 }
             }
         }
     }
-    // the last block to finish is not tracked; the step counter is advanced by a dedicated
-    // single-thread launch (cfg_ddim_advance_kernel) enqueued right after this kernel.
+    // the step counter is advanced by a dedicated single-thread launch (cfg_ddim_advance_kernel)
+    // enqueued right after this kernel.
 }
 
 __global__ void cfg_ddim_advance_kernel(int32_t* step_idx) {
@@ -94,6 +110,8 @@ int cfg_ddim_validate(const pp_cfg_ddim_desc& d) {
         PP_REQUIRE(d.next_c >= 4 && d.n_copies >= 1, "cfg_ddim: next_in needs next_c >= 4, n_copies >= 1");
         PP_REQUIRE(d.extra_c == 0 || d.extra, "cfg_ddim: extra_c without extra");
         PP_REQUIRE(4 + d.extra_c <= d.next_c, "cfg_ddim: next_c too small for 4 + extra_c");
+        PP_REQUIRE(d.next_c % 4 == 0 && (reinterpret_cast<uintptr_t>(d.next_in) & 7) == 0,
+                   "cfg_ddim: next_in needs next_c %% 4 == 0 and 8-byte alignment");
     }
     return PP_OK;
 }
@@ -145,31 +163,37 @@ int time_embed_launch(const float* timesteps, const int32_t* step_idx, void* out
 }
 
 // ------------------------------------------------------------------------------------
-// Upsample2D's F.interpolate(scale_factor=2.0, mode="nearest") on NHWC bf16.
+// Upsample2D's F.interpolate(mode="nearest") on NHWC bf16: scale_factor=2.0, or an explicit output
+// size when the latent is not a multiple of 8 (unet_2d_condition.py:1120-1126,1311-1312). Source index
+// as in PyTorch's nearest kernel: min(floor(dst * (float)in / out), in - 1).
 // ------------------------------------------------------------------------------------
-__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int nb, int h, int w,
-                                  int cv) {
+__global__ void upsample_nearest_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int nb, int h, int w,
+                                        int cv, int ho, int wo, float sy, float sx, int exact2x) {
     pdl_wait();  // inputs come from the preceding kernel
     pdl_launch_dependents();
-    const int64_t total = (int64_t)nb * (2 * h) * (2 * w) * cv;
+    const int64_t total = (int64_t)nb * ho * wo * cv;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % cv);
         int64_t p = i / cv;
-        const int ox = (int)(p % (2 * w)); p /= (2 * w);
-        const int oy = (int)(p % (2 * h));
-        const int n = (int)(p / (2 * h));
-        y[i] = __ldg(&x[(((int64_t)n * h + (oy >> 1)) * w + (ox >> 1)) * cv + c]);
+        const int ox = (int)(p % wo); p /= wo;
+        const int oy = (int)(p % ho);
+        const int n = (int)(p / ho);
+        const int iy = exact2x ? (oy >> 1) : min((int)floorf((float)oy * sy), h - 1);
+        const int ix = exact2x ? (ox >> 1) : min((int)floorf((float)ox * sx), w - 1);
+        y[i] = __ldg(&x[(((int64_t)n * h + iy) * w + ix) * cv + c]);
     }
 }
 
-int upsample2x_launch(const void* x, void* y, int nb, int h, int w, int c, cudaStream_t s) {
-    PP_REQUIRE(x && y, "upsample2x: null pointer");
-    PP_REQUIRE(nb > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "upsample2x: bad shape");
-    const int64_t total = (int64_t)nb * 4 * h * w * (c / 8);
+int upsample_nearest_launch(const void* x, void* y, int nb, int h, int w, int c, int ho, int wo, cudaStream_t s) {
+    PP_REQUIRE(x && y, "upsample: null pointer");
+    PP_REQUIRE(nb > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && ho > 0 && wo > 0, "upsample: bad shape");
+    const int64_t total = (int64_t)nb * ho * wo * (c / 8);
     const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
-    PP_CUDA_CHECK(launch(upsample2x_kernel, blocks, 256, 0, s, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), nb,
-                                             h, w, c / 8));
+    const int exact = (ho == 2 * h && wo == 2 * w) ? 1 : 0;
+    PP_CUDA_CHECK(launch(upsample_nearest_kernel, blocks, 256, 0, s, reinterpret_cast<const uint4*>(x),
+                         reinterpret_cast<uint4*>(y), nb, h, w, c / 8, ho, wo, (float)h / (float)ho,
+                         (float)w / (float)wo, exact));
     PP_CUDA_CHECK(cudaGetLastError());
     return PP_OK;
 }
@@ -272,7 +296,11 @@ int nhwc_to_nchw_launch(const void* x, int x_is_fp32, float* y, int nb, int c, i
 
 extern "C" {
 pp_status pp_upsample2x(const void* x, void* y, int32_t nb, int32_t h, int32_t w, int32_t c, pp_stream s) {
-    return pp::upsample2x_launch(x, y, nb, h, w, c, reinterpret_cast<cudaStream_t>(s));
+    return pp::upsample_nearest_launch(x, y, nb, h, w, c, 2 * h, 2 * w, reinterpret_cast<cudaStream_t>(s));
+}
+pp_status pp_upsample_nearest(const void* x, void* y, int32_t nb, int32_t h, int32_t w, int32_t c, int32_t ho,
+                              int32_t wo, pp_stream s) {
+    return pp::upsample_nearest_launch(x, y, nb, h, w, c, ho, wo, reinterpret_cast<cudaStream_t>(s));
 }
 pp_status pp_add(const void* a, const void* b, void* y, int64_t n, pp_stream s) {
     return pp::add_launch(a, b, y, n, reinterpret_cast<cudaStream_t>(s));

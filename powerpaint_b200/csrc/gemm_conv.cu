@@ -48,7 +48,58 @@ __host__ __device__ constexpr int tmem_cols_for(int n) {
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
-    return act == PP_ACT_SILU ? silu_f(v) : v;
+    return act == PP_ACT_SILU ? silu_f(v) : act == PP_ACT_QUICK_GELU ? quick_gelu_f(v) : v;
+}
+
+// effective alpha of a launch: the recorded constant times an optional device-side factor (the
+// per-step side-net scale, read through the device step counter so a captured graph stays valid)
+__device__ __forceinline__ float effective_alpha(const GemmKParams& p) {
+    float a = p.alpha;
+    if (p.alpha_dev) a *= __ldg(p.alpha_dev + (int64_t)(p.alpha_step ? *p.alpha_step : 0) * p.alpha_stride);
+    return a;
+}
+
+// Column sums of the staged output tile for the consumer's GroupNorm. L threads (consecutive lanes of a
+// warp) share one 8-channel piece and split the rows of a sample segment between them (row = l, l + L, ...:
+// conflict-free shared-memory reads); v[] holds {sum, sum of squares} interleaved per channel. A halving
+// butterfly leaves every lane with 16 / L of the 16 totals, in memory order, so the group stores one
+// contiguous 64-byte run.
+template <int L>
+__device__ __forceinline__ void stats_butterfly_store(const float (&v)[16], int l, float* dst, bool write) {
+    float a[8], b[4], c[2];
+    {
+        const bool hi = (l & (L / 2)) != 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float send = hi ? v[k] : v[k + 8], keep = hi ? v[k + 8] : v[k];
+            a[k] = keep + __shfl_xor_sync(0xffffffffu, send, L / 2);
+        }
+    }
+    {
+        const bool hi = (l & (L / 4)) != 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float send = hi ? a[k] : a[k + 4], keep = hi ? a[k + 4] : a[k];
+            b[k] = keep + __shfl_xor_sync(0xffffffffu, send, L / 4);
+        }
+    }
+    {
+        const bool hi = (l & (L / 8)) != 0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float send = hi ? b[k] : b[k + 2], keep = hi ? b[k + 2] : b[k];
+            c[k] = keep + __shfl_xor_sync(0xffffffffu, send, L / 8);
+        }
+    }
+    if constexpr (L == 8) {
+        if (write) *reinterpret_cast<float2*>(dst + 2 * l) = make_float2(c[0], c[1]);
+    } else {
+        static_assert(L == 16, "row lanes");
+        const bool hi = (l & 1) != 0;
+        const float send = hi ? c[0] : c[1], keep = hi ? c[1] : c[0];
+        const float d = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        if (write) dst[l] = d;
+    }
 }
 
 // (m_tile, n_tile) of the tiles one persistent CTA walks: tile = blockIdx.x + i * gridDim.x, n fastest.
@@ -76,8 +127,8 @@ struct TileWalk {
 // at this tile's bias staged in shared memory (column n0 - n_base), r1/r2 hold the 8 bf16 residual
 // values that were loaded ahead of time (vector path only).
 template <bool kVec>
-__device__ __forceinline__ void epilogue_store8(const GemmKParams& p, float (&v)[8], int64_t row, int grp, int n0,
-                                                const float* sbias, uint4 r1, uint4 r2) {
+__device__ __forceinline__ void epilogue_store8(const GemmKParams& p, float alpha, float (&v)[8], int64_t row, int grp,
+                                                int n0, const float* sbias, uint4 r1, uint4 r2) {
     if (p.bias) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] += sbias[j];
@@ -100,7 +151,7 @@ __device__ __forceinline__ void epilogue_store8(const GemmKParams& p, float (&v)
         }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] *= p.alpha;
+    for (int j = 0; j < 8; ++j) v[j] *= alpha;
     if (p.res2) {
         if (kVec) {
             v[0] += bf16_lo(r2.x); v[1] += bf16_hi(r2.x); v[2] += bf16_lo(r2.y); v[3] += bf16_hi(r2.y);
@@ -276,12 +327,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                         tma_load_2d(dstA, &p.tmA[src], full_bar(s), cc, m_tile * BLOCK_M);
                     } else if (p.a_mode == PP_A_CONV3X3) {
                         tma_load_4d(dstA, &p.tmA[src], full_bar(s), cc, x0 + kx - 1, y0 + ky - 1, nb0);
-                    } else {
+                    } else if (p.a_mode == PP_A_CONV3X3_S2) {
                         // stride 2: input (2*oy + ky - 1, 2*ox + kx - 1) = parity plane (py, px) at
                         // (oy + dy, ox + dx) with d = -1 for k == 0 else 0, parity = (k != 1)
                         const int py = (ky != 1), px = (kx != 1);
                         const int dy = (ky == 0) ? -1 : 0, dx = (kx == 0) ? -1 : 0;
                         tma_load_4d(dstA, &p.tmA[py * 2 + px], full_bar(s), cc, x0 + dx, y0 + dy, nb0);
+                    } else {
+                        // stride 2 over the bottom/right zero-padded input: (2*oy + ky, 2*ox + kx) = parity
+                        // plane (k & 1) at (o + (k >> 1)); the pad row / column is TMA's out-of-bounds zero
+                        tma_load_4d(dstA, &p.tmA[(ky & 1) * 2 + (kx & 1)], full_bar(s), cc, x0 + (kx >> 1), y0 + (ky >> 1),
+                                    nb0);
                     }
                     tma_load_2d(dstB, &p.tmB, full_bar(s), it * BLOCK_K, n_tile * BLOCK_N);
                     if (++ch == cpt) {
@@ -417,9 +473,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 // the four 8-column groups of a chunk are independent straight-line code: the common
                 // case (tile fully inside the matrix, all 32 rows of the warp valid) has no per-group
                 // branches at all, and launches without residual / row-vector terms skip those adds.
-                const float alpha = p.alpha;
+                const float alpha = effective_alpha(p);
                 const bool has_r1 = p.res1 != nullptr, has_r2 = p.res2 != nullptr, has_rv = p.rowvec != nullptr;
-                const bool silu = p.act == PP_ACT_SILU;
+                const int act = p.act;
                 const __nv_bfloat16* r1row = p.res1 + row * p.ldr1 + n_base;
                 const __nv_bfloat16* r2row = p.res2 + row * p.ldr2 + n_base;
                 const float* rvrow = p.rowvec + (int64_t)grp * p.rowvec_ld + n_base;
@@ -433,9 +489,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 tmem_ld32(taddr + half * 32, accA);
                 // ---- store helper: 8 fp32 -> (silu) -> bf16 -> 16-byte store
                 auto store8 = [&](float (&v)[8], int col) {
-                    if (silu) {
+                    if (act == PP_ACT_SILU) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+                    } else if (act == PP_ACT_QUICK_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = quick_gelu_f(v[j]);
                     }
                     uint4 q;
                     q.x = pack_bf16x2(v[0], v[1]);
@@ -509,6 +568,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 // residuals of a 32-column chunk are fetched one chunk ahead (the first chunk's
                 // before the accumulator is even ready), so their latency hides behind TMEM
                 // reads and the previous chunk's stores
+                const float alpha1 = effective_alpha(p);
                 uint4 c1[4], c2[4], x1[4], x2[4];
                 auto fetch = [&](int c0, uint4 (&a)[4], uint4 (&b)[4]) {
 #pragma unroll
@@ -539,9 +599,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(accv[g * 8 + j]);
                                 if (vec_ok && n0 + 8 <= p.N)
-                                    epilogue_store8<true>(p, v, row, grp, n0, sbias + c0 + g * 8, c1[g], c2[g]);
+                                    epilogue_store8<true>(p, alpha1, v, row, grp, n0, sbias + c0 + g * 8, c1[g], c2[g]);
                                 else
-                                    epilogue_store8<false>(p, v, row, grp, n0, sbias + c0 + g * 8, c1[g], c2[g]);
+                                    epilogue_store8<false>(p, alpha1, v, row, grp, n0, sbias + c0 + g * 8, c1[g], c2[g]);
                             }
                         }
                     }
@@ -569,6 +629,38 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                     if (grow >= 0 && out_base + pc * 8 < n_out)
                         *reinterpret_cast<uint4*>(outp + grow * p.ldc + out_base + pc * 8) =
                             *reinterpret_cast<const uint4*>(s_out + rr * OUT_PITCH + pc * 16);
+                }
+                if constexpr (MODE == 0) {
+                    // GroupNorm partial sums of exactly the bf16 values the consumer will read
+                    if (p.chan_stats) {
+                        constexpr int L = (BLOCK_N <= 128) ? 16 : 8;
+                        if (etid < PIECES * L) {  // warp-uniform: PIECES * L is a multiple of 32
+                            const int piece = etid / L, l = etid % L;
+                            const int col0 = n_base + piece * 8;
+                            const int seg_rows = 1 << p.stat_seg_rows_log2;
+                            for (int sg = 0; sg < p.stat_segs; ++sg) {
+                                float v[16];
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                                const int rb = sg << p.stat_seg_rows_log2;
+                                for (int rr = rb + l; rr < rb + seg_rows; rr += L) {
+                                    if (s_row[rr] >= 0) {
+                                        const uint4 q = *reinterpret_cast<const uint4*>(s_out + rr * OUT_PITCH + piece * 16);
+                                        const float x[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
+                                                            bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) {
+                                            v[2 * j] += x[j];
+                                            v[2 * j + 1] = fmaf(x[j], x[j], v[2 * j + 1]);
+                                        }
+                                    }
+                                }
+                                float* dst = p.chan_stats +
+                                             (((int64_t)m_tile * p.stat_segs + sg) * p.N + col0) * 2;
+                                stats_butterfly_store<L>(v, l, dst, col0 < p.N);
+                            }
+                        }
+                    }
                 }
             }
             // park the next tile's bias in the other staging buffer; everyone has finished reading
@@ -617,12 +709,15 @@ static int launch_variant(const GemmLaunch& l, cudaStream_t s) {
 // launches are pure and can be stream-captured)
 template <int BLOCK_N, int MODE>
 static int ensure_attr() {
-    static bool done = false;
-    if (!done) {
+    // the attribute is per device: one flag per device ordinal
+    static bool done[PP_MAX_DEVICES] = {};
+    int dev = 0;
+    PP_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= PP_MAX_DEVICES || !done[dev]) {
         PP_CUDA_CHECK(cudaFuncSetAttribute(gemm_conv_kernel<BLOCK_N, MODE>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem_for_block_n(BLOCK_N)));
-        done = true;
+        if (dev >= 0 && dev < PP_MAX_DEVICES) done[dev] = true;
     }
     return PP_OK;
 }
@@ -674,56 +769,40 @@ static int pick_block_n(int N, int m_tiles, bool geglu) {
     return best ? best : 128;
 }
 
-int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
-    GemmLaunch l;
-    memset(&l, 0, sizeof(l));
-    GemmKParams& p = l.p;
-    PP_REQUIRE(d.a_mode >= PP_A_MATRIX && d.a_mode <= PP_A_CONV3X3_S2, "gemm: bad a_mode %d", d.a_mode);
+// Tile geometry of a launch (everything that needs no device or driver): validation of the shape
+// fields, the conv pixel box, the tile width and the walk. Shared by gemm_prepare and the host-only
+// statistics-geometry query.
+static int gemm_geometry(const pp_gemm_desc& d, GemmKParams& p, int* block_n_out) {
+    PP_REQUIRE(d.a_mode >= PP_A_MATRIX && d.a_mode <= PP_A_CONV3X3_S2P0, "gemm: bad a_mode %d", d.a_mode);
     PP_REQUIRE(d.epilogue >= PP_EPI_PLAIN && d.epilogue <= PP_EPI_TRANSPOSED, "gemm: bad epilogue %d", d.epilogue);
     PP_REQUIRE(d.a0 && d.b && d.out, "gemm: null operand pointer");
     PP_REQUIRE(d.c0 > 0 && d.c0 % 8 == 0, "gemm: c0=%d must be a positive multiple of 8", d.c0);
     PP_REQUIRE((d.a1 == nullptr) == (d.c1 == 0), "gemm: a1/c1 mismatch");
     PP_REQUIRE(d.c1 % 8 == 0, "gemm: c1=%d must be a multiple of 8", d.c1);
     PP_REQUIRE(d.N > 0, "gemm: N must be positive");
+    PP_REQUIRE(d.act >= PP_ACT_NONE && d.act <= PP_ACT_QUICK_GELU, "gemm: bad act %d", d.act);
     const int taps = d.a_mode == PP_A_MATRIX ? 1 : 9;
-    const bool packed_k = taps == 9 || d.a1 != nullptr;
     p.a_mode = d.a_mode;
     p.chunks0 = ceil_div(d.c0, 64);
     p.chunks1 = d.a1 ? ceil_div(d.c1, 64) : 0;
     p.num_k_iters = taps * (p.chunks0 + p.chunks1);
-    const int64_t kw = packed_k ? (int64_t)taps * (pad64(d.c0) + pad64(d.c1)) : d.c0;
-    const int64_t ldb = packed_k ? kw : d.ldb;
-    PP_REQUIRE(ldb >= kw && ldb % 8 == 0, "gemm: ldb=%lld invalid for K=%lld", (long long)ldb, (long long)kw);
-
     int m_tiles;
     if (d.a_mode == PP_A_MATRIX) {
         PP_REQUIRE(d.M > 0, "gemm: M must be positive");
-        PP_REQUIRE(d.lda0 >= d.c0 && d.lda0 % 8 == 0, "gemm: lda0=%lld invalid", (long long)d.lda0);
         p.M = d.M;
         m_tiles = ceil_div(d.M, BLOCK_M);
         p.a_bytes = A_STAGE_BYTES;
-        uint64_t dims[2] = {(uint64_t)d.c0, (uint64_t)d.M};
-        uint64_t str[1] = {(uint64_t)d.lda0 * 2};
-        uint32_t box[2] = {64, BLOCK_M};
-        int rc = make_tmap_bf16(&p.tmA[0], d.a0, 2, dims, str, box, true);
-        if (rc) return rc;
-        if (d.a1) {
-            PP_REQUIRE(d.lda1 >= d.c1 && d.lda1 % 8 == 0, "gemm: lda1=%lld invalid", (long long)d.lda1);
-            uint64_t dims1[2] = {(uint64_t)d.c1, (uint64_t)d.M};
-            uint64_t str1[1] = {(uint64_t)d.lda1 * 2};
-            rc = make_tmap_bf16(&p.tmA[1], d.a1, 2, dims1, str1, box, true);
-            if (rc) return rc;
-        }
     } else {
         PP_REQUIRE(d.nb > 0 && d.h > 0 && d.w > 0, "gemm: conv dims must be positive");
-        const bool s2 = d.a_mode == PP_A_CONV3X3_S2;
+        const bool s2 = d.a_mode != PP_A_CONV3X3;
         if (s2) {
-            PP_REQUIRE(d.h % 2 == 0 && d.w % 2 == 0, "gemm: stride-2 conv needs even h, w (got %d x %d)", d.h, d.w);
+            PP_REQUIRE(d.h >= 2 && d.w >= 2, "gemm: stride-2 conv needs h, w >= 2 (got %d x %d)", d.h, d.w);
             PP_REQUIRE(d.a1 == nullptr, "gemm: stride-2 conv takes a single source");
         }
         p.nb = d.nb;
-        p.ho = s2 ? d.h / 2 : d.h;
-        p.wo = s2 ? d.w / 2 : d.w;
+        // pad 1: ceil(h / 2); bottom/right pad (S2P0): floor(h / 2)
+        p.ho = d.a_mode == PP_A_CONV3X3_S2 ? (d.h + 1) / 2 : s2 ? d.h / 2 : d.h;
+        p.wo = d.a_mode == PP_A_CONV3X3_S2 ? (d.w + 1) / 2 : s2 ? d.w / 2 : d.w;
         p.M = d.nb * p.ho * p.wo;
         // pick the pixel box (bw, bh, bn), bw*bh*bn <= 128, minimising padded volume
         int64_t best_cost = -1;
@@ -745,8 +824,86 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
         p.tiles_y = ceil_div(p.ho, p.bh);
         m_tiles = p.tiles_x * p.tiles_y * ceil_div(p.nb, p.bn);
         p.a_bytes = (uint32_t)(p.bw * p.bh * p.bn) * 128u;
+    }
+    p.N = d.N;
+    const bool geglu = d.epilogue == PP_EPI_GEGLU;
+    int bn = d.block_n ? d.block_n : pick_block_n(d.N, m_tiles, geglu);
+    PP_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "gemm: block_n %d unsupported", bn);
+    p.m_tiles = m_tiles;
+    p.n_tiles = ceil_div(d.N, bn);
+    *block_n_out = bn;
+    return PP_OK;
+}
+
+static bool gemm_fast_mode(const pp_gemm_desc& d) {
+    const int64_t rv_ld = d.rowvec_ld ? d.rowvec_ld : d.N;
+    return d.epilogue == PP_EPI_PLAIN && !d.out_fp32 && d.N % 8 == 0 &&
+           (!d.rowvec || (rv_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d.rowvec) & 15) == 0));
+}
+
+int gemm_stats_geometry(const pp_gemm_desc& d, pp_stats_geom* g) {
+    memset(g, 0, sizeof(*g));
+    GemmKParams p;
+    memset(&p, 0, sizeof(p));
+    int bn = 0;
+    int rc = gemm_geometry(d, p, &bn);
+    if (rc) return rc;
+    g->channels = d.N;
+    if (!gemm_fast_mode(d)) return PP_OK;  // statistics come from the bf16 staging tile of the fast epilogue
+    const int min_rows = 16;               // >= the row lanes of the statistics pass
+    if (d.a_mode == PP_A_MATRIX) {
+        const int hw = d.rows_per_group;
+        if (hw <= 0 || d.M % hw != 0) return PP_OK;
+        if (hw % BLOCK_M == 0) {
+            g->segs = 1; g->seg_rows = BLOCK_M; g->tiles_per_group = hw / BLOCK_M;
+        } else if (BLOCK_M % hw == 0 && hw >= min_rows) {
+            g->segs = BLOCK_M / hw; g->seg_rows = hw; g->tiles_per_group = 1;
+        } else {
+            return PP_OK;
+        }
+        g->tiles_x = g->tiles_per_group; g->tiles_y = 1; g->bw = g->seg_rows; g->bh = 1; g->wo = hw; g->ho = 1;
+    } else {
+        if (p.bw * p.bh < min_rows) return PP_OK;
+        g->segs = p.bn; g->seg_rows = p.bw * p.bh; g->tiles_per_group = p.tiles_x * p.tiles_y;
+        g->tiles_x = p.tiles_x; g->tiles_y = p.tiles_y; g->bw = p.bw; g->bh = p.bh; g->wo = p.wo; g->ho = p.ho;
+    }
+    g->supported = 1;
+    g->bytes = (int64_t)p.m_tiles * g->segs * d.N * 2 * (int64_t)sizeof(float);
+    return PP_OK;
+}
+
+int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
+    GemmLaunch l;
+    memset(&l, 0, sizeof(l));
+    GemmKParams& p = l.p;
+    int bn = 0;
+    {
+        int rc = gemm_geometry(d, p, &bn);
+        if (rc) return rc;
+    }
+    const int taps = d.a_mode == PP_A_MATRIX ? 1 : 9;
+    const bool packed_k = taps == 9 || d.a1 != nullptr;
+    const int64_t kw = packed_k ? (int64_t)taps * (pad64(d.c0) + pad64(d.c1)) : d.c0;
+    const int64_t ldb = packed_k ? kw : d.ldb;
+    PP_REQUIRE(ldb >= kw && ldb % 8 == 0, "gemm: ldb=%lld invalid for K=%lld", (long long)ldb, (long long)kw);
+
+    if (d.a_mode == PP_A_MATRIX) {
+        PP_REQUIRE(d.lda0 >= d.c0 && d.lda0 % 8 == 0, "gemm: lda0=%lld invalid", (long long)d.lda0);
+        uint64_t dims[2] = {(uint64_t)d.c0, (uint64_t)d.M};
+        uint64_t str[1] = {(uint64_t)d.lda0 * 2};
+        uint32_t box[2] = {64, BLOCK_M};
+        int rc = make_tmap_bf16(&p.tmA[0], d.a0, 2, dims, str, box, true);
+        if (rc) return rc;
+        if (d.a1) {
+            PP_REQUIRE(d.lda1 >= d.c1 && d.lda1 % 8 == 0, "gemm: lda1=%lld invalid", (long long)d.lda1);
+            uint64_t dims1[2] = {(uint64_t)d.c1, (uint64_t)d.M};
+            uint64_t str1[1] = {(uint64_t)d.lda1 * 2};
+            rc = make_tmap_bf16(&p.tmA[1], d.a1, 2, dims1, str1, box, true);
+            if (rc) return rc;
+        }
+    } else {
         uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
-        if (!s2) {
+        if (d.a_mode == PP_A_CONV3X3) {
             const void* srcs[2] = {d.a0, d.a1};
             const int cs[2] = {d.c0, d.c1};
             for (int i = 0; i < 2; ++i) {
@@ -757,11 +914,15 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
                 if (rc) return rc;
             }
         } else {
+            // parity planes: plane (py, px) holds input rows py, py + 2, ... (ceil((h - py) / 2) of them) and
+            // columns px, px + 2, ...; for odd h / w the planes differ in size and the missing last row /
+            // column reads as TMA's out-of-bounds zero, which is exactly the conv's padding
             for (int py = 0; py < 2; ++py)
                 for (int px = 0; px < 2; ++px) {
                     const __nv_bfloat16* base =
                         reinterpret_cast<const __nv_bfloat16*>(d.a0) + ((int64_t)py * d.w + px) * d.c0;
-                    uint64_t dims[4] = {(uint64_t)d.c0, (uint64_t)d.w / 2, (uint64_t)d.h / 2, (uint64_t)d.nb};
+                    uint64_t dims[4] = {(uint64_t)d.c0, (uint64_t)(d.w + 1 - px) / 2, (uint64_t)(d.h + 1 - py) / 2,
+                                        (uint64_t)d.nb};
                     uint64_t str[3] = {(uint64_t)d.c0 * 2 * 2, (uint64_t)d.c0 * 2 * d.w * 2,
                                        (uint64_t)d.c0 * 2 * d.w * d.h};
                     int rc = make_tmap_bf16(&p.tmA[py * 2 + px], base, 4, dims, str, box, true);
@@ -769,10 +930,7 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
                 }
         }
     }
-    p.N = d.N;
     const bool geglu = d.epilogue == PP_EPI_GEGLU;
-    int bn = d.block_n ? d.block_n : pick_block_n(d.N, m_tiles, geglu);
-    PP_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "gemm: block_n %d unsupported", bn);
     if (geglu) {
         PP_REQUIRE(d.N % bn == 0, "gemm: GEGLU needs N %% block_n == 0 (N=%d, block_n=%d)", d.N, bn);
         PP_REQUIRE(!d.out_fp32 && !d.rowvec && !d.res1 && !d.res2, "gemm: GEGLU epilogue takes bias only");
@@ -801,6 +959,9 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
     p.res2 = reinterpret_cast<const __nv_bfloat16*>(d.res2);
     p.ldr2 = d.ldr2;
     p.alpha = d.alpha;
+    p.alpha_dev = d.alpha_dev;
+    p.alpha_step = d.alpha_step;
+    p.alpha_stride = d.alpha_stride;
     p.out = d.out;
     p.ldc = d.ldc;
     p.t_rows = d.t_rows;
@@ -821,8 +982,6 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
         if (d.res2) PP_REQUIRE(d.ldr2 % 8 == 0 && (reinterpret_cast<uintptr_t>(d.res2) & 15) == 0, "gemm: res2 alignment");
         if (d.bias) PP_REQUIRE((reinterpret_cast<uintptr_t>(d.bias) & 15) == 0, "gemm: bias alignment");
     }
-    p.m_tiles = m_tiles;
-    p.n_tiles = ceil_div(d.N, bn);
     {
         const long tiles = (long)p.m_tiles * p.n_tiles;
         l.grid = dim3((unsigned)std::min<long>(tiles, num_sms()), 1, 1);
@@ -831,9 +990,19 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
     if (geglu) {
         l.mode = 2;
     } else {
-        const bool fast = d.epilogue == PP_EPI_PLAIN && !d.out_fp32 && d.N % 8 == 0 &&
-                          (!d.rowvec || (p.rowvec_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d.rowvec) & 15) == 0));
-        l.mode = fast ? 0 : 1;
+        l.mode = gemm_fast_mode(d) ? 0 : 1;
+    }
+    if (d.chan_stats) {
+        pp_stats_geom g;
+        int rc = gemm_stats_geometry(d, &g);
+        if (rc) return rc;
+        PP_REQUIRE(g.supported && l.mode == 0, "gemm: chan_stats requested but this launch cannot emit statistics "
+                   "(query pp_gemm_stats_geometry first)");
+        PP_REQUIRE((reinterpret_cast<uintptr_t>(d.chan_stats) & 15) == 0, "gemm: chan_stats not 16-byte aligned");
+        p.chan_stats = d.chan_stats;
+        p.stat_segs = g.segs;
+        p.stat_seg_rows_log2 = 0;
+        while ((1 << p.stat_seg_rows_log2) < g.seg_rows) ++p.stat_seg_rows_log2;
     }
     {
         int rc = ensure_attr_for(bn, l.mode);
@@ -844,6 +1013,14 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
 }
 
 }  // namespace pp
+
+extern "C" pp_status pp_gemm_stats_geometry(const pp_gemm_desc* d, pp_stats_geom* out) {
+    if (!d || !out) {
+        pp::set_last_error("pp_gemm_stats_geometry: null argument");
+        return pp::PP_ERR_INVALID;
+    }
+    return pp::gemm_stats_geometry(*d, out);
+}
 
 extern "C" pp_status pp_gemm_conv(const pp_gemm_desc* d, pp_stream stream) {
     if (!d) {

@@ -5,10 +5,15 @@
 // conv_norm_out (powerpaint/models/unet_2d_condition.py:466,1351-1353); nn.LayerNorm(C)
 // x3 per BasicTransformerBlock. Statistics are biased (divide by count), computed in fp32.
 //
-// These kernels are HBM-bound: GroupNorm reads x twice (stats pass + apply pass; the second
-// read is normally an L2 hit on B200's 126 MB L2) and writes y once; LayerNorm reads once
-// (row held in registers) and writes once. Algorithmic bytes: GN 2*|x|*2B (+1 re-read),
-// LN 2*|x|*2B.
+// These kernels are HBM-bound. GroupNorm statistics normally come for free: the GEMM / conv that
+// PRODUCED the tensor emits per-tile channel sums from its epilogue (pp_gemm_desc.chan_stats) and a tiny
+// finalize kernel folds them into (mean, rstd) per (sample, group), so GroupNorm is ONE pass (read x,
+// write y). Tensors without producer statistics (odd shapes, ControlNet skip sums) take the standalone
+// statistics kernel (a second read, normally an L2 hit). LayerNorm reads once (row held in registers)
+// and writes once. Algorithmic bytes: GN 2*|x|*2B, LN 2*|x|*2B.
+// Variance: every path combines per-block / per-tile (count, mean, M2) with Chan's parallel formula in
+// fp64, so a large mean over a small spread does not cancel (the fp32 sums being combined each cover at
+// most a few hundred elements).
 //
 // GroupNorm also performs the up-path `torch.cat([hidden, skip], dim=1)`
 // (unet_2d_blocks.py:2589,2732): it normalises over the virtual concat of two sources and
@@ -61,7 +66,7 @@ static GnGeometry gn_geometry(int batch, int hw, int C, int groups) {
 
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, const __nv_bfloat16* __restrict__ x1,
                                 int c0, int c1, int hw, int groups, int pix_per_block,
-                                float* __restrict__ stats, uint32_t* __restrict__ tickets,
+                                float eps, float* __restrict__ stats, uint32_t* __restrict__ tickets,
                                 float* __restrict__ partials) {
     pdl_wait();  // inputs come from the preceding kernel
     pdl_launch_dependents();
@@ -128,13 +133,92 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, const __nv
     __syncthreads();
     if (*sh_ticket != (uint32_t)(chunks - 1)) return;
     __threadfence();
-    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) {
-        const float* pp_ = partials + ((int64_t)n * chunks * groups) * 2 + i;
-        float acc = 0.f;
-        for (int ch = 0; ch < chunks; ++ch) acc += __ldcg(pp_ + (int64_t)ch * groups * 2);
-        stats[(int64_t)n * groups * 2 + i] = acc;
+    // (count, mean, M2) of every chunk combined in chunk order (Chan et al.), fp64: the fp32 sums of one
+    // chunk cover a few hundred elements, the combination across chunks does not cancel
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        const float* pp_ = partials + (((int64_t)n * chunks) * groups + g) * 2;
+        double cnt = 0.0, mean = 0.0, m2 = 0.0;
+        for (int ch = 0; ch < chunks; ++ch) {
+            const double s = (double)__ldcg(pp_ + (int64_t)ch * groups * 2);
+            const double ss = (double)__ldcg(pp_ + (int64_t)ch * groups * 2 + 1);
+            const int pix = min(pix_per_block, hw - ch * pix_per_block);
+            const double cb = (double)pix * (double)cpg;
+            const double mb = s / cb;
+            const double m2b = fmax(ss - s * mb, 0.0);
+            const double delta = mb - mean, tot = cnt + cb;
+            mean += delta * (cb / tot);
+            m2 += m2b + delta * delta * (cnt * cb / tot);
+            cnt = tot;
+        }
+        stats[((int64_t)n * groups + g) * 2] = (float)mean;
+        stats[((int64_t)n * groups + g) * 2 + 1] = (float)(1.0 / sqrt(m2 / cnt + (double)eps));
     }
     if (threadIdx.x == 0) tickets[n] = 0u;  // ready for the next call
+}
+
+// GroupNorm statistics from the producers' epilogue partial sums (pp_gemm_desc.chan_stats): one block per
+// sample. Every thread folds the tiles of its channels (fixed order), the channels of a group are then
+// folded per group; all in fp64 with Chan's combination. Writes (mean, rstd) like gn_stats_kernel.
+struct GnPartSrc {
+    const float* part;
+    int channels, segs, tiles_per_group, tiles_x, tiles_y, bw, bh, wo, ho;
+};
+
+__global__ void gn_finalize_kernel(GnPartSrc s0, GnPartSrc s1, int groups, float eps, float* __restrict__ stats) {
+    pdl_wait();
+    pdl_launch_dependents();
+    extern __shared__ double shd[];  // [C] mean, [C] M2
+    const int C = s0.channels + s1.channels;
+    const int cpg = C / groups;
+    const int n = blockIdx.x;
+    double* sh_mean = shd;
+    double* sh_m2 = shd + C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const GnPartSrc& s = c < s0.channels ? s0 : s1;
+        const int cl = c < s0.channels ? c : c - s0.channels;
+        const int gidx = n / s.segs, seg = n - gidx * s.segs;
+        const float* base = s.part + (((int64_t)gidx * s.tiles_per_group * s.segs + seg) * s.channels + cl) * 2;
+        const int64_t tstride = (int64_t)s.segs * s.channels * 2;
+        double cnt = 0.0, mean = 0.0, m2 = 0.0;
+        int tx = 0, ty = 0;
+        for (int t0 = 0; t0 < s.tiles_per_group; t0 += 8) {
+            float2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                v[u] = t0 + u < s.tiles_per_group ? __ldcg(reinterpret_cast<const float2*>(base + (t0 + u) * tstride))
+                                                  : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (t0 + u < s.tiles_per_group) {
+                    const double cb = (double)(min(s.bw, s.wo - tx * s.bw) * min(s.bh, s.ho - ty * s.bh));
+                    const double sm = (double)v[u].x, ss = (double)v[u].y;
+                    const double mb = sm / cb;
+                    const double m2b = fmax(ss - sm * mb, 0.0);
+                    const double delta = mb - mean, tot = cnt + cb;
+                    mean += delta * (cb / tot);
+                    m2 += m2b + delta * delta * (cnt * cb / tot);
+                    cnt = tot;
+                    if (++tx == s.tiles_x) { tx = 0; ++ty; }
+                }
+            }
+        }
+        sh_mean[c] = mean;
+        sh_m2[c] = m2;
+    }
+    __syncthreads();
+    const double per_ch = (double)s0.wo * (double)s0.ho;  // pixels per sample
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double cnt = 0.0, mean = 0.0, m2 = 0.0;
+        for (int cc = 0; cc < cpg; ++cc) {
+            const double mb = sh_mean[g * cpg + cc], m2b = sh_m2[g * cpg + cc];
+            const double delta = mb - mean, tot = cnt + per_ch;
+            mean += delta * (per_ch / tot);
+            m2 += m2b + delta * delta * (cnt * per_ch / tot);
+            cnt = tot;
+        }
+        stats[((int64_t)n * groups + g) * 2] = (float)mean;
+        stats[((int64_t)n * groups + g) * 2 + 1] = (float)(1.0 / sqrt(m2 / cnt + (double)eps));
+    }
 }
 
 // GroupNorm pass 2: y = (x - mean) * rstd * gamma + beta, optional SiLU; writes the concat.
@@ -142,7 +226,7 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, const __nv
 // mean / rstd live in registers for the whole kernel) and strides over pixels: 32-bit index math only.
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, const __nv_bfloat16* __restrict__ x1,
                                 int c0, int c1, int hw, int groups, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, float eps, int silu,
+                                const float* __restrict__ beta, int silu,
                                 const float* __restrict__ stats, __nv_bfloat16* __restrict__ y,
                                 int pix_per_block) {
     pdl_wait();  // inputs come from the preceding kernel
@@ -160,16 +244,12 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, const __nv
     int cs, co;
     if (c < c0) { src = x0; cs = c0; co = c; } else { src = x1; cs = c1; co = c - c0; }
     // per-channel scale / shift: y = x * a + b with a = rstd * gamma, b = beta - mean * a
-    const float inv_cnt = 1.0f / ((float)cpg * (float)hw);
     float a[8], bsh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int g = (c + j) / cpg;
-        const float s = __ldg(&stats[((int64_t)n * groups + g) * 2]);
-        const float ss = __ldg(&stats[((int64_t)n * groups + g) * 2 + 1]);
-        const float mean = s * inv_cnt;
-        const float var = fmaxf(ss * inv_cnt - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + eps);
+        const float mean = __ldg(&stats[((int64_t)n * groups + g) * 2]);
+        const float rstd = __ldg(&stats[((int64_t)n * groups + g) * 2 + 1]);
         a[j] = rstd * __ldg(gamma + c + j);
         bsh[j] = __ldg(beta + c + j) - mean * a[j];
     }
@@ -211,10 +291,27 @@ int group_norm_validate(const pp_gn_desc& d) {
     PP_REQUIRE(d.groups > 0 && C % d.groups == 0, "group_norm: C=%d not divisible by groups=%d", C, d.groups);
     PP_REQUIRE(C / 8 <= 1024, "group_norm: C=%d too large", C);
     PP_REQUIRE(d.batch > 0 && d.hw > 0, "group_norm: empty input");
+    PP_REQUIRE((reinterpret_cast<uintptr_t>(d.stats) & 15) == 0, "group_norm: scratch not 16-byte aligned");
+    if (d.from_partials) {
+        PP_REQUIRE(d.part0 && d.geom0.supported && d.geom0.channels == d.c0, "group_norm: part0 / geom0 invalid");
+        PP_REQUIRE((d.x1 == nullptr) || (d.part1 && d.geom1.supported && d.geom1.channels == d.c1),
+                   "group_norm: part1 / geom1 invalid");
+        PP_REQUIRE(d.geom0.wo * d.geom0.ho == d.hw && (!d.x1 || d.geom1.wo * d.geom1.ho == d.hw),
+                   "group_norm: partial-sum geometry does not cover hw=%d pixels", d.hw);
+        PP_REQUIRE((size_t)C * 16 <= 48 * 1024, "group_norm: C=%d too large for the finalize kernel", C);
+        return PP_OK;
+    }
     PP_REQUIRE(gn_geometry(d.batch, d.hw, C, d.groups).smem <= 48 * 1024,
                "group_norm: C=%d needs more than 48 KB of shared memory for the block reduction", C);
-    PP_REQUIRE((reinterpret_cast<uintptr_t>(d.stats) & 15) == 0, "group_norm: scratch not 16-byte aligned");
     return PP_OK;
+}
+
+static GnPartSrc part_src(const float* part, const pp_stats_geom& g) {
+    GnPartSrc s;
+    s.part = part;
+    s.channels = g.channels; s.segs = g.segs; s.tiles_per_group = g.tiles_per_group;
+    s.tiles_x = g.tiles_x; s.tiles_y = g.tiles_y; s.bw = g.bw; s.bh = g.bh; s.wo = g.wo; s.ho = g.ho;
+    return s;
 }
 
 int64_t group_norm_scratch_bytes(int batch, int hw, int channels, int groups) {
@@ -230,15 +327,22 @@ int group_norm_launch(const pp_gn_desc& d, cudaStream_t s) {
     uint8_t* scratch = reinterpret_cast<uint8_t*>(d.stats);
     uint32_t* tickets = reinterpret_cast<uint32_t*>(scratch + g.ticket_offset);
     float* partials = reinterpret_cast<float*>(scratch + g.partial_offset);
-    if (!d.stats_prezeroed) PP_CUDA_CHECK(cudaMemsetAsync(tickets, 0, sizeof(uint32_t) * d.batch, s));
     const int threads = g.threads, chunks = g.chunks, ppb = g.ppb;
-    PP_CUDA_CHECK(launch(gn_stats_kernel, dim3(chunks, d.batch), threads, g.smem, s,
-        reinterpret_cast<const __nv_bfloat16*>(d.x0), reinterpret_cast<const __nv_bfloat16*>(d.x1), d.c0,
-        d.c1, d.hw, d.groups, ppb, d.stats, tickets, partials));
+    if (d.from_partials) {
+        GnPartSrc s0 = part_src(d.part0, d.geom0), s1;
+        memset(&s1, 0, sizeof(s1));
+        if (d.x1) s1 = part_src(d.part1, d.geom1);
+        PP_CUDA_CHECK(launch(gn_finalize_kernel, dim3(d.batch), 256, (size_t)C * 16, s, s0, s1, d.groups, d.eps, d.stats));
+    } else {
+        if (!d.stats_prezeroed) PP_CUDA_CHECK(cudaMemsetAsync(tickets, 0, sizeof(uint32_t) * d.batch, s));
+        PP_CUDA_CHECK(launch(gn_stats_kernel, dim3(chunks, d.batch), threads, g.smem, s,
+            reinterpret_cast<const __nv_bfloat16*>(d.x0), reinterpret_cast<const __nv_bfloat16*>(d.x1), d.c0,
+            d.c1, d.hw, d.groups, ppb, d.eps, d.stats, tickets, partials));
+    }
     PP_CUDA_CHECK(cudaGetLastError());
     PP_CUDA_CHECK(launch(gn_apply_kernel, dim3(chunks, d.batch), threads, 0, s, 
         reinterpret_cast<const __nv_bfloat16*>(d.x0), reinterpret_cast<const __nv_bfloat16*>(d.x1), d.c0,
-        d.c1, d.hw, d.groups, d.gamma, d.beta, d.eps, d.silu, d.stats,
+        d.c1, d.hw, d.groups, d.gamma, d.beta, d.silu, d.stats,
         reinterpret_cast<__nv_bfloat16*>(d.y), ppb));
     PP_CUDA_CHECK(cudaGetLastError());
     return PP_OK;

@@ -38,11 +38,19 @@ struct GemmKParams {
     const __nv_bfloat16* res2;
     int64_t ldr2;
     float alpha;
+    const float* alpha_dev;     // optional device multiplier: alpha *= alpha_dev[*alpha_step * alpha_stride]
+    const int32_t* alpha_step;  // (NULL: index 0) — per-step side-net scale without re-recording the program
+    int32_t alpha_stride;
     void* out;
     int64_t ldc;
     int32_t t_rows;
     int64_t t_ld;
     int32_t t_fp16;
+    // per-channel partial sums of the stored tile for the consumer's GroupNorm (mode 0 only):
+    // chan_stats[(m_tile * stat_segs + seg)][N][2] = {sum, sum of squares} over the valid rows of the segment
+    float* chan_stats;
+    int32_t stat_segs;           // samples per m-tile (1, 2 or 4 ...)
+    int32_t stat_seg_rows_log2;  // rows of one sample inside the tile
 };
 
 struct GemmLaunch {
@@ -81,12 +89,13 @@ int attn_prepare(const pp_attn_desc& d, AttnLaunch* out);
 int attn_launch(const AttnLaunch& l, cudaStream_t s);
 
 // ---------------------------------------------------------------- simple ops
+int gemm_stats_geometry(const pp_gemm_desc& d, pp_stats_geom* out);
 int group_norm_launch(const pp_gn_desc& d, cudaStream_t s);
 int group_norm_validate(const pp_gn_desc& d);
 int64_t group_norm_scratch_bytes(int batch, int hw, int channels, int groups);
 int layer_norm_launch(const void* x, void* y, const float* gamma, const float* beta, int rows,
                       int c, float eps, cudaStream_t s);
-int upsample2x_launch(const void* x, void* y, int nb, int h, int w, int c, cudaStream_t s);
+int upsample_nearest_launch(const void* x, void* y, int nb, int h, int w, int c, int ho, int wo, cudaStream_t s);
 int add_launch(const void* a, const void* b, void* y, int64_t n, cudaStream_t s);
 int time_embed_launch(const float* timesteps, const int32_t* step_idx, void* out, int batch,
                       int dim, cudaStream_t s);

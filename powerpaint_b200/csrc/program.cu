@@ -20,7 +20,7 @@ enum OpKind {
 };
 
 struct LnArgs { const void* x; void* y; const float* gamma; const float* beta; int rows, c; float eps; };
-struct UpArgs { const void* x; void* y; int nb, h, w, c; };
+struct UpArgs { const void* x; void* y; int nb, h, w, c, ho, wo; };
 struct AddArgs { const void* a; const void* b; void* y; int64_t n; };
 struct TeArgs { const float* timesteps; const int32_t* step_idx; void* out; int batch, dim; };
 struct MsArgs { void* ptr; int64_t bytes; };
@@ -57,7 +57,7 @@ static int run_op(const Op& op, cudaStream_t s) {
         case OP_ATTN: return attn_launch(op.attn, s);
         case OP_GN: return group_norm_launch(op.gn, s);
         case OP_LN: return layer_norm_launch(op.ln.x, op.ln.y, op.ln.gamma, op.ln.beta, op.ln.rows, op.ln.c, op.ln.eps, s);
-        case OP_UPSAMPLE: return upsample2x_launch(op.up.x, op.up.y, op.up.nb, op.up.h, op.up.w, op.up.c, s);
+        case OP_UPSAMPLE: return upsample_nearest_launch(op.up.x, op.up.y, op.up.nb, op.up.h, op.up.w, op.up.c, op.up.ho, op.up.wo, s);
         case OP_ADD: return add_launch(op.add.a, op.add.b, op.add.y, op.add.n, s);
         case OP_TIME_EMBED: return time_embed_launch(op.te.timesteps, op.te.step_idx, op.te.out, op.te.batch, op.te.dim, s);
         case OP_CFG_DDIM: return cfg_ddim_launch(op.ddim, s);
@@ -157,7 +157,19 @@ pp_status pp_program_add_upsample2x(pp_program* p, const void* x, void* y, int32
     PP_REQUIRE(x && y && nb > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "pp_program_add_upsample2x: invalid arguments");
     pp::Op op;
     op.kind = pp::OP_UPSAMPLE;
-    op.up = {x, y, nb, h, w, c};
+    op.up = {x, y, nb, h, w, c, 2 * h, 2 * w};
+    p->ops.push_back(op);
+    return pp::PP_OK;
+}
+
+pp_status pp_program_add_upsample_nearest(pp_program* p, const void* x, void* y, int32_t nb, int32_t h,
+                                          int32_t w, int32_t c, int32_t ho, int32_t wo) {
+    PP_PROG_CHECK(p);
+    PP_REQUIRE(x && y && nb > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && ho > 0 && wo > 0,
+               "pp_program_add_upsample_nearest: invalid arguments");
+    pp::Op op;
+    op.kind = pp::OP_UPSAMPLE;
+    op.up = {x, y, nb, h, w, c, ho, wo};
     p->ops.push_back(op);
     return pp::PP_OK;
 }

@@ -94,7 +94,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 extern "C" {
 
 const char* pp_last_error(void) { return pp::last_error(); }
-int pp_abi_version(void) { return 1; }
+int pp_abi_version(void) { return 2; }
 int pp_device_supported(void) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;

@@ -19,11 +19,18 @@ the constant input channels (mask, masked-image latents, BrushNet condition) are
 
 All nets read ONE shared input buffer [n, h*w, 16]: channels 0..3 = latents, 4.. = the constant
 channels of whichever net consumes them; nets that do not consume a channel carry zero weights
-for it (weights are zero-padded at pack time), so no per-net concat exists.
+for it (weights are zero-padded at pack time), so no per-net concat exists. The constant channels are
+written once per call; the step kernel only refreshes the four latent channels.
+
+Per-step coefficient row (8 floats, `coef[step]`): 0-4 DDIM (sqrt(a_t), sqrt(1-a_t), sqrt(a_prev),
+sqrt(1-a_prev-sigma^2), sigma), 5 guidance scale, 6 side-net conditioning scale x keep flag of the step
+(`brushnet_keep` / `controlnet_keep`, Brushnet_CA.py:1369-1376,1403-1409, ControlNet.py:1652-1658), 7 spare.
+A recorded plan therefore serves every guidance / conditioning scale and every control_guidance window.
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, Optional
+from collections import OrderedDict
+from typing import Callable, Optional, Sequence
 
 import torch
 
@@ -32,6 +39,7 @@ from .engine import NetEngine, Plan
 
 MAX_STEPS = 1000
 X_IN_C = 16
+COEF_GUIDANCE, COEF_SIDE_SCALE = 5, 6
 
 
 class FusedDenoiser:
@@ -45,17 +53,28 @@ class FusedDenoiser:
         self.unet = unet
         self.side = side
         self.mode = mode
-        self._cache: Dict[tuple, dict] = {}
+        # recorded plans, least recently used first; a plan owns its activation pool (a few GB at C2), so only
+        # MAX_PLANS shapes are kept
+        self._cache: "OrderedDict[tuple, dict]" = OrderedDict()
         self._stream: Optional[torch.cuda.Stream] = None
 
+    MAX_PLANS = 2
+
     # ------------------------------------------------------------------ plan
-    def _get(self, B: int, h: int, w: int, do_cfg: bool, ctx_len: int, side_scale: float, with_noise: bool,
+    def _get(self, B: int, h: int, w: int, do_cfg: bool, ctx_len: int, with_noise: bool,
              extra_per_copy: bool) -> dict:
-        key = (B, h, w, do_cfg, ctx_len, float(side_scale), with_noise, extra_per_copy, id(self.unet.engine()),
-               id(self.side.engine()) if self.side is not None else 0)
+        # the key carries the parameter generation of each model: `load_state_dict` / `.to()` invalidate it,
+        # and the cached entry keeps its engines alive, so a recycled id() can never alias a stale program
+        key = (B, h, w, do_cfg, ctx_len, with_noise, extra_per_copy, self.unet.generation,
+               self.side.generation if self.side is not None else -1)
         st = self._cache.get(key)
         if st is not None:
+            self._cache.move_to_end(key)
             return st
+        for k in [k for k in self._cache if k[-2:] != key[-2:]]:
+            del self._cache[k]  # plans recorded against replaced weights
+        while len(self._cache) >= self.MAX_PLANS:
+            self._cache.popitem(last=False)
         dev = self.unet.device
         nb = 2 * B if do_cfg else B
         ue: NetEngine = self.unet.engine()
@@ -64,21 +83,22 @@ class FusedDenoiser:
         timesteps = torch.zeros(MAX_STEPS, dtype=torch.float32, device=dev)
         step_idx = torch.zeros(1, dtype=torch.int32, device=dev)
         coef = torch.zeros(MAX_STEPS, 8, dtype=torch.float32, device=dev)
-        shared = dict(program=prog, ctx_program=ctxprog, x_in=x_in, timesteps=timesteps, step_idx=step_idx)
+        pool = Plan()  # the nets of one step share one activation pool
+        shared = dict(program=prog, ctx_program=ctxprog, x_in=x_in, timesteps=timesteps, step_idx=step_idx, pool=pool,
+                      scale_dev=(coef[:, COEF_SIDE_SCALE], step_idx, 8))
         st = dict(B=B, nb=nb, h=h, w=w, do_cfg=do_cfg, x_in=x_in, timesteps=timesteps, step_idx=step_idx, coef=coef,
                   program=prog, ctx_program=ctxprog, graph=False, with_noise=with_noise,
-                  extra_per_copy=extra_per_copy)
+                  extra_per_copy=extra_per_copy, engines=(ue, self.side.engine() if self.side is not None else None))
         side_plan: Optional[Plan] = None
         if self.mode == "brushnet":
             se: NetEngine = self.side.engine()
             side_plan = se._build_plan(nb, h, w, ctx_len, False, False, True, 0, shared=shared)
-            se.append_brushnet_outputs(side_plan, float(side_scale))
+            se.append_brushnet_outputs(side_plan, 1.0, scale_dev=shared["scale_dev"])
             shared_u = dict(shared, adds=(side_plan.outputs["down"], side_plan.outputs["mid"], side_plan.outputs["up"]))
             uplan = ue._build_plan(nb, h, w, ctx_len, True, False, True, 0, shared=shared_u)
         elif self.mode == "controlnet":
             se = self.side.engine()
-            side_plan = se._build_plan(nb, h, w, ctx_len, False, False, True, 0,
-                                       shared=dict(shared, cn_scale=float(side_scale)))
+            side_plan = se._build_plan(nb, h, w, ctx_len, False, False, True, 0, shared=shared)
             shared_u = dict(shared, cn=(side_plan.outputs["down"], side_plan.outputs["mid"]))
             uplan = ue._build_plan(nb, h, w, ctx_len, False, True, True, 0, shared=shared_u)
         else:
@@ -93,8 +113,7 @@ class FusedDenoiser:
                                    coef=coef, step_idx=step_idx, advance_step=True,
                                    noise=st["noise"] if with_noise else None, guidance_scale=0.0,
                                    guidance_from_coef=True, do_cfg=do_cfg, batch=B, hw=h * w, next_in=x_in,
-                                   next_c=X_IN_C, n_copies=2 if do_cfg else 1, extra=st["extra"], extra_c=5,
-                                   extra_per_copy=extra_per_copy))
+                                   next_c=X_IN_C, n_copies=2 if do_cfg else 1, extra=None, extra_c=0))
         st["bytes"] = uplan.bytes + (side_plan.bytes if side_plan else 0)
         self._cache[key] = st
         return st
@@ -117,13 +136,15 @@ class FusedDenoiser:
     def run(self, *, latents: torch.Tensor, prompt_embeds: torch.Tensor, timesteps, coef: torch.Tensor,
             guidance_scale: float, extra: Optional[torch.Tensor] = None,
             side_prompt_embeds: Optional[torch.Tensor] = None, control_image: Optional[torch.Tensor] = None,
-            side_scale: float = 1.0, noise_fn: Optional[Callable[[int], torch.Tensor]] = None,
+            side_scale: float = 1.0, side_keep: Optional[Sequence[float]] = None,
+            noise_fn: Optional[Callable[[int], torch.Tensor]] = None,
             callback: Optional[Callable[[int, int, torch.Tensor], Optional[torch.Tensor]]] = None,
             use_graph: bool = True) -> torch.Tensor:
         """latents [B,4,h,w]; prompt_embeds [nb,77,768] for the UNet (negative half first when CFG);
         extra [B or nb,5,h,w] = constant channels (v1/controlnet: mask + masked-image latents;
         brushnet: conditioning latents + mask; nb rows = one set per CFG half); side_prompt_embeds
-        for the side net; coef [n,8] from `DDIMScheduler.step_coefficients`; `noise_fn(i)` supplies
+        for the side net; `side_scale` x `side_keep[i]` (default 1) scales the side net's residuals at step i;
+        coef [n,8] from `DDIMScheduler.step_coefficients`; `noise_fn(i)` supplies
         the eta > 0 variance noise of step i. `callback(i, t, latents_nchw)` may return replacement
         latents. Returns the final latents [B,4,h,w] fp32."""
         B, _, h, w = latents.shape
@@ -140,10 +161,12 @@ class FusedDenoiser:
         dev = self.unet.device
         if self._stream is None:
             self._stream = torch.cuda.Stream(device=dev)
+        if side_keep is not None and len(side_keep) != n_steps:
+            raise ValueError("side_keep needs one entry per step")
         cur = torch.cuda.current_stream(dev)
         self._stream.wait_stream(cur)
-        with torch.cuda.stream(self._stream):
-            st = self._get(B, h, w, do_cfg, prompt_embeds.shape[1], side_scale, noise_fn is not None, extra_per_copy)
+        with torch.cuda.device(dev), torch.cuda.stream(self._stream):
+            st = self._get(B, h, w, do_cfg, prompt_embeds.shape[1], noise_fn is not None, extra_per_copy)
             # ---- per-call inputs (all outside the loop)
             st["latents"].copy_(ops.nhwc_fp32_from_nchw(latents.to(dev)))
             if extra is not None:
@@ -154,7 +177,9 @@ class FusedDenoiser:
             ts = torch.as_tensor([float(t) for t in timesteps], dtype=torch.float32)
             st["timesteps"][:n_steps].copy_(ts.to(dev))
             cf = coef.clone().float()
-            cf[:, 5] = float(guidance_scale)
+            cf[:, COEF_GUIDANCE] = float(guidance_scale)
+            keep = torch.ones(n_steps) if side_keep is None else torch.tensor([float(k) for k in side_keep])
+            cf[:, COEF_SIDE_SCALE] = float(side_scale) * keep
             st["coef"][:n_steps].copy_(cf.to(dev))
             st["step_idx"].zero_()
             st["uplan"].inputs["ctx"].copy_(prompt_embeds.to(dev, torch.bfloat16))

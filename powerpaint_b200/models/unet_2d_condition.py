@@ -84,7 +84,7 @@ class _HotPathModel(nn.Module):
         for name, shape in param_shapes(cfg, self.KIND).items():
             self._register(name, torch.zeros(shape))
         self._engine: Optional[NetEngine] = None
-        self._ctx_key = None
+        self._generation = 0  # bumped whenever the parameters change: recorded programs of older engines are stale
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
 
     # ---- parameter tree with diffusers names
@@ -99,7 +99,11 @@ class _HotPathModel(nn.Module):
 
     def _invalidate(self):
         self._engine = None
-        self._ctx_key = None
+        self._generation += 1
+
+    @property
+    def generation(self) -> int:
+        return self._generation
 
     def _apply(self, fn, *a, **k):  # .to() / .cuda() / .half() move parameters: repack lazily
         self._invalidate()
@@ -169,12 +173,11 @@ class _HotPathModel(nn.Module):
         xn = ops.nchw_to_nhwc(x.float().contiguous(), x_in.shape[-1])
         x_in.copy_(xn.view_as(x_in))
         plan.inputs["timesteps"].copy_(self._timesteps(timestep, nb, sample.device))
-        ctx = encoder_hidden_states
-        key = (ctx.data_ptr(), ctx._version, tuple(ctx.shape), id(plan))
-        if key != self._ctx_key:
-            plan.inputs["ctx"].copy_(ctx.to(torch.bfloat16))
-            plan.ctx_program.run()
-            self._ctx_key = key
+        # the cross-attention K / V^T projections of the prompt are recomputed on every eager forward (32 tiny
+        # GEMMs over [nb, 77, 768]): an address / version key is not a content identity — a new prompt tensor
+        # commonly lands on the freed block of the previous one. The fused loop projects once per call.
+        plan.inputs["ctx"].copy_(encoder_hidden_states.to(torch.bfloat16))
+        plan.ctx_program.run()
 
     @staticmethod
     def _to_nchw(t: torch.Tensor, nb, h, w, dtype) -> torch.Tensor:
@@ -212,6 +215,15 @@ class UNet2DConditionModel(_HotPathModel):
         is_brushnet = (down_block_add_samples is not None and mid_block_add_sample is not None
                        and up_block_add_samples is not None)
         is_controlnet = mid_block_additional_residual is not None and down_block_additional_residuals is not None
+        with torch.cuda.device(self.device):  # launches go to the stream of the model's device
+            return self._forward(sample, timestep, encoder_hidden_states, is_brushnet, is_controlnet,
+                                 down_block_add_samples, mid_block_add_sample, up_block_add_samples,
+                                 down_block_additional_residuals, mid_block_additional_residual, return_dict)
+
+    def _forward(self, sample, timestep, encoder_hidden_states, is_brushnet, is_controlnet, down_block_add_samples,
+                 mid_block_add_sample, up_block_add_samples, down_block_additional_residuals,
+                 mid_block_additional_residual, return_dict):
+        nb, _, h, w = sample.shape
         eng = self.engine()
         plan = eng.plan(nb, h, w, encoder_hidden_states.shape[1], with_brushnet_adds=is_brushnet,
                         with_controlnet_res=is_controlnet)
@@ -253,7 +265,6 @@ class BrushNetModel(_HotPathModel):
         super().__init__(cfg, **kw)
         self.config.brushnet_conditioning_channel_order = "rgb"
         self.config.global_pool_conditions = False
-        self._scaled_plans: Dict[tuple, object] = {}
 
     @classmethod
     def from_unet(cls, unet: UNet2DConditionModel, brushnet_conditioning_channel_order: str = "rgb",
@@ -284,21 +295,6 @@ class BrushNetModel(_HotPathModel):
         bn._out_dtype = unet.dtype
         return bn
 
-    def _plan_scaled(self, nb, h, w, ctx_len, scale: float):
-        key = (nb, h, w, ctx_len, float(scale))
-        p = self._scaled_plans.get(key)
-        if p is None:
-            eng = self.engine()
-            # a fresh plan per scale: alpha is baked into the recorded zero-conv epilogues
-            p = eng._build_plan(nb, h, w, ctx_len, False, False, False, 0)
-            eng.append_brushnet_outputs(p, float(scale))
-            self._scaled_plans[key] = p
-        return p
-
-    def _invalidate(self):
-        super()._invalidate()
-        self._scaled_plans = {}
-
     @torch.no_grad()
     def forward(self, sample: torch.FloatTensor, timestep: Union[torch.Tensor, float, int],
                 encoder_hidden_states: torch.Tensor, brushnet_cond: torch.FloatTensor,
@@ -314,13 +310,16 @@ class BrushNetModel(_HotPathModel):
             if v is not None:
                 raise NotImplementedError(f"`{name}` is outside the PowerPaint SD-1.5 hot path")
         nb, _, h, w = sample.shape
-        plan = self._plan_scaled(nb, h, w, encoder_hidden_states.shape[1], conditioning_scale)
-        self._load_inputs(plan, sample, timestep, encoder_hidden_states, extra_channels=brushnet_cond)
-        plan.program.launch()
-        shapes_d, shape_m, shapes_u = self.engine()._state_shapes(nb, h, w)
-        down = [self._to_nchw(t, nb, s[1], s[2], self.dtype) for t, s in zip(plan.outputs["down"], shapes_d)]
-        mid = self._to_nchw(plan.outputs["mid"], nb, shape_m[1], shape_m[2], self.dtype)
-        up = [self._to_nchw(t, nb, s[1], s[2], self.dtype) for t, s in zip(plan.outputs["up"], shapes_u)]
+        with torch.cuda.device(self.device):
+            # one recorded program for every conditioning_scale: the zero-conv epilogues read it from a device scalar
+            plan = self.engine().plan(nb, h, w, encoder_hidden_states.shape[1], brushnet_outputs=True)
+            plan.scale_dev.fill_(float(conditioning_scale))
+            self._load_inputs(plan, sample, timestep, encoder_hidden_states, extra_channels=brushnet_cond)
+            plan.program.launch()
+            shapes_d, shape_m, shapes_u = self.engine()._state_shapes(nb, h, w)
+            down = [self._to_nchw(t, nb, s[1], s[2], self.dtype) for t, s in zip(plan.outputs["down"], shapes_d)]
+            mid = self._to_nchw(plan.outputs["mid"], nb, shape_m[1], shape_m[2], self.dtype)
+            up = [self._to_nchw(t, nb, s[1], s[2], self.dtype) for t, s in zip(plan.outputs["up"], shapes_u)]
         if not return_dict:
             return (down, mid, up)
         return BrushNetOutput(down_block_res_samples=down, mid_block_res_sample=mid, up_block_res_samples=up)
@@ -334,11 +333,6 @@ class ControlNetModel(_HotPathModel):
             kw["in_channels"] = 4
         super().__init__(cfg, **kw)
         self.config.global_pool_conditions = False
-        self._cond_key = None
-
-    def _invalidate(self):
-        super()._invalidate()
-        self._cond_key = None
 
     @torch.no_grad()
     def forward(self, sample: torch.FloatTensor, timestep: Union[torch.Tensor, float, int],
@@ -353,21 +347,23 @@ class ControlNetModel(_HotPathModel):
         nb, _, h, w = sample.shape
         if tuple(controlnet_cond.shape[2:]) != (8 * h, 8 * w):
             raise ValueError("controlnet_cond must be 8x the latent resolution")
-        eng = self.engine()
-        plan = eng.plan(nb, h, w, encoder_hidden_states.shape[1])
-        ckey = (controlnet_cond.data_ptr(), controlnet_cond._version, tuple(controlnet_cond.shape), id(plan))
-        if ckey != self._cond_key:  # t-independent: embedded once per control image
+        with torch.cuda.device(self.device):
+            eng = self.engine()
+            plan = eng.plan(nb, h, w, encoder_hidden_states.shape[1])
+            # t-independent: the 8-conv embedding is re-run only when the staged control
+            # image actually differs (content comparison on the device; an address is not an identity)
             ci = plan.inputs["cond_in"]
-            ci.copy_(ops.nchw_to_nhwc(controlnet_cond.float().contiguous(), ci.shape[-1]).view_as(ci))
-            plan.cond_program.run()
-            self._cond_key = ckey
-        self._load_inputs(plan, sample, timestep, encoder_hidden_states)
-        plan.program.launch()
-        shapes_d, shape_m, _ = eng._state_shapes(nb, h, w)
-        s = float(conditioning_scale)
-        down = [self._to_nchw(t, nb, sh[1], sh[2], torch.float32).mul_(s).to(self.dtype)
-                for t, sh in zip(plan.outputs["down"], shapes_d)]
-        mid = self._to_nchw(plan.outputs["mid"], nb, shape_m[1], shape_m[2], torch.float32).mul_(s).to(self.dtype)
+            new_ci = ops.nchw_to_nhwc(controlnet_cond.float().contiguous(), ci.shape[-1]).view_as(ci)
+            if not plan.outputs.get("cond_valid") or not torch.equal(new_ci, ci):
+                ci.copy_(new_ci)
+                plan.cond_program.run()
+                plan.outputs["cond_valid"] = True
+            plan.scale_dev.fill_(float(conditioning_scale))
+            self._load_inputs(plan, sample, timestep, encoder_hidden_states)
+            plan.program.launch()
+            shapes_d, shape_m, _ = eng._state_shapes(nb, h, w)
+            down = [self._to_nchw(t, nb, sh[1], sh[2], self.dtype) for t, sh in zip(plan.outputs["down"], shapes_d)]
+            mid = self._to_nchw(plan.outputs["mid"], nb, shape_m[1], shape_m[2], self.dtype)
         if not return_dict:
             return (down, mid)
         return ControlNetOutput(down_block_res_samples=down, mid_block_res_sample=mid)

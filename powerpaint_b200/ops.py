@@ -96,7 +96,9 @@ def gemm_desc(*, a0: torch.Tensor, w: torch.Tensor, out: torch.Tensor, N_: int,
               rows_per_group: int = 0, rowvec_ld: int = 0, res1: Optional[torch.Tensor] = None, ldr1: int = 0,
               res2: Optional[torch.Tensor] = None, ldr2: int = 0, alpha: float = 1.0,
               act: int = N.PP_ACT_NONE, epilogue: int = N.PP_EPI_PLAIN, ldc: int = 0,
-              out_fp32: bool = False, t_rows: int = 0, t_ld: int = 0, block_n: int = 0, t_fp16: bool = False) -> Desc:
+              out_fp32: bool = False, t_rows: int = 0, t_ld: int = 0, block_n: int = 0, t_fp16: bool = False,
+              alpha_dev: Optional[torch.Tensor] = None, alpha_step: Optional[torch.Tensor] = None,
+              alpha_stride: int = 0, chan_stats: Optional[torch.Tensor] = None) -> Desc:
     d = N.GemmDesc()
     d.a_mode, d.epilogue = a_mode, epilogue
     d.a0, d.a1 = N.ptr(a0), N.ptr(a1)
@@ -119,7 +121,21 @@ def gemm_desc(*, a0: torch.Tensor, w: torch.Tensor, out: torch.Tensor, N_: int,
     d.t_rows, d.t_ld = t_rows, t_ld
     d.block_n = block_n
     d.t_fp16 = 1 if t_fp16 else 0
-    return Desc("gemm", d, (a0, a1, w, out, bias, rowvec, res1, res2))
+    d.alpha_dev, d.alpha_step, d.alpha_stride = N.ptr(alpha_dev), N.ptr(alpha_step), alpha_stride
+    d.chan_stats = N.ptr(chan_stats)
+    return Desc("gemm", d, [a0, a1, w, out, bias, rowvec, res1, res2, alpha_dev, alpha_step, chan_stats])
+
+
+def gemm_stats_geometry(desc: Desc) -> "N.StatsGeom":
+    """host-only: can this GEMM emit GroupNorm partial sums from its epilogue, and in which layout"""
+    g = N.StatsGeom()
+    N.check(N.lib().pp_gemm_stats_geometry(C.byref(desc.c), C.byref(g)), "pp_gemm_stats_geometry")
+    return g
+
+
+def attach_chan_stats(desc: Desc, buf: torch.Tensor) -> None:
+    desc.c.chan_stats = N.ptr(buf)
+    desc.keep.append(buf)
 
 
 def attn_desc(*, q, k, vt, out, batch, heads, d, nq, nk, q_ld, k_ld, vt_ld, o_ld,
@@ -142,7 +158,7 @@ def gn_scratch_bytes(batch: int, hw: int, channels: int, groups: int) -> int:
 
 
 def gn_desc(*, x0, x1, c0, c1, batch, hw, groups, gamma, beta, eps, silu, y, stats=None,
-            stats_prezeroed=False) -> Desc:
+            stats_prezeroed=False, part0=None, geom0=None, part1=None, geom1=None) -> Desc:
     """`stats`: scratch of gn_scratch_bytes() bytes (fp32 tensor, 16-byte aligned); allocated (zeroed) here
     when omitted."""
     if stats is None:
@@ -155,7 +171,12 @@ def gn_desc(*, x0, x1, c0, c1, batch, hw, groups, gamma, beta, eps, silu, y, sta
     g.gamma, g.beta, g.eps, g.silu = N.ptr(gamma), N.ptr(beta), eps, 1 if silu else 0
     g.stats, g.y = N.ptr(stats), N.ptr(y)
     g.stats_prezeroed = 1 if stats_prezeroed else 0
-    return Desc("gn", g, (x0, x1, gamma, beta, stats, y))
+    if part0 is not None:
+        g.from_partials = 1
+        g.part0, g.geom0 = N.ptr(part0), geom0
+        if x1 is not None:
+            g.part1, g.geom1 = N.ptr(part1), geom1
+    return Desc("gn", g, (x0, x1, gamma, beta, stats, y, part0, part1))
 
 
 def cfg_ddim_desc(*, eps, eps_fp32, eps_ld, latents, coef, step_idx, advance_step, noise,
@@ -200,6 +221,13 @@ def layer_norm(x, y, gamma, beta, eps):
 def upsample2x(x, y):
     nb, h, w, c = x.shape
     N.check(N.lib().pp_upsample2x(N.ptr(x), N.ptr(y), nb, h, w, c, N.current_stream()), "pp_upsample2x")
+
+
+def upsample_nearest(x, y):
+    """F.interpolate(size=y.shape[1:3], mode="nearest") on NHWC bf16"""
+    nb, h, w, c = x.shape
+    N.check(N.lib().pp_upsample_nearest(N.ptr(x), N.ptr(y), nb, h, w, c, y.shape[1], y.shape[2],
+                                        N.current_stream()), "pp_upsample_nearest")
 
 
 def add(a, b, y):
@@ -277,6 +305,11 @@ class Program:
     def add_upsample2x(self, x, y, nb, h, w, c):
         N.check(N.lib().pp_program_add_upsample2x(self._h, N.ptr(x), N.ptr(y), nb, h, w, c),
                 "pp_program_add_upsample2x")
+        self._keep.append((x, y))
+
+    def add_upsample_nearest(self, x, y, nb, h, w, c, ho, wo):
+        N.check(N.lib().pp_program_add_upsample_nearest(self._h, N.ptr(x), N.ptr(y), nb, h, w, c, ho, wo),
+                "pp_program_add_upsample_nearest")
         self._keep.append((x, y))
 
     def add_add(self, a, b, y, n):

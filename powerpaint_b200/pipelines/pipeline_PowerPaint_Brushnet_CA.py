@@ -225,9 +225,8 @@ class StableDiffusionPowerPaintBrushNetPipeline(StableDiffusionInpaintPipeline):
         extra_step_kwargs = self.prepare_extra_step_kwargs(generator, eta)
         keep = [1.0 - float(i / len(ts) < control_guidance_start[0] or (i + 1) / len(ts) > control_guidance_end[0])
                 for i in range(len(ts))]
-        if any(k != 1.0 for k in keep):
-            raise NotImplementedError("control_guidance_start/end other than (0, 1) change the BrushNet scale per "
-                                      "step; the fused program bakes one scale (app.py uses the defaults)")
+        # `brushnet_keep` (:1369-1376) x brushnet_conditioning_scale (:1403-1409) = the per-step scale row of the
+        # device coefficient table the recorded program indexes
         coef = self.scheduler.step_coefficients(ts, eta=extra_step_kwargs.get("eta", 0.0))
         noise_fn = None
         if eta > 0:
@@ -240,10 +239,16 @@ class StableDiffusionPowerPaintBrushNetPipeline(StableDiffusionInpaintPipeline):
             def cb(i, t, lat):
                 new = None
                 if callback_on_step_end is not None:
-                    kw = {k: {"latents": lat, "prompt_embeds": prompt_embeds,
-                              "negative_prompt_embeds": negative_prompt_embeds}[k]
+                    # the reference hands out the encoded tensors (:1451-1459): [neg; pos] split again
+                    neg_e, pos_e = (prompt_embeds.chunk(2) if do_cfg else (None, prompt_embeds))
+                    kw = {k: {"latents": lat, "prompt_embeds": pos_e, "negative_prompt_embeds": neg_e}[k]
                           for k in callback_on_step_end_tensor_inputs}
-                    outs = callback_on_step_end(pipe, i, t, kw)
+                    outs = callback_on_step_end(pipe, i, t, kw) or {}
+                    for k in ("prompt_embeds", "negative_prompt_embeds"):
+                        if k in outs and outs[k] is not kw.get(k):
+                            raise NotImplementedError(
+                                f"callback_on_step_end returned a replacement `{k}`: the cross-attention K/V of the "
+                                "prompt are projected once per call, replacing them mid-loop is not supported")
                     new = outs.pop("latents", lat)
                     lat = new
                 if callback is not None and i % (callback_steps or 1) == 0:
@@ -252,6 +257,7 @@ class StableDiffusionPowerPaintBrushNetPipeline(StableDiffusionInpaintPipeline):
         latents = self.denoiser().run(latents=latents, prompt_embeds=prompt_embedsU, side_prompt_embeds=prompt_embeds,
                                       timesteps=ts, coef=coef, guidance_scale=guidance_scale,
                                       extra=conditioning_latents, side_scale=float(brushnet_conditioning_scale),
+                                      side_keep=keep,
                                       noise_fn=noise_fn, callback=cb)
         if output_type != "latent":
             image_o = self.vae.decode((latents / self.vae.config.scaling_factor).to(self.vae.dtype),

@@ -115,9 +115,8 @@ class StableDiffusionControlNetInpaintPipeline(StableDiffusionInpaintPipeline):
         extra_step_kwargs = self.prepare_extra_step_kwargs(generator, eta)
         keep = [1.0 - float(i / len(timesteps) < control_guidance_start[0]
                             or (i + 1) / len(timesteps) > control_guidance_end[0]) for i in range(len(timesteps))]
-        if any(k != 1.0 for k in keep):
-            raise NotImplementedError("control_guidance_start/end other than (0, 1) are not supported by the fused "
-                                      "program (one ControlNet scale is baked in)")
+        # `controlnet_keep` (ref:pipeline_PowerPaint_ControlNet.py:1652-1658): the per-step scale
+        # conditioning_scale * keep[i] sits in the device coefficient table the recorded program indexes
         coef = self.scheduler.step_coefficients(timesteps, eta=extra_step_kwargs.get("eta", 0.0))
         noise_fn = None
         if eta > 0:
@@ -135,7 +134,8 @@ class StableDiffusionControlNetInpaintPipeline(StableDiffusionInpaintPipeline):
                                       control_image=control, timesteps=timesteps, coef=coef,
                                       guidance_scale=guidance_scale,
                                       extra=torch.cat([mask, masked_image_latents], dim=1),
-                                      side_scale=float(controlnet_conditioning_scale), noise_fn=noise_fn, callback=cb)
+                                      side_scale=float(controlnet_conditioning_scale), side_keep=keep,
+                                      noise_fn=noise_fn, callback=cb)
         if output_type != "latent":
             image_o = self.vae.decode((latents / self.vae.config.scaling_factor).to(self.vae.dtype),
                                       return_dict=False)[0]

@@ -100,12 +100,13 @@ class _ControlNetCoefficientDenoiser:
 
     @torch.no_grad()
     def run(self, *, latents, prompt_embeds, side_prompt_embeds, control_image, timesteps, coef, guidance_scale,
-            extra, side_scale, noise_fn=None, callback=None):
+            extra, side_scale, side_keep=None, noise_fn=None, callback=None):
         do_cfg = guidance_scale > 1.0
         for i, t in enumerate(timesteps):
             x4 = torch.cat([latents] * 2) if do_cfg else latents
             ex = torch.cat([extra] * 2) if do_cfg else extra
-            d, m = self.controlnet(x4, int(t), side_prompt_embeds, control_image, side_scale)
+            d, m = self.controlnet(x4, int(t), side_prompt_embeds, control_image,
+                                   side_scale * (side_keep[i] if side_keep is not None else 1.0))
             eps = self.unet(torch.cat([x4, ex], dim=1), int(t), prompt_embeds, down_block_additional_residuals=d,
                             mid_block_additional_residual=m)
             if do_cfg:
@@ -184,11 +185,12 @@ class _BrushNetCoefficientDenoiser:
 
     @torch.no_grad()
     def run(self, *, latents, prompt_embeds, side_prompt_embeds, timesteps, coef, guidance_scale, extra, side_scale,
-            noise_fn=None, callback=None):
+            side_keep=None, noise_fn=None, callback=None):
         do_cfg = guidance_scale > 1.0
         for i, t in enumerate(timesteps):
             x = torch.cat([latents] * 2) if do_cfg else latents
-            d, m, u = self.brushnet(x, int(t), side_prompt_embeds, extra, side_scale)
+            d, m, u = self.brushnet(x, int(t), side_prompt_embeds, extra,
+                                    side_scale * (side_keep[i] if side_keep is not None else 1.0))
             eps = self.unet(x, int(t), prompt_embeds, down_block_add_samples=d, mid_block_add_sample=m,
                             up_block_add_samples=u)
             if do_cfg:
