@@ -121,6 +121,10 @@ class UNet2DConditionOracle(nn.Module):
                 mid_block_add_sample: Optional[torch.Tensor] = None,
                 up_block_add_samples: Optional[List[torch.Tensor]] = None):
         ctx = encoder_hidden_states
+        # unet_2d_condition.py:1112-1126: the upsample size is forwarded when a spatial dim is not a multiple
+        # of 2 ** (number of upsamplers)
+        factor = 2 ** sum(1 for b in self.up_blocks if b.upsamplers is not None)
+        forward_upsample_size = any(d % factor != 0 for d in sample.shape[-2:])
         emb = self.time_embed(sample, timestep)
         sample = self.conv_in(sample)
         is_controlnet = mid_block_additional_residual is not None and down_block_additional_residuals is not None
@@ -154,7 +158,10 @@ class UNet2DConditionOracle(nn.Module):
             if is_brushnet and len(up_block_add_samples) > 0:
                 k = n + (blk.upsamplers is not None)
                 adds = [up_block_add_samples.pop(0) for _ in range(k)]
-            sample = blk(sample, res, emb, ctx, None, adds)
+            # :1310-1312 — the size of the next block's first skip
+            upsample_size = (res_samples[-1].shape[2:] if forward_upsample_size and i != len(self.up_blocks) - 1
+                             else None)
+            sample = blk(sample, res, emb, ctx, upsample_size, adds)
         sample = F.silu(self.conv_norm_out(sample))
         return self.conv_out(sample)
 

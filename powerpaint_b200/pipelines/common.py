@@ -52,6 +52,13 @@ def prepare_mask_and_masked_image(image, mask, height, width, return_image: bool
     if isinstance(image, torch.Tensor):
         if not isinstance(mask, torch.Tensor):
             raise TypeError(f"`image` is a torch.Tensor but `mask` (type: {type(mask)} is not")
+        # uint8 tensors (NCHW, any device) are the device-resident form of the uint8 numpy / PIL inputs the
+        # reference converts with `/ 127.5 - 1` and `/ 255` (:123-140): < 1 MB per 512^2 image over PCIe, the
+        # conversion runs where the tensor lives
+        if image.dtype == torch.uint8:
+            image = image.to(torch.float32) / 127.5 - 1.0
+        if mask.dtype == torch.uint8:
+            mask = mask.to(torch.float32) / 255.0
         if image.ndim == 3:
             assert image.shape[0] == 3, "Image outside a batch should be of shape (3, H, W)"
             image = image.unsqueeze(0)
@@ -105,6 +112,9 @@ def preprocess_image(image, height=None, width=None, do_normalize=True) -> torch
     pipeline_PowerPaint_ControlNet.py:320-322)."""
     if isinstance(image, torch.Tensor):
         t = image if image.ndim == 4 else image.unsqueeze(0)
+        if t.dtype == torch.uint8:  # device-resident form of a uint8 numpy / PIL input
+            t = t.to(torch.float32) / 255.0
+            return 2.0 * t - 1.0 if do_normalize else t
         t = t.to(torch.float32)
         if do_normalize and t.min() >= 0:
             t = 2.0 * t - 1.0

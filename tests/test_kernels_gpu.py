@@ -358,3 +358,191 @@ def test_program_and_graph(ops):
     ref = F.conv2d(ref, wt.float(), None, padding=1).to(BF16).float().permute(0, 2, 3, 1)
     ref = F.layer_norm(ref, (c,), gamma, beta, 1e-5)
     assert _rel(z, ref) < 2e-2
+
+
+# --------------------------------------------------------------------------- round-2 kernels
+def _gn_from_producers(ops, prods, groups, silu=True, eps=1e-5):
+    """prods: list of (out [B, hw, c] bf16, partials, geometry); GroupNorm over their channel concat
+    driven by the producers' epilogue statistics, against torch on the stored bf16 values"""
+    x0, p0, g0 = prods[0]
+    x1, p1, g1 = prods[1] if len(prods) > 1 else (None, None, None)
+    B, hw, c0 = x0.shape
+    c1 = x1.shape[-1] if x1 is not None else 0
+    gen = torch.Generator(device="cuda").manual_seed(c0 + c1)
+    gamma = torch.randn(c0 + c1, device=_dev(), generator=gen)
+    beta = torch.randn(c0 + c1, device=_dev(), generator=gen)
+    y = torch.zeros(B, hw, c0 + c1, device=_dev(), dtype=BF16)
+    stats = torch.full(((ops.gn_scratch_bytes(B, hw, c0 + c1, groups) + 3) // 4,), float("nan"), device=_dev())
+    ops.run(ops.gn_desc(x0=x0, x1=x1, c0=c0, c1=c1, batch=B, hw=hw, groups=groups, gamma=gamma, beta=beta, eps=eps,
+                        silu=silu, stats=stats, y=y, part0=p0, geom0=g0, part1=p1, geom1=g1))
+    torch.cuda.synchronize()
+    x = torch.cat([x0, x1], -1) if x1 is not None else x0
+    ref = F.group_norm(x.float().permute(0, 2, 1), groups, gamma, beta, eps)
+    if silu:
+        ref = F.silu(ref)
+    return _rel(y.permute(0, 2, 1), ref)
+
+
+def _conv_with_stats(ops, nb, h, w, cin, cout, seed, stride2=False, block_n=0, mean_shift=0.0):
+    from powerpaint_b200 import _native as nat
+
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(nb, h, w, cin, device=_dev(), generator=g).to(BF16)
+    wt = (torch.randn(cout, cin, 3, 3, device=_dev(), generator=g) / math.sqrt(9 * cin)).to(BF16)
+    bias = torch.randn(cout, device=_dev(), generator=g) + mean_shift
+    ho, wo = ((h + 1) // 2, (w + 1) // 2) if stride2 else (h, w)
+    out = torch.full((nb, ho * wo, cout), float("nan"), device=_dev(), dtype=BF16)
+    d = ops.gemm_desc(a0=x, w=ops.pack_conv3x3_weight(wt.float()), out=out, N_=cout,
+                      a_mode=nat.PP_A_CONV3X3_S2 if stride2 else nat.PP_A_CONV3X3, c0=cin, nb=nb, h=h, w_=w, bias=bias,
+                      block_n=block_n)
+    geo = ops.gemm_stats_geometry(d)
+    assert geo.supported, "this shape should be able to emit statistics"
+    part = torch.full((int(geo.bytes) // 4,), float("nan"), device=_dev())
+    ops.attach_chan_stats(d, part)
+    ops.run(d)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), wt.float(), bias, stride=2 if stride2 else 1, padding=1)
+    assert _rel(out.view(nb, ho, wo, cout).permute(0, 3, 1, 2), ref) < 6e-3
+    return out, part, geo
+
+
+@pytest.mark.parametrize("nb,h,w,cin,cout,bn,s2", [(2, 64, 64, 64, 320, 0, False), (5, 8, 8, 128, 1280, 0, False),
+                                                   (3, 16, 16, 64, 640, 128, False), (2, 12, 20, 64, 64, 64, False),
+                                                   (3, 32, 32, 64, 256, 256, False), (2, 32, 32, 64, 320, 0, True),
+                                                   (3, 4, 4, 64, 320, 0, False), (2, 13, 27, 64, 320, 0, True)])
+def test_group_norm_from_conv_epilogue_stats(ops, nb, h, w, cin, cout, bn, s2):
+    out, part, geo = _conv_with_stats(ops, nb, h, w, cin, cout, seed=nb + h + cout, stride2=s2, block_n=bn)
+    groups = 32 if cout % 32 == 0 else 8
+    assert _gn_from_producers(ops, [(out, part, geo)], groups) < 5e-3
+
+
+def test_group_norm_from_stats_concat_of_conv_and_linear(ops):
+    """the up-path concat: hidden state from a 3x3 conv, skip from a transformer's proj_out (matrix mode,
+    hw = 256 rows per sample and hw = 64: two samples per 128-row tile)"""
+    for hw_side, nb in ((16, 3), (8, 5)):
+        hw = hw_side * hw_side
+        out0, p0, g0 = _conv_with_stats(ops, nb, hw_side, hw_side, 64, 640, seed=hw)
+        g = torch.Generator(device="cuda").manual_seed(hw + 1)
+        a = torch.randn(nb * hw, 320, device=_dev(), generator=g).to(BF16)
+        wl = (torch.randn(320, 320, device=_dev(), generator=g) / math.sqrt(320)).to(BF16)
+        res = torch.randn(nb * hw, 320, device=_dev(), generator=g).to(BF16)
+        out1 = torch.zeros(nb, hw, 320, device=_dev(), dtype=BF16)
+        d = ops.gemm_desc(a0=a, w=wl, out=out1, N_=320, M=nb * hw, res1=res, rows_per_group=hw)
+        geo = ops.gemm_stats_geometry(d)
+        assert geo.supported and geo.segs == max(1, 128 // hw)
+        p1 = torch.full((int(geo.bytes) // 4,), float("nan"), device=_dev())
+        ops.attach_chan_stats(d, p1)
+        ops.run(d)
+        torch.cuda.synchronize()
+        assert _rel(out1.view(nb * hw, 320), a.float() @ wl.float().t() + res.float()) < 6e-3
+        assert _gn_from_producers(ops, [(out0, p0, g0), (out1, p1, geo)], 32) < 5e-3
+
+
+def test_group_norm_large_mean_small_spread(ops):
+    """a group whose mean dwarfs its spread (late-UNet activations on real checkpoints): the statistics are
+    combined as (count, mean, M2) in fp64, so the variance does not cancel — both statistics paths"""
+    B, hw, c = 2, 4096, 64
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = (torch.randn(B, hw, c, device=_dev(), generator=g) * 0.25 + 120.0).to(BF16)
+    gamma = torch.ones(c, device=_dev())
+    beta = torch.zeros(c, device=_dev())
+    y = torch.zeros_like(x)
+    ops.run(ops.gn_desc(x0=x, x1=None, c0=c, c1=0, batch=B, hw=hw, groups=8, gamma=gamma, beta=beta, eps=1e-5,
+                        silu=False, y=y))
+    torch.cuda.synchronize()
+    ref = F.group_norm(x.double().permute(0, 2, 1), 8, None, None, 1e-5).float()
+    assert _rel(y.permute(0, 2, 1), ref) < 1e-2, _rel(y.permute(0, 2, 1), ref)
+    out, part, geo = _conv_with_stats(ops, 2, 32, 32, 64, 64, seed=77, mean_shift=200.0)
+    assert _gn_from_producers(ops, [(out, part, geo)], 8, silu=False) < 1e-2
+
+
+@pytest.mark.parametrize("nb,h,w,c", [(2, 13, 27, 64), (1, 3, 2, 32), (2, 15, 15, 128), (3, 7, 64, 32)])
+def test_conv3x3_stride2_odd_sizes(ops, nb, h, w, c):
+    """Downsample2D on an odd feature map (latents that are not multiples of 8): output ceil(h/2) x ceil(w/2)"""
+    from powerpaint_b200 import _native as nat
+
+    g = torch.Generator(device="cuda").manual_seed(h * w + c)
+    x = torch.randn(nb, c, h, w, device=_dev(), generator=g).to(BF16)
+    wt = (torch.randn(c, c, 3, 3, device=_dev(), generator=g) / math.sqrt(9 * c)).to(BF16)
+    bias = torch.randn(c, device=_dev(), generator=g)
+    ho, wo = (h + 1) // 2, (w + 1) // 2
+    out = torch.full((nb, ho, wo, c), float("nan"), device=_dev(), dtype=BF16)
+    ops.run(ops.gemm_desc(a0=x.permute(0, 2, 3, 1).contiguous(), w=ops.pack_conv3x3_weight(wt.float()), out=out, N_=c,
+                          a_mode=nat.PP_A_CONV3X3_S2, c0=c, nb=nb, h=h, w_=w, bias=bias))
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float(), wt.float(), bias, stride=2, padding=1)
+    assert ref.shape[-2:] == (ho, wo)
+    assert _rel(out.permute(0, 3, 1, 2), ref) < 6e-3
+
+
+@pytest.mark.parametrize("nb,h,w,c", [(2, 64, 64, 128), (1, 16, 24, 32), (2, 9, 7, 64)])
+def test_conv3x3_stride2_pad_bottom_right(ops, nb, h, w, c):
+    """the VAE encoder's Downsample2D(padding=0): conv(F.pad(x, (0, 1, 0, 1)), stride 2)"""
+    from powerpaint_b200 import _native as nat
+
+    g = torch.Generator(device="cuda").manual_seed(h + w + c)
+    x = torch.randn(nb, c, h, w, device=_dev(), generator=g).to(BF16)
+    wt = (torch.randn(c, c, 3, 3, device=_dev(), generator=g) / math.sqrt(9 * c)).to(BF16)
+    bias = torch.randn(c, device=_dev(), generator=g)
+    ref = F.conv2d(F.pad(x.float(), (0, 1, 0, 1)), wt.float(), bias, stride=2)
+    ho, wo = ref.shape[-2:]
+    assert (ho, wo) == (h // 2, w // 2)
+    out = torch.full((nb, ho, wo, c), float("nan"), device=_dev(), dtype=BF16)
+    ops.run(ops.gemm_desc(a0=x.permute(0, 2, 3, 1).contiguous(), w=ops.pack_conv3x3_weight(wt.float()), out=out, N_=c,
+                          a_mode=nat.PP_A_CONV3X3_S2P0, c0=c, nb=nb, h=h, w_=w, bias=bias))
+    torch.cuda.synchronize()
+    assert _rel(out.permute(0, 3, 1, 2), ref) < 6e-3
+
+
+def test_upsample_nearest_to_size_and_device_alpha_and_quick_gelu(ops):
+    from powerpaint_b200 import _native as nat
+
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for (h, w, ho, wo) in ((54, 40, 107, 80), (6, 10, 12, 20), (5, 5, 9, 10), (27, 20, 54, 40)):
+        x = torch.randn(2, h, w, 64, device=_dev(), generator=g).to(BF16)
+        y = torch.zeros(2, ho, wo, 64, device=_dev(), dtype=BF16)
+        ops.upsample_nearest(x, y)
+        ref = F.interpolate(x.permute(0, 3, 1, 2).float(), size=(ho, wo), mode="nearest").permute(0, 2, 3, 1)
+        assert torch.equal(y.float(), ref), (h, w, ho, wo)
+    # alpha read from a device table through a device-side step index
+    M, N, K = 256, 320, 320
+    a = torch.randn(M, K, device=_dev(), generator=g).to(BF16)
+    w_ = (torch.randn(N, K, device=_dev(), generator=g) / math.sqrt(K)).to(BF16)
+    bias = torch.randn(N, device=_dev(), generator=g)
+    table = torch.zeros(4, 8, device=_dev())
+    table[:, 6] = torch.tensor([1.0, 0.5, 0.0, 2.0])
+    step = torch.zeros(1, dtype=torch.int32, device=_dev())
+    for mode_n in (N, 4):  # fast bf16 epilogue and the generic one (ragged N)
+        out = torch.zeros(M, mode_n, device=_dev(), dtype=BF16)
+        d = ops.gemm_desc(a0=a, w=w_[:mode_n].contiguous(), out=out, N_=mode_n, M=M, bias=bias[:mode_n].contiguous(),
+                          alpha=0.5, alpha_dev=table[:, 6], alpha_step=step, alpha_stride=8)
+        for i, s in enumerate([1.0, 0.5, 0.0, 2.0]):
+            step.fill_(i)
+            ops.run(d)
+            torch.cuda.synchronize()
+            ref = (a.float() @ w_[:mode_n].float().t() + bias[:mode_n]) * (0.5 * s)
+            assert (out.float() - ref).abs().max().item() < 0.03 * max(ref.abs().max().item(), 1.0)
+    out = torch.zeros(M, N, device=_dev(), dtype=BF16)
+    ops.run(ops.gemm_desc(a0=a, w=w_, out=out, N_=N, M=M, bias=bias, act=nat.PP_ACT_QUICK_GELU))
+    torch.cuda.synchronize()
+    pre = a.float() @ w_.float().t() + bias
+    assert _rel(out, pre * torch.sigmoid(1.702 * pre)) < 6e-3
+
+
+def test_attention_16384_tokens_d40(ops):
+    """the C4 (1024^2 outpaint) self-attention shape: 128 x 128 latent tokens, d = 40"""
+    B, H, d, n = 1, 2, 40, 16384
+    g = torch.Generator(device="cuda").manual_seed(11)
+    C_ = H * d
+    q = torch.randn(B, n, C_, device=_dev(), generator=g).to(BF16)
+    k = torch.randn(B, n, C_, device=_dev(), generator=g).to(BF16)
+    v = torch.randn(B, n, C_, device=_dev(), generator=g).to(torch.float16)
+    vt = v.transpose(1, 2).contiguous()
+    out = torch.full((B, n, C_), float("nan"), device=_dev(), dtype=BF16)
+    ops.run(ops.attn_desc(q=q, k=k, vt=vt, out=out, batch=B, heads=H, d=d, nq=n, nk=n, q_ld=C_, k_ld=C_, vt_ld=n,
+                          o_ld=C_, q_batch_stride=n * C_, k_batch_stride=n * C_, scale=1.0 / math.sqrt(d)))
+    torch.cuda.synchronize()
+    qh, kh, vh = (t.float().view(B, n, H, d).transpose(1, 2) for t in (q, k, v))
+    ref = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(B, n, C_)
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < 1.5e-2, _rel(out, ref)

@@ -305,3 +305,197 @@ def test_loop_v1_sd15_5steps():
                                 guidance_scale=7.5, extra=torch.cat([mask, ml], 1))
     print(f"sd15 5-step loop: rel-L2 {_rel(got, ref):.3e} cos {_cos(got, ref):.5f}")
     assert _rel(got, ref) < 5e-2 and _cos(got, ref) > 0.998
+
+
+# --------------------------------------------------------------------------- SD-1.5-size configs (BASELINE.json)
+def _bf16_copy(om):
+    import copy
+
+    return copy.deepcopy(om).to(torch.bfloat16)
+
+
+def _report(name, **kv):
+    """numbers quoted in BASELINE.md are written next to the test log (gpurun_out/ travels back)"""
+    import json
+    import os
+
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", "parity_report.jsonl"), "a") as f:
+        f.write(json.dumps(dict(test=name, **kv)) + "\n")
+    print(name, kv)
+
+
+def test_loop_brushnet_sd15_c3():
+    """C3 (PowerPaint-v2-1 BrushNet), SD-1.5 size: one image x CFG (UNet batch 2 + BrushNet batch 2), 64x64
+    latents, 5 DDIM steps, brushnet scale 1.0 with a control_guidance window that drops the last step
+    (ref:pipeline_PowerPaint_Brushnet_CA.py:1384-1449, keep flags :1369-1376)"""
+    from oracle.pipelines import loop_brushnet
+    from powerpaint_b200.denoise import FusedDenoiser
+
+    nets = _nets(4, [("unet", 4, 1234), ("brushnet", 4, 99)], tiny=False)
+    (om_u, pm_u, o), (om_b, pm_b, _) = nets["unet"], nets["brushnet"]
+    g = torch.Generator(device=DEV).manual_seed(1)
+    B, h = 1, 64
+    lat = torch.randn(B, 4, h, h, device=DEV, generator=g)
+    emb_t = torch.randn(2 * B, 77, 768, device=DEV, generator=g) * 0.5
+    emb_u = torch.randn(2 * B, 77, 768, device=DEV, generator=g) * 0.5
+    cond = torch.randn(2 * B, 5, h, h, device=DEV, generator=g)
+    so, sp, ts = _scheds(5)
+    den = FusedDenoiser(pm_u, pm_b, "brushnet")
+    for keep in (None, [1.0, 1.0, 1.0, 1.0, 0.0]):
+        ref = loop_brushnet(om_u, om_b, so, lat, emb_t, emb_u, cond, 7.5, 1.0, keep=keep)
+        got = den.run(latents=lat, prompt_embeds=emb_u, side_prompt_embeds=emb_t, timesteps=ts,
+                      coef=sp.step_coefficients(ts), guidance_scale=7.5, extra=cond, side_scale=1.0, side_keep=keep)
+        _report("loop_brushnet_sd15_c3", keep=keep, rel=_rel(got, ref), cos=_cos(got, ref))
+        assert torch.isfinite(got).all()
+        assert _rel(got, ref) < 5e-2 and _cos(got, ref) > 0.999, (_rel(got, ref), _cos(got, ref))
+    assert len(den._cache) == 1, "one recorded plan serves every conditioning scale / keep window"
+
+
+def test_loop_controlnet_sd15_c5():
+    """C5 (v1 + ControlNet), SD-1.5 size: one image x CFG, 64x64 latents, 5 DDIM steps, scale 0.5
+    (ref:pipeline_PowerPaint_ControlNet.py:1663-1735)"""
+    from oracle.pipelines import loop_controlnet
+    from powerpaint_b200.denoise import FusedDenoiser
+
+    nets = _nets(9, [("unet", 9, 1234), ("controlnet", 4, 77)], tiny=False)
+    (om_u, pm_u, o), (om_c, pm_c, _) = nets["unet"], nets["controlnet"]
+    g = torch.Generator(device=DEV).manual_seed(2)
+    B, h = 1, 64
+    lat = torch.randn(B, 4, h, h, device=DEV, generator=g)
+    emb = torch.randn(2 * B, 77, 768, device=DEV, generator=g) * 0.5
+    mask = (torch.rand(B, 1, h, h, device=DEV, generator=g) > 0.5).float()
+    ml = torch.randn(B, 4, h, h, device=DEV, generator=g)
+    ctrl2 = torch.cat([torch.rand(B, 3, 8 * h, 8 * h, device=DEV, generator=g)] * 2)
+    so, sp, ts = _scheds(5)
+    ref = loop_controlnet(om_u, om_c, so, lat, emb, mask, ml, ctrl2, 7.5, 0.5)
+    got = FusedDenoiser(pm_u, pm_c, "controlnet").run(latents=lat, prompt_embeds=emb, side_prompt_embeds=emb,
+                                                      control_image=ctrl2, timesteps=ts,
+                                                      coef=sp.step_coefficients(ts), guidance_scale=7.5,
+                                                      extra=torch.cat([mask, ml], 1), side_scale=0.5)
+    _report("loop_controlnet_sd15_c5", rel=_rel(got, ref), cos=_cos(got, ref))
+    assert torch.isfinite(got).all()
+    assert _rel(got, ref) < 5e-2 and _cos(got, ref) > 0.999, (_rel(got, ref), _cos(got, ref))
+
+
+def test_pipeline_controlnet_call_tiny():
+    """the ControlNet pipeline's public `__call__` on the GPU (host tensors in, latents out) against the oracle
+    loop fed the same prepared tensors, including a control_guidance window"""
+    from oracle.ddim import DDIMOracle
+    from oracle.pipelines import loop_controlnet
+    from powerpaint_b200.models.autoencoder_kl import AutoencoderKL
+    from powerpaint_b200.pipelines import StableDiffusionControlNetInpaintPipeline
+    from powerpaint_b200.pipelines.common import prepare_mask_and_masked_image, randn_tensor, vae_encode
+    from powerpaint_b200.schedulers import DDIMScheduler
+
+    nets = _nets(9, [("unet", 9, 1234), ("controlnet", 4, 77)])
+    (om_u, pm_u, o), (om_c, pm_c, _) = nets["unet"], nets["controlnet"]
+    vae = AutoencoderKL.synthetic(tiny=True).to(DEV)
+    pipe = StableDiffusionControlNetInpaintPipeline(vae=vae, text_encoder=None, tokenizer=None, unet=pm_u,
+                                                    controlnet=pm_c, scheduler=DDIMScheduler(), safety_checker=None)
+    B, H = 2, 64
+    g = torch.Generator().manual_seed(8)
+    img = torch.rand(B, 3, H, H, generator=g) * 2 - 1
+    mask = torch.zeros(B, 1, H, H)
+    mask[:, :, 16:48, 8:40] = 1
+    ctrl = torch.rand(B, 3, H, H, generator=g)
+    pe = torch.randn(B, 77, o.cross_attention_dim, generator=g) * 0.5
+    ne = torch.randn(B, 77, o.cross_attention_dim, generator=g) * 0.5
+    steps = 6
+    out = pipe(image=img, mask=mask, control_image=ctrl, prompt_embeds=pe, negative_prompt_embeds=ne, height=H,
+               width=H, num_inference_steps=steps, guidance_scale=7.5, controlnet_conditioning_scale=0.5,
+               control_guidance_start=0.0, control_guidance_end=0.7,
+               generator=torch.Generator().manual_seed(13), output_type="latent", return_dict=False)[0]
+    assert out.shape == (B, 4, H // 8, H // 8)
+    gen = torch.Generator().manual_seed(13)
+    m, mi = prepare_mask_and_masked_image(img, mask, H, H)
+    lat = randn_tensor((B, 4, H // 8, H // 8), generator=gen, device=DEV, dtype=torch.float32)
+    m_l = torch.nn.functional.interpolate(m, size=(H // 8, H // 8)).to(DEV)
+    ml = vae_encode(vae, mi.to(DEV), gen)
+    so = DDIMOracle()
+    so.set_timesteps(steps)
+    keep = [1.0 - float(i / steps < 0.0 or (i + 1) / steps > 0.7) for i in range(steps)]
+    assert keep == [1.0, 1.0, 1.0, 1.0, 0.0, 0.0]
+    ref = loop_controlnet(om_u, om_c, so, lat, torch.cat([ne, pe]).to(DEV), m_l, ml, torch.cat([ctrl] * 2).to(DEV), 7.5,
+                          0.5, keep=keep)
+    assert _rel(out, ref) < 5e-2 and _cos(out, ref) > 0.998, (_rel(out, ref), _cos(out, ref))
+
+
+def test_loop_v1_c4_1024():
+    """C4 (v1 outpainting at 1024^2): UNet batch 2, 128x128 latents (16384-token d = 40 self-attention),
+    2 DDIM steps (ref:pipeline_PowerPaint.py:988-1035)"""
+    from oracle.pipelines import loop_v1
+    from powerpaint_b200.denoise import FusedDenoiser
+
+    nets = _nets(9, [("unet", 9, 1234)], tiny=False)
+    om, pm, o = nets["unet"]
+    g = torch.Generator(device=DEV).manual_seed(4)
+    B, h = 1, 128
+    lat = torch.randn(B, 4, h, h, device=DEV, generator=g)
+    emb = torch.randn(2 * B, 77, 768, device=DEV, generator=g) * 0.5
+    mask = torch.ones(B, 1, h, h, device=DEV)
+    mask[:, :, 32:96, 32:96] = 0  # outpainting: keep the centre
+    ml = torch.randn(B, 4, h, h, device=DEV, generator=g)
+    so, sp, ts = _scheds(2)
+    ref = loop_v1(om, so, lat, emb, mask, ml, 7.5)
+    got = FusedDenoiser(pm).run(latents=lat, prompt_embeds=emb, timesteps=ts, coef=sp.step_coefficients(ts),
+                                guidance_scale=7.5, extra=torch.cat([mask, ml], 1))
+    _report("loop_v1_c4_1024", rel=_rel(got, ref), cos=_cos(got, ref))
+    assert torch.isfinite(got).all()
+    assert _rel(got, ref) < 5e-2 and _cos(got, ref) > 0.999, (_rel(got, ref), _cos(got, ref))
+
+
+def test_loop_v1_sd15_50steps_trajectory():
+    """The full 50-step DDIM trajectory of C2's per-image work (SD-1.5 size, one image x CFG): SURVEY §8d asks
+    final latents rel-L2 <= 5e-2 and cosine >= 0.999 against the fp32 oracle. The same trajectory is also run
+    through the oracle modules in torch bf16 eager (the reference's own library path) as the sanity bound."""
+    from oracle.ddim import DDIMOracle
+    from oracle.pipelines import loop_v1
+    from powerpaint_b200.denoise import FusedDenoiser
+
+    nets = _nets(9, [("unet", 9, 1234)], tiny=False)
+    om, pm, o = nets["unet"]
+    g = torch.Generator(device=DEV).manual_seed(0)
+    B, h = 1, 64
+    lat = torch.randn(B, 4, h, h, device=DEV, generator=g)
+    emb = torch.randn(2 * B, 77, 768, device=DEV, generator=g) * 0.5
+    mask = (torch.rand(B, 1, h, h, device=DEV, generator=g) > 0.75).float()
+    ml = torch.randn(B, 4, h, h, device=DEV, generator=g)
+    so, sp, ts = _scheds(50)
+    ref = loop_v1(om, so, lat, emb, mask, ml, 7.5)
+    got = FusedDenoiser(pm).run(latents=lat, prompt_embeds=emb, timesteps=ts, coef=sp.step_coefficients(ts),
+                                guidance_scale=7.5, extra=torch.cat([mask, ml], 1))
+    om16 = _bf16_copy(om)
+    so16 = DDIMOracle()
+    so16.set_timesteps(50)
+    e16 = loop_v1(om16, so16, lat.to(torch.bfloat16), emb.to(torch.bfloat16), mask.to(torch.bfloat16),
+                  ml.to(torch.bfloat16), 7.5).float()
+    _report("loop_v1_sd15_50steps", rel=_rel(got, ref), cos=_cos(got, ref), rel_torch_bf16_eager=_rel(e16, ref),
+            cos_torch_bf16_eager=_cos(e16, ref))
+    assert torch.isfinite(got).all()
+    assert _rel(got, ref) < 5e-2 and _cos(got, ref) > 0.999, (_rel(got, ref), _cos(got, ref))
+
+
+def test_odd_latent_size_v1_640x856():
+    """the reference's canonical call recipe resizes the short side to 640 and rounds to multiples of 8 PIXELS
+    (ref:app.py:258-269,317-321), e.g. 640 x 856 -> an 80 x 107 latent: odd intermediate resolutions
+    (107 -> 54 -> 27 -> 14) through the stride-2 convs and `upsample_size` (ref:unet_2d_condition.py:1120-1126,
+    1311-1312)"""
+    from oracle.pipelines import loop_v1
+    from powerpaint_b200.denoise import FusedDenoiser
+
+    nets = _nets(9, [("unet", 9, 1234)], tiny=False)
+    om, pm, o = nets["unet"]
+    g = torch.Generator(device=DEV).manual_seed(6)
+    B, h, w = 1, 80, 107
+    lat = torch.randn(B, 4, h, w, device=DEV, generator=g)
+    emb = torch.randn(2 * B, 77, 768, device=DEV, generator=g) * 0.5
+    mask = (torch.rand(B, 1, h, w, device=DEV, generator=g) > 0.6).float()
+    ml = torch.randn(B, 4, h, w, device=DEV, generator=g)
+    so, sp, ts = _scheds(3)
+    ref = loop_v1(om, so, lat, emb, mask, ml, 7.5)
+    got = FusedDenoiser(pm).run(latents=lat, prompt_embeds=emb, timesteps=ts, coef=sp.step_coefficients(ts),
+                                guidance_scale=7.5, extra=torch.cat([mask, ml], 1))
+    _report("odd_latent_v1_640x856", rel=_rel(got, ref), cos=_cos(got, ref))
+    assert got.shape == ref.shape and torch.isfinite(got).all()
+    assert _rel(got, ref) < 5e-2 and _cos(got, ref) > 0.999, (_rel(got, ref), _cos(got, ref))
