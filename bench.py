@@ -17,7 +17,8 @@ per-GPU batch.
          timed, max over ranks.
   e2e    the same metric through the reference-facing pipeline `__call__` with pinned HOST buffers: uint8 images
          and masks + prompt embeddings uploaded by each rank for its own shard, normalised on the device, VAE
-         encode, 50 fused steps, VAE decode, uint8 images gathered to rank 0 (NCCL) and read back to the host.
+         encode, 50 fused steps, VAE decode (all on the repo's kernels), uint8 images gathered to rank 0 (NCCL) and
+         read back to the host (output_type="uint8": the device-side form of the uint8 arrays "pil" is built from).
   roofline  tensor-bound: algorithmic FLOPs of one denoising step / mean device time of one recorded step program
          (one CUDA-graph replay), against the measured sustained bf16 peak of MEASURED_PEAKS.json.
   cpu_baseline  the fp32 oracle port of the v1 loop on the host cores (bounded sample, fixed thread count).
@@ -221,7 +222,7 @@ def build_pipeline(cfg, dev):
                                            StableDiffusionPowerPaintBrushNetPipeline)
     from powerpaint_b200.schedulers import DDIMScheduler
 
-    vae = AutoencoderKL.synthetic(seed=4321).to(dev).to(torch.bfloat16)
+    vae = AutoencoderKL.synthetic(seed=4321).to(dev)
     mode = cfg["mode"]
     if mode == "brushnet":
         unet = UNet2DConditionModel.synthetic(NetConfig(in_channels=4), seed=1234).to(dev)
@@ -399,21 +400,20 @@ def run_gpu_arm(args):
     req = synth_requests(cfg, seed=rank)
     host = {k: v.pin_memory() for k, v in req.items()}
     stage = {k: torch.empty_like(v, device=dev) for k, v in req.items()}
-    out_host = torch.empty(B * world, 3, H, H, dtype=torch.uint8).pin_memory() if rank == 0 else None
+    out_host = torch.empty(B * world, H, H, 3, dtype=torch.uint8).pin_memory() if rank == 0 else None
 
     def e2e_once():
         for k in host:  # every rank uploads its own shard (no funnel through rank 0)
             stage[k].copy_(host[k], non_blocking=True)
         common = dict(image=stage["image"], mask=stage["mask"], prompt_embeds=stage["pe"],
                       negative_prompt_embeds=stage["ne"], height=H, width=H, num_inference_steps=DDIM_STEPS,
-                      guidance_scale=GUIDANCE, generator=torch.Generator().manual_seed(rank), output_type="pt")
+                      guidance_scale=GUIDANCE, generator=torch.Generator().manual_seed(rank), output_type="uint8")
         if cfg["mode"] == "brushnet":
             res = pipe(prompt_embedsU=stage["peU"], brushnet_conditioning_scale=1.0, **common).images
         elif cfg["mode"] == "controlnet":
             res = pipe(control_image=stage["control"], controlnet_conditioning_scale=0.5, **common).images
         else:
             res = pipe(**common).images
-        res = (res * 255).round().to(torch.uint8)
         if dist is not None:
             from powerpaint_b200.parallel import gather_images
 

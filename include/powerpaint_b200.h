@@ -205,6 +205,22 @@ pp_status pp_nchw_to_nhwc(const float* x, void* y, int32_t nb, int32_t c, int32_
 pp_status pp_nhwc_to_nchw(const void* x, int32_t x_is_fp32, float* y, int32_t nb, int32_t c,
                           int32_t hw, int32_t c_ld, pp_stream stream);
 
+/* ------------------------------------------------------------------ VAE attention / image I/O */
+/* p[r, :] = softmax(s[r, :]): fp32 scores in, bf16 probabilities out, cols <= 16384. The VAE mid-block
+   attention (one head of 512 channels; pipeline_PowerPaint.py:657-669,:1051 through vae.encode / decode) runs as
+   S = Q K^T (pp_gemm_conv, fp32 out, alpha = 1/sqrt(512)) -> pp_softmax_rows -> O = P V (pp_gemm_conv). */
+pp_status pp_softmax_rows(const float* s, void* p, int64_t rows, int32_t cols, int64_t ld_s, int64_t ld_p,
+                          pp_stream stream);
+/* uint8 NCHW [nb,3,h,w] (+ mask [nb,1,h,w]: mask_mode 1 = uint8, 2 = fp32, 0 = none) -> bf16 NHWC
+   [nb, hw, c_pad]: (px * scale + shift) * (mask < 0.5), channels >= 3 zero — `prepare_mask_and_masked_image`
+   (pipeline_PowerPaint.py:39-153) on the device */
+pp_status pp_image_preprocess_u8(const uint8_t* image, const void* mask, int32_t mask_mode, void* out, int32_t nb,
+                                 int32_t hw, int32_t c_pad, float scale, float shift, pp_stream stream);
+/* decoded image NHWC (channels 0..2 of c_ld) -> clamp(x/2 + 0.5, 0, 1) as uint8 NHWC [nb,hw,3] (x255, rounded)
+   and / or fp32 NCHW [nb,3,hw] — `VaeImageProcessor.postprocess` (pipeline_PowerPaint.py:1062) */
+pp_status pp_image_postprocess(const void* x, int32_t x_is_fp32, int32_t c_ld, uint8_t* out_u8, float* out_f32,
+                               int32_t nb, int32_t hw, pp_stream stream);
+
 /* ------------------------------------------------------------------ CFG + DDIM */
 typedef struct pp_cfg_ddim_desc {
     /* eps: model output for the 2*batch CFG-duplicated samples (unconditional half first),
@@ -257,6 +273,8 @@ pp_status pp_program_add_time_embed(pp_program* p, const float* timesteps,
                                     const int32_t* step_idx, void* out, int32_t batch, int32_t dim);
 pp_status pp_program_add_cfg_ddim(pp_program* p, const pp_cfg_ddim_desc* d);
 pp_status pp_program_add_memset(pp_program* p, void* ptr, int64_t bytes);
+pp_status pp_program_add_softmax_rows(pp_program* p, const float* s, void* out, int64_t rows, int32_t cols,
+                                      int64_t ld_s, int64_t ld_p);
 int32_t pp_program_num_ops(const pp_program* p);
 /* number of kernel launches one run enqueues */
 int32_t pp_program_num_launches(const pp_program* p);

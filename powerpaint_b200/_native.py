@@ -105,6 +105,10 @@ _SIGNATURES = {
     "pp_nchw_to_nhwc": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
     "pp_nhwc_to_nchw": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, vp]),
     "pp_cfg_ddim_step": (C.c_int, [C.POINTER(CfgDdimDesc), vp]),
+    "pp_softmax_rows": (C.c_int, [vp, vp, i64, i32, i64, i64, vp]),
+    "pp_image_preprocess_u8": (C.c_int, [vp, vp, i32, vp, i32, i32, i32, f32, f32, vp]),
+    "pp_image_postprocess": (C.c_int, [vp, i32, i32, vp, vp, i32, i32, vp]),
+    "pp_program_add_softmax_rows": (C.c_int, [vp, vp, vp, i64, i32, i64, i64]),
     "pp_program_create": (C.c_int, [C.POINTER(vp)]),
     "pp_program_destroy": (None, [vp]),
     "pp_program_add_gemm": (C.c_int, [vp, C.POINTER(GemmDesc)]),

@@ -102,6 +102,11 @@ int time_embed_launch(const float* timesteps, const int32_t* step_idx, void* out
 int nchw_to_nhwc_launch(const float* x, void* y, int nb, int c, int hw, int c_pad, cudaStream_t s);
 int nhwc_to_nchw_launch(const void* x, int x_is_fp32, float* y, int nb, int c, int hw, int c_ld,
                         cudaStream_t s);
+int softmax_rows_launch(const float* s, void* p, int64_t rows, int cols, int64_t ld_s, int64_t ld_p, cudaStream_t st);
+int image_preprocess_launch(const uint8_t* img, const void* mask, int mask_mode, void* out, int nb, int hw, int c_pad,
+                            float scale, float shift, cudaStream_t s);
+int image_postprocess_launch(const void* x, int x_fp32, int c_ld, uint8_t* out_u8, float* out_f32, int nb, int hw,
+                             cudaStream_t s);
 int cfg_ddim_validate(const pp_cfg_ddim_desc& d);
 int cfg_ddim_launch(const pp_cfg_ddim_desc& d, cudaStream_t s);
 

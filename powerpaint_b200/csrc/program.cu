@@ -16,7 +16,7 @@
 namespace pp {
 
 enum OpKind {
-    OP_GEMM, OP_ATTN, OP_GN, OP_LN, OP_UPSAMPLE, OP_ADD, OP_TIME_EMBED, OP_CFG_DDIM, OP_MEMSET
+    OP_GEMM, OP_ATTN, OP_GN, OP_LN, OP_UPSAMPLE, OP_ADD, OP_TIME_EMBED, OP_CFG_DDIM, OP_MEMSET, OP_SOFTMAX
 };
 
 struct LnArgs { const void* x; void* y; const float* gamma; const float* beta; int rows, c; float eps; };
@@ -24,6 +24,7 @@ struct UpArgs { const void* x; void* y; int nb, h, w, c, ho, wo; };
 struct AddArgs { const void* a; const void* b; void* y; int64_t n; };
 struct TeArgs { const float* timesteps; const int32_t* step_idx; void* out; int batch, dim; };
 struct MsArgs { void* ptr; int64_t bytes; };
+struct SmArgs { const float* s; void* p; int64_t rows; int cols; int64_t ld_s, ld_p; };
 
 struct Op {
     OpKind kind;
@@ -37,6 +38,7 @@ struct Op {
         TeArgs te;
         pp_cfg_ddim_desc ddim;
         MsArgs ms;
+        SmArgs sm;
     };
     Op() { memset(this, 0, sizeof(*this)); }
 };
@@ -64,6 +66,7 @@ static int run_op(const Op& op, cudaStream_t s) {
         case OP_MEMSET:
             PP_CUDA_CHECK(cudaMemsetAsync(op.ms.ptr, 0, (size_t)op.ms.bytes, s));
             return PP_OK;
+        case OP_SOFTMAX: return softmax_rows_launch(op.sm.s, op.sm.p, op.sm.rows, op.sm.cols, op.sm.ld_s, op.sm.ld_p, s);
     }
     set_last_error("program: unknown op kind %d", (int)op.kind);
     return PP_ERR_INVALID;
@@ -213,6 +216,18 @@ pp_status pp_program_add_memset(pp_program* p, void* ptr, int64_t bytes) {
     pp::Op op;
     op.kind = pp::OP_MEMSET;
     op.ms = {ptr, bytes};
+    p->ops.push_back(op);
+    return pp::PP_OK;
+}
+
+pp_status pp_program_add_softmax_rows(pp_program* p, const float* s, void* out, int64_t rows, int32_t cols,
+                                      int64_t ld_s, int64_t ld_p) {
+    PP_PROG_CHECK(p);
+    PP_REQUIRE(s && out && rows > 0 && cols > 0 && cols <= 16384 && ld_s >= cols && ld_p >= cols,
+               "pp_program_add_softmax_rows: invalid arguments");
+    pp::Op op;
+    op.kind = pp::OP_SOFTMAX;
+    op.sm = {s, out, rows, cols, ld_s, ld_p};
     p->ops.push_back(op);
     return pp::PP_OK;
 }

@@ -234,6 +234,47 @@ def add(a, b, y):
     N.check(N.lib().pp_add(N.ptr(a), N.ptr(b), N.ptr(y), a.numel(), N.current_stream()), "pp_add")
 
 
+def softmax_rows(s: torch.Tensor, p: torch.Tensor):
+    """p = softmax(s, dim=-1): fp32 [rows, cols] -> bf16 [rows, cols]"""
+    rows, cols = s.shape
+    N.check(N.lib().pp_softmax_rows(N.ptr(s), N.ptr(p), rows, cols, s.stride(0), p.stride(0), N.current_stream()),
+            "pp_softmax_rows")
+
+
+def image_preprocess_u8(image: torch.Tensor, mask: Optional[torch.Tensor], c_pad: int = 8, scale: float = 1 / 127.5,
+                        shift: float = -1.0) -> torch.Tensor:
+    """uint8 NCHW image (+ uint8 / fp32 [n,1,h,w] mask: the hole is zeroed) -> bf16 NHWC [n, h*w, c_pad]"""
+    _req(image, torch.uint8, "image")
+    nb, c, h, w = image.shape
+    if c != 3:
+        raise ValueError("image must have 3 channels")
+    mode = 0
+    if mask is not None:
+        if tuple(mask.shape) != (nb, 1, h, w) or not mask.is_contiguous() or not mask.is_cuda:
+            raise ValueError("mask must be a contiguous CUDA [n, 1, h, w] tensor")
+        mode = 1 if mask.dtype == torch.uint8 else 2
+        if mode == 2 and mask.dtype != torch.float32:
+            raise TypeError("mask must be uint8 or float32")
+    out = torch.empty(nb, h * w, c_pad, dtype=BF16, device=image.device)
+    N.check(N.lib().pp_image_preprocess_u8(N.ptr(image), N.ptr(mask), mode, N.ptr(out), nb, h * w, c_pad, scale, shift,
+                                           N.current_stream()), "pp_image_preprocess_u8")
+    return out
+
+
+def image_postprocess(x: torch.Tensor, nb: int, h: int, w: int, *, uint8: bool):
+    """decoded NHWC image [nb, h*w, c_ld] -> uint8 NHWC [nb,h,w,3] (uint8=True) or fp32 NCHW [nb,3,h,w] in [0,1]"""
+    c_ld = x.shape[-1]
+    if uint8:
+        out = torch.empty(nb, h, w, 3, dtype=torch.uint8, device=x.device)
+        a, b = N.ptr(out), None
+    else:
+        out = torch.empty(nb, 3, h, w, dtype=torch.float32, device=x.device)
+        a, b = None, N.ptr(out)
+    N.check(N.lib().pp_image_postprocess(N.ptr(x), 1 if x.dtype == torch.float32 else 0, c_ld, a, b, nb, h * w,
+                                         N.current_stream()), "pp_image_postprocess")
+    return out
+
+
 def time_embed(timesteps, out, step_idx=None):
     batch, dim = out.shape
     N.check(N.lib().pp_time_embed(N.ptr(timesteps), N.ptr(step_idx), N.ptr(out), batch, dim,
@@ -311,6 +352,11 @@ class Program:
         N.check(N.lib().pp_program_add_upsample_nearest(self._h, N.ptr(x), N.ptr(y), nb, h, w, c, ho, wo),
                 "pp_program_add_upsample_nearest")
         self._keep.append((x, y))
+
+    def add_softmax_rows(self, s, p, rows, cols, ld_s, ld_p):
+        N.check(N.lib().pp_program_add_softmax_rows(self._h, N.ptr(s), N.ptr(p), rows, cols, ld_s, ld_p),
+                "pp_program_add_softmax_rows")
+        self._keep.append((s, p))
 
     def add_add(self, a, b, y, n):
         N.check(N.lib().pp_program_add_add(self._h, N.ptr(a), N.ptr(b), N.ptr(y), n), "pp_program_add_add")

@@ -152,6 +152,36 @@ def postprocess_image(image: torch.Tensor, output_type: str = "pil", do_denormal
     raise ValueError(f"unsupported output_type {output_type}")
 
 
+def decode_latents(vae, latents: torch.Tensor, output_type: str):
+    """`vae.decode(latents / scaling_factor)` + `VaeImageProcessor.postprocess` (pipeline_PowerPaint.py:1051,:1062).
+    With the kernel-backed AutoencoderKL the denormalisation (and for "pil" / "uint8" the x255 rounding) is fused
+    into the pass that reads the decoded image; "uint8" (an extension: uint8 NHWC tensor left on the device, what
+    "pil" images are built from) lets a serving loop gather / download 1 byte per channel."""
+    z = latents / vae.config.scaling_factor
+    if hasattr(vae, "decode_postprocessed"):
+        if output_type in ("pil", "uint8"):
+            u8 = vae.decode_postprocessed(z, uint8=True)
+            if output_type == "uint8":
+                return u8
+            arr = u8.cpu().numpy()
+            return [PIL.Image.fromarray(a) for a in arr]
+        if output_type in ("pt", "np"):
+            img = vae.decode_postprocessed(z, uint8=False)
+            return img if output_type == "pt" else img.cpu().permute(0, 2, 3, 1).float().numpy()
+        raise ValueError(f"unsupported output_type {output_type}")
+    image = vae.decode(z.to(vae.dtype), return_dict=False)[0]
+    if output_type == "uint8":
+        image = postprocess_image(image.float(), output_type="pt")
+        return (image * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    return postprocess_image(image.float(), output_type=output_type)
+
+
+def uint8_device_inputs(vae, image, mask) -> bool:
+    """uint8 CUDA image + mask tensors and a VAE that can read them directly (one fused pre-processing kernel)"""
+    return (torch.is_tensor(image) and torch.is_tensor(mask) and image.dtype == torch.uint8 and image.is_cuda
+            and mask.is_cuda and image.ndim == 4 and mask.ndim == 4 and hasattr(vae, "encode_uint8"))
+
+
 def encode_text(tokenizer, text_encoder, prompts, device, max_length=None) -> torch.Tensor:
     """tokenize (max_length padding, truncation) + text encoder last hidden state"""
     max_length = max_length or tokenizer.model_max_length

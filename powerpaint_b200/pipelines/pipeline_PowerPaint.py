@@ -19,8 +19,8 @@ import torch
 
 from ..denoise import FusedDenoiser
 from ..models.unet_2d_condition import UNet2DConditionModel
-from .common import (StableDiffusionPipelineOutput, encode_text, postprocess_image, prepare_mask_and_masked_image,
-                     randn_tensor, vae_encode)
+from .common import (StableDiffusionPipelineOutput, decode_latents, encode_text, prepare_mask_and_masked_image,
+                     randn_tensor, uint8_device_inputs, vae_encode)
 
 
 class StableDiffusionInpaintPipeline:
@@ -181,7 +181,10 @@ class StableDiffusionInpaintPipeline:
                              "Noise.However, either the image or the noise timestep has not been provided.")
         image_latents = None
         if return_image_latents or (latents is None and not is_strength_max):
-            image_latents = vae_encode(self.vae, image.to(device=device, dtype=dtype), generator)
+            if image.dtype == torch.uint8:  # device-resident uint8 request: normalised inside the encoder's first pass
+                image_latents = self.vae.config.scaling_factor * self.vae.encode_uint8(image).sample(generator).float()
+            else:
+                image_latents = vae_encode(self.vae, image.to(device=device, dtype=dtype), generator)
         if latents is None:
             noise = randn_tensor(shape, generator=generator, device=device, dtype=dtype)
             latents = noise if is_strength_max else self.scheduler.add_noise(image_latents, noise, timestep)
@@ -201,11 +204,20 @@ class StableDiffusionInpaintPipeline:
         """nearest-resize the mask to latent resolution, VAE-encode the masked image (:671-710).
         Unlike the reference this returns ONE copy per image even under CFG: the duplication
         (`torch.cat([mask] * 2)`, :703-706) happens inside the fused step kernel."""
+        if masked_image.dtype == torch.uint8:
+            # uint8 fast path: `masked_image` is the raw image, the hole is zeroed inside the pre-processing kernel
+            full_mask = mask.contiguous()
+            masked_image_latents = (self.vae.config.scaling_factor *
+                                    self.vae.encode_uint8(masked_image, full_mask).sample(generator).float())
+            mask = (mask >= 128).to(dtype) if mask.dtype == torch.uint8 else (mask >= 0.5).to(dtype)
+        else:
+            masked_image_latents = None
         mask = torch.nn.functional.interpolate(mask, size=(height // self.vae_scale_factor,
                                                            width // self.vae_scale_factor))
         mask = mask.to(device=device, dtype=dtype)
-        masked_image = masked_image.to(device=device, dtype=dtype)
-        masked_image_latents = vae_encode(self.vae, masked_image, generator)
+        if masked_image_latents is None:
+            masked_image = masked_image.to(device=device, dtype=dtype)
+            masked_image_latents = vae_encode(self.vae, masked_image, generator)
         for name, t in (("masks", mask), ("images", masked_image_latents)):
             if t.shape[0] < batch_size and batch_size % t.shape[0] != 0:
                 raise ValueError(f"The passed {name} and the required batch size don't match: {t.shape[0]} {name} "
@@ -254,7 +266,15 @@ class StableDiffusionInpaintPipeline:
             raise ValueError(f"After adjusting the num_inference_steps by strength parameter: {strength}, the number "
                              f"of pipeline steps is {num_inference_steps} which is < 1 and not appropriate for this "
                              "pipeline.")
-        mask, masked_image, init_image = prepare_mask_and_masked_image(image, mask, height, width, return_image=True)
+        if uint8_device_inputs(self.vae, image, mask):
+            # device-resident uint8 request (< 1 MB per 512^2 image over PCIe): `image / 127.5 - 1`, the mask
+            # threshold and `image * (mask < 0.5)` (:123-147) run inside the VAE encoder's input kernel
+            if image.shape[-2:] != mask.shape[-2:] or image.shape[0] != mask.shape[0] or mask.shape[1] != 1:
+                raise ValueError("uint8 image [B,3,H,W] and mask [B,1,H,W] must agree in batch and size")
+            masked_image = init_image = image.contiguous()
+        else:
+            mask, masked_image, init_image = prepare_mask_and_masked_image(image, mask, height, width,
+                                                                           return_image=True)
         num_channels_latents = self.vae.config.latent_channels
         num_channels_unet = self.unet.config.in_channels
         if num_channels_unet != 9:
@@ -295,11 +315,7 @@ class StableDiffusionInpaintPipeline:
                                       guidance_scale=guidance_scale,
                                       extra=torch.cat([mask, masked_image_latents], dim=1), noise_fn=noise_fn,
                                       callback=cb)
-        if output_type != "latent":
-            image = self.vae.decode((latents / self.vae.config.scaling_factor).to(self.vae.dtype), return_dict=False)[0]
-        else:
-            image = latents
-        image = postprocess_image(image.float(), output_type=output_type)
+        image = latents if output_type == "latent" else decode_latents(self.vae, latents, output_type)
         if not return_dict:
             return (image, None)
         return StableDiffusionPipelineOutput(images=image, nsfw_content_detected=None)

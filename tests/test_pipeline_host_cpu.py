@@ -40,7 +40,7 @@ class _CoefficientDenoiser:
 def test_v1_call_host_side_matches_oracle_loop(strength, steps, kept):
     from powerpaint_b200.engine import NetConfig
     from powerpaint_b200.models import UNet2DConditionModel, synthetic_state_dict
-    from powerpaint_b200.models.autoencoder_kl import AutoencoderKL
+    from oracle.vae import AutoencoderKLOracle as AutoencoderKL
     from powerpaint_b200.pipelines import StableDiffusionInpaintPipeline
     from powerpaint_b200.pipelines.common import prepare_mask_and_masked_image, randn_tensor, vae_encode
     from powerpaint_b200.schedulers import DDIMScheduler
@@ -123,7 +123,7 @@ def test_controlnet_call_host_side_matches_oracle_loop(strength, steps, kept):
     from oracle.unet import ControlNetOracle
     from powerpaint_b200.engine import NetConfig
     from powerpaint_b200.models import ControlNetModel, UNet2DConditionModel, synthetic_state_dict
-    from powerpaint_b200.models.autoencoder_kl import AutoencoderKL
+    from oracle.vae import AutoencoderKLOracle as AutoencoderKL
     from powerpaint_b200.pipelines import StableDiffusionControlNetInpaintPipeline
     from powerpaint_b200.pipelines.common import prepare_mask_and_masked_image, randn_tensor, vae_encode
     from powerpaint_b200.schedulers import DDIMScheduler
@@ -206,7 +206,7 @@ def test_brushnet_call_host_side_matches_oracle_loop():
     from oracle.unet import BrushNetOracle
     from powerpaint_b200.engine import NetConfig
     from powerpaint_b200.models import BrushNetModel, UNet2DConditionModel, synthetic_state_dict
-    from powerpaint_b200.models.autoencoder_kl import AutoencoderKL
+    from oracle.vae import AutoencoderKLOracle as AutoencoderKL
     from powerpaint_b200.pipelines import StableDiffusionPowerPaintBrushNetPipeline
     from powerpaint_b200.pipelines.common import randn_tensor
     from powerpaint_b200.schedulers import DDIMScheduler

@@ -147,7 +147,7 @@ def test_loop_controlnet_tiny():
 def test_pipeline_v1_call_tiny():
     """the public `__call__`: host tensors in, latents out, against the oracle fed the same prepared tensors"""
     from oracle.pipelines import loop_v1
-    from powerpaint_b200.models.autoencoder_kl import AutoencoderKL
+    from oracle.vae import AutoencoderKLOracle as AutoencoderKL
     from powerpaint_b200.pipelines import StableDiffusionInpaintPipeline
     from powerpaint_b200.pipelines.common import prepare_mask_and_masked_image, randn_tensor, vae_encode
     from powerpaint_b200.schedulers import DDIMScheduler
@@ -197,7 +197,7 @@ def test_pipeline_v1_strength_below_one_tiny():
     from the VAE-encoded image noised to the first kept timestep"""
     from oracle.ddim import DDIMOracle
     from oracle.pipelines import loop_v1
-    from powerpaint_b200.models.autoencoder_kl import AutoencoderKL
+    from oracle.vae import AutoencoderKLOracle as AutoencoderKL
     from powerpaint_b200.pipelines import StableDiffusionInpaintPipeline
     from powerpaint_b200.pipelines.common import prepare_mask_and_masked_image, randn_tensor, vae_encode
     from powerpaint_b200.schedulers import DDIMScheduler
@@ -244,7 +244,7 @@ def test_pipeline_v1_strength_below_one_tiny():
 def test_pipeline_brushnet_call_tiny():
     from oracle.ddim import DDIMOracle
     from oracle.pipelines import loop_brushnet
-    from powerpaint_b200.models.autoencoder_kl import AutoencoderKL
+    from oracle.vae import AutoencoderKLOracle as AutoencoderKL
     from powerpaint_b200.pipelines import StableDiffusionPowerPaintBrushNetPipeline
     from powerpaint_b200.pipelines.common import preprocess_image, randn_tensor
     from powerpaint_b200.schedulers import DDIMScheduler
@@ -383,7 +383,7 @@ def test_pipeline_controlnet_call_tiny():
     loop fed the same prepared tensors, including a control_guidance window"""
     from oracle.ddim import DDIMOracle
     from oracle.pipelines import loop_controlnet
-    from powerpaint_b200.models.autoencoder_kl import AutoencoderKL
+    from oracle.vae import AutoencoderKLOracle as AutoencoderKL
     from powerpaint_b200.pipelines import StableDiffusionControlNetInpaintPipeline
     from powerpaint_b200.pipelines.common import prepare_mask_and_masked_image, randn_tensor, vae_encode
     from powerpaint_b200.schedulers import DDIMScheduler
