@@ -250,8 +250,42 @@ typedef struct pp_cfg_ddim_desc {
     int32_t extra_c;
     int32_t guidance_from_coef; /* != 0: guidance scale = coef[row][5] (graph-replay friendly) */
     int32_t extra_per_copy;     /* != 0: extra is [n_copies*batch, hw, extra_c] (one set per CFG half) */
+    /* 4-channel-UNet blend after the step (pipeline_PowerPaint.py:1025-1035):
+         x = (1 - m) * (a * x0 + sqrt(1 - a^2) * noise_b) + m * x,  a = coef[row][7] (sqrt(alpha_bar) of the NEXT
+       timestep, 1 for the last step); x0 / m are the FIRST image's latents [hw, 4] / latent mask [hw] (the
+       reference indexes `[:1]` and broadcasts over the batch), noise_b [batch, hw, 4]. NULL = no blend. */
+    const float* blend_x0;
+    const float* blend_mask;
+    const float* blend_noise;
 } pp_cfg_ddim_desc;
 pp_status pp_cfg_ddim_step(const pp_cfg_ddim_desc* d, pp_stream stream);
+
+/* CFG combine + UniPCMultistepScheduler.step (solver_order 2, bh2, predict_x0, epsilon prediction; the v2 app's
+   scheduler, app.py:197) + next-step input build. The multistep update is linear in the tensors it touches, so
+   the host folds the schedule into per-step scalars (ucoef rows of 12 floats):
+     m_t    = u[0] * x + u[1] * eps                                   (x0 prediction, `convert_model_output`)
+     x_c    = u[2] != 0 ? u[3] * last + u[4] * m1 + u[5] * m2 + u[6] * m_t : x      (UniC corrector)
+     x_next = u[7] * x_c + u[8] * m_t + u[9] * m1                                     (UniP predictor)
+     last <- x_c, m2 <- m1, m1 <- m_t, latents <- x_next
+   guidance scale = coef[row][5] of the shared 8-float table. State tensors are fp32 NHWC [batch, hw, 4]. */
+typedef struct pp_unipc_desc {
+    const void* eps;
+    int32_t eps_fp32;
+    int32_t eps_ld;
+    float* latents;
+    float* last_sample;
+    float* m1;
+    float* m2;
+    const float* coef;   /* [n_steps, 8], column 5 = guidance scale */
+    const float* ucoef;  /* [n_steps, 12] */
+    int32_t* step_idx;
+    int32_t advance_step;
+    int32_t do_cfg;
+    int32_t batch, hw;
+    void* next_in;       /* bf16 NHWC [n_copies*batch, hw, next_c]: channels 0..3 refreshed */
+    int32_t next_c, n_copies;
+} pp_unipc_desc;
+pp_status pp_unipc_step(const pp_unipc_desc* d, pp_stream stream);
 
 /* ------------------------------------------------------------------ programs */
 /* A program records op descriptors once (tensor maps are encoded at record time) and
@@ -272,6 +306,7 @@ pp_status pp_program_add_add(pp_program* p, const void* a, const void* b, void* 
 pp_status pp_program_add_time_embed(pp_program* p, const float* timesteps,
                                     const int32_t* step_idx, void* out, int32_t batch, int32_t dim);
 pp_status pp_program_add_cfg_ddim(pp_program* p, const pp_cfg_ddim_desc* d);
+pp_status pp_program_add_unipc(pp_program* p, const pp_unipc_desc* d);
 pp_status pp_program_add_memset(pp_program* p, void* ptr, int64_t bytes);
 pp_status pp_program_add_softmax_rows(pp_program* p, const float* s, void* out, int64_t rows, int32_t cols,
                                       int64_t ld_s, int64_t ld_p);

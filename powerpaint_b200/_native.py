@@ -84,6 +84,17 @@ class CfgDdimDesc(C.Structure):
         ("batch", i32), ("hw", i32),
         ("next_in", vp), ("next_c", i32), ("n_copies", i32),
         ("extra", vp), ("extra_c", i32), ("guidance_from_coef", i32), ("extra_per_copy", i32),
+        ("blend_x0", vp), ("blend_mask", vp), ("blend_noise", vp),
+    ]
+
+
+class UniPCDesc(C.Structure):
+    _fields_ = [
+        ("eps", vp), ("eps_fp32", i32), ("eps_ld", i32),
+        ("latents", vp), ("last_sample", vp), ("m1", vp), ("m2", vp),
+        ("coef", vp), ("ucoef", vp), ("step_idx", vp), ("advance_step", i32), ("do_cfg", i32),
+        ("batch", i32), ("hw", i32),
+        ("next_in", vp), ("next_c", i32), ("n_copies", i32),
     ]
 
 
@@ -105,6 +116,8 @@ _SIGNATURES = {
     "pp_nchw_to_nhwc": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
     "pp_nhwc_to_nchw": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, vp]),
     "pp_cfg_ddim_step": (C.c_int, [C.POINTER(CfgDdimDesc), vp]),
+    "pp_unipc_step": (C.c_int, [C.POINTER(UniPCDesc), vp]),
+    "pp_program_add_unipc": (C.c_int, [vp, C.POINTER(UniPCDesc)]),
     "pp_softmax_rows": (C.c_int, [vp, vp, i64, i32, i64, i64, vp]),
     "pp_image_preprocess_u8": (C.c_int, [vp, vp, i32, vp, i32, i32, i32, f32, f32, vp]),
     "pp_image_postprocess": (C.c_int, [vp, i32, i32, vp, vp, i32, i32, vp]),

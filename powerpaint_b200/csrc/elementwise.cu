@@ -68,6 +68,17 @@ __global__ void cfg_ddim_kernel(pp_cfg_ddim_desc d) {
             const float x0 = (x[j] - s1a_t * eps) * inv_sa_t;
             xp[j] = sa_p * x0 + dir_c * eps + sigma * nz[j];
         }
+        if (d.blend_x0) {
+            // 4-channel UNet: keep the known region on the noised original (pipeline_PowerPaint.py:1025-1035)
+            const float a = cf[7], s1a = sqrtf(fmaxf(1.f - a * a, 0.f));
+            const int64_t pix = i % d.hw;
+            const float m = __ldg(d.blend_mask + pix);
+            const float4 o4 = __ldg(reinterpret_cast<const float4*>(d.blend_x0) + pix);
+            const float4 n4 = __ldg(reinterpret_cast<const float4*>(d.blend_noise) + i);
+            const float o[4] = {o4.x, o4.y, o4.z, o4.w}, nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xp[j] = (1.f - m) * (a * o[j] + s1a * nn[j]) + m * xp[j];
+        }
         *reinterpret_cast<float4*>(d.latents + i * 4) = make_float4(xp[0], xp[1], xp[2], xp[3]);
         if (d.next_in) {
             __nv_bfloat16* ni = reinterpret_cast<__nv_bfloat16*>(d.next_in);
@@ -106,6 +117,8 @@ int cfg_ddim_validate(const pp_cfg_ddim_desc& d) {
     PP_REQUIRE(d.batch > 0 && d.hw > 0, "cfg_ddim: empty input");
     PP_REQUIRE(d.eps_ld >= 4, "cfg_ddim: eps_ld must be >= 4");
     PP_REQUIRE(!d.advance_step || d.step_idx, "cfg_ddim: advance_step needs step_idx");
+    PP_REQUIRE((d.blend_x0 == nullptr) == (d.blend_mask == nullptr) && (d.blend_x0 == nullptr) == (d.blend_noise == nullptr),
+               "cfg_ddim: blend_x0 / blend_mask / blend_noise go together");
     if (d.next_in) {
         PP_REQUIRE(d.next_c >= 4 && d.n_copies >= 1, "cfg_ddim: next_in needs next_c >= 4, n_copies >= 1");
         PP_REQUIRE(d.extra_c == 0 || d.extra, "cfg_ddim: extra_c without extra");
@@ -123,6 +136,90 @@ int cfg_ddim_launch(const pp_cfg_ddim_desc& d, cudaStream_t s) {
     const int threads = 128;
     const int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, 148 * 8);
     PP_CUDA_CHECK(launch(cfg_ddim_kernel, blocks, threads, 0, s, d));
+    PP_CUDA_CHECK(cudaGetLastError());
+    if (d.advance_step) {
+        PP_CUDA_CHECK(launch(cfg_ddim_advance_kernel, 1, 1, 0, s, d.step_idx));
+        PP_CUDA_CHECK(cudaGetLastError());
+    }
+    return PP_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// Fused CFG + UniPCMultistepScheduler.step (order-2 bh2 predictor-corrector in x0 space; see
+// include/powerpaint_b200.h for the folded per-step scalars) + next-input refresh. One thread per pixel,
+// 16-byte accesses; state (last corrected sample, the two previous x0 predictions) stays fp32 in HBM.
+// Algorithmic bytes per pixel (CFG): eps 32 + 4 state reads x 16 + 4 state writes x 16 + next input 16 = 176 B.
+// ------------------------------------------------------------------------------------
+__global__ void unipc_step_kernel(pp_unipc_desc d) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int64_t total = (int64_t)d.batch * d.hw;
+    const int step = d.step_idx ? *d.step_idx : 0;
+    const float gscale = d.coef[(int64_t)step * 8 + 5];
+    const float* u = d.ucoef + (int64_t)step * 12;
+    const float u0 = u[0], u1 = u[1], use_c = u[2], u3 = u[3], u4 = u[4], u5 = u[5], u6 = u[6], u7 = u[7], u8 = u[8], u9 = u[9];
+    const bool eps_vec = d.eps_fp32 && d.eps_ld == 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float eu[4], ec[4];
+        if (eps_vec) {
+            const float4* e = reinterpret_cast<const float4*>(d.eps);
+            const float4 a = __ldg(e + i), c = __ldg(e + i + (d.do_cfg ? total : 0));
+            eu[0] = a.x; eu[1] = a.y; eu[2] = a.z; eu[3] = a.w;
+            ec[0] = c.x; ec[1] = c.y; ec[2] = c.z; ec[3] = c.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t iu = i * d.eps_ld + j, ic = (i + (d.do_cfg ? total : 0)) * d.eps_ld + j;
+                eu[j] = d.eps_fp32 ? reinterpret_cast<const float*>(d.eps)[iu]
+                                   : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(d.eps)[iu]);
+                ec[j] = d.eps_fp32 ? reinterpret_cast<const float*>(d.eps)[ic]
+                                   : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(d.eps)[ic]);
+            }
+        }
+        const float4 x4 = *reinterpret_cast<const float4*>(d.latents + i * 4);
+        const float4 l4 = *reinterpret_cast<const float4*>(d.last_sample + i * 4);
+        const float4 a4 = *reinterpret_cast<const float4*>(d.m1 + i * 4);
+        const float4 b4 = *reinterpret_cast<const float4*>(d.m2 + i * 4);
+        const float x[4] = {x4.x, x4.y, x4.z, x4.w}, ls[4] = {l4.x, l4.y, l4.z, l4.w};
+        const float m1[4] = {a4.x, a4.y, a4.z, a4.w}, m2[4] = {b4.x, b4.y, b4.z, b4.w};
+        float mt[4], xc[4], xn[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float eps = d.do_cfg ? eu[j] + gscale * (ec[j] - eu[j]) : eu[j];
+            mt[j] = u0 * x[j] + u1 * eps;
+            xc[j] = use_c != 0.f ? u3 * ls[j] + u4 * m1[j] + u5 * m2[j] + u6 * mt[j] : x[j];
+            xn[j] = u7 * xc[j] + u8 * mt[j] + u9 * m1[j];
+        }
+        *reinterpret_cast<float4*>(d.last_sample + i * 4) = make_float4(xc[0], xc[1], xc[2], xc[3]);
+        *reinterpret_cast<float4*>(d.m2 + i * 4) = a4;
+        *reinterpret_cast<float4*>(d.m1 + i * 4) = make_float4(mt[0], mt[1], mt[2], mt[3]);
+        *reinterpret_cast<float4*>(d.latents + i * 4) = make_float4(xn[0], xn[1], xn[2], xn[3]);
+        if (d.next_in) {
+            __nv_bfloat16* ni = reinterpret_cast<__nv_bfloat16*>(d.next_in);
+            const uint2 v = make_uint2(pack_bf16x2(xn[0], xn[1]), pack_bf16x2(xn[2], xn[3]));
+            for (int cpy = 0; cpy < d.n_copies; ++cpy)
+                *reinterpret_cast<uint2*>(ni + ((int64_t)cpy * total + i) * d.next_c) = v;
+        }
+    }
+}
+
+int unipc_validate(const pp_unipc_desc& d) {
+    PP_REQUIRE(d.eps && d.latents && d.last_sample && d.m1 && d.m2 && d.coef && d.ucoef, "unipc: null pointer");
+    PP_REQUIRE(d.batch > 0 && d.hw > 0 && d.eps_ld >= 4, "unipc: invalid shape");
+    PP_REQUIRE(!d.advance_step || d.step_idx, "unipc: advance_step needs step_idx");
+    if (d.next_in)
+        PP_REQUIRE(d.next_c >= 4 && d.next_c % 4 == 0 && d.n_copies >= 1 && (reinterpret_cast<uintptr_t>(d.next_in) & 7) == 0,
+                   "unipc: next_in needs next_c %% 4 == 0, n_copies >= 1 and 8-byte alignment");
+    return PP_OK;
+}
+
+int unipc_launch(const pp_unipc_desc& d, cudaStream_t s) {
+    int rc = unipc_validate(d);
+    if (rc) return rc;
+    const int64_t total = (int64_t)d.batch * d.hw;
+    const int blocks = (int)std::min<int64_t>((total + 127) / 128, 148 * 8);
+    PP_CUDA_CHECK(launch(unipc_step_kernel, blocks, 128, 0, s, d));
     PP_CUDA_CHECK(cudaGetLastError());
     if (d.advance_step) {
         PP_CUDA_CHECK(launch(cfg_ddim_advance_kernel, 1, 1, 0, s, d.step_idx));
@@ -316,6 +413,10 @@ pp_status pp_nchw_to_nhwc(const float* x, void* y, int32_t nb, int32_t c, int32_
 pp_status pp_nhwc_to_nchw(const void* x, int32_t x_is_fp32, float* y, int32_t nb, int32_t c, int32_t hw,
                           int32_t c_ld, pp_stream s) {
     return pp::nhwc_to_nchw_launch(x, x_is_fp32, y, nb, c, hw, c_ld, reinterpret_cast<cudaStream_t>(s));
+}
+pp_status pp_unipc_step(const pp_unipc_desc* d, pp_stream s) {
+    if (!d) { pp::set_last_error("pp_unipc_step: null descriptor"); return pp::PP_ERR_INVALID; }
+    return pp::unipc_launch(*d, reinterpret_cast<cudaStream_t>(s));
 }
 pp_status pp_cfg_ddim_step(const pp_cfg_ddim_desc* d, pp_stream s) {
     if (!d) { pp::set_last_error("pp_cfg_ddim_step: null descriptor"); return pp::PP_ERR_INVALID; }

@@ -109,5 +109,7 @@ int image_postprocess_launch(const void* x, int x_fp32, int c_ld, uint8_t* out_u
                              cudaStream_t s);
 int cfg_ddim_validate(const pp_cfg_ddim_desc& d);
 int cfg_ddim_launch(const pp_cfg_ddim_desc& d, cudaStream_t s);
+int unipc_validate(const pp_unipc_desc& d);
+int unipc_launch(const pp_unipc_desc& d, cudaStream_t s);
 
 }  // namespace pp

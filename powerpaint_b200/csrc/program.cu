@@ -16,7 +16,7 @@
 namespace pp {
 
 enum OpKind {
-    OP_GEMM, OP_ATTN, OP_GN, OP_LN, OP_UPSAMPLE, OP_ADD, OP_TIME_EMBED, OP_CFG_DDIM, OP_MEMSET, OP_SOFTMAX
+    OP_GEMM, OP_ATTN, OP_GN, OP_LN, OP_UPSAMPLE, OP_ADD, OP_TIME_EMBED, OP_CFG_DDIM, OP_MEMSET, OP_SOFTMAX, OP_UNIPC
 };
 
 struct LnArgs { const void* x; void* y; const float* gamma; const float* beta; int rows, c; float eps; };
@@ -39,6 +39,7 @@ struct Op {
         pp_cfg_ddim_desc ddim;
         MsArgs ms;
         SmArgs sm;
+        pp_unipc_desc unipc;
     };
     Op() { memset(this, 0, sizeof(*this)); }
 };
@@ -66,6 +67,7 @@ static int run_op(const Op& op, cudaStream_t s) {
         case OP_MEMSET:
             PP_CUDA_CHECK(cudaMemsetAsync(op.ms.ptr, 0, (size_t)op.ms.bytes, s));
             return PP_OK;
+        case OP_UNIPC: return unipc_launch(op.unipc, s);
         case OP_SOFTMAX: return softmax_rows_launch(op.sm.s, op.sm.p, op.sm.rows, op.sm.cols, op.sm.ld_s, op.sm.ld_p, s);
     }
     set_last_error("program: unknown op kind %d", (int)op.kind);
@@ -76,6 +78,7 @@ static int launches_of(const Op& op) {
     switch (op.kind) {
         case OP_GN: return 2;  // stats + apply (the stats memset is a memset node, not a kernel)
         case OP_CFG_DDIM: return op.ddim.advance_step ? 2 : 1;
+        case OP_UNIPC: return op.unipc.advance_step ? 2 : 1;
         case OP_MEMSET: return 0;
         default: return 1;
     }
@@ -206,6 +209,18 @@ pp_status pp_program_add_cfg_ddim(pp_program* p, const pp_cfg_ddim_desc* d) {
     pp::Op op;
     op.kind = pp::OP_CFG_DDIM;
     op.ddim = *d;
+    p->ops.push_back(op);
+    return pp::PP_OK;
+}
+
+pp_status pp_program_add_unipc(pp_program* p, const pp_unipc_desc* d) {
+    PP_PROG_CHECK(p);
+    if (!d) { pp::set_last_error("pp_program_add_unipc: null descriptor"); return pp::PP_ERR_INVALID; }
+    int rc = pp::unipc_validate(*d);
+    if (rc) return rc;
+    pp::Op op;
+    op.kind = pp::OP_UNIPC;
+    op.unipc = *d;
     p->ops.push_back(op);
     return pp::PP_OK;
 }

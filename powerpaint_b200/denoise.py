@@ -62,16 +62,16 @@ class FusedDenoiser:
 
     # ------------------------------------------------------------------ plan
     def _get(self, B: int, h: int, w: int, do_cfg: bool, ctx_len: int, with_noise: bool,
-             extra_per_copy: bool) -> dict:
+             extra_per_copy: bool, sched: str = "ddim", blend: bool = False) -> dict:
         # the key carries the parameter generation of each model: `load_state_dict` / `.to()` invalidate it,
         # and the cached entry keeps its engines alive, so a recycled id() can never alias a stale program
-        key = (B, h, w, do_cfg, ctx_len, with_noise, extra_per_copy, self.unet.generation,
+        key = (B, h, w, do_cfg, ctx_len, with_noise, extra_per_copy, sched, blend, self.unet.generation,
                self.side.generation if self.side is not None else -1)
         st = self._cache.get(key)
         if st is not None:
             self._cache.move_to_end(key)
             return st
-        for k in [k for k in self._cache if k[-2:] != key[-2:]]:
+        for k in [k for k in self._cache if k[-2:] != key[-2:]]:  # (unet generation, side generation)
             del self._cache[k]  # plans recorded against replaced weights
         while len(self._cache) >= self.MAX_PLANS:
             self._cache.popitem(last=False)
@@ -109,11 +109,27 @@ class FusedDenoiser:
         st["latents"] = torch.zeros(B, h * w, 4, dtype=torch.float32, device=dev)
         st["extra"] = torch.zeros(n_extra, h * w, 5, dtype=torch.float32, device=dev)
         st["noise"] = torch.zeros(B, h * w, 4, dtype=torch.float32, device=dev)
-        prog.add(ops.cfg_ddim_desc(eps=uplan.outputs["eps"], eps_fp32=True, eps_ld=4, latents=st["latents"],
-                                   coef=coef, step_idx=step_idx, advance_step=True,
-                                   noise=st["noise"] if with_noise else None, guidance_scale=0.0,
-                                   guidance_from_coef=True, do_cfg=do_cfg, batch=B, hw=h * w, next_in=x_in,
-                                   next_c=X_IN_C, n_copies=2 if do_cfg else 1, extra=None, extra_c=0))
+        if sched == "unipc":
+            # UniPCMultistepScheduler (the v2 app's scheduler, app.py:197): multistep state lives next to the latents
+            for k in ("last_sample", "m1", "m2"):
+                st[k] = torch.zeros(B, h * w, 4, dtype=torch.float32, device=dev)
+            st["ucoef"] = torch.zeros(MAX_STEPS, 12, dtype=torch.float32, device=dev)
+            prog.add(ops.unipc_desc(eps=uplan.outputs["eps"], eps_fp32=True, eps_ld=4, latents=st["latents"],
+                                    last_sample=st["last_sample"], m1=st["m1"], m2=st["m2"], coef=coef,
+                                    ucoef=st["ucoef"], step_idx=step_idx, advance_step=True, do_cfg=do_cfg, batch=B,
+                                    hw=h * w, next_in=x_in, next_c=X_IN_C, n_copies=2 if do_cfg else 1))
+        else:
+            if blend:  # 4-channel UNet: known region kept on the noised original after every step
+                st["blend_x0"] = torch.zeros(h * w, 4, dtype=torch.float32, device=dev)
+                st["blend_mask"] = torch.zeros(h * w, dtype=torch.float32, device=dev)
+                st["blend_noise"] = torch.zeros(B, h * w, 4, dtype=torch.float32, device=dev)
+            prog.add(ops.cfg_ddim_desc(eps=uplan.outputs["eps"], eps_fp32=True, eps_ld=4, latents=st["latents"],
+                                       coef=coef, step_idx=step_idx, advance_step=True,
+                                       noise=st["noise"] if with_noise else None, guidance_scale=0.0,
+                                       guidance_from_coef=True, do_cfg=do_cfg, batch=B, hw=h * w, next_in=x_in,
+                                       next_c=X_IN_C, n_copies=2 if do_cfg else 1, extra=None, extra_c=0,
+                                       blend_x0=st.get("blend_x0"), blend_mask=st.get("blend_mask"),
+                                       blend_noise=st.get("blend_noise")))
         st["bytes"] = uplan.bytes + (side_plan.bytes if side_plan else 0)
         self._cache[key] = st
         return st
@@ -137,7 +153,8 @@ class FusedDenoiser:
             guidance_scale: float, extra: Optional[torch.Tensor] = None,
             side_prompt_embeds: Optional[torch.Tensor] = None, control_image: Optional[torch.Tensor] = None,
             side_scale: float = 1.0, side_keep: Optional[Sequence[float]] = None,
-            noise_fn: Optional[Callable[[int], torch.Tensor]] = None,
+            noise_fn: Optional[Callable[[int], torch.Tensor]] = None, ucoef: Optional[torch.Tensor] = None,
+            blend: Optional[dict] = None,
             callback: Optional[Callable[[int, int, torch.Tensor], Optional[torch.Tensor]]] = None,
             use_graph: bool = True) -> torch.Tensor:
         """latents [B,4,h,w]; prompt_embeds [nb,77,768] for the UNet (negative half first when CFG);
@@ -145,7 +162,10 @@ class FusedDenoiser:
         brushnet: conditioning latents + mask; nb rows = one set per CFG half); side_prompt_embeds
         for the side net; `side_scale` x `side_keep[i]` (default 1) scales the side net's residuals at step i;
         coef [n,8] from `DDIMScheduler.step_coefficients`; `noise_fn(i)` supplies
-        the eta > 0 variance noise of step i. `callback(i, t, latents_nchw)` may return replacement
+        the eta > 0 variance noise of step i; `ucoef` [n,12] (`UniPCMultistepScheduler.unipc_coefficients`) selects
+        the UniPC step kernel instead of DDIM; `blend` = dict(x0 [1,4,h,w], mask [1,1,h,w], noise [B,4,h,w],
+        sqrt_alpha [n]) is the 4-channel-UNet blend (ref pipeline_PowerPaint.py:1025-1035).
+        `callback(i, t, latents_nchw)` may return replacement
         latents. Returns the final latents [B,4,h,w] fp32."""
         B, _, h, w = latents.shape
         nb = prompt_embeds.shape[0]
@@ -166,7 +186,17 @@ class FusedDenoiser:
         cur = torch.cuda.current_stream(dev)
         self._stream.wait_stream(cur)
         with torch.cuda.device(dev), torch.cuda.stream(self._stream):
-            st = self._get(B, h, w, do_cfg, prompt_embeds.shape[1], noise_fn is not None, extra_per_copy)
+            sched = "unipc" if ucoef is not None else "ddim"
+            if sched == "unipc" and (noise_fn is not None or blend is not None):
+                raise NotImplementedError("eta / the 4-channel blend are DDIM-only on the fused path")
+            st = self._get(B, h, w, do_cfg, prompt_embeds.shape[1], noise_fn is not None, extra_per_copy, sched,
+                           blend is not None)
+            if sched == "unipc":
+                if len(ucoef) != n_steps:
+                    raise ValueError("ucoef needs one row per step")
+                st["ucoef"][:n_steps].copy_(ucoef.to(dev, torch.float32))
+                for k in ("last_sample", "m1", "m2"):
+                    st[k].zero_()
             # ---- per-call inputs (all outside the loop)
             st["latents"].copy_(ops.nhwc_fp32_from_nchw(latents.to(dev)))
             if extra is not None:
@@ -180,6 +210,11 @@ class FusedDenoiser:
             cf[:, COEF_GUIDANCE] = float(guidance_scale)
             keep = torch.ones(n_steps) if side_keep is None else torch.tensor([float(k) for k in side_keep])
             cf[:, COEF_SIDE_SCALE] = float(side_scale) * keep
+            if blend is not None:
+                cf[:, 7] = torch.as_tensor(blend["sqrt_alpha"], dtype=torch.float32)
+                st["blend_x0"].copy_(ops.nhwc_fp32_from_nchw(blend["x0"][:1].to(dev))[0])
+                st["blend_mask"].copy_(blend["mask"][:1].to(dev, torch.float32).reshape(-1))
+                st["blend_noise"].copy_(ops.nhwc_fp32_from_nchw(blend["noise"].to(dev)))
             st["coef"][:n_steps].copy_(cf.to(dev))
             st["step_idx"].zero_()
             st["uplan"].inputs["ctx"].copy_(prompt_embeds.to(dev, torch.bfloat16))

@@ -181,7 +181,8 @@ def gn_desc(*, x0, x1, c0, c1, batch, hw, groups, gamma, beta, eps, silu, y, sta
 
 def cfg_ddim_desc(*, eps, eps_fp32, eps_ld, latents, coef, step_idx, advance_step, noise,
                   guidance_scale, do_cfg, batch, hw, next_in=None, next_c=0, n_copies=0,
-                  extra=None, extra_c=0, guidance_from_coef=False, extra_per_copy=False) -> Desc:
+                  extra=None, extra_c=0, guidance_from_coef=False, extra_per_copy=False, blend_x0=None,
+                  blend_mask=None, blend_noise=None) -> Desc:
     d = N.CfgDdimDesc()
     d.eps, d.eps_fp32, d.eps_ld = N.ptr(eps), 1 if eps_fp32 else 0, eps_ld
     d.latents, d.coef, d.step_idx = N.ptr(latents), N.ptr(coef), N.ptr(step_idx)
@@ -193,7 +194,20 @@ def cfg_ddim_desc(*, eps, eps_fp32, eps_ld, latents, coef, step_idx, advance_ste
     d.extra, d.extra_c = N.ptr(extra), extra_c
     d.guidance_from_coef = 1 if guidance_from_coef else 0
     d.extra_per_copy = 1 if extra_per_copy else 0
-    return Desc("cfg_ddim", d, (eps, latents, coef, step_idx, noise, next_in, extra))
+    d.blend_x0, d.blend_mask, d.blend_noise = N.ptr(blend_x0), N.ptr(blend_mask), N.ptr(blend_noise)
+    return Desc("cfg_ddim", d, (eps, latents, coef, step_idx, noise, next_in, extra, blend_x0, blend_mask, blend_noise))
+
+
+def unipc_desc(*, eps, eps_fp32, eps_ld, latents, last_sample, m1, m2, coef, ucoef, step_idx, advance_step, do_cfg,
+               batch, hw, next_in=None, next_c=0, n_copies=0) -> Desc:
+    d = N.UniPCDesc()
+    d.eps, d.eps_fp32, d.eps_ld = N.ptr(eps), 1 if eps_fp32 else 0, eps_ld
+    d.latents, d.last_sample, d.m1, d.m2 = N.ptr(latents), N.ptr(last_sample), N.ptr(m1), N.ptr(m2)
+    d.coef, d.ucoef, d.step_idx = N.ptr(coef), N.ptr(ucoef), N.ptr(step_idx)
+    d.advance_step, d.do_cfg = 1 if advance_step else 0, 1 if do_cfg else 0
+    d.batch, d.hw = batch, hw
+    d.next_in, d.next_c, d.n_copies = N.ptr(next_in), next_c, n_copies
+    return Desc("unipc", d, (eps, latents, last_sample, m1, m2, coef, ucoef, step_idx, next_in))
 
 
 # --------------------------------------------------------------------------- immediate mode
@@ -208,6 +222,8 @@ def run(desc: Desc) -> None:
         N.check(L.pp_group_norm(C.byref(desc.c), s), "pp_group_norm")
     elif desc.kind == "cfg_ddim":
         N.check(L.pp_cfg_ddim_step(C.byref(desc.c), s), "pp_cfg_ddim_step")
+    elif desc.kind == "unipc":
+        N.check(L.pp_unipc_step(C.byref(desc.c), s), "pp_unipc_step")
     else:
         raise ValueError(desc.kind)
 
@@ -334,7 +350,8 @@ class Program:
     def add(self, desc: Desc) -> None:
         L = N.lib()
         fn = {"gemm": L.pp_program_add_gemm, "attn": L.pp_program_add_attention,
-              "gn": L.pp_program_add_group_norm, "cfg_ddim": L.pp_program_add_cfg_ddim}[desc.kind]
+              "gn": L.pp_program_add_group_norm, "cfg_ddim": L.pp_program_add_cfg_ddim,
+              "unipc": L.pp_program_add_unipc}[desc.kind]
         N.check(fn(self._h, C.byref(desc.c)), f"pp_program_add_{desc.kind}")
         self._keep.append(desc.keep)
 

@@ -277,21 +277,25 @@ class StableDiffusionInpaintPipeline:
                                                                            return_image=True)
         num_channels_latents = self.vae.config.latent_channels
         num_channels_unet = self.unet.config.in_channels
-        if num_channels_unet != 9:
-            raise ValueError(f"The unet {self.unet.__class__} should have 9 input channels (inpainting checkpoint), "
-                             f"not {num_channels_unet}; the 4-channel blend path (:1025-1035) is not built")
+        if num_channels_unet not in (4, 9):
+            raise ValueError(f"The unet {self.unet.__class__} should have either 4 or 9 input channels, not "
+                             f"{num_channels_unet}.")
+        return_image_latents = num_channels_unet == 4
         total = batch_size * num_images_per_prompt
         # strength < 1 (ref:pipeline_PowerPaint.py:916-941): start part-way down the schedule from the encoded
         # image noised to the first kept timestep; the fused loop just sees a shorter timestep / coefficient table
         latent_timestep = timesteps[:1].repeat(total)
         is_strength_max = strength == 1.0
-        latents, noise = self.prepare_latents(total, num_channels_latents, height, width, torch.float32, device,
-                                              generator, latents, image=init_image, timestep=latent_timestep,
-                                              is_strength_max=is_strength_max, return_noise=True,
-                                              return_image_latents=False)
+        outs = self.prepare_latents(total, num_channels_latents, height, width, torch.float32, device,
+                                    generator, latents, image=init_image, timestep=latent_timestep,
+                                    is_strength_max=is_strength_max, return_noise=True,
+                                    return_image_latents=return_image_latents)
+        latents, noise = outs[0], outs[1]
+        image_latents = outs[2] if return_image_latents else None
         mask, masked_image_latents = self.prepare_mask_latents(mask, masked_image, total, height, width, torch.float32,
                                                                device, generator, do_cfg)
-        if num_channels_latents + mask.shape[1] + masked_image_latents.shape[1] != num_channels_unet:
+        if num_channels_unet == 9 and \
+                num_channels_latents + mask.shape[1] + masked_image_latents.shape[1] != num_channels_unet:
             raise ValueError("Incorrect configuration settings! The config of `pipeline.unet` expects "
                              f"{num_channels_unet} input channels but received {num_channels_latents} + "
                              f"{mask.shape[1]} + {masked_image_latents.shape[1]}.")
@@ -299,8 +303,19 @@ class StableDiffusionInpaintPipeline:
         if not hasattr(self.scheduler, "step_coefficients"):
             raise TypeError("the fused loop needs powerpaint_b200.schedulers.DDIMScheduler (step_coefficients)")
         coef = self.scheduler.step_coefficients(timesteps, eta=extra_step_kwargs.get("eta", 0.0))
+        ucoef = None
+        if getattr(self.scheduler, "kind", "ddim") == "unipc":
+            ucoef = self.scheduler.unipc_coefficients(first=len(self.scheduler.timesteps) - len(timesteps))
+        blend = None
+        if num_channels_unet == 4:
+            # 4-channel UNet (:1025-1035): after every step the known region is reset to the original latents noised
+            # to the NEXT timestep (un-noised after the last step); the reference indexes image_latents[:1] / mask[:1]
+            ac = self.scheduler.alphas_cumprod
+            sqrt_alpha = [float(ac[int(timesteps[i + 1])]) ** 0.5 if i < len(timesteps) - 1 else 1.0
+                          for i in range(len(timesteps))]
+            blend = dict(x0=image_latents, mask=mask, noise=noise, sqrt_alpha=sqrt_alpha)
         noise_fn = None
-        if eta > 0:
+        if eta > 0 and "eta" in extra_step_kwargs:  # schedulers without `eta` ignore it (signature sniffing, :536-551)
             shape = latents.shape
 
             def noise_fn(i):
@@ -313,8 +328,8 @@ class StableDiffusionInpaintPipeline:
                 return None
         latents = self.denoiser().run(latents=latents, prompt_embeds=prompt_embeds, timesteps=timesteps, coef=coef,
                                       guidance_scale=guidance_scale,
-                                      extra=torch.cat([mask, masked_image_latents], dim=1), noise_fn=noise_fn,
-                                      callback=cb)
+                                      extra=torch.cat([mask, masked_image_latents], dim=1) if num_channels_unet == 9
+                                      else None, noise_fn=noise_fn, ucoef=ucoef, blend=blend, callback=cb)
         image = latents if output_type == "latent" else decode_latents(self.vae, latents, output_type)
         if not return_dict:
             return (image, None)

@@ -236,8 +236,10 @@ class StableDiffusionPowerPaintBrushNetPipeline(StableDiffusionInpaintPipeline):
         # `brushnet_keep` (:1369-1376) x brushnet_conditioning_scale (:1403-1409) = the per-step scale row of the
         # device coefficient table the recorded program indexes
         coef = self.scheduler.step_coefficients(ts, eta=extra_step_kwargs.get("eta", 0.0))
+        # the v2 app runs UniPC (app.py:197): its folded per-step scalars select the UniPC step kernel
+        ucoef = self.scheduler.unipc_coefficients() if getattr(self.scheduler, "kind", "ddim") == "unipc" else None
         noise_fn = None
-        if eta > 0:
+        if eta > 0 and "eta" in extra_step_kwargs:  # schedulers without `eta` ignore it (signature sniffing, :536-551)
             def noise_fn(i):
                 return randn_tensor(shape, generator=generator, device=device, dtype=torch.float32)
         cb = None
@@ -265,7 +267,7 @@ class StableDiffusionPowerPaintBrushNetPipeline(StableDiffusionInpaintPipeline):
         latents = self.denoiser().run(latents=latents, prompt_embeds=prompt_embedsU, side_prompt_embeds=prompt_embeds,
                                       timesteps=ts, coef=coef, guidance_scale=guidance_scale,
                                       extra=conditioning_latents, side_scale=float(brushnet_conditioning_scale),
-                                      side_keep=keep,
+                                      side_keep=keep, ucoef=ucoef,
                                       noise_fn=noise_fn, callback=cb)
         image_o = latents if output_type == "latent" else decode_latents(self.vae, latents, output_type)
         if not return_dict:

@@ -124,8 +124,11 @@ class StableDiffusionControlNetInpaintPipeline(StableDiffusionInpaintPipeline):
         # `controlnet_keep` (ref:pipeline_PowerPaint_ControlNet.py:1652-1658): the per-step scale
         # conditioning_scale * keep[i] sits in the device coefficient table the recorded program indexes
         coef = self.scheduler.step_coefficients(timesteps, eta=extra_step_kwargs.get("eta", 0.0))
+        ucoef = None
+        if getattr(self.scheduler, "kind", "ddim") == "unipc":
+            ucoef = self.scheduler.unipc_coefficients(first=len(self.scheduler.timesteps) - len(timesteps))
         noise_fn = None
-        if eta > 0:
+        if eta > 0 and "eta" in extra_step_kwargs:  # schedulers without `eta` ignore it (signature sniffing, :536-551)
             shape = latents.shape
 
             def noise_fn(i):
@@ -141,7 +144,7 @@ class StableDiffusionControlNetInpaintPipeline(StableDiffusionInpaintPipeline):
                                       guidance_scale=guidance_scale,
                                       extra=torch.cat([mask, masked_image_latents], dim=1),
                                       side_scale=float(controlnet_conditioning_scale), side_keep=keep,
-                                      noise_fn=noise_fn, callback=cb)
+                                      noise_fn=noise_fn, ucoef=ucoef, callback=cb)
         image_o = latents if output_type == "latent" else decode_latents(self.vae, latents, output_type)
         if not return_dict:
             return (image_o, None)

@@ -19,7 +19,9 @@ class _CoefficientDenoiser:
         self.calls = []
 
     @torch.no_grad()
-    def run(self, *, latents, prompt_embeds, timesteps, coef, guidance_scale, extra, noise_fn=None, callback=None):
+    def run(self, *, latents, prompt_embeds, timesteps, coef, guidance_scale, extra, noise_fn=None, callback=None,
+            ucoef=None, blend=None):
+        assert ucoef is None and blend is None  # DDIM, 9-channel UNet
         self.calls.append((tuple(latents.shape), [int(t) for t in timesteps], tuple(coef.shape)))
         do_cfg = guidance_scale > 1.0
         for i, t in enumerate(timesteps):
@@ -100,7 +102,7 @@ class _ControlNetCoefficientDenoiser:
 
     @torch.no_grad()
     def run(self, *, latents, prompt_embeds, side_prompt_embeds, control_image, timesteps, coef, guidance_scale,
-            extra, side_scale, side_keep=None, noise_fn=None, callback=None):
+            extra, side_scale, side_keep=None, noise_fn=None, callback=None, ucoef=None):
         do_cfg = guidance_scale > 1.0
         for i, t in enumerate(timesteps):
             x4 = torch.cat([latents] * 2) if do_cfg else latents
@@ -185,7 +187,7 @@ class _BrushNetCoefficientDenoiser:
 
     @torch.no_grad()
     def run(self, *, latents, prompt_embeds, side_prompt_embeds, timesteps, coef, guidance_scale, extra, side_scale,
-            side_keep=None, noise_fn=None, callback=None):
+            side_keep=None, noise_fn=None, callback=None, ucoef=None):
         do_cfg = guidance_scale > 1.0
         for i, t in enumerate(timesteps):
             x = torch.cat([latents] * 2) if do_cfg else latents

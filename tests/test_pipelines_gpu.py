@@ -499,3 +499,92 @@ def test_odd_latent_size_v1_640x856():
     _report("odd_latent_v1_640x856", rel=_rel(got, ref), cos=_cos(got, ref))
     assert got.shape == ref.shape and torch.isfinite(got).all()
     assert _rel(got, ref) < 5e-2 and _cos(got, ref) > 0.999, (_rel(got, ref), _cos(got, ref))
+
+
+# --------------------------------------------------------------------------- UniPC and the 4-channel blend path
+def test_loop_brushnet_unipc_tiny():
+    """the v2 app's scheduler (UniPCMultistepScheduler.from_config(pipe.scheduler.config), ref app.py:197): the
+    fused CFG + UniPC step kernel against the stepwise oracle scheduler inside the oracle BrushNet loop"""
+    from oracle.pipelines import loop_brushnet
+    from oracle.unipc import UniPCOracle
+    from powerpaint_b200.denoise import FusedDenoiser
+    from powerpaint_b200.schedulers import DDIMScheduler, UniPCMultistepScheduler
+
+    nets = _nets(4, [("unet", 4, 1234), ("brushnet", 4, 99)])
+    (om_u, pm_u, o), (om_b, pm_b, _) = nets["unet"], nets["brushnet"]
+    g = torch.Generator(device=DEV).manual_seed(3)
+    B, h = 2, 8
+    lat = torch.randn(B, 4, h, h, device=DEV, generator=g)
+    emb_t = torch.randn(2 * B, 77, o.cross_attention_dim, device=DEV, generator=g) * 0.5
+    emb_u = torch.randn(2 * B, 77, o.cross_attention_dim, device=DEV, generator=g) * 0.5
+    cond = torch.randn(2 * B, 5, h, h, device=DEV, generator=g)
+    steps = 10
+    so = UniPCOracle()
+    so.set_timesteps(steps)
+    sp = UniPCMultistepScheduler.from_config(DDIMScheduler().config)
+    sp.set_timesteps(steps)
+    assert [int(t) for t in sp.timesteps] == [int(t) for t in so.timesteps]
+    ref = loop_brushnet(om_u, om_b, so, lat, emb_t, emb_u, cond, 7.5, 1.0)
+    got = FusedDenoiser(pm_u, pm_b, "brushnet").run(latents=lat, prompt_embeds=emb_u, side_prompt_embeds=emb_t,
+                                                    timesteps=sp.timesteps, coef=sp.step_coefficients(),
+                                                    ucoef=sp.unipc_coefficients(), guidance_scale=7.5, extra=cond,
+                                                    side_scale=1.0)
+    assert _rel(got, ref) < 5e-2 and _cos(got, ref) > 0.998, (_rel(got, ref), _cos(got, ref))
+    # the eager scheduler.step (multistep state kept like diffusers) == the oracle on random eps
+    so.set_timesteps(6)
+    sp.set_timesteps(6)
+    x_o = x_p = lat
+    for t in so.timesteps:
+        eps = torch.randn(B, 4, h, h, device=DEV, generator=g)
+        x_o = so.step(eps, int(t), x_o)
+        x_p = sp.step(eps, int(t), x_p).prev_sample
+    assert _rel(x_p, x_o) < 1e-4, _rel(x_p, x_o)
+
+
+def test_pipeline_v1_four_channel_unet_blend():
+    """a 4-channel (non-inpainting) UNet in the v1 pipeline: after every step the known region is reset to the
+    original latents noised to the next timestep (ref pipeline_PowerPaint.py:1025-1035, incl. the `[:1]` indexing)"""
+    from oracle.ddim import DDIMOracle
+    from powerpaint_b200.pipelines import StableDiffusionInpaintPipeline
+    from powerpaint_b200.pipelines.common import prepare_mask_and_masked_image, randn_tensor, vae_encode
+    from powerpaint_b200.schedulers import DDIMScheduler
+    from oracle.vae import AutoencoderKLOracle
+
+    nets = _nets(4, [("unet", 4, 1234)])
+    om, pm, o = nets["unet"]
+    vae = AutoencoderKLOracle.synthetic(tiny=True).to(DEV)
+    pipe = StableDiffusionInpaintPipeline(vae=vae, text_encoder=None, tokenizer=None, unet=pm,
+                                          scheduler=DDIMScheduler(), safety_checker=None)
+    B, H = 2, 64
+    g = torch.Generator().manual_seed(4)
+    img = torch.rand(B, 3, H, H, generator=g) * 2 - 1
+    mask = torch.zeros(B, 1, H, H)
+    mask[:, :, 16:48, 24:56] = 1
+    pe = torch.randn(B, 77, o.cross_attention_dim, generator=g) * 0.5
+    ne = torch.randn(B, 77, o.cross_attention_dim, generator=g) * 0.5
+    steps = 5
+    out = pipe(image=img, mask=mask, prompt_embeds=pe, negative_prompt_embeds=ne, height=H, width=H,
+               num_inference_steps=steps, guidance_scale=7.5, generator=torch.Generator().manual_seed(17),
+               output_type="latent", return_dict=False)[0]
+    # the reference's order of RNG use (:916-962): image latents, noise, masked-image latents
+    gen = torch.Generator().manual_seed(17)
+    m, mi, init = prepare_mask_and_masked_image(img, mask, H, H, return_image=True)
+    image_latents = vae_encode(vae, init.to(DEV), gen)
+    noise = randn_tensor((B, 4, H // 8, H // 8), generator=gen, device=DEV, dtype=torch.float32)
+    m_l = torch.nn.functional.interpolate(m, size=(H // 8, H // 8)).to(DEV)
+    so = DDIMOracle()
+    so.set_timesteps(steps)
+    emb = torch.cat([ne, pe]).to(DEV)
+    lat = noise
+    ts = [int(t) for t in so.timesteps]
+    with torch.no_grad():
+        for i, t in enumerate(ts):
+            eps = om(torch.cat([lat] * 2), t, emb)
+            u, c = eps.chunk(2)
+            lat = so.step(u + 7.5 * (c - u), t, lat)
+            proper = image_latents[:1]
+            if i < len(ts) - 1:
+                a = so.alphas_cumprod[ts[i + 1]].to(DEV)
+                proper = a ** 0.5 * proper + (1 - a) ** 0.5 * noise
+            lat = (1 - m_l[:1]) * proper + m_l[:1] * lat
+    assert _rel(out, lat) < 5e-2 and _cos(out, lat) > 0.998, (_rel(out, lat), _cos(out, lat))
