@@ -376,6 +376,7 @@ class AutoencoderKL(nn.Module):
     def encode(self, x: torch.Tensor, return_dict: bool = True):
         """x [B,3,H,W] in [-1,1] -> `.latent_dist` (DiagonalGaussianDistribution over [B,8,H/8,W/8] moments)"""
         nb, c, H, W = x.shape
+        self.engine()  # raises on CPU parameters: there is no CPU path
         with torch.cuda.device(self.device):
             xn = ops.nchw_to_nhwc(x.to(self.device).float().contiguous(), 8)
             dist = DiagonalGaussianDistribution(self._moments(xn, nb, H, W))
@@ -386,6 +387,7 @@ class AutoencoderKL(nn.Module):
         """uint8 NCHW image (hole zeroed where mask >= 0.5) straight into the encoder: `image / 127.5 - 1`,
         binarise, `image * (mask < 0.5)` (pipeline_PowerPaint.py:123-147) and the layout change are one kernel"""
         nb, c, H, W = image_u8.shape
+        self.engine()
         with torch.cuda.device(self.device):
             xn = ops.image_preprocess_u8(image_u8.contiguous(), mask, c_pad=8)
             return DiagonalGaussianDistribution(self._moments(xn, nb, H, W))
@@ -403,6 +405,7 @@ class AutoencoderKL(nn.Module):
 
     @torch.no_grad()
     def decode(self, z: torch.Tensor, return_dict: bool = True, generator=None):
+        self.engine()
         with torch.cuda.device(self.device):
             img, nb, H, W = self._decode_nhwc(z)
             out = ops.nhwc_to_nchw(img.view(nb, H, W, 4), 3).to(self._out_dtype)
@@ -412,6 +415,7 @@ class AutoencoderKL(nn.Module):
     def decode_postprocessed(self, z: torch.Tensor, uint8: bool) -> torch.Tensor:
         """decode + `VaeImageProcessor.postprocess` denormalisation in one pass over the image:
         uint8 NHWC [B,H,W,3] (what "pil" output is built from) or fp32 NCHW in [0,1] ("pt" / "np")"""
+        self.engine()
         with torch.cuda.device(self.device):
             img, nb, H, W = self._decode_nhwc(z)
             return ops.image_postprocess(img, nb, H, W, uint8=uint8)

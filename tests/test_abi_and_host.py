@@ -149,3 +149,36 @@ def test_shard_ranges():
     assert shard_ranges(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
     with pytest.raises(ValueError):
         shard_ranges(4, 0)
+
+
+def test_gemm_stats_geometry_is_a_pure_host_query():
+    """which GEMMs / convs can emit GroupNorm partial sums from their epilogue, and in which layout"""
+    from powerpaint_b200 import _native as nat
+    from powerpaint_b200 import ops
+
+    a = torch.zeros(8, dtype=torch.bfloat16)  # only non-null pointers are needed: nothing is launched
+
+    def conv(nb, h, w, cin, cout, s2=False):
+        return ops.gemm_desc(a0=a, w=a, out=a, N_=cout, a_mode=nat.PP_A_CONV3X3_S2 if s2 else nat.PP_A_CONV3X3, c0=cin,
+                             nb=nb, h=h, w_=w)
+    g = ops.gemm_stats_geometry(conv(16, 64, 64, 320, 320))
+    assert g.supported and g.segs == 1 and g.seg_rows == 128 and g.tiles_per_group == 32 and g.wo * g.ho == 4096
+    assert g.bytes == 16 * 32 * 320 * 2 * 4
+    g = ops.gemm_stats_geometry(conv(16, 8, 8, 1280, 1280))
+    assert g.supported and g.segs == 2 and g.seg_rows == 64 and g.tiles_per_group == 1
+    g = ops.gemm_stats_geometry(conv(2, 107, 80, 320, 320, s2=True))
+    assert g.supported and (g.wo, g.ho) == (40, 54)
+    g = ops.gemm_stats_geometry(conv(4, 2, 2, 128, 128))
+    assert g.supported and g.segs == 4 and g.seg_rows == 32 and (g.wo, g.ho) == (2, 2)  # a mostly-padding pixel box
+    g = ops.gemm_stats_geometry(conv(64, 1, 1, 128, 128))
+    assert not g.supported  # 2 tile rows per sample: the consumer runs its own statistics pass
+    g = ops.gemm_stats_geometry(conv(2, 64, 64, 320, 4))
+    assert not g.supported  # ragged N takes the generic epilogue
+    lin = ops.gemm_desc(a0=a, w=a, out=a, N_=320, M=16 * 4096, c0=320, rows_per_group=4096)
+    g = ops.gemm_stats_geometry(lin)
+    assert g.supported and g.segs == 1 and g.tiles_per_group == 32
+    lin = ops.gemm_desc(a0=a, w=a, out=a, N_=1280, M=6 * 64, c0=1280, rows_per_group=64)
+    g = ops.gemm_stats_geometry(lin)
+    assert g.supported and g.segs == 2 and g.seg_rows == 64
+    lin = ops.gemm_desc(a0=a, w=a, out=a, N_=320, M=2 * 8560, c0=320, rows_per_group=8560)
+    assert not ops.gemm_stats_geometry(lin).supported  # 80 x 107 latent: samples straddle the 128-row tiles

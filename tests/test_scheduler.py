@@ -95,3 +95,44 @@ def test_strength_subset_of_the_schedule_matches_oracle():
         x = sap * ((x - s1a * eps) / sa) + dirc * eps
         ref = so.step(eps, t, ref)
     assert torch.allclose(x, ref, atol=1e-5)
+
+
+def test_unipc_folded_coefficients_match_stepwise_oracle():
+    """UniPCMultistepScheduler.from_config(DDIM config) (ref app.py:197): timesteps and the 10 folded scalars per
+    step reproduce the stepwise predictor-corrector restatement (oracle/unipc.py) on random tensors"""
+    import torch
+
+    from oracle.unipc import UniPCOracle
+    from powerpaint_b200.schedulers import DDIMScheduler, UniPCMultistepScheduler
+
+    for n in (50, 20, 7, 2, 1):
+        o = UniPCOracle()
+        o.set_timesteps(n)
+        s = UniPCMultistepScheduler.from_config(DDIMScheduler().config)
+        s.set_timesteps(n)
+        assert s.config.timestep_spacing == "leading" and s.config.steps_offset == 1 and s.config.solver_order == 2
+        assert [int(t) for t in o.timesteps] == [int(t) for t in s.timesteps]
+        u = s.unipc_coefficients().double()
+        assert u.shape == (n, 12) and float(u[0, 2]) == 0.0 and (n == 1 or float(u[1, 2]) == 1.0)
+        g = torch.Generator().manual_seed(n)
+        xo = torch.randn(2, 4, 8, 8, generator=g)
+        xs = xo.double().clone()
+        last, m1, m2 = torch.zeros_like(xs), torch.zeros_like(xs), torch.zeros_like(xs)
+        for i, t in enumerate(o.timesteps):
+            eps = torch.randn(2, 4, 8, 8, generator=g)
+            xo = o.step(eps, int(t), xo)
+            r = u[i]
+            mt = r[0] * xs + r[1] * eps.double()
+            xc = r[3] * last + r[4] * m1 + r[5] * m2 + r[6] * mt if r[2] != 0 else xs
+            last, m2, m1, xs = xc, m1, mt, r[7] * xc + r[8] * mt + r[9] * m1
+        assert ((xs - xo.double()).norm() / xo.double().norm()).item() < 1e-4
+    s = UniPCMultistepScheduler.from_config(DDIMScheduler().config)
+    s.set_timesteps(50)
+    assert [int(t) for t in s.timesteps[:3]] == [951, 932, 913] and int(s.timesteps[-1]) == 20
+    # strength < 1: the history starts empty at the first kept step
+    u5 = s.unipc_coefficients(first=45)
+    assert u5.shape == (5, 12) and float(u5[0, 2]) == 0.0 and float(u5[0, 9]) == 0.0 and float(u5[-1, 9]) == 0.0
+    import pytest
+
+    with pytest.raises(NotImplementedError):
+        UniPCMultistepScheduler(solver_order=3)

@@ -53,3 +53,25 @@ def test_synthetic_state_dict_loads_into_oracle():
     m.load_state_dict(sd, strict=True)
     sd2 = synthetic_state_dict(n, "unet", seed=7)
     assert all(torch.equal(sd[k], sd2[k]) for k in sd)
+
+
+def test_vae_param_layout_matches_torch_restatement():
+    """the kernel-backed AutoencoderKL carries exactly the diffusers state-dict names / shapes of the torch
+    restatement (so `vae/diffusion_pytorch_model.safetensors` loads into either)"""
+    from oracle.vae import AutoencoderKLOracle
+    from powerpaint_b200.models.autoencoder_kl import AutoencoderKL, vae_param_shapes
+
+    for kw in (dict(), dict(block_out_channels=(16, 32, 32, 32), norm_num_groups=8, layers_per_block=1)):
+        o = AutoencoderKLOracle(**kw)
+        want = {k: tuple(v.shape) for k, v in o.state_dict().items()}
+        got = dict(vae_param_shapes(block_out_channels=kw.get("block_out_channels", (128, 256, 512, 512)),
+                                    layers_per_block=kw.get("layers_per_block", 2)))
+        assert got == want, set(got) ^ set(want)
+    p = AutoencoderKL.synthetic(tiny=True)
+    o = AutoencoderKLOracle(block_out_channels=(16, 32, 32, 32), norm_num_groups=8, layers_per_block=1)
+    o.load_state_dict(p.state_dict(), strict=True)
+    import pytest
+    import torch
+
+    with pytest.raises(RuntimeError):
+        p.encode(torch.zeros(1, 3, 64, 64))  # CPU parameters: there is no CPU path
