@@ -221,6 +221,17 @@ pp_status pp_image_preprocess_u8(const uint8_t* image, const void* mask, int32_t
 pp_status pp_image_postprocess(const void* x, int32_t x_is_fp32, int32_t c_ld, uint8_t* out_u8, float* out_f32,
                                int32_t nb, int32_t hw, pp_stream stream);
 
+/* ------------------------------------------------------------------ text encoder */
+/* out[r] = (idx[r] < vocab ? base[idx[r]] : ext[idx[r] - vocab]) + pos[r % seq]  (bf16 [rows, dim]; fp32 tables).
+   CLIP token + position embedding with the EmbeddingLayerWithFixes task-prompt splice (utils.py:256-483) resolved
+   by the host into one gather index per position. */
+pp_status pp_embed_gather(const int32_t* idx, const float* base, const float* ext, const float* pos, void* out,
+                          int32_t rows, int32_t vocab, int32_t seq, int32_t dim, pp_stream stream);
+/* causal softmax(q k^T * scale) v over seq <= 128 tokens; qkv [batch*seq, 3*heads*d] bf16 (q | k | v),
+   out [batch*seq, heads*d] — the CLIP text transformer's self-attention (pipeline_PowerPaint.py:317-518) */
+pp_status pp_causal_attention_small(const void* qkv, void* out, int32_t batch, int32_t seq, int32_t heads, int32_t d,
+                                    float scale, pp_stream stream);
+
 /* ------------------------------------------------------------------ CFG + DDIM */
 typedef struct pp_cfg_ddim_desc {
     /* eps: model output for the 2*batch CFG-duplicated samples (unconditional half first),
@@ -308,6 +319,10 @@ pp_status pp_program_add_time_embed(pp_program* p, const float* timesteps,
 pp_status pp_program_add_cfg_ddim(pp_program* p, const pp_cfg_ddim_desc* d);
 pp_status pp_program_add_unipc(pp_program* p, const pp_unipc_desc* d);
 pp_status pp_program_add_memset(pp_program* p, void* ptr, int64_t bytes);
+pp_status pp_program_add_embed_gather(pp_program* p, const int32_t* idx, const float* base, const float* ext,
+                                      const float* pos, void* out, int32_t rows, int32_t vocab, int32_t seq, int32_t dim);
+pp_status pp_program_add_causal_attention_small(pp_program* p, const void* qkv, void* out, int32_t batch, int32_t seq,
+                                                int32_t heads, int32_t d, float scale);
 pp_status pp_program_add_softmax_rows(pp_program* p, const float* s, void* out, int64_t rows, int32_t cols,
                                       int64_t ld_s, int64_t ld_p);
 int32_t pp_program_num_ops(const pp_program* p);

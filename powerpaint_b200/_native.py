@@ -119,6 +119,10 @@ _SIGNATURES = {
     "pp_unipc_step": (C.c_int, [C.POINTER(UniPCDesc), vp]),
     "pp_program_add_unipc": (C.c_int, [vp, C.POINTER(UniPCDesc)]),
     "pp_softmax_rows": (C.c_int, [vp, vp, i64, i32, i64, i64, vp]),
+    "pp_embed_gather": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "pp_causal_attention_small": (C.c_int, [vp, vp, i32, i32, i32, i32, f32, vp]),
+    "pp_program_add_embed_gather": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32]),
+    "pp_program_add_causal_attention_small": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, f32]),
     "pp_image_preprocess_u8": (C.c_int, [vp, vp, i32, vp, i32, i32, i32, f32, f32, vp]),
     "pp_image_postprocess": (C.c_int, [vp, i32, i32, vp, vp, i32, i32, vp]),
     "pp_program_add_softmax_rows": (C.c_int, [vp, vp, vp, i64, i32, i64, i64]),

@@ -107,6 +107,10 @@ int image_preprocess_launch(const uint8_t* img, const void* mask, int mask_mode,
                             float scale, float shift, cudaStream_t s);
 int image_postprocess_launch(const void* x, int x_fp32, int c_ld, uint8_t* out_u8, float* out_f32, int nb, int hw,
                              cudaStream_t s);
+int embed_gather_launch(const int32_t* idx, const float* base, const float* ext, const float* pos, void* out, int rows,
+                        int vocab, int seq, int dim, cudaStream_t s);
+int causal_attention_small_launch(const void* qkv, void* out, int batch, int seq, int heads, int d, float scale,
+                                  cudaStream_t s);
 int cfg_ddim_validate(const pp_cfg_ddim_desc& d);
 int cfg_ddim_launch(const pp_cfg_ddim_desc& d, cudaStream_t s);
 int unipc_validate(const pp_unipc_desc& d);

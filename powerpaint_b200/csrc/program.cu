@@ -16,7 +16,7 @@
 namespace pp {
 
 enum OpKind {
-    OP_GEMM, OP_ATTN, OP_GN, OP_LN, OP_UPSAMPLE, OP_ADD, OP_TIME_EMBED, OP_CFG_DDIM, OP_MEMSET, OP_SOFTMAX, OP_UNIPC
+    OP_GEMM, OP_ATTN, OP_GN, OP_LN, OP_UPSAMPLE, OP_ADD, OP_TIME_EMBED, OP_CFG_DDIM, OP_MEMSET, OP_SOFTMAX, OP_UNIPC, OP_EMBED, OP_CAUSAL_ATTN
 };
 
 struct LnArgs { const void* x; void* y; const float* gamma; const float* beta; int rows, c; float eps; };
@@ -24,6 +24,8 @@ struct UpArgs { const void* x; void* y; int nb, h, w, c, ho, wo; };
 struct AddArgs { const void* a; const void* b; void* y; int64_t n; };
 struct TeArgs { const float* timesteps; const int32_t* step_idx; void* out; int batch, dim; };
 struct MsArgs { void* ptr; int64_t bytes; };
+struct EmArgs { const int32_t* idx; const float* base; const float* ext; const float* pos; void* out; int rows, vocab, seq, dim; };
+struct CaArgs { const void* qkv; void* out; int batch, seq, heads, d; float scale; };
 struct SmArgs { const float* s; void* p; int64_t rows; int cols; int64_t ld_s, ld_p; };
 
 struct Op {
@@ -39,6 +41,8 @@ struct Op {
         pp_cfg_ddim_desc ddim;
         MsArgs ms;
         SmArgs sm;
+        EmArgs em;
+        CaArgs ca;
         pp_unipc_desc unipc;
     };
     Op() { memset(this, 0, sizeof(*this)); }
@@ -68,6 +72,8 @@ static int run_op(const Op& op, cudaStream_t s) {
             PP_CUDA_CHECK(cudaMemsetAsync(op.ms.ptr, 0, (size_t)op.ms.bytes, s));
             return PP_OK;
         case OP_UNIPC: return unipc_launch(op.unipc, s);
+        case OP_EMBED: return embed_gather_launch(op.em.idx, op.em.base, op.em.ext, op.em.pos, op.em.out, op.em.rows, op.em.vocab, op.em.seq, op.em.dim, s);
+        case OP_CAUSAL_ATTN: return causal_attention_small_launch(op.ca.qkv, op.ca.out, op.ca.batch, op.ca.seq, op.ca.heads, op.ca.d, op.ca.scale, s);
         case OP_SOFTMAX: return softmax_rows_launch(op.sm.s, op.sm.p, op.sm.rows, op.sm.cols, op.sm.ld_s, op.sm.ld_p, s);
     }
     set_last_error("program: unknown op kind %d", (int)op.kind);
@@ -221,6 +227,30 @@ pp_status pp_program_add_unipc(pp_program* p, const pp_unipc_desc* d) {
     pp::Op op;
     op.kind = pp::OP_UNIPC;
     op.unipc = *d;
+    p->ops.push_back(op);
+    return pp::PP_OK;
+}
+
+pp_status pp_program_add_embed_gather(pp_program* p, const int32_t* idx, const float* base, const float* ext,
+                                      const float* pos, void* out, int32_t rows, int32_t vocab, int32_t seq, int32_t dim) {
+    PP_PROG_CHECK(p);
+    PP_REQUIRE(idx && base && pos && out && rows > 0 && vocab > 0 && seq > 0 && dim > 0 && dim % 4 == 0,
+               "pp_program_add_embed_gather: invalid arguments");
+    pp::Op op;
+    op.kind = pp::OP_EMBED;
+    op.em = {idx, base, ext, pos, out, rows, vocab, seq, dim};
+    p->ops.push_back(op);
+    return pp::PP_OK;
+}
+
+pp_status pp_program_add_causal_attention_small(pp_program* p, const void* qkv, void* out, int32_t batch, int32_t seq,
+                                                int32_t heads, int32_t d, float scale) {
+    PP_PROG_CHECK(p);
+    PP_REQUIRE(qkv && out && batch > 0 && heads > 0 && seq > 0 && seq <= 128 && (d == 8 || d == 16 || d == 32 || d == 64),
+               "pp_program_add_causal_attention_small: invalid arguments");
+    pp::Op op;
+    op.kind = pp::OP_CAUSAL_ATTN;
+    op.ca = {qkv, out, batch, seq, heads, d, scale};
     p->ops.push_back(op);
     return pp::PP_OK;
 }

@@ -375,6 +375,16 @@ class Program:
                 "pp_program_add_softmax_rows")
         self._keep.append((s, p))
 
+    def add_embed_gather(self, idx, base, ext, pos, out, rows, vocab, seq, dim):
+        N.check(N.lib().pp_program_add_embed_gather(self._h, N.ptr(idx), N.ptr(base), N.ptr(ext), N.ptr(pos), N.ptr(out),
+                                                    rows, vocab, seq, dim), "pp_program_add_embed_gather")
+        self._keep.append((idx, base, ext, pos, out))
+
+    def add_causal_attention_small(self, qkv, out, batch, seq, heads, d, scale):
+        N.check(N.lib().pp_program_add_causal_attention_small(self._h, N.ptr(qkv), N.ptr(out), batch, seq, heads, d,
+                                                              scale), "pp_program_add_causal_attention_small")
+        self._keep.append((qkv, out))
+
     def add_add(self, a, b, y, n):
         N.check(N.lib().pp_program_add_add(self._h, N.ptr(a), N.ptr(b), N.ptr(y), n), "pp_program_add_add")
         self._keep.append((a, b, y))

@@ -89,3 +89,34 @@ def test_tradoff_blend_property():
     """tradoff = 1 => blended embeddings == promptA embeddings (pipeline_PowerPaint.py:423)"""
     a, b = torch.randn(2, 77, 8), torch.randn(2, 77, 8)
     assert torch.equal(a * 1.0 + (1 - 1.0) * b, a)
+
+
+def EmbeddingRuns(row, start):
+    return (row == start).nonzero().flatten().tolist()
+
+
+def test_gpu_text_encoder_gather_plan_equals_embedding_layer(setup):
+    """host logic of the kernel-backed CLIPTextModel: the task-prompt splice resolved to ONE gather index per
+    position reproduces EmbeddingLayerWithFixes.forward (pinned above against the reference) exactly — including
+    the adjacent-run scan quirk and the asserts on malformed runs"""
+    from powerpaint_b200.models.clip_text import CLIPTextModel
+
+    gold, tok, te, layer = setup
+    m = CLIPTextModel.from_transformers(te)
+    assert m.text_model.embeddings.token_embedding is layer
+    V = m.config.vocab_size
+    for case in gold["cases"]:
+        ids = tok(case["prompt"], padding="max_length", max_length=77, truncation=True, return_tensors="pt").input_ids
+        idx, ext = m._gather_plan(ids)
+        table = torch.cat([layer.wrapped.weight.detach(), ext], 0)
+        got = table[idx.long()]
+        with torch.no_grad():
+            want = layer(ids)
+        assert torch.equal(got, want), case["prompt"]
+        n_runs = sum(len(EmbeddingRuns(ids[0], tok.get_token_info(n)["start"])) for n in ("P_ctxt", "P_shape", "P_obj"))
+        assert int((idx >= V).sum()) <= 10 * n_runs  # <=: the quirk leaves an adjacent second run un-replaced
+    bad = torch.tensor([[tok.get_token_info("P_obj")["start"], 5, 6] + [0] * 74])
+    with pytest.raises(AssertionError):
+        m._gather_plan(bad)
+    with pytest.raises(RuntimeError):
+        m(ids)  # CPU parameters: there is no CPU path
