@@ -28,6 +28,7 @@
 //    (BrushNet / ControlNet feature injection, unet_2d_condition.py:1223,1300) → SiLU /
 //    GEGLU gate → bf16 or fp32 store, optionally transposed (V^T for the attention kernel).
 #include <algorithm>
+#include <type_traits>
 
 #include <cuda_fp16.h>
 
@@ -485,8 +486,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 const bool plain = !has_r1 && !has_r2 && !has_rv;
                 mbar_wait(tmem_full_bar(acc), acc_ph);
                 tc_fence_after();
+                // column split between the two warps of a lane quarter: alternating 32-column chunks, except for the
+                // 160-wide tile (5 chunks would split 3 / 2): there each warp takes one contiguous 80-column half
+                // as 32 + 32 + 16, so both finish together
+                constexpr bool kSplitHalves = BLOCK_N == 160;
                 uint32_t accA[32], accB[32];
-                tmem_ld32(taddr + half * 32, accA);
+                tmem_ld32(taddr + (kSplitHalves ? half * 80 : half * 32), accA);
                 // ---- store helper: 8 fp32 -> (silu) -> bf16 -> 16-byte store
                 auto store8 = [&](float (&v)[8], int col) {
                     if (act == PP_ACT_SILU) {
@@ -503,11 +508,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                     q.w = pack_bf16x2(v[6], v[7]);
                     *reinterpret_cast<uint4*>(s_out + r * OUT_PITCH + col * 2) = q;
                 };
-                // ---- one 32-column chunk
-                auto process = [&](const uint32_t (&accv)[32], int c0) {
+                // ---- one chunk of NG 8-column groups (32 or 16 columns)
+                auto process = [&](const uint32_t* accv, auto ng_tag, int c0) {
+                    constexpr int NG = decltype(ng_tag)::value;
                     if (full && plain) {
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
+                        for (int g = 0; g < NG; ++g) {
                             const int col = c0 + g * 8;
                             const float4 b0 = *reinterpret_cast<const float4*>(sbias + col);
                             const float4 b1 = *reinterpret_cast<const float4*>(sbias + col + 4);
@@ -522,11 +528,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                     }
                     // general: residuals / row vector / ragged tile. All loads of the chunk are issued
                     // before any arithmetic so their latencies overlap.
-                    uint4 q1[4], q2[4];
-                    float4 t0[4], t1[4];
-                    bool ok[4];
+                    uint4 q1[NG], q2[NG];
+                    float4 t0[NG], t1[NG];
+                    bool ok[NG];
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
+                    for (int g = 0; g < NG; ++g) {
                         const int col = c0 + g * 8;
                         ok[g] = valid && col < ncols;
                         q1[g] = (ok[g] && has_r1) ? __ldg(reinterpret_cast<const uint4*>(r1row + col)) : make_uint4(0, 0, 0, 0);
@@ -535,7 +541,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                         t1[g] = (ok[g] && has_rv) ? __ldg(reinterpret_cast<const float4*>(rvrow + col + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
+                    for (int g = 0; g < NG; ++g) {
                         const int col = c0 + g * 8;
                         if (ok[g]) {
                             const float4 b0 = *reinterpret_cast<const float4*>(sbias + col);
@@ -553,15 +559,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                         }
                     }
                 };
-#pragma unroll 1
-                for (int c0 = half * 32; c0 < BLOCK_N; c0 += 128) {
+                using G4 = std::integral_constant<int, 4>;
+                using G2 = std::integral_constant<int, 2>;
+                if constexpr (kSplitHalves) {
+                    const int cb = half * 80;
+                    uint32_t accC[16];
                     tmem_wait_ld();
-                    if (c0 + 64 < BLOCK_N) tmem_ld32(taddr + c0 + 64, accB);
-                    process(accA, c0);
-                    if (c0 + 64 < BLOCK_N) {
+                    tmem_ld32(taddr + cb + 32, accB);
+                    process(accA, G4{}, cb);
+                    tmem_wait_ld();
+                    tmem_ld16(taddr + cb + 64, accC);
+                    process(accB, G4{}, cb + 32);
+                    tmem_wait_ld();
+                    process(accC, G2{}, cb + 64);
+                } else {
+#pragma unroll 1
+                    for (int c0 = half * 32; c0 < BLOCK_N; c0 += 128) {
                         tmem_wait_ld();
-                        if (c0 + 128 < BLOCK_N) tmem_ld32(taddr + c0 + 128, accA);
-                        process(accB, c0 + 64);
+                        if (c0 + 64 < BLOCK_N) tmem_ld32(taddr + c0 + 64, accB);
+                        process(accA, G4{}, c0);
+                        if (c0 + 64 < BLOCK_N) {
+                            tmem_wait_ld();
+                            if (c0 + 128 < BLOCK_N) tmem_ld32(taddr + c0 + 128, accA);
+                            process(accB, G4{}, c0 + 64);
+                        }
                     }
                 }
             } else {

@@ -62,6 +62,38 @@ def gnorm(nb, hw, c, silu=True):
     return lambda: ops.run(d)
 
 
+def conv_gn_fused(nb, h, w, c):
+    """conv emitting GroupNorm partial sums from its epilogue + the consumer GroupNorm (finalize + apply)"""
+    x = torch.randn(nb, h * w, c, device=dev, generator=g).to(BF)
+    wt = ops.pack_conv3x3_weight(torch.randn(c, c, 3, 3, device=dev, generator=g) / math.sqrt(9 * c))
+    out = torch.empty(nb, h * w, c, device=dev, dtype=BF)
+    d = ops.gemm_desc(a0=x, w=wt, out=out, N_=c, a_mode=nat.PP_A_CONV3X3, c0=c, nb=nb, h=h, w_=w,
+                      bias=torch.zeros(c, device=dev))
+    geo = ops.gemm_stats_geometry(d)
+    part = torch.empty(int(geo.bytes) // 4, device=dev)
+    ops.attach_chan_stats(d, part)
+    y = torch.empty_like(out)
+    gd = ops.gn_desc(x0=out, x1=None, c0=c, c1=0, y=y, gamma=torch.ones(c, device=dev), beta=torch.zeros(c, device=dev),
+                     batch=nb, hw=h * w, groups=32, eps=1e-5, silu=True, part0=part, geom0=geo)
+
+    def run():
+        ops.run(d)
+        ops.run(gd)
+    return run
+
+
+def cfg_ddim(B, hw):
+    eps = torch.randn(2 * B, hw, 4, device=dev, generator=g)
+    lat = torch.randn(B, hw, 4, device=dev, generator=g)
+    coef = torch.tensor([[0.6, 0.8, 0.7, 0.71, 0.0, 7.5, 1.0, 1.0]], device=dev)
+    nxt = torch.zeros(2 * B, hw, 16, device=dev, dtype=BF)
+    step = torch.zeros(1, dtype=torch.int32, device=dev)
+    d = ops.cfg_ddim_desc(eps=eps, eps_fp32=True, eps_ld=4, latents=lat, coef=coef, step_idx=step, advance_step=False,
+                          noise=None, guidance_scale=7.5, do_cfg=True, batch=B, hw=hw, next_in=nxt, next_c=16,
+                          n_copies=2, guidance_from_coef=True)
+    return lambda: ops.run(d)
+
+
 def lnorm(rows, c):
     x = torch.randn(rows, c, device=dev, generator=g).to(BF)
     y = torch.empty_like(x)
@@ -86,6 +118,12 @@ cases = [
     ("groupnorm+silu 320ch @64x64 b16 [TB/s]", gnorm(16, 4096, 320), 3 * 16 * 4096 * 320 * 2),
     ("groupnorm+silu 640ch @32x32 b16 [TB/s]", gnorm(16, 1024, 640), 3 * 16 * 1024 * 640 * 2),
     ("layernorm 320ch M=65536 [TB/s]", lnorm(65536, 320), 2 * 65536 * 320 * 2),
+    # conv (84 MB in + out) + one-pass GroupNorm (84 MB): the GroupNorm share is (this - plain conv)
+    ("conv320+stats+groupnorm @64x64 b16 [fused]", conv_gn_fused(16, 64, 64, 320), 2 * 16 * 4096 * 320 * 2880),
+    # 80 B per pixel (BASELINE / DESIGN): eps 32 + latents 32 + next input 16
+    ("cfg_ddim C2 8x64x64 [TB/s]", cfg_ddim(8, 4096), 8 * 4096 * 80),
+    ("conv 128->128 @512x512 b8 (VAE decoder)", conv(8, 512, 512, 128, 128), 2 * 8 * 262144 * 128 * 1152),
+    ("conv 256->256 @512x512 b8 (VAE upsampler)", conv(8, 512, 512, 256, 256), 2 * 8 * 262144 * 256 * 2304),
 ]
 only = sys.argv[1] if len(sys.argv) > 1 else None
 for name, fn, flops in cases:
