@@ -71,9 +71,10 @@ enum {
 enum { PP_ACT_NONE = 0, PP_ACT_SILU = 1, PP_ACT_QUICK_GELU = 2 /* x * sigmoid(1.702 x): CLIP text encoder MLP */ };
 
 /* Geometry of the per-channel GroupNorm partial sums a GEMM / conv can emit from its epilogue
-   (pp_gemm_desc.chan_stats) and pp_group_norm consumes (pp_gn_desc.part0 / part1): one {sum, sum of
-   squares} pair per (m-tile, sample segment of the tile, output channel), fp32,
-   laid out [m_tiles][segs][N][2]. Filled by pp_gemm_stats_geometry(). */
+   (pp_gemm_desc.chan_stats) and pp_group_norm consumes (pp_gn_desc.part0 / part1): one record
+   {sum of (x - shift), sum of (x - shift)^2, shift, 0} per (m-tile, sample segment of the tile, output channel),
+   fp32, laid out [m_tiles][segs][N][4]; shift = the segment's first row, so the variance does not cancel for a
+   large mean over a small spread. Filled by pp_gemm_stats_geometry(). */
 typedef struct pp_stats_geom {
     int32_t supported;   /* 0: this GEMM cannot emit statistics (the consumer runs its own statistics pass) */
     int32_t channels;    /* N */

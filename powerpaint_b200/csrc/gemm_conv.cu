@@ -62,11 +62,13 @@ __device__ __forceinline__ float effective_alpha(const GemmKParams& p) {
 
 // Column sums of the staged output tile for the consumer's GroupNorm. L threads (consecutive lanes of a
 // warp) share one 8-channel piece and split the rows of a sample segment between them (row = l, l + L, ...:
-// conflict-free shared-memory reads); v[] holds {sum, sum of squares} interleaved per channel. A halving
-// butterfly leaves every lane with 16 / L of the 16 totals, in memory order, so the group stores one
-// contiguous 64-byte run.
+// conflict-free shared-memory reads); v[] holds {sum, sum of squares} interleaved per channel, both of
+// x - shift where shift is the segment's first row (so a large mean over a small spread does not cancel when
+// the consumer forms the variance). A halving butterfly leaves every lane with 16 / L of the 16 totals, in
+// memory order; per channel the record is {sum, sum of squares, shift, 0} (16 bytes).
 template <int L>
-__device__ __forceinline__ void stats_butterfly_store(const float (&v)[16], int l, float* dst, bool write) {
+__device__ __forceinline__ void stats_butterfly_store(const float (&v)[16], const float (&shift)[8], int l, float* dst,
+                                                      bool write) {
     float a[8], b[4], c[2];
     {
         const bool hi = (l & (L / 2)) != 0;
@@ -92,14 +94,24 @@ __device__ __forceinline__ void stats_butterfly_store(const float (&v)[16], int 
             c[k] = keep + __shfl_xor_sync(0xffffffffu, send, L / 8);
         }
     }
+    // per channel: {sum of (x - shift), sum of (x - shift)^2, shift, 0}; lane -> channel via a static select
+    auto shift_of = [&](int ch) {
+        float r = shift[0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) r = ch == j ? shift[j] : r;
+        return r;
+    };
     if constexpr (L == 8) {
-        if (write) *reinterpret_cast<float2*>(dst + 2 * l) = make_float2(c[0], c[1]);
+        if (write) *reinterpret_cast<float4*>(dst + 4 * l) = make_float4(c[0], c[1], shift_of(l), 0.f);
     } else {
         static_assert(L == 16, "row lanes");
         const bool hi = (l & 1) != 0;
         const float send = hi ? c[0] : c[1], keep = hi ? c[1] : c[0];
         const float d = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-        if (write) dst[l] = d;
+        if (write) {
+            dst[4 * (l >> 1) + (l & 1)] = d;
+            if (!hi) *reinterpret_cast<float2*>(dst + 4 * (l >> 1) + 2) = make_float2(shift_of(l >> 1), 0.f);
+        }
     }
 }
 
@@ -664,6 +676,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) v[j] = 0.f;
                                 const int rb = sg << p.stat_seg_rows_log2;
+                                // the segment's first row is its shift (valid whenever the segment holds any row:
+                                // it is the pixel-box origin of the sample / the sample's first row of the tile)
+                                float sh[8];
+                                {
+                                    const uint4 q = *reinterpret_cast<const uint4*>(s_out + rb * OUT_PITCH + piece * 16);
+                                    const bool okr = s_row[rb] >= 0;
+                                    sh[0] = okr ? bf16_lo(q.x) : 0.f; sh[1] = okr ? bf16_hi(q.x) : 0.f;
+                                    sh[2] = okr ? bf16_lo(q.y) : 0.f; sh[3] = okr ? bf16_hi(q.y) : 0.f;
+                                    sh[4] = okr ? bf16_lo(q.z) : 0.f; sh[5] = okr ? bf16_hi(q.z) : 0.f;
+                                    sh[6] = okr ? bf16_lo(q.w) : 0.f; sh[7] = okr ? bf16_hi(q.w) : 0.f;
+                                }
                                 for (int rr = rb + l; rr < rb + seg_rows; rr += L) {
                                     if (s_row[rr] >= 0) {
                                         const uint4 q = *reinterpret_cast<const uint4*>(s_out + rr * OUT_PITCH + piece * 16);
@@ -671,14 +694,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                                                             bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
 #pragma unroll
                                         for (int j = 0; j < 8; ++j) {
-                                            v[2 * j] += x[j];
-                                            v[2 * j + 1] = fmaf(x[j], x[j], v[2 * j + 1]);
+                                            const float dlt = x[j] - sh[j];
+                                            v[2 * j] += dlt;
+                                            v[2 * j + 1] = fmaf(dlt, dlt, v[2 * j + 1]);
                                         }
                                     }
                                 }
                                 float* dst = p.chan_stats +
-                                             (((int64_t)m_tile * p.stat_segs + sg) * p.N + col0) * 2;
-                                stats_butterfly_store<L>(v, l, dst, col0 < p.N);
+                                             (((int64_t)m_tile * p.stat_segs + sg) * p.N + col0) * 4;
+                                stats_butterfly_store<L>(v, sh, l, dst, col0 < p.N);
                             }
                         }
                     }
@@ -889,7 +913,7 @@ int gemm_stats_geometry(const pp_gemm_desc& d, pp_stats_geom* g) {
         g->tiles_x = p.tiles_x; g->tiles_y = p.tiles_y; g->bw = p.bw; g->bh = p.bh; g->wo = p.wo; g->ho = p.ho;
     }
     g->supported = 1;
-    g->bytes = (int64_t)p.m_tiles * g->segs * d.N * 2 * (int64_t)sizeof(float);
+    g->bytes = (int64_t)p.m_tiles * g->segs * d.N * 4 * (int64_t)sizeof(float);
     return PP_OK;
 }
 

@@ -11,9 +11,9 @@
 // write y). Tensors without producer statistics (odd shapes, ControlNet skip sums) take the standalone
 // statistics kernel (a second read, normally an L2 hit). LayerNorm reads once (row held in registers)
 // and writes once. Algorithmic bytes: GN 2*|x|*2B, LN 2*|x|*2B.
-// Variance: every path combines per-block / per-tile (count, mean, M2) with Chan's parallel formula in
-// fp64, so a large mean over a small spread does not cancel (the fp32 sums being combined each cover at
-// most a few hundred elements).
+// Variance: every path sums x - shift (shift = an element of the group / of the tile), so a large mean over a
+// small spread does not cancel; per-tile records with different shifts are combined as (count, mean, M2)
+// with Chan's parallel formula in fp64.
 //
 // GroupNorm also performs the up-path `torch.cat([hidden, skip], dim=1)`
 // (unet_2d_blocks.py:2589,2732): it normalises over the virtual concat of two sources and
@@ -64,6 +64,13 @@ static GnGeometry gn_geometry(int batch, int hw, int C, int groups) {
     return g;
 }
 
+// shift of a (sample, group): its first element (pixel 0, first channel of the group) in the virtual concat
+__device__ __forceinline__ float gn_group_shift(const __nv_bfloat16* x0, const __nv_bfloat16* x1, int c0, int c1, int hw,
+                                                int n, int c) {
+    const __nv_bfloat16* p = c < c0 ? x0 + ((int64_t)n * hw) * c0 + c : x1 + ((int64_t)n * hw) * c1 + (c - c0);
+    return __bfloat162float(__ldg(p));
+}
+
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, const __nv_bfloat16* __restrict__ x1,
                                 int c0, int c1, int hw, int groups, int pix_per_block,
                                 float eps, float* __restrict__ stats, uint32_t* __restrict__ tickets,
@@ -87,15 +94,18 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, const __nv
         if (c < c0) { src = x0; cs = c0; co = c; } else { src = x1; cs = c1; co = c - c0; }
         const int p_begin = blockIdx.x * pix_per_block;
         const int p_end = min(hw, p_begin + pix_per_block);
-        float s[8], ss[8];
+        float s[8], ss[8], sh8[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
+        for (int j = 0; j < 8; ++j) {
+            s[j] = 0.f; ss[j] = 0.f;
+            sh8[j] = gn_group_shift(x0, x1, c0, c1, hw, n, ((c + j) / cpg) * cpg);
+        }
         const __nv_bfloat16* sp = src + ((int64_t)n * hw) * cs + co;
         auto accumulate = [&](const uint4& q) {
             const float v[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
                                 bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { s[j] += v[j]; ss[j] += v[j] * v[j]; }
+            for (int j = 0; j < 8; ++j) { const float dlt = v[j] - sh8[j]; s[j] += dlt; ss[j] = fmaf(dlt, dlt, ss[j]); }
         };
         // four independent 16-byte loads in flight per thread
         int p = p_begin + pl;
@@ -133,25 +143,20 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, const __nv
     __syncthreads();
     if (*sh_ticket != (uint32_t)(chunks - 1)) return;
     __threadfence();
-    // (count, mean, M2) of every chunk combined in chunk order (Chan et al.), fp64: the fp32 sums of one
-    // chunk cover a few hundred elements, the combination across chunks does not cancel
+    // every block summed (x - shift) with the SAME per-(sample, group) shift (the group's first element), so the
+    // block partials add up directly; the sums are of spread-sized numbers, the last step runs in fp64
     for (int g = threadIdx.x; g < groups; g += blockDim.x) {
         const float* pp_ = partials + (((int64_t)n * chunks) * groups + g) * 2;
-        double cnt = 0.0, mean = 0.0, m2 = 0.0;
+        double s = 0.0, ss = 0.0;
         for (int ch = 0; ch < chunks; ++ch) {
-            const double s = (double)__ldcg(pp_ + (int64_t)ch * groups * 2);
-            const double ss = (double)__ldcg(pp_ + (int64_t)ch * groups * 2 + 1);
-            const int pix = min(pix_per_block, hw - ch * pix_per_block);
-            const double cb = (double)pix * (double)cpg;
-            const double mb = s / cb;
-            const double m2b = fmax(ss - s * mb, 0.0);
-            const double delta = mb - mean, tot = cnt + cb;
-            mean += delta * (cb / tot);
-            m2 += m2b + delta * delta * (cnt * cb / tot);
-            cnt = tot;
+            s += (double)__ldcg(pp_ + (int64_t)ch * groups * 2);
+            ss += (double)__ldcg(pp_ + (int64_t)ch * groups * 2 + 1);
         }
-        stats[((int64_t)n * groups + g) * 2] = (float)mean;
-        stats[((int64_t)n * groups + g) * 2 + 1] = (float)(1.0 / sqrt(m2 / cnt + (double)eps));
+        const double cnt = (double)hw * (double)cpg;
+        const double md = s / cnt;
+        const double var = fmax(ss / cnt - md * md, 0.0);
+        stats[((int64_t)n * groups + g) * 2] = (float)((double)gn_group_shift(x0, x1, c0, c1, hw, n, g * cpg) + md);
+        stats[((int64_t)n * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
     }
     if (threadIdx.x == 0) tickets[n] = 0u;  // ready for the next call
 }
@@ -177,23 +182,25 @@ __global__ void gn_finalize_kernel(GnPartSrc s0, GnPartSrc s1, int groups, float
         const GnPartSrc& s = c < s0.channels ? s0 : s1;
         const int cl = c < s0.channels ? c : c - s0.channels;
         const int gidx = n / s.segs, seg = n - gidx * s.segs;
-        const float* base = s.part + (((int64_t)gidx * s.tiles_per_group * s.segs + seg) * s.channels + cl) * 2;
-        const int64_t tstride = (int64_t)s.segs * s.channels * 2;
+        const float* base = s.part + (((int64_t)gidx * s.tiles_per_group * s.segs + seg) * s.channels + cl) * 4;
+        const int64_t tstride = (int64_t)s.segs * s.channels * 4;
         double cnt = 0.0, mean = 0.0, m2 = 0.0;
         int tx = 0, ty = 0;
         for (int t0 = 0; t0 < s.tiles_per_group; t0 += 8) {
-            float2 v[8];
+            float4 v[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-                v[u] = t0 + u < s.tiles_per_group ? __ldcg(reinterpret_cast<const float2*>(base + (t0 + u) * tstride))
-                                                  : make_float2(0.f, 0.f);
+                v[u] = t0 + u < s.tiles_per_group ? __ldcg(reinterpret_cast<const float4*>(base + (t0 + u) * tstride))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 if (t0 + u < s.tiles_per_group) {
                     const double cb = (double)(min(s.bw, s.wo - tx * s.bw) * min(s.bh, s.ho - ty * s.bh));
+                    // the tile's sums are of (x - shift): no cancellation inside the tile
                     const double sm = (double)v[u].x, ss = (double)v[u].y;
-                    const double mb = sm / cb;
-                    const double m2b = fmax(ss - sm * mb, 0.0);
+                    const double md = sm / cb;
+                    const double m2b = fmax(ss - sm * md, 0.0);
+                    const double mb = (double)v[u].z + md;
                     const double delta = mb - mean, tot = cnt + cb;
                     mean += delta * (cb / tot);
                     m2 += m2b + delta * delta * (cnt * cb / tot);

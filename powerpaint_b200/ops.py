@@ -411,7 +411,15 @@ class Program:
         N.check(N.lib().pp_program_run(self._h, N.current_stream()), "pp_program_run")
 
     def build_graph(self) -> None:
-        N.check(N.lib().pp_program_graph_build(self._h, N.current_stream()), "pp_program_graph_build")
+        """capture the recorded launches into a CUDA graph. Capture does not execute anything and cannot run on the
+        legacy default stream, so it always happens on a private stream; the graph is later launched on whatever
+        stream is current."""
+        cur = torch.cuda.current_stream()
+        cap = torch.cuda.Stream(device=cur.device)
+        cap.wait_stream(cur)
+        with torch.cuda.stream(cap):
+            N.check(N.lib().pp_program_graph_build(self._h, cap.cuda_stream), "pp_program_graph_build")
+        cur.wait_stream(cap)
         self._graph = True
 
     def launch(self) -> None:

@@ -163,7 +163,7 @@ def test_gemm_stats_geometry_is_a_pure_host_query():
                              nb=nb, h=h, w_=w)
     g = ops.gemm_stats_geometry(conv(16, 64, 64, 320, 320))
     assert g.supported and g.segs == 1 and g.seg_rows == 128 and g.tiles_per_group == 32 and g.wo * g.ho == 4096
-    assert g.bytes == 16 * 32 * 320 * 2 * 4
+    assert g.bytes == 16 * 32 * 320 * 4 * 4  # {sum, sum of squares, shift, pad} per (tile, channel)
     g = ops.gemm_stats_geometry(conv(16, 8, 8, 1280, 1280))
     assert g.supported and g.segs == 2 and g.seg_rows == 64 and g.tiles_per_group == 1
     g = ops.gemm_stats_geometry(conv(2, 107, 80, 320, 320, s2=True))
