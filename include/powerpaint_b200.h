@@ -26,6 +26,15 @@
  *   pp_cfg_ddim_step  CFG combine + DDIMScheduler.step + next-step input build
  *                     (pipelines/pipeline_PowerPaint.py:990-996,1018-1023;
  *                      pipeline_PowerPaint_Brushnet_CA.py:1390,1444-1449)
+ *   pp_unipc_step     CFG combine + UniPCMultistepScheduler.step (the v2 app's scheduler, app.py:197)
+ *   pp_upsample_nearest  Upsample2D with an explicit output size (unet_2d_condition.py:1120-1126,1311-1312)
+ *   pp_gemm_stats_geometry  host-only: layout of the GroupNorm partial sums a GEMM / conv emits from its
+ *                     epilogue (pp_gemm_desc.chan_stats -> pp_gn_desc.part0 / part1)
+ *   pp_softmax_rows, pp_image_preprocess_u8, pp_image_postprocess   VAE attention softmax and the uint8
+ *                     pre/post-processing either side of vae.encode / vae.decode
+ *                     (pipeline_PowerPaint.py:39-153,657-669,1051,1062)
+ *   pp_embed_gather, pp_causal_attention_small   CLIP text encoder: embeddings with the task-prompt splice
+ *                     (utils/utils.py:256-483) and the causal 77-token attention (pipeline_PowerPaint.py:317-518)
  *   pp_program_*      a recorded list of the above, replayed per denoising step
  *                     (the `for i, t in enumerate(timesteps)` loops,
  *                      pipeline_PowerPaint.py:988-1041, Brushnet_CA.py:1384-1466,
@@ -213,10 +222,10 @@ pp_status pp_nhwc_to_nchw(const void* x, int32_t x_is_fp32, float* y, int32_t nb
 pp_status pp_softmax_rows(const float* s, void* p, int64_t rows, int32_t cols, int64_t ld_s, int64_t ld_p,
                           pp_stream stream);
 /* uint8 NCHW [nb,3,h,w] (+ mask [nb,1,h,w]: mask_mode 1 = uint8, 2 = fp32, 0 = none) -> bf16 NHWC
-   [nb, hw, c_pad]: (px * scale + shift) * (mask < 0.5), channels >= 3 zero — `prepare_mask_and_masked_image`
+   [nb, hw, c_pad]: (px / divisor + shift) * (mask < 0.5), channels >= 3 zero — `prepare_mask_and_masked_image`
    (pipeline_PowerPaint.py:39-153) on the device */
 pp_status pp_image_preprocess_u8(const uint8_t* image, const void* mask, int32_t mask_mode, void* out, int32_t nb,
-                                 int32_t hw, int32_t c_pad, float scale, float shift, pp_stream stream);
+                                 int32_t hw, int32_t c_pad, float divisor, float shift, pp_stream stream);
 /* decoded image NHWC (channels 0..2 of c_ld) -> clamp(x/2 + 0.5, 0, 1) as uint8 NHWC [nb,hw,3] (x255, rounded)
    and / or fp32 NCHW [nb,3,hw] — `VaeImageProcessor.postprocess` (pipeline_PowerPaint.py:1062) */
 pp_status pp_image_postprocess(const void* x, int32_t x_is_fp32, int32_t c_ld, uint8_t* out_u8, float* out_f32,

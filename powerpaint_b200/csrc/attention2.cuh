@@ -29,6 +29,13 @@
 #ifndef ATT2_POLY
 #define ATT2_POLY 0
 #endif
+// cycles by which softmax group 1 delays its first block, so that the two groups run out of phase: one
+// group's serial part (barrier round trips, P store, PV / next-S issue) then hides under the other group's
+// exponentials instead of both idling the MUFU pipe together. The issuer's strict k = 2j + t order sustains
+// any lag between one MMA latency and one block. 0 = off.
+#ifndef ATT2_STAGGER
+#define ATT2_STAGGER 0
+#endif
 
 namespace pp {
 
@@ -191,6 +198,12 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
         float c;  // pinned in a register (otherwise re-fetched from the constant bank per element)
         asm volatile("mov.f32 %0, %1;" : "=f"(c) : "f"(p.scale_log2));
         float m_ref = 0.f;
+#if ATT2_STAGGER > 0
+        if (t == 1 && nkv > 4) {
+            const long long t_start = clock64();
+            while (clock64() - t_start < ATT2_STAGGER) {}
+        }
+#endif
         for (int j = 0; j < nkv; ++j) {
             const int k = 2 * j + t, buf = k % NBUF;
             const uint32_t tS = tmem_base + buf * 128 + lane_addr;

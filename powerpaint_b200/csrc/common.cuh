@@ -143,6 +143,25 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, 
         : "memory");
 }
 
+// TMA stores (tile mode, bulk-group completion): shared::cta -> global, out-of-bounds parts of the box are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk groups have finished READING their shared-memory source (it may be overwritten)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have completed entirely (global writes performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, fences, TMEM <-> registers
 // ----------------------------------------------------------------------------
@@ -395,6 +414,9 @@ const char* last_error();
 // the last error.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+// swizzle_bytes: 0 (none), 64 or 128
+int make_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
 }  // namespace pp
 

@@ -229,12 +229,16 @@ __device__ __forceinline__ void epilogue_store8(const GemmKParams& p, float alph
 __host__ __device__ constexpr int stages_for(int block_n) {
     return block_n <= 64 ? 8 : block_n <= 128 ? 5 : block_n <= 160 ? 5 : 3;
 }
-// Output staging tile (bf16 [128][block_n] with a 16-byte row pad against bank conflicts): the epilogue
-// writes its accumulator rows here and the 256 epilogue threads then copy whole rows out, so global
-// stores are row-contiguous runs instead of 32 scattered 16-byte pieces per instruction (measured:
-// the scattered stores alone cost 14 of 36 us on the K = 320 projection GEMMs).
-__host__ __device__ constexpr int out_pitch_for(int block_n) { return block_n * 2 + 16; }
-__host__ __device__ constexpr int out_stage_bytes_for(int block_n) { return 128 * out_pitch_for(block_n) + 128 * 8; }
+// Output staging tile: the epilogue writes its accumulator rows (bf16) into shared memory laid out as the boxes
+// of a TMA store — 64-column sub-tiles [128 rows][128 B] with the 128-byte swizzle (the 160-wide tile ends in a
+// 32-column sub-tile [128][64 B] with the 64-byte swizzle) — and ONE thread hands them to the TMA unit, which
+// writes whole rows and clips whatever lies outside the tensor (ragged conv tiles, rows >= M, columns >= N).
+// History: scattered 16-byte global stores cost 14 of 36 us on the K = 320 projections (round 1: staged tile +
+// copy loop); the copy loop of the 256 epilogue threads was then ~30 % of the epilogue's samples (r02 ncu), and
+// the epilogue is what bounds those GEMMs (the MMA issuer spins on tmem_empty) — the TMA store removes it.
+__host__ __device__ constexpr int out_stage_bytes_for(int block_n) {
+    return (block_n / 64) * 16384 + (block_n % 64) * 256 + 128 * 8 + 1024;
+}
 
 // Persistent, warp-specialised kernel: grid = min(#tiles, #SMs); each CTA walks tiles
 // blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, so CTAs running concurrently share A tiles
@@ -267,11 +271,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     // bias of the current / next tile, staged by the epilogue warps: [2][BLOCK_N] floats
     float* sbias_all = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));
-    // output staging: global row index of each tile row (-1 = invalid), then the padded bf16 tile
-    constexpr int OUT_PITCH = out_pitch_for(BLOCK_N);
+    // output staging: validity of each tile row (statistics pass), then the swizzled bf16 tile (1024-byte aligned)
     long long* s_row = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(sbias_all) + 2 * BLOCK_N * 4);
-    uint8_t* s_out = reinterpret_cast<uint8_t*>(
-        (reinterpret_cast<uintptr_t>(s_row + 128) + 15) & ~static_cast<uintptr_t>(15));
+    const uint32_t s_out_addr = (smem_u32(s_row + 128) + 1023u) & ~1023u;
+    uint8_t* s_out = smem_raw + (s_out_addr - smem_u32(smem_raw));
+    // 16-byte piece of row r holding columns [col, col + 8) of the staged tile
+    auto stage_ptr = [&](int r, int col) -> uint8_t* {
+        const int sub = col >> 6, c = (col & 63) >> 3;
+        if ((BLOCK_N % 64) != 0 && sub == BLOCK_N / 64)  // 32-column remainder sub-tile, 64-byte swizzle
+            return s_out + sub * 16384 + r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
+        return s_out + sub * 16384 + r * 128 + ((c ^ (r & 7)) << 4);
+    };
 
     const int warp = threadIdx.x >> 5;
     const int n_tiles = p.n_tiles;
@@ -284,6 +294,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
     if (warp == W_PROD && elect_one()) {
         prefetch_tmap(&p.tmA[0]);
         prefetch_tmap(&p.tmB);
+        if constexpr (MODE != 1) prefetch_tmap(&p.tmOut[0]);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -476,7 +487,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                             q.y = pack_bf16x2(v[2], v[3]);
                             q.z = pack_bf16x2(v[4], v[5]);
                             q.w = pack_bf16x2(v[6], v[7]);
-                            *reinterpret_cast<uint4*>(s_out + r * OUT_PITCH + (c0 + h8) * 2) = q;
+                            *reinterpret_cast<uint4*>(stage_ptr(r, c0 + h8)) = q;
                         }
                     }
                 }
@@ -492,7 +503,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 const __nv_bfloat16* r1row = p.res1 + row * p.ldr1 + n_base;
                 const __nv_bfloat16* r2row = p.res2 + row * p.ldr2 + n_base;
                 const float* rvrow = p.rowvec + (int64_t)grp * p.rowvec_ld + n_base;
-                __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + n_base;
                 const int ncols = min(BLOCK_N, p.N - n_base);  // multiple of 8
                 const bool full = ncols == BLOCK_N && __all_sync(0xffffffffu, valid);
                 const bool plain = !has_r1 && !has_r2 && !has_rv;
@@ -518,7 +528,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                     q.y = pack_bf16x2(v[2], v[3]);
                     q.z = pack_bf16x2(v[4], v[5]);
                     q.w = pack_bf16x2(v[6], v[7]);
-                    *reinterpret_cast<uint4*>(s_out + r * OUT_PITCH + col * 2) = q;
+                    *reinterpret_cast<uint4*>(stage_ptr(r, col)) = q;
                 };
                 // ---- one chunk of NG 8-column groups (32 or 16 columns)
                 auto process = [&](const uint32_t* accv, auto ng_tag, int c0) {
@@ -647,21 +657,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
             __syncwarp();
             if (lane_id() == 0) mbar_arrive(tmem_empty_bar(acc));
             if constexpr (MODE != 1) {
-                // coalesced copy-out of the staged tile: consecutive threads write consecutive 16-byte
-                // pieces of one output row
+                // hand the staged tile to the TMA unit: generic-proxy writes -> async proxy, one barrier, one thread
+                // issues the stores (one per sub-tile); the unit writes whole rows and clips out-of-range parts
+                fence_proxy_async_smem();
                 if (half == 0) s_row[r] = valid ? (long long)row : -1ll;
                 epi_sync();
                 constexpr int OUT_COLS = MODE == 2 ? BLOCK_N / 2 : BLOCK_N;
                 constexpr int PIECES = OUT_COLS / 8;
-                const int out_base = n_tile * OUT_COLS;
-                const int n_out = MODE == 2 ? p.N / 2 : p.N;
-                __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
-                for (int idx = etid; idx < 128 * PIECES; idx += GEMM_EPI_WARPS * 32) {
-                    const int rr = idx / PIECES, pc = idx - rr * PIECES;
-                    const long long grow = s_row[rr];
-                    if (grow >= 0 && out_base + pc * 8 < n_out)
-                        *reinterpret_cast<uint4*>(outp + grow * p.ldc + out_base + pc * 8) =
-                            *reinterpret_cast<const uint4*>(s_out + rr * OUT_PITCH + pc * 16);
+                if (etid == 0) {
+                    const int out_base = n_tile * OUT_COLS;
+                    const int n_out = MODE == 2 ? p.N / 2 : p.N;
+                    int x0 = 0, y0 = 0, nb0 = 0;
+                    if (p.a_mode != PP_A_MATRIX) tile_origin(m_tile, x0, y0, nb0);
+#pragma unroll
+                    for (int sub = 0; sub * 64 < OUT_COLS; ++sub) {
+                        const int col = out_base + sub * 64;
+                        if (col >= n_out) break;
+                        const CUtensorMap* tm = (OUT_COLS - sub * 64) >= 64 ? &p.tmOut[0] : &p.tmOut[1];
+                        if (p.a_mode == PP_A_MATRIX) tma_store_2d(tm, s_out_addr + sub * 16384, col, m_tile * BLOCK_M);
+                        else tma_store_4d(tm, s_out_addr + sub * 16384, col, x0, y0, nb0);
+                    }
+                    bulk_commit_group();
                 }
                 if constexpr (MODE == 0) {
                     // GroupNorm partial sums of exactly the bf16 values the consumer will read
@@ -680,7 +696,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                                 // it is the pixel-box origin of the sample / the sample's first row of the tile)
                                 float sh[8];
                                 {
-                                    const uint4 q = *reinterpret_cast<const uint4*>(s_out + rb * OUT_PITCH + piece * 16);
+                                    const uint4 q = *reinterpret_cast<const uint4*>(stage_ptr(rb, piece * 8));
                                     const bool okr = s_row[rb] >= 0;
                                     sh[0] = okr ? bf16_lo(q.x) : 0.f; sh[1] = okr ? bf16_hi(q.x) : 0.f;
                                     sh[2] = okr ? bf16_lo(q.y) : 0.f; sh[3] = okr ? bf16_hi(q.y) : 0.f;
@@ -689,7 +705,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                                 }
                                 for (int rr = rb + l; rr < rb + seg_rows; rr += L) {
                                     if (s_row[rr] >= 0) {
-                                        const uint4 q = *reinterpret_cast<const uint4*>(s_out + rr * OUT_PITCH + piece * 16);
+                                        const uint4 q = *reinterpret_cast<const uint4*>(stage_ptr(rr, piece * 8));
                                         const float x[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
                                                             bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
 #pragma unroll
@@ -711,7 +727,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
             // park the next tile's bias in the other staging buffer; everyone has finished reading
             // the buffer of tile lt-1 (same slot) long ago, the barrier orders this tile's writes
             if (etid < BLOCK_N) sbias_all[(acc ^ 1u) * BLOCK_N + etid] = bias_next;
+            if constexpr (MODE != 1) {
+                if (etid == 0) bulk_wait_read_all();  // the TMA unit has read the staged tile: it may be overwritten
+            }
             epi_sync();
+        }
+        if constexpr (MODE != 1) {
+            if (etid == 0) bulk_wait_all();  // global writes of the last tile performed before the CTA retires
         }
     }
 
@@ -730,7 +752,7 @@ static inline int pad64(int c) { return ceil_div(c, 64) * 64; }
 
 static size_t smem_for_block_n(int bn) {
     return (size_t)stages_for(bn) * (A_STAGE_BYTES + bn * BLOCK_K * 2) + 8 * (2 * stages_for(bn) + 6) + 2 * bn * 4 +
-           out_stage_bytes_for(bn) + 16 + 1024;
+           out_stage_bytes_for(bn) + 16 + 1024;  // out_stage_bytes_for includes the row table and the 1 KB alignment slack
 }
 
 static int num_sms() {
@@ -801,7 +823,7 @@ static int pick_block_n(int N, int m_tiles, bool geglu) {
     int best = 0;
     double best_cost = 1e30;
     for (int c : cands) {
-        if (geglu && (c == 64 || N % c != 0)) continue;
+        if (geglu && (c == 64 || c == 160 || N % c != 0)) continue;  // 160: 80 output columns are no TMA-store box
         const int nt = ceil_div(N, c);
         const long tiles = (long)m_tiles * nt;
         const long rounds = (tiles + sms - 1) / sms;
@@ -978,6 +1000,7 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
     const bool geglu = d.epilogue == PP_EPI_GEGLU;
     if (geglu) {
         PP_REQUIRE(d.N % bn == 0, "gemm: GEGLU needs N %% block_n == 0 (N=%d, block_n=%d)", d.N, bn);
+        PP_REQUIRE(bn == 128 || bn == 256, "gemm: GEGLU block_n must be 128 or 256 (got %d)", bn);
         PP_REQUIRE(!d.out_fp32 && !d.rowvec && !d.res1 && !d.res2, "gemm: GEGLU epilogue takes bias only");
         PP_REQUIRE(d.ldc % 8 == 0, "gemm: GEGLU ldc must be a multiple of 8");
     }
@@ -1036,6 +1059,29 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
         l.mode = 2;
     } else {
         l.mode = gemm_fast_mode(d) ? 0 : 1;
+    }
+    if (l.mode != 1) {
+        // TMA-store boxes of the staged output tile: 64 columns (128-byte swizzle), and a 32-column box (64-byte
+        // swizzle) for the tail of the 160-wide tile; tensor extents clip ragged tiles and columns >= N
+        const uint64_t n_out = geglu ? (uint64_t)d.N / 2 : (uint64_t)d.N;
+        const int out_cols = geglu ? bn / 2 : bn;
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t inner = k == 0 ? 64u : 32u;
+            if (k == 1 && out_cols % 64 == 0) break;
+            int rc;
+            if (d.a_mode == PP_A_MATRIX) {
+                uint64_t dims[2] = {n_out, (uint64_t)d.M};
+                uint64_t str[1] = {(uint64_t)d.ldc * 2};
+                uint32_t box[2] = {inner, BLOCK_M};
+                rc = make_tmap_bf16_sw(&p.tmOut[k], d.out, 2, dims, str, box, k == 0 ? 128 : 64);
+            } else {
+                uint64_t dims[4] = {n_out, (uint64_t)p.wo, (uint64_t)p.ho, (uint64_t)p.nb};
+                uint64_t str[3] = {(uint64_t)d.ldc * 2, (uint64_t)d.ldc * 2 * p.wo, (uint64_t)d.ldc * 2 * p.wo * p.ho};
+                uint32_t box[4] = {inner, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+                rc = make_tmap_bf16_sw(&p.tmOut[k], d.out, 4, dims, str, box, k == 0 ? 128 : 64);
+            }
+            if (rc) return rc;
+        }
     }
     if (d.chan_stats) {
         pp_stats_geom g;

@@ -91,10 +91,10 @@ int softmax_rows_launch(const float* s, void* p, int64_t rows, int cols, int64_t
 // uint8 NCHW image (+ optional uint8 / fp32 mask) -> bf16 NHWC [n, h*w, c_pad] in [-1, 1], channels
 // beyond 3 zero; with a mask the hole is zeroed: out = image * (mask < 0.5) (masked_image, :147).
 // mask_mode: 0 none, 1 uint8 [n,1,h,w] (value / 255 binarised at 0.5), 2 fp32 [n,1,h,w].
-// scale / shift: out = px * scale + shift (image: 1/127.5, -1; control image: 1/255, 0).
+// out = px / divisor + shift in fp32 like the reference's `image / 127.5 - 1.0` (control image: / 255, + 0).
 // ------------------------------------------------------------------------------------
 __global__ void image_preprocess_kernel(const uint8_t* __restrict__ img, const void* __restrict__ mask, int mask_mode,
-                                        __nv_bfloat16* __restrict__ out, int hw, int c_pad, float scale, float shift,
+                                        __nv_bfloat16* __restrict__ out, int hw, int c_pad, float divisor, float shift,
                                         int64_t total) {
     pdl_wait();
     pdl_launch_dependents();
@@ -107,7 +107,7 @@ __global__ void image_preprocess_kernel(const uint8_t* __restrict__ img, const v
         const uint8_t* src = img + n * 3 * hw + p;
         float v[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) v[c] = ((float)src[(int64_t)c * hw] * scale + shift) * keep;
+        for (int c = 0; c < 3; ++c) v[c] = (__fdiv_rn((float)src[(int64_t)c * hw], divisor) + shift) * keep;
         __nv_bfloat16* o = out + i * c_pad;
         uint2 q = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], 0.f));
         *reinterpret_cast<uint2*>(o) = q;
@@ -116,14 +116,14 @@ __global__ void image_preprocess_kernel(const uint8_t* __restrict__ img, const v
 }
 
 int image_preprocess_launch(const uint8_t* img, const void* mask, int mask_mode, void* out, int nb, int hw, int c_pad,
-                            float scale, float shift, cudaStream_t s) {
-    PP_REQUIRE(img && out && nb > 0 && hw > 0, "image_preprocess: invalid arguments");
+                            float divisor, float shift, cudaStream_t s) {
+    PP_REQUIRE(img && out && nb > 0 && hw > 0 && divisor != 0.f, "image_preprocess: invalid arguments");
     PP_REQUIRE(c_pad >= 4 && c_pad % 4 == 0, "image_preprocess: c_pad=%d must be a multiple of 4 >= 4", c_pad);
     PP_REQUIRE(mask_mode >= 0 && mask_mode <= 2 && (mask_mode == 0 || mask), "image_preprocess: mask / mask_mode mismatch");
     const int64_t total = (int64_t)nb * hw;
     const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
     PP_CUDA_CHECK(launch(image_preprocess_kernel, blocks, 256, 0, s, img, mask, mask_mode,
-                         reinterpret_cast<__nv_bfloat16*>(out), hw, c_pad, scale, shift, total));
+                         reinterpret_cast<__nv_bfloat16*>(out), hw, c_pad, divisor, shift, total));
     PP_CUDA_CHECK(cudaGetLastError());
     return PP_OK;
 }
@@ -175,8 +175,8 @@ pp_status pp_softmax_rows(const float* s, void* p, int64_t rows, int32_t cols, i
     return pp::softmax_rows_launch(s, p, rows, cols, ld_s, ld_p, reinterpret_cast<cudaStream_t>(stream));
 }
 pp_status pp_image_preprocess_u8(const uint8_t* image, const void* mask, int32_t mask_mode, void* out, int32_t nb,
-                                 int32_t hw, int32_t c_pad, float scale, float shift, pp_stream stream) {
-    return pp::image_preprocess_launch(image, mask, mask_mode, out, nb, hw, c_pad, scale, shift,
+                                 int32_t hw, int32_t c_pad, float divisor, float shift, pp_stream stream) {
+    return pp::image_preprocess_launch(image, mask, mask_mode, out, nb, hw, c_pad, divisor, shift,
                                        reinterpret_cast<cudaStream_t>(stream));
 }
 pp_status pp_image_postprocess(const void* x, int32_t x_is_fp32, int32_t c_ld, uint8_t* out_u8, float* out_f32,

@@ -169,7 +169,8 @@ struct GnPartSrc {
     int channels, segs, tiles_per_group, tiles_x, tiles_y, bw, bh, wo, ho;
 };
 
-__global__ void gn_finalize_kernel(GnPartSrc s0, GnPartSrc s1, int groups, float eps, float* __restrict__ stats) {
+__global__ void __launch_bounds__(512) gn_finalize_kernel(GnPartSrc s0, GnPartSrc s1, int groups, float eps,
+                                                          float* __restrict__ stats) {
     pdl_wait();
     pdl_launch_dependents();
     extern __shared__ double shd[];  // [C] mean, [C] M2
@@ -184,7 +185,10 @@ __global__ void gn_finalize_kernel(GnPartSrc s0, GnPartSrc s1, int groups, float
         const int gidx = n / s.segs, seg = n - gidx * s.segs;
         const float* base = s.part + (((int64_t)gidx * s.tiles_per_group * s.segs + seg) * s.channels + cl) * 4;
         const int64_t tstride = (int64_t)s.segs * s.channels * 4;
-        double cnt = 0.0, mean = 0.0, m2 = 0.0;
+        // every tile summed x - shift_tile; re-reference the sums to ONE shift R (the first tile's) and add them up:
+        //   sum(x - R) = A + n d,  sum((x - R)^2) = B + 2 d A + n d^2,  d = shift_tile - R   (fp64, no divisions)
+        const double R = (double)__ldcg(base + 2);
+        double S = 0.0, SS = 0.0, cnt = 0.0;
         int tx = 0, ty = 0;
         for (int t0 = 0; t0 < s.tiles_per_group; t0 += 8) {
             float4 v[8];
@@ -196,35 +200,34 @@ __global__ void gn_finalize_kernel(GnPartSrc s0, GnPartSrc s1, int groups, float
             for (int u = 0; u < 8; ++u) {
                 if (t0 + u < s.tiles_per_group) {
                     const double cb = (double)(min(s.bw, s.wo - tx * s.bw) * min(s.bh, s.ho - ty * s.bh));
-                    // the tile's sums are of (x - shift): no cancellation inside the tile
-                    const double sm = (double)v[u].x, ss = (double)v[u].y;
-                    const double md = sm / cb;
-                    const double m2b = fmax(ss - sm * md, 0.0);
-                    const double mb = (double)v[u].z + md;
-                    const double delta = mb - mean, tot = cnt + cb;
-                    mean += delta * (cb / tot);
-                    m2 += m2b + delta * delta * (cnt * cb / tot);
-                    cnt = tot;
+                    const double A = (double)v[u].x, B = (double)v[u].y, d = (double)v[u].z - R;
+                    S += A + cb * d;
+                    SS += B + d * (2.0 * A + cb * d);
+                    cnt += cb;
                     if (++tx == s.tiles_x) { tx = 0; ++ty; }
                 }
             }
         }
-        sh_mean[c] = mean;
-        sh_m2[c] = m2;
+        const double md = S / cnt;
+        sh_mean[c] = R + md;
+        sh_m2[c] = fmax(SS - S * md, 0.0);
     }
     __syncthreads();
     const double per_ch = (double)s0.wo * (double)s0.ho;  // pixels per sample
     for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        double cnt = 0.0, mean = 0.0, m2 = 0.0;
+        // channels of the group, re-referenced to the first channel's mean in the same way
+        const double R = sh_mean[g * cpg];
+        double S = 0.0, SS = 0.0;
         for (int cc = 0; cc < cpg; ++cc) {
-            const double mb = sh_mean[g * cpg + cc], m2b = sh_m2[g * cpg + cc];
-            const double delta = mb - mean, tot = cnt + per_ch;
-            mean += delta * (per_ch / tot);
-            m2 += m2b + delta * delta * (cnt * per_ch / tot);
-            cnt = tot;
+            const double d = sh_mean[g * cpg + cc] - R;
+            S += per_ch * d;
+            SS += sh_m2[g * cpg + cc] + per_ch * d * d;
         }
-        stats[((int64_t)n * groups + g) * 2] = (float)mean;
-        stats[((int64_t)n * groups + g) * 2 + 1] = (float)(1.0 / sqrt(m2 / cnt + (double)eps));
+        const double cnt = per_ch * (double)cpg;
+        const double md = S / cnt;
+        const double var = fmax(SS - S * md, 0.0) / cnt;
+        stats[((int64_t)n * groups + g) * 2] = (float)(R + md);
+        stats[((int64_t)n * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
     }
 }
 
@@ -339,7 +342,8 @@ int group_norm_launch(const pp_gn_desc& d, cudaStream_t s) {
         GnPartSrc s0 = part_src(d.part0, d.geom0), s1;
         memset(&s1, 0, sizeof(s1));
         if (d.x1) s1 = part_src(d.part1, d.geom1);
-        PP_CUDA_CHECK(launch(gn_finalize_kernel, dim3(d.batch), 256, (size_t)C * 16, s, s0, s1, d.groups, d.eps, d.stats));
+        const int fthreads = std::min(512, (C + 31) / 32 * 32);
+        PP_CUDA_CHECK(launch(gn_finalize_kernel, dim3(d.batch), fthreads, (size_t)C * 16, s, s0, s1, d.groups, d.eps, d.stats));
     } else {
         if (!d.stats_prezeroed) PP_CUDA_CHECK(cudaMemsetAsync(tickets, 0, sizeof(uint32_t) * d.batch, s));
         PP_CUDA_CHECK(launch(gn_stats_kernel, dim3(chunks, d.batch), threads, g.smem, s,

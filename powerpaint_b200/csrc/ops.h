@@ -16,6 +16,7 @@ namespace pp {
 struct GemmKParams {
     CUtensorMap tmA[4];  // matrix/conv: [src0, src1]; stride-2 conv: 4 parity maps
     CUtensorMap tmB;
+    CUtensorMap tmOut[2];  // output tile store (modes 0 / 2): 64-column boxes, and the 32-column remainder box
     int32_t a_mode;
     int32_t M, N;            // GEMM extents (conv: M = nb*ho*wo)
     int32_t num_k_iters;     // total 64-wide K chunks
@@ -104,7 +105,7 @@ int nhwc_to_nchw_launch(const void* x, int x_is_fp32, float* y, int nb, int c, i
                         cudaStream_t s);
 int softmax_rows_launch(const float* s, void* p, int64_t rows, int cols, int64_t ld_s, int64_t ld_p, cudaStream_t st);
 int image_preprocess_launch(const uint8_t* img, const void* mask, int mask_mode, void* out, int nb, int hw, int c_pad,
-                            float scale, float shift, cudaStream_t s);
+                            float divisor, float shift, cudaStream_t s);
 int image_postprocess_launch(const void* x, int x_fp32, int c_ld, uint8_t* out_u8, float* out_f32, int nb, int hw,
                              cudaStream_t s);
 int embed_gather_launch(const int32_t* idx, const float* base, const float* ext, const float* pos, void* out, int rows,

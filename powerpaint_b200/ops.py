@@ -257,7 +257,7 @@ def softmax_rows(s: torch.Tensor, p: torch.Tensor):
             "pp_softmax_rows")
 
 
-def image_preprocess_u8(image: torch.Tensor, mask: Optional[torch.Tensor], c_pad: int = 8, scale: float = 1 / 127.5,
+def image_preprocess_u8(image: torch.Tensor, mask: Optional[torch.Tensor], c_pad: int = 8, divisor: float = 127.5,
                         shift: float = -1.0) -> torch.Tensor:
     """uint8 NCHW image (+ uint8 / fp32 [n,1,h,w] mask: the hole is zeroed) -> bf16 NHWC [n, h*w, c_pad]"""
     _req(image, torch.uint8, "image")
@@ -272,7 +272,7 @@ def image_preprocess_u8(image: torch.Tensor, mask: Optional[torch.Tensor], c_pad
         if mode == 2 and mask.dtype != torch.float32:
             raise TypeError("mask must be uint8 or float32")
     out = torch.empty(nb, h * w, c_pad, dtype=BF16, device=image.device)
-    N.check(N.lib().pp_image_preprocess_u8(N.ptr(image), N.ptr(mask), mode, N.ptr(out), nb, h * w, c_pad, scale, shift,
+    N.check(N.lib().pp_image_preprocess_u8(N.ptr(image), N.ptr(mask), mode, N.ptr(out), nb, h * w, c_pad, divisor, shift,
                                            N.current_stream()), "pp_image_preprocess_u8")
     return out
 

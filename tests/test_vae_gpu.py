@@ -106,7 +106,7 @@ def test_softmax_rows_and_image_kernels():
     out = ops.image_preprocess_u8(img, None, c_pad=8)
     ref = (img.float() / 127.5 - 1).permute(0, 2, 3, 1).reshape(2, 240, 3)
     assert torch.equal(out[..., :3].float(), ref.to(torch.bfloat16).float()) and (out[..., 3:] == 0).all()
-    ctl = ops.image_preprocess_u8(img, None, c_pad=8, scale=1 / 255.0, shift=0.0)
+    ctl = ops.image_preprocess_u8(img, None, c_pad=8, divisor=255.0, shift=0.0)
     assert torch.equal(ctl[..., :3].float(), (img.float() / 255).permute(0, 2, 3, 1).reshape(2, 240, 3).to(torch.bfloat16).float())
 
 
