@@ -137,11 +137,28 @@ typedef struct pp_gemm_desc {
     /* optional GroupNorm partial sums of the stored output (bf16 row-major outputs only), see pp_stats_geom;
        rows_per_group must hold the rows per sample in PP_A_MATRIX mode */
     float* chan_stats;
+    /* LayerNorm folded into the GEMMs either side of it (BasicTransformerBlock norm1/2/3):
+       PRODUCER (PP_A_MATRIX, bf16 row-major output): row_stats != NULL makes the epilogue emit, per output row and
+       per half n-tile, one record {sum of (x - shift), sum of (x - shift)^2, shift, count} (fp32 x 4) of the values
+       it stores, laid out [records][row_stats_ld] with records = pp_gemm_row_stats_records(desc).
+       CONSUMER: ln_rec != NULL applies LayerNorm(A) algebraically in the epilogue. With W' = W * gamma (folded into
+       b on the host), ln_u[n] = sum_k W'[n, k] and bias[n] = sum_k W[n, k] beta[k] (+ the layer's own bias):
+         acc' = rstd[m] * (acc - mean[m] * ln_u[n]),  mean / rstd from the ln_nrec records of row m (Chan's
+       combination, eps = ln_eps); everything after (bias, GEGLU gate, transposed store ...) is unchanged. */
+    float* row_stats;
+    int64_t row_stats_ld;
+    const float* ln_rec;
+    int32_t ln_nrec;
+    int64_t ln_ld;
+    const float* ln_u;
+    float ln_eps;
 } pp_gemm_desc;
 
 pp_status pp_gemm_conv(const pp_gemm_desc* d, pp_stream stream);
 /* host-only query: can this GEMM emit GroupNorm partial sums, and with which layout */
 pp_status pp_gemm_stats_geometry(const pp_gemm_desc* d, pp_stats_geom* out);
+/* host-only query: number of per-row LayerNorm records this GEMM emits through row_stats (0: it cannot emit them) */
+int32_t pp_gemm_row_stats_records(const pp_gemm_desc* d);
 
 /* ------------------------------------------------------------------ attention */
 typedef struct pp_attn_desc {
@@ -340,6 +357,8 @@ int32_t pp_program_num_ops(const pp_program* p);
 int32_t pp_program_num_launches(const pp_program* p);
 /* enqueue every recorded op on `stream` (plain launches) */
 pp_status pp_program_run(pp_program* p, pp_stream stream);
+/* diagnostic: replay only ops [first, first + count) as plain launches */
+pp_status pp_program_run_range(pp_program* p, int32_t first, int32_t count, pp_stream stream);
 /* capture the program into a CUDA graph (once), then replay it with pp_program_graph_launch */
 pp_status pp_program_graph_build(pp_program* p, pp_stream stream);
 pp_status pp_program_graph_launch(pp_program* p, pp_stream stream);

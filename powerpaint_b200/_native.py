@@ -19,7 +19,7 @@ _lib = None
 PP_A_MATRIX, PP_A_CONV3X3, PP_A_CONV3X3_S2, PP_A_CONV3X3_S2P0 = 0, 1, 2, 3
 PP_EPI_PLAIN, PP_EPI_GEGLU, PP_EPI_TRANSPOSED = 0, 1, 2
 PP_ACT_NONE, PP_ACT_SILU, PP_ACT_QUICK_GELU = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 vp = C.c_void_p
 i32 = C.c_int32
@@ -53,6 +53,8 @@ class GemmDesc(C.Structure):
         ("block_n", i32), ("t_fp16", i32),
         ("alpha_dev", vp), ("alpha_step", vp), ("alpha_stride", i32),
         ("chan_stats", vp),
+        ("row_stats", vp), ("row_stats_ld", i64),
+        ("ln_rec", vp), ("ln_nrec", i32), ("ln_ld", i64), ("ln_u", vp), ("ln_eps", f32),
     ]
 
 
@@ -105,6 +107,7 @@ _SIGNATURES = {
     "pp_device_supported": (C.c_int, []),
     "pp_gemm_conv": (C.c_int, [C.POINTER(GemmDesc), vp]),
     "pp_gemm_stats_geometry": (C.c_int, [C.POINTER(GemmDesc), C.POINTER(StatsGeom)]),
+    "pp_gemm_row_stats_records": (i32, [C.POINTER(GemmDesc)]),
     "pp_attention": (C.c_int, [C.POINTER(AttnDesc), vp]),
     "pp_group_norm": (C.c_int, [C.POINTER(GnDesc), vp]),
     "pp_group_norm_scratch_bytes": (i64, [i32, i32, i32, i32]),
@@ -127,6 +130,7 @@ _SIGNATURES = {
     "pp_image_postprocess": (C.c_int, [vp, i32, i32, vp, vp, i32, i32, vp]),
     "pp_program_add_softmax_rows": (C.c_int, [vp, vp, vp, i64, i32, i64, i64]),
     "pp_program_create": (C.c_int, [C.POINTER(vp)]),
+    "pp_program_run_range": (C.c_int, [vp, i32, i32, vp]),
     "pp_program_destroy": (None, [vp]),
     "pp_program_add_gemm": (C.c_int, [vp, C.POINTER(GemmDesc)]),
     "pp_program_add_attention": (C.c_int, [vp, C.POINTER(AttnDesc)]),

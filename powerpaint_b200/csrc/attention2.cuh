@@ -321,7 +321,16 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
             }
             tc_fence_before();
             __syncwarp();
-            if (lane_id() == 0) mbar_arrive(bar_p_full(t));
+            if (lane_id() == 0) {
+                // With three score buffers the scores of block j + 1 are in tensor memory before the group has
+                // finished block j, so a fast warp can run a whole block ahead of a slow one; its arrival for block
+                // j + 1 would then complete the 4-count phase of block j and release PV(j) while the slow warp's rows
+                // of P(j) are still raw scores (seen as NaN rows at 16384 tokens, where 128 blocks give the warps time
+                // to drift). A warp therefore hands over block j only once the whole group has handed over block j - 1.
+                // (NBUF == 2: S(k + 2) is issued after PV(k), which needs all four warps — no run-ahead.)
+                if (NBUF == 3 && j > 0) mbar_wait(bar_p_full(t), (j - 1) & 1);
+                mbar_arrive(bar_p_full(t));
+            }
         }
         // epilogue: O[:, :d] / O[:, d]
         mbar_wait(bar_pv_done(t), (nkv - 1) & 1);

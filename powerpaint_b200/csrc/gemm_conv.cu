@@ -249,7 +249,8 @@ __host__ __device__ constexpr int out_stage_bytes_for(int block_n) {
 //               epilogue of tile i overlaps the main loop of tile i+1
 // MODE selects the epilogue flavour at compile time (keeps the hot epilogue short and the
 // instruction footprint small): 0 = bf16 row-major output, N % 8 == 0 (bias, rowvec, two residuals,
-// alpha, SiLU), 1 = generic (fp32 / transposed / ragged N), 2 = GEGLU.
+// alpha, SiLU), 1 = generic (fp32 / transposed / ragged N), 2 = GEGLU, 3 = mode 0 emitting the per-row records of the
+// consumer's LayerNorm, 4 = mode 0 with LayerNorm of A applied algebraically (bias only).
 template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid_constant__ GemmKParams p) {
     constexpr int STAGES = stages_for(BLOCK_N);
@@ -272,7 +273,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
     // bias of the current / next tile, staged by the epilogue warps: [2][BLOCK_N] floats
     float* sbias_all = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));
     // output staging: validity of each tile row (statistics pass), then the swizzled bf16 tile (1024-byte aligned)
-    long long* s_row = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(sbias_all) + 2 * BLOCK_N * 4);
+    // column sums of the gamma-folded weights (LayerNorm fold), staged like the bias: [2][BLOCK_N] floats
+    float* su_all = sbias_all + 2 * BLOCK_N;
+    long long* s_row = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(sbias_all) + 4 * BLOCK_N * 4);
     const uint32_t s_out_addr = (smem_u32(s_row + 128) + 1023u) & ~1023u;
     uint8_t* s_out = smem_raw + (s_out_addr - smem_u32(smem_raw));
     // 16-byte piece of row r holding columns [col, col + 8) of the staged tile
@@ -421,11 +424,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p.bias + n));
             return v;
         };
+        // LayerNorm of A folded into this epilogue: modes 1 and 2 decide at run time; of the fast bf16 flavours only
+        // mode 4 carries it (and only mode 3 emits the records), so the big convs in mode 0 keep their register budget
+        const bool ln = (MODE == 1 || MODE == 2 || MODE == 4) && p.ln_rec != nullptr;
+        auto load_u = [&](int n_tile_of) -> float {
+            const int n = n_tile_of * BLOCK_N + etid;
+            float v = 0.f;
+            if (ln && etid < BLOCK_N && n < p.N)
+                asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p.ln_u + n));
+            return v;
+        };
         // stage the first tile's bias
         TileWalk tw(blockIdx.x, gridDim.x, n_tiles);
         if (blockIdx.x < num_tiles) {
             const float b0 = load_bias(tw.n);
-            if (etid < BLOCK_N) sbias_all[etid] = b0;
+            const float u0 = load_u(tw.n);
+            if (etid < BLOCK_N) {
+                sbias_all[etid] = b0;
+                su_all[etid] = u0;
+            }
         }
         epi_sync();
         uint32_t lt = 0;
@@ -435,9 +452,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
             const uint32_t acc = lt & 1u;
             const uint32_t acc_ph = (lt >> 1) & 1u;
             const float* sbias = sbias_all + acc * BLOCK_N;
+            const float* su = su_all + acc * BLOCK_N;
             // bias of the next tile: issue the load now, park it in smem at the end of this tile
             const int next_tile = tile + gridDim.x;
             const float bias_next = next_tile < num_tiles ? load_bias(tw.n) : 0.f;
+            const float u_next = next_tile < num_tiles ? load_u(tw.n) : 0.f;
             // output row of this thread
             bool valid;
             int64_t row;
@@ -460,6 +479,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
             }
             const int n_base = n_tile * BLOCK_N;
             const uint32_t taddr = tmem_base + lane_addr + acc * BLOCK_N;
+            // LayerNorm fold: acc' = ln_rs * acc + ln_nm * u[n] with ln_rs = rstd, ln_nm = -rstd * mean of this row,
+            // from the producer's per-row records (Chan's combination of the half-tile partials)
+            float ln_rs = 1.f, ln_nm = 0.f;
+            if (ln && valid) {
+                float cnt = 0.f, mean = 0.f, m2 = 0.f;
+                for (int i = 0; i < p.ln_nrec; ++i) {
+                    const float4 rc = __ldg(p.ln_rec + (int64_t)i * p.ln_ld + row);
+                    if (rc.w > 0.f) {
+                        const float inv = __fdividef(1.f, rc.w);
+                        const float mi = fmaf(rc.x, inv, rc.z);
+                        const float m2i = fmaxf(fmaf(-rc.x * inv, rc.x, rc.y), 0.f);
+                        const float tot = cnt + rc.w;
+                        const float wgt = __fdividef(rc.w, tot);
+                        const float dl = mi - mean;
+                        mean = fmaf(dl, wgt, mean);
+                        m2 += m2i + dl * dl * cnt * wgt;
+                        cnt = tot;
+                    }
+                }
+                const float var = cnt > 0.f ? __fdividef(m2, cnt) : 0.f;
+                ln_rs = rsqrtf(var + p.ln_eps);
+                ln_nm = -ln_rs * mean;
+            }
             if constexpr (MODE == 2) {
                 constexpr int HALF = BLOCK_N / 2;
                 const int o_base = n_tile * HALF;  // output column of this tile
@@ -478,8 +520,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                             float v[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                const float a = __uint_as_float(ra[h8 + j]) + sbias[c0 + h8 + j];
-                                const float g = __uint_as_float(rg[h8 + j]) + sbias[HALF + c0 + h8 + j];
+                                float a = __uint_as_float(ra[h8 + j]), g = __uint_as_float(rg[h8 + j]);
+                                if (ln) {
+                                    a = fmaf(a, ln_rs, fmaf(ln_nm, su[c0 + h8 + j], sbias[c0 + h8 + j]));
+                                    g = fmaf(g, ln_rs, fmaf(ln_nm, su[HALF + c0 + h8 + j], sbias[HALF + c0 + h8 + j]));
+                                } else {
+                                    a += sbias[c0 + h8 + j];
+                                    g += sbias[HALF + c0 + h8 + j];
+                                }
                                 v[j] = a * gelu_tanh_f(g);
                             }
                             uint4 q;
@@ -491,7 +539,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                         }
                     }
                 }
-            } else if constexpr (MODE == 0) {
+            } else if constexpr (MODE == 0 || MODE == 3 || MODE == 4) {
                 // lean path: per-row base pointers, 32-bit column offsets, uniform flags hoisted.
                 // The epilogue runs with only two warps per scheduler, so it is latency-bound unless
                 // the four 8-column groups of a chunk are independent straight-line code: the common
@@ -514,8 +562,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 constexpr bool kSplitHalves = BLOCK_N == 160;
                 uint32_t accA[32], accB[32];
                 tmem_ld32(taddr + (kSplitHalves ? half * 80 : half * 32), accA);
+                // per-row partial sums for the consumer's LayerNorm (this warp's columns of the row): shifted by the
+                // first value seen so a large common offset does not cancel in the variance
+                constexpr bool want_rows = MODE == 3;  // mode 3 is only selected with row_stats set
+                // (packed fp32x2 arithmetic: three instructions per column pair)
+                uint64_t st_s1 = 0ull, st_s2 = 0ull;  // {even, odd} column lanes of sum and sum of squares
+                float st_shift = 0.f, st_cnt = 0.f;
                 // ---- store helper: 8 fp32 -> (silu) -> bf16 -> 16-byte store
                 auto store8 = [&](float (&v)[8], int col) {
+                    if (want_rows) {
+                        if (st_cnt == 0.f) st_shift = v[0];
+                        const uint64_t sh2 = pack_f32x2(st_shift, st_shift);
+#pragma unroll
+                        for (int j = 0; j < 8; j += 2) {
+                            const uint64_t d = sub_f32x2(pack_f32x2(v[j], v[j + 1]), sh2);
+                            st_s1 = add_f32x2(st_s1, d);
+                            st_s2 = fma_f32x2(d, d, st_s2);
+                        }
+                        st_cnt += 8.f;
+                    }
                     if (act == PP_ACT_SILU) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
@@ -533,6 +598,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 // ---- one chunk of NG 8-column groups (32 or 16 columns)
                 auto process = [&](const uint32_t* accv, auto ng_tag, int c0) {
                     constexpr int NG = decltype(ng_tag)::value;
+                    if constexpr (MODE == 4) {
+                        // LayerNorm-folded consumer (q|k, cross-attention q): acc' = rstd * (acc - mean * u[n]) + bias
+                        // fused as two FMAs; these launches carry no residual / row vector
+#pragma unroll
+                        for (int g = 0; g < NG; ++g) {
+                            const int col = c0 + g * 8;
+                            if (valid && col < ncols) {
+                                const float4 b0 = *reinterpret_cast<const float4*>(sbias + col);
+                                const float4 b1 = *reinterpret_cast<const float4*>(sbias + col + 4);
+                                const float4 u0 = *reinterpret_cast<const float4*>(su + col);
+                                const float4 u1 = *reinterpret_cast<const float4*>(su + col + 4);
+                                float v[8];  // alpha == 1 for LayerNorm-folded launches (checked at prepare time)
+                                v[0] = fmaf(__uint_as_float(accv[g * 8 + 0]), ln_rs, fmaf(ln_nm, u0.x, b0.x));
+                                v[1] = fmaf(__uint_as_float(accv[g * 8 + 1]), ln_rs, fmaf(ln_nm, u0.y, b0.y));
+                                v[2] = fmaf(__uint_as_float(accv[g * 8 + 2]), ln_rs, fmaf(ln_nm, u0.z, b0.z));
+                                v[3] = fmaf(__uint_as_float(accv[g * 8 + 3]), ln_rs, fmaf(ln_nm, u0.w, b0.w));
+                                v[4] = fmaf(__uint_as_float(accv[g * 8 + 4]), ln_rs, fmaf(ln_nm, u1.x, b1.x));
+                                v[5] = fmaf(__uint_as_float(accv[g * 8 + 5]), ln_rs, fmaf(ln_nm, u1.y, b1.y));
+                                v[6] = fmaf(__uint_as_float(accv[g * 8 + 6]), ln_rs, fmaf(ln_nm, u1.z, b1.z));
+                                v[7] = fmaf(__uint_as_float(accv[g * 8 + 7]), ln_rs, fmaf(ln_nm, u1.w, b1.w));
+                                store8(v, col);
+                            }
+                        }
+                        return;
+                    } else {
                     if (full && plain) {
 #pragma unroll
                         for (int g = 0; g < NG; ++g) {
@@ -580,9 +670,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                             store8(v, col);
                         }
                     }
+                    }
                 };
                 using G4 = std::integral_constant<int, 4>;
                 using G2 = std::integral_constant<int, 2>;
+#ifdef GEMM_EXP_NOEPI  // experiment: drain the accumulator only (what does the tile cost without the epilogue math?)
+                tmem_wait_ld();
+                if (false)
+#endif
                 if constexpr (kSplitHalves) {
                     const int cb = half * 80;
                     uint32_t accC[16];
@@ -607,6 +702,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                         }
                     }
                 }
+                if (want_rows && valid)
+                    p.row_stats[(int64_t)(n_tile * 2 + half) * p.row_stats_ld + row] =
+                        make_float4(f32x2_lo(st_s1) + f32x2_hi(st_s1), f32x2_lo(st_s2) + f32x2_hi(st_s2), st_shift, st_cnt);
             } else {
                 // residuals of a 32-column chunk are fetched one chunk ahead (the first chunk's
                 // before the accumulator is even ready), so their latency hides behind TMEM
@@ -641,6 +739,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                                 float v[8];
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(accv[g * 8 + j]);
+                                if (ln) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], ln_rs, ln_nm * su[c0 + g * 8 + j]);
+                                }
                                 if (vec_ok && n0 + 8 <= p.N)
                                     epilogue_store8<true>(p, alpha1, v, row, grp, n0, sbias + c0 + g * 8, c1[g], c2[g]);
                                 else
@@ -674,12 +776,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                         const int col = out_base + sub * 64;
                         if (col >= n_out) break;
                         const CUtensorMap* tm = (OUT_COLS - sub * 64) >= 64 ? &p.tmOut[0] : &p.tmOut[1];
+#ifndef GEMM_EXP_NOSTORE  // experiment: no global write of the tile
                         if (p.a_mode == PP_A_MATRIX) tma_store_2d(tm, s_out_addr + sub * 16384, col, m_tile * BLOCK_M);
                         else tma_store_4d(tm, s_out_addr + sub * 16384, col, x0, y0, nb0);
+#endif
                     }
                     bulk_commit_group();
                 }
-                if constexpr (MODE == 0) {
+                if constexpr (MODE == 0 || MODE == 3 || MODE == 4) {
                     // GroupNorm partial sums of exactly the bf16 values the consumer will read
                     if (p.chan_stats) {
                         constexpr int L = (BLOCK_N <= 128) ? 16 : 8;
@@ -726,7 +830,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
             }
             // park the next tile's bias in the other staging buffer; everyone has finished reading
             // the buffer of tile lt-1 (same slot) long ago, the barrier orders this tile's writes
-            if (etid < BLOCK_N) sbias_all[(acc ^ 1u) * BLOCK_N + etid] = bias_next;
+            if (etid < BLOCK_N) {
+                sbias_all[(acc ^ 1u) * BLOCK_N + etid] = bias_next;
+                su_all[(acc ^ 1u) * BLOCK_N + etid] = u_next;
+            }
             if constexpr (MODE != 1) {
                 if (etid == 0) bulk_wait_read_all();  // the TMA unit has read the staged tile: it may be overwritten
             }
@@ -751,7 +858,7 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int pad64(int c) { return ceil_div(c, 64) * 64; }
 
 static size_t smem_for_block_n(int bn) {
-    return (size_t)stages_for(bn) * (A_STAGE_BYTES + bn * BLOCK_K * 2) + 8 * (2 * stages_for(bn) + 6) + 2 * bn * 4 +
+    return (size_t)stages_for(bn) * (A_STAGE_BYTES + bn * BLOCK_K * 2) + 8 * (2 * stages_for(bn) + 6) + 4 * bn * 4 +
            out_stage_bytes_for(bn) + 16 + 1024;  // out_stage_bytes_for includes the row table and the 1 KB alignment slack
 }
 
@@ -790,18 +897,26 @@ static int ensure_attr() {
 }
 
 #define PP_GEMM_DISPATCH(FN, bn, mode, ...)                                      \
-    switch ((bn) * 4 + (mode)) {                                                 \
-        case 64 * 4 + 0: return FN<64, 0>(__VA_ARGS__);                          \
-        case 64 * 4 + 1: return FN<64, 1>(__VA_ARGS__);                          \
-        case 128 * 4 + 0: return FN<128, 0>(__VA_ARGS__);                        \
-        case 128 * 4 + 1: return FN<128, 1>(__VA_ARGS__);                        \
-        case 128 * 4 + 2: return FN<128, 2>(__VA_ARGS__);                        \
-        case 160 * 4 + 0: return FN<160, 0>(__VA_ARGS__);                        \
-        case 160 * 4 + 1: return FN<160, 1>(__VA_ARGS__);                        \
-        case 160 * 4 + 2: return FN<160, 2>(__VA_ARGS__);                        \
-        case 256 * 4 + 0: return FN<256, 0>(__VA_ARGS__);                        \
-        case 256 * 4 + 1: return FN<256, 1>(__VA_ARGS__);                        \
-        case 256 * 4 + 2: return FN<256, 2>(__VA_ARGS__);                        \
+    switch ((bn) * 8 + (mode)) {                                                 \
+        case 64 * 8 + 0: return FN<64, 0>(__VA_ARGS__);                          \
+        case 64 * 8 + 1: return FN<64, 1>(__VA_ARGS__);                          \
+        case 64 * 8 + 3: return FN<64, 3>(__VA_ARGS__);                          \
+        case 128 * 8 + 3: return FN<128, 3>(__VA_ARGS__);                        \
+        case 160 * 8 + 3: return FN<160, 3>(__VA_ARGS__);                        \
+        case 256 * 8 + 3: return FN<256, 3>(__VA_ARGS__);                        \
+        case 64 * 8 + 4: return FN<64, 4>(__VA_ARGS__);                          \
+        case 128 * 8 + 4: return FN<128, 4>(__VA_ARGS__);                        \
+        case 160 * 8 + 4: return FN<160, 4>(__VA_ARGS__);                        \
+        case 256 * 8 + 4: return FN<256, 4>(__VA_ARGS__);                        \
+        case 128 * 8 + 0: return FN<128, 0>(__VA_ARGS__);                        \
+        case 128 * 8 + 1: return FN<128, 1>(__VA_ARGS__);                        \
+        case 128 * 8 + 2: return FN<128, 2>(__VA_ARGS__);                        \
+        case 160 * 8 + 0: return FN<160, 0>(__VA_ARGS__);                        \
+        case 160 * 8 + 1: return FN<160, 1>(__VA_ARGS__);                        \
+        case 160 * 8 + 2: return FN<160, 2>(__VA_ARGS__);                        \
+        case 256 * 8 + 0: return FN<256, 0>(__VA_ARGS__);                        \
+        case 256 * 8 + 1: return FN<256, 1>(__VA_ARGS__);                        \
+        case 256 * 8 + 2: return FN<256, 2>(__VA_ARGS__);                        \
     }
 
 static int ensure_attr_for(int block_n, int mode) {
@@ -939,6 +1054,17 @@ int gemm_stats_geometry(const pp_gemm_desc& d, pp_stats_geom* g) {
     return PP_OK;
 }
 
+// records per row a GEMM emits for the consumer's LayerNorm: one per half n-tile (the two epilogue warps that share a
+// TMEM lane quarter each own a set of columns); 0 = this launch cannot emit them
+int gemm_row_stats_records(const pp_gemm_desc& d) {
+    GemmKParams p;
+    memset(&p, 0, sizeof(p));
+    int bn = 0;
+    if (gemm_geometry(d, p, &bn)) return 0;
+    if (d.a_mode != PP_A_MATRIX || !gemm_fast_mode(d) || d.act != PP_ACT_NONE) return 0;
+    return 2 * p.n_tiles;
+}
+
 int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
     GemmLaunch l;
     memset(&l, 0, sizeof(l));
@@ -1058,7 +1184,8 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
     if (geglu) {
         l.mode = 2;
     } else {
-        l.mode = gemm_fast_mode(d) ? 0 : 1;
+        PP_REQUIRE(!(d.row_stats && d.ln_rec), "gemm: a launch either emits LayerNorm records or consumes them");
+        l.mode = gemm_fast_mode(d) ? (d.row_stats ? 3 : d.ln_rec ? 4 : 0) : 1;
     }
     if (l.mode != 1) {
         // TMA-store boxes of the staged output tile: 64 columns (128-byte swizzle), and a 32-column box (64-byte
@@ -1087,13 +1214,33 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
         pp_stats_geom g;
         int rc = gemm_stats_geometry(d, &g);
         if (rc) return rc;
-        PP_REQUIRE(g.supported && l.mode == 0, "gemm: chan_stats requested but this launch cannot emit statistics "
+        PP_REQUIRE(g.supported && (l.mode == 0 || l.mode >= 3), "gemm: chan_stats requested but this launch cannot emit statistics "
                    "(query pp_gemm_stats_geometry first)");
         PP_REQUIRE((reinterpret_cast<uintptr_t>(d.chan_stats) & 15) == 0, "gemm: chan_stats not 16-byte aligned");
         p.chan_stats = d.chan_stats;
         p.stat_segs = g.segs;
         p.stat_seg_rows_log2 = 0;
         while ((1 << p.stat_seg_rows_log2) < g.seg_rows) ++p.stat_seg_rows_log2;
+    }
+    if (d.row_stats) {
+        PP_REQUIRE(gemm_row_stats_records(d) > 0, "gemm: row_stats requested but this launch cannot emit them "
+                   "(query pp_gemm_row_stats_records first)");
+        PP_REQUIRE(d.row_stats_ld >= d.M && (reinterpret_cast<uintptr_t>(d.row_stats) & 15) == 0,
+                   "gemm: row_stats_ld=%lld < M or row_stats not 16-byte aligned", (long long)d.row_stats_ld);
+        p.row_stats = reinterpret_cast<float4*>(d.row_stats);
+        p.row_stats_ld = d.row_stats_ld;
+    }
+    if (d.ln_rec) {
+        PP_REQUIRE(d.a_mode == PP_A_MATRIX && d.ln_u && d.ln_nrec > 0 && d.ln_ld >= d.M && d.ln_eps > 0.f,
+                   "gemm: LayerNorm fold needs PP_A_MATRIX, ln_u, ln_nrec > 0, ln_ld >= M, ln_eps > 0");
+        PP_REQUIRE(!d.res1 && !d.res2 && !d.rowvec && !d.a1 && d.alpha == 1.0f && !d.alpha_dev,
+                   "gemm: LayerNorm-folded launches take bias only (no residual / row vector / alpha)");
+        PP_REQUIRE((reinterpret_cast<uintptr_t>(d.ln_rec) & 15) == 0, "gemm: ln_rec not 16-byte aligned");
+        p.ln_rec = reinterpret_cast<const float4*>(d.ln_rec);
+        p.ln_nrec = d.ln_nrec;
+        p.ln_ld = d.ln_ld;
+        p.ln_u = d.ln_u;
+        p.ln_eps = d.ln_eps;
     }
     {
         int rc = ensure_attr_for(bn, l.mode);
@@ -1112,6 +1259,8 @@ extern "C" pp_status pp_gemm_stats_geometry(const pp_gemm_desc* d, pp_stats_geom
     }
     return pp::gemm_stats_geometry(*d, out);
 }
+
+extern "C" int32_t pp_gemm_row_stats_records(const pp_gemm_desc* d) { return d ? pp::gemm_row_stats_records(*d) : 0; }
 
 extern "C" pp_status pp_gemm_conv(const pp_gemm_desc* d, pp_stream stream) {
     if (!d) {

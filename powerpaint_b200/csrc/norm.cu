@@ -169,61 +169,59 @@ struct GnPartSrc {
     int channels, segs, tiles_per_group, tiles_x, tiles_y, bw, bh, wo, ho;
 };
 
-__global__ void __launch_bounds__(512) gn_finalize_kernel(GnPartSrc s0, GnPartSrc s1, int groups, float eps,
-                                                          float* __restrict__ stats) {
+// One WARP per (sample, group): the lanes split the (channel, tile) records of the group, every record is re-referenced
+// to ONE shift R (the group's first record) so the shifted sums simply add up, and a fixed-order butterfly folds the
+// lanes — bit-identical from run to run. (The first version ran one block per sample with one thread per channel
+// walking all tiles serially: 16 blocks, 11.6 us per launch, 3.4 % of the C2 step for 61 launches.)
+constexpr int GN_FIN_WARPS = 4;
+__global__ void __launch_bounds__(GN_FIN_WARPS * 32) gn_finalize_kernel(GnPartSrc s0, GnPartSrc s1, int groups, int batch,
+                                                                       float eps, float* __restrict__ stats) {
     pdl_wait();
     pdl_launch_dependents();
-    extern __shared__ double shd[];  // [C] mean, [C] M2
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * GN_FIN_WARPS + (threadIdx.x >> 5);  // (sample, group)
+    if (item >= batch * groups) return;
+    const int n = item / groups, g = item - n * groups;
     const int C = s0.channels + s1.channels;
     const int cpg = C / groups;
-    const int n = blockIdx.x;
-    double* sh_mean = shd;
-    double* sh_m2 = shd + C;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const GnPartSrc& s = c < s0.channels ? s0 : s1;
-        const int cl = c < s0.channels ? c : c - s0.channels;
-        const int gidx = n / s.segs, seg = n - gidx * s.segs;
-        const float* base = s.part + (((int64_t)gidx * s.tiles_per_group * s.segs + seg) * s.channels + cl) * 4;
-        const int64_t tstride = (int64_t)s.segs * s.channels * 4;
-        // every tile summed x - shift_tile; re-reference the sums to ONE shift R (the first tile's) and add them up:
-        //   sum(x - R) = A + n d,  sum((x - R)^2) = B + 2 d A + n d^2,  d = shift_tile - R   (fp64, no divisions)
-        const double R = (double)__ldcg(base + 2);
-        double S = 0.0, SS = 0.0, cnt = 0.0;
-        int tx = 0, ty = 0;
-        for (int t0 = 0; t0 < s.tiles_per_group; t0 += 8) {
-            float4 v[8];
+    // the group's channels [c_lo, c_hi) may straddle the two sources of a skip concat
+    const int c_lo = g * cpg, c_hi = c_lo + cpg;
+    auto rec_base = [&](const GnPartSrc& src, int cl) -> const float* {
+        const int gidx = n / src.segs, seg = n - gidx * src.segs;
+        return src.part + (((int64_t)gidx * src.tiles_per_group * src.segs + seg) * src.channels + cl) * 4;
+    };
+    const double R = (double)__ldcg((c_lo < s0.channels ? rec_base(s0, c_lo) : rec_base(s1, c_lo - s0.channels)) + 2);
+    // sum(x - R) = A + n d,  sum((x - R)^2) = B + 2 d A + n d^2,  d = shift_tile - R
+    double S = 0.0, SS = 0.0, cnt = 0.0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                v[u] = t0 + u < s.tiles_per_group ? __ldcg(reinterpret_cast<const float4*>(base + (t0 + u) * tstride))
-                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (t0 + u < s.tiles_per_group) {
-                    const double cb = (double)(min(s.bw, s.wo - tx * s.bw) * min(s.bh, s.ho - ty * s.bh));
-                    const double A = (double)v[u].x, B = (double)v[u].y, d = (double)v[u].z - R;
-                    S += A + cb * d;
-                    SS += B + d * (2.0 * A + cb * d);
-                    cnt += cb;
-                    if (++tx == s.tiles_x) { tx = 0; ++ty; }
-                }
-            }
+    for (int si = 0; si < 2; ++si) {
+        const GnPartSrc& src = si == 0 ? s0 : s1;
+        const int off = si == 0 ? 0 : s0.channels;
+        const int a = max(c_lo, off) - off, b = min(c_hi, off + src.channels) - off;  // local channel range
+        if (b <= a) continue;
+        const int T = src.tiles_per_group;
+        const int items = (b - a) * T;  // (channel, tile) records, split across the lanes
+        const float* base = rec_base(src, a);
+        const int64_t tstride = (int64_t)src.segs * src.channels * 4;
+#pragma unroll 4
+        for (int i = lane; i < items; i += 32) {
+            const int cc = i / T, t = i - cc * T;
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(base + cc * 4 + t * tstride));
+            const int ty = t / src.tiles_x, tx = t - ty * src.tiles_x;
+            const double cb = (double)(min(src.bw, src.wo - tx * src.bw) * min(src.bh, src.ho - ty * src.bh));
+            const double A = (double)v.x, B = (double)v.y, d = (double)v.z - R;
+            S += A + cb * d;
+            SS += B + d * (2.0 * A + cb * d);
+            cnt += cb;
         }
-        const double md = S / cnt;
-        sh_mean[c] = R + md;
-        sh_m2[c] = fmax(SS - S * md, 0.0);
     }
-    __syncthreads();
-    const double per_ch = (double)s0.wo * (double)s0.ho;  // pixels per sample
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        // channels of the group, re-referenced to the first channel's mean in the same way
-        const double R = sh_mean[g * cpg];
-        double S = 0.0, SS = 0.0;
-        for (int cc = 0; cc < cpg; ++cc) {
-            const double d = sh_mean[g * cpg + cc] - R;
-            S += per_ch * d;
-            SS += sh_m2[g * cpg + cc] + per_ch * d * d;
-        }
-        const double cnt = per_ch * (double)cpg;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        S += __shfl_xor_sync(0xffffffffu, S, o);
+        SS += __shfl_xor_sync(0xffffffffu, SS, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0) {
         const double md = S / cnt;
         const double var = fmax(SS - S * md, 0.0) / cnt;
         stats[((int64_t)n * groups + g) * 2] = (float)(R + md);
@@ -342,8 +340,9 @@ int group_norm_launch(const pp_gn_desc& d, cudaStream_t s) {
         GnPartSrc s0 = part_src(d.part0, d.geom0), s1;
         memset(&s1, 0, sizeof(s1));
         if (d.x1) s1 = part_src(d.part1, d.geom1);
-        const int fthreads = std::min(512, (C + 31) / 32 * 32);
-        PP_CUDA_CHECK(launch(gn_finalize_kernel, dim3(d.batch), fthreads, (size_t)C * 16, s, s0, s1, d.groups, d.eps, d.stats));
+        const int items = d.batch * d.groups;
+        PP_CUDA_CHECK(launch(gn_finalize_kernel, dim3((items + GN_FIN_WARPS - 1) / GN_FIN_WARPS), GN_FIN_WARPS * 32, 0, s, s0,
+                             s1, d.groups, d.batch, d.eps, d.stats));
     } else {
         if (!d.stats_prezeroed) PP_CUDA_CHECK(cudaMemsetAsync(tickets, 0, sizeof(uint32_t) * d.batch, s));
         PP_CUDA_CHECK(launch(gn_stats_kernel, dim3(chunks, d.batch), threads, g.smem, s,

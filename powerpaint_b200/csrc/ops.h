@@ -52,12 +52,20 @@ struct GemmKParams {
     float* chan_stats;
     int32_t stat_segs;           // samples per m-tile (1, 2 or 4 ...)
     int32_t stat_seg_rows_log2;  // rows of one sample inside the tile
+    // LayerNorm fold (see pp_gemm_desc): records emitted per row and half n-tile / consumed by the epilogue
+    float4* row_stats;
+    int64_t row_stats_ld;
+    const float4* ln_rec;
+    int32_t ln_nrec;
+    int64_t ln_ld;
+    const float* ln_u;
+    float ln_eps;
 };
 
 struct GemmLaunch {
     GemmKParams p;
     int block_n;
-    int mode;  // epilogue flavour: 0 fast bf16, 1 generic, 2 GEGLU
+    int mode;  // epilogue flavour: 0 fast bf16, 1 generic, 2 GEGLU, 3 fast bf16 + LayerNorm records out, 4 fast bf16 + LayerNorm of A
     dim3 grid;
     size_t smem;
 };
@@ -91,6 +99,7 @@ int attn_launch(const AttnLaunch& l, cudaStream_t s);
 
 // ---------------------------------------------------------------- simple ops
 int gemm_stats_geometry(const pp_gemm_desc& d, pp_stats_geom* out);
+int gemm_row_stats_records(const pp_gemm_desc& d);
 int group_norm_launch(const pp_gn_desc& d, cudaStream_t s);
 int group_norm_validate(const pp_gn_desc& d);
 int64_t group_norm_scratch_bytes(int batch, int hw, int channels, int groups);

@@ -296,6 +296,21 @@ pp_status pp_program_run(pp_program* p, pp_stream stream) {
     return pp::PP_OK;
 }
 
+/* diagnostic: replay ops [first, first + count) as plain launches (bisecting a recorded step op by op) */
+pp_status pp_program_run_range(pp_program* p, int32_t first, int32_t count, pp_stream stream) {
+    if (!p) { pp::set_last_error("pp_program_run_range: null program"); return pp::PP_ERR_INVALID; }
+    if (first < 0 || count < 0 || (size_t)first + (size_t)count > p->ops.size()) {
+        pp::set_last_error("pp_program_run_range: [%d, %d) outside the %zu recorded ops", first, first + count, p->ops.size());
+        return pp::PP_ERR_INVALID;
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    for (int32_t i = first; i < first + count; ++i) {
+        int rc = pp::run_op(p->ops[i], s);
+        if (rc) return rc;
+    }
+    return pp::PP_OK;
+}
+
 pp_status pp_program_graph_build(pp_program* p, pp_stream stream) {
     if (!p) { pp::set_last_error("pp_program_graph_build: null program"); return pp::PP_ERR_INVALID; }
     if (p->exec) return pp::PP_OK;

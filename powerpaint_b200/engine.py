@@ -78,6 +78,7 @@ class Plan:
         self.free: Dict[int, List[torch.Tensor]] = {}  # size -> raw blocks whose last reader has been recorded
         self.raw_of: Dict[int, torch.Tensor] = {}      # data_ptr of a live view -> its raw block
         self.chan_stats: Dict[int, tuple] = {}         # data_ptr of a tensor -> (partials, geometry) its producer emits
+        self.row_stats: Dict[int, torch.Tensor] = {}   # data_ptr of a tensor -> per-row LayerNorm records of its producer
         self.scale_dev: Optional[torch.Tensor] = None  # eager side-net forward: 1-float conditioning scale
 
 
@@ -143,6 +144,28 @@ class NetEngine:
     def w_qk(self, prefix: str) -> torch.Tensor:
         return self._cached("qk:" + prefix, lambda: torch.cat(
             [self._raw(prefix + ".to_q.weight"), self._raw(prefix + ".to_k.weight")], 0).to(BF16).contiguous())
+
+    # LayerNorm folded into the GEMMs either side of it (PP_B200_LN_FOLD=0: standalone LayerNorm kernel)
+    LN_FOLD = os.environ.get("PP_B200_LN_FOLD", "1") != "0"
+
+    def w_ln_folded(self, key: str, wnames, ln_name: str, bias_name: Optional[str] = None, geglu: bool = False):
+        """Weights of the GEMM that consumes LayerNorm(x): y = LN(x) W^T + b = rstd (x W'^T - mean u) + b' with
+        W' = W * gamma (bf16), u = row sums of the bf16 W' (what the tensor core multiplies), b' = W beta + b.
+        Returns (W' bf16 [N, K], u fp32 [N], b' fp32 [N]); `geglu`: rows tile-interleaved like `w_geglu`."""
+        def make():
+            w = torch.cat([self._raw(n + ".weight").reshape(self._raw(n + ".weight").shape[0], -1) for n in wnames], 0)
+            gamma, beta = self._raw(ln_name + ".weight"), self._raw(ln_name + ".bias")
+            b = w.double() @ beta.double()
+            if bias_name is not None:
+                b = b + self._raw(bias_name).double()
+            wf = (w * gamma[None, :]).to(BF16)
+            u = wf.double().sum(1)
+            if geglu:  # value / gate rows interleaved per tile; u and b' ride the same permutation
+                wi, u = ops.pack_geglu_weight(wf.float(), u.float(), self.GEGLU_BLOCK_N)
+                _, b = ops.pack_geglu_weight(wf.float(), b.float(), self.GEGLU_BLOCK_N)
+                wf = wi  # bf16 -> fp32 -> bf16 is exact
+            return wf.contiguous(), u.float().contiguous(), b.float().contiguous()
+        return self._cached("lnf:" + key, make)
 
     GEGLU_BLOCK_N = 128
 
@@ -211,9 +234,12 @@ class NetEngine:
             if raw is None:
                 continue  # not a plan buffer (a weight, a shared input) or already released
             ent = plan.chan_stats.pop(t.data_ptr(), None)
+            rec = plan.row_stats.pop(t.data_ptr(), None)
             plan.free.setdefault(raw.numel(), []).append(raw)
             if ent is not None:
                 self._free(plan, ent[0])  # the producer's partial sums die with the tensor they describe
+            if rec is not None:
+                self._free(plan, rec)
 
     def _with_stats(self, plan: Plan, desc, out: torch.Tensor) -> None:
         """let this GEMM / conv emit the GroupNorm partial sums of its output from the epilogue"""
@@ -281,18 +307,30 @@ class NetEngine:
 
     def _linear(self, plan, prog, x, M, wname, n_out, *, w=None, bias=None, res1=None, res2=None, alpha=1.0,
                 act=N.PP_ACT_NONE, out=None, out_fp32=False, a1=None, c1=0, ldc=0, lda0=0, stats_hw=0,
-                alpha_dev=None, alpha_step=None, alpha_stride=0):
-        """`stats_hw` > 0: rows per sample; the GEMM then emits GroupNorm partial sums of its output"""
+                alpha_dev=None, alpha_step=None, alpha_stride=0, row_stats=False, ln=None):
+        """`stats_hw` > 0: rows per sample; the GEMM then emits GroupNorm partial sums of its output.
+        `row_stats`: also emit the per-row LayerNorm records of the output (returned as `plan.row_stats[out]`);
+        `ln` = (records, u, eps): LayerNorm of `x` folded into this GEMM."""
         if out is None:
             out = self._buf(plan, M, n_out, dtype=torch.float32 if out_fp32 else BF16)
         desc = ops.gemm_desc(a0=x, a1=a1, c1=c1, w=w if w is not None else self.w_linear(wname), out=out, N_=n_out,
                              M=M, bias=bias, res1=res1, res2=res2, alpha=alpha, act=act, out_fp32=out_fp32,
                              ldc=ldc, lda0=lda0, rows_per_group=stats_hw, alpha_dev=alpha_dev,
-                             alpha_step=alpha_step, alpha_stride=alpha_stride)
+                             alpha_step=alpha_step, alpha_stride=alpha_stride, ln=ln)
         if stats_hw:
             self._with_stats(plan, desc, out)
+        if row_stats:
+            nrec = ops.gemm_row_stats_records(desc)
+            if nrec > 0:
+                rec = self._buf(plan, nrec, M, 4, dtype=torch.float32)
+                ops.attach_row_stats(desc, rec)
+                plan.row_stats[out.data_ptr()] = rec
         prog.add(desc)
         return out
+
+    def _ln_of(self, plan, x):
+        """per-row LayerNorm records of x emitted by its producer, or None (then the standalone kernel runs)"""
+        return plan.row_stats.get(x.data_ptr()) if self.LN_FOLD else None
 
     def _resnet(self, plan, prog, name, x0, x1, nb, h, w, cout, tproj, *, out_scale=1.0, add=None):
         """ResnetBlock2D on the (virtual) concat of x0 and x1."""
@@ -338,34 +376,51 @@ class NetEngine:
         d = C // heads
         scale = 1.0 / math.sqrt(d)
         g = self._gn(plan, prog, x, None, nb, hw, name + ".norm", 1e-6, False)
-        t0 = self._linear(plan, prog, g, M, name + ".proj_in", C, bias=self.vec(name + ".proj_in.bias"))
+        fold = self.LN_FOLD
+        t0 = self._linear(plan, prog, g, M, name + ".proj_in", C, bias=self.vec(name + ".proj_in.bias"), row_stats=fold)
         self._free(plan, g)
         b = name + ".transformer_blocks.0"
-        # --- self attention
-        l1 = self._buf(plan, M, C)
-        prog.add_layer_norm(t0, l1, self.vec(b + ".norm1.weight"), self.vec(b + ".norm1.bias"), M, C, 1e-5)
-        qk = self._linear(plan, prog, l1, M, None, 2 * C, w=self.w_qk(b + ".attn1"))
         hw_ld = _ceil(hw, 8)
+        # --- self attention. LayerNorm (norm1) is folded into q|k and V^T: the producer of t0 left per-row records,
+        # the consumers multiply the raw t0 by W * gamma and finish the normalisation in their epilogues
+        rec = self._ln_of(plan, t0)
         vt = self._buf(plan, nb, C, hw_ld, dtype=torch.float16)  # fp16 V^T: P is fp16 in pp_attention
-        prog.add(ops.gemm_desc(a0=l1, w=self.w_linear(b + ".attn1.to_v"), out=vt, N_=C, M=M,
-                               epilogue=N.PP_EPI_TRANSPOSED, t_rows=hw, t_ld=hw_ld, t_fp16=True))
-        self._free(plan, l1)
+        if rec is not None:
+            wqk, uqk, bqk = self.w_ln_folded(b + ".attn1.qk", [b + ".attn1.to_q", b + ".attn1.to_k"], b + ".norm1")
+            wv, uv, bv = self.w_ln_folded(b + ".attn1.v", [b + ".attn1.to_v"], b + ".norm1")
+            qk = self._linear(plan, prog, t0, M, None, 2 * C, w=wqk, bias=bqk, ln=(rec, uqk, 1e-5))
+            prog.add(ops.gemm_desc(a0=t0, w=wv, out=vt, N_=C, M=M, bias=bv, epilogue=N.PP_EPI_TRANSPOSED, t_rows=hw,
+                                   t_ld=hw_ld, t_fp16=True, ln=(rec, uv, 1e-5)))
+        else:
+            l1 = self._buf(plan, M, C)
+            prog.add_layer_norm(t0, l1, self.vec(b + ".norm1.weight"), self.vec(b + ".norm1.bias"), M, C, 1e-5)
+            qk = self._linear(plan, prog, l1, M, None, 2 * C, w=self.w_qk(b + ".attn1"))
+            prog.add(ops.gemm_desc(a0=l1, w=self.w_linear(b + ".attn1.to_v"), out=vt, N_=C, M=M,
+                                   epilogue=N.PP_EPI_TRANSPOSED, t_rows=hw, t_ld=hw_ld, t_fp16=True))
+            self._free(plan, l1)
         a1 = self._buf(plan, M, C)
         prog.add(ops.attn_desc(q=qk, k=qk[:, C:], vt=vt, out=a1, batch=nb, heads=heads, d=d, nq=hw, nk=hw,
                                q_ld=2 * C, k_ld=2 * C, vt_ld=hw_ld, o_ld=C, q_batch_stride=hw * 2 * C,
                                k_batch_stride=hw * 2 * C, scale=scale))
         self._free(plan, qk, vt)
-        t1 = self._linear(plan, prog, a1, M, b + ".attn1.to_out.0", C, bias=self.vec(b + ".attn1.to_out.0.bias"), res1=t0)
+        t1 = self._linear(plan, prog, a1, M, b + ".attn1.to_out.0", C, bias=self.vec(b + ".attn1.to_out.0.bias"), res1=t0,
+                          row_stats=fold)
         self._free(plan, a1, t0)
         # --- cross attention (K / V^T of the prompt are projected once per prompt: never recycled)
-        l2 = self._buf(plan, M, C)
-        prog.add_layer_norm(t1, l2, self.vec(b + ".norm2.weight"), self.vec(b + ".norm2.bias"), M, C, 1e-5)
-        q2 = self._linear(plan, prog, l2, M, b + ".attn2.to_q", C)
-        self._free(plan, l2)
+        rec = self._ln_of(plan, t1)
+        if rec is not None:
+            wq, uq, bq = self.w_ln_folded(b + ".attn2.q", [b + ".attn2.to_q"], b + ".norm2")
+            q2 = self._linear(plan, prog, t1, M, None, C, w=wq, bias=bq, ln=(rec, uq, 1e-5))
+        else:
+            l2 = self._buf(plan, M, C)
+            prog.add_layer_norm(t1, l2, self.vec(b + ".norm2.weight"), self.vec(b + ".norm2.bias"), M, C, 1e-5)
+            q2 = self._linear(plan, prog, l2, M, b + ".attn2.to_q", C)
+            self._free(plan, l2)
         nk = ctx.shape[1]
         nk_ld = _ceil(nk, 8)
         k2 = torch.empty(nb * nk, C, dtype=BF16, device=self.device)
-        v2t = torch.empty(nb, C, nk_ld, dtype=torch.float16, device=self.device)
+        # zeros: the pad columns nk..nk_ld are never written (nor read: the tensor map ends at nk), keep them clean
+        v2t = torch.zeros(nb, C, nk_ld, dtype=torch.float16, device=self.device)
         plan.bytes += (k2.numel() + v2t.numel()) * 2
         self._linear(plan, ctxprog, ctx, nb * nk, b + ".attn2.to_k", C, out=k2)
         ctxprog.add(ops.gemm_desc(a0=ctx, w=self.w_linear(b + ".attn2.to_v"), out=v2t, N_=C, M=nb * nk,
@@ -374,17 +429,26 @@ class NetEngine:
         prog.add(ops.attn_desc(q=q2, k=k2, vt=v2t, out=a2, batch=nb, heads=heads, d=d, nq=hw, nk=nk, q_ld=C, k_ld=C,
                                vt_ld=nk_ld, o_ld=C, q_batch_stride=hw * C, k_batch_stride=nk * C, scale=scale))
         self._free(plan, q2)
-        t2 = self._linear(plan, prog, a2, M, b + ".attn2.to_out.0", C, bias=self.vec(b + ".attn2.to_out.0.bias"), res1=t1)
+        t2 = self._linear(plan, prog, a2, M, b + ".attn2.to_out.0", C, bias=self.vec(b + ".attn2.to_out.0.bias"), res1=t1,
+                          row_stats=fold)
         self._free(plan, a2, t1)
-        # --- feed-forward (GEGLU)
-        l3 = self._buf(plan, M, C)
-        prog.add_layer_norm(t2, l3, self.vec(b + ".norm3.weight"), self.vec(b + ".norm3.bias"), M, C, 1e-5)
-        wg, bg = self.w_geglu(b + ".ff.net.0.proj")
+        # --- feed-forward (GEGLU), norm3 folded the same way
+        rec = self._ln_of(plan, t2)
+        if rec is not None:
+            wg, ug, bg = self.w_ln_folded(b + ".ff.geglu", [b + ".ff.net.0.proj"], b + ".norm3",
+                                          bias_name=b + ".ff.net.0.proj.bias", geglu=True)
+            ln3, a_ff = (rec, ug, 1e-5), t2
+        else:
+            l3 = self._buf(plan, M, C)
+            prog.add_layer_norm(t2, l3, self.vec(b + ".norm3.weight"), self.vec(b + ".norm3.bias"), M, C, 1e-5)
+            wg, bg = self.w_geglu(b + ".ff.net.0.proj")
+            ln3, a_ff = None, l3
         F_ = wg.shape[0] // 2
         ffh = self._buf(plan, M, F_)
-        prog.add(ops.gemm_desc(a0=l3, w=wg, out=ffh, N_=2 * F_, M=M, bias=bg, epilogue=N.PP_EPI_GEGLU,
-                               block_n=self.GEGLU_BLOCK_N))
-        self._free(plan, l3)
+        prog.add(ops.gemm_desc(a0=a_ff, w=wg, out=ffh, N_=2 * F_, M=M, bias=bg, epilogue=N.PP_EPI_GEGLU,
+                               block_n=self.GEGLU_BLOCK_N, ln=ln3))
+        if ln3 is None:
+            self._free(plan, a_ff)
         t3 = self._linear(plan, prog, ffh, M, b + ".ff.net.2", C, bias=self.vec(b + ".ff.net.2.bias"), res1=t2)
         self._free(plan, ffh, t2)
         # --- proj_out + the Transformer2DModel residual (+ BrushNet add)

@@ -98,7 +98,10 @@ def gemm_desc(*, a0: torch.Tensor, w: torch.Tensor, out: torch.Tensor, N_: int,
               act: int = N.PP_ACT_NONE, epilogue: int = N.PP_EPI_PLAIN, ldc: int = 0,
               out_fp32: bool = False, t_rows: int = 0, t_ld: int = 0, block_n: int = 0, t_fp16: bool = False,
               alpha_dev: Optional[torch.Tensor] = None, alpha_step: Optional[torch.Tensor] = None,
-              alpha_stride: int = 0, chan_stats: Optional[torch.Tensor] = None) -> Desc:
+              alpha_stride: int = 0, chan_stats: Optional[torch.Tensor] = None,
+              ln: Optional[tuple] = None) -> Desc:
+    """`ln` = (records [nrec, ld, 4] fp32, u [N] fp32, eps): LayerNorm of A folded into the epilogue — `w` must
+    carry gamma (W * gamma) and `bias` the W @ beta term (include/powerpaint_b200.h)"""
     d = N.GemmDesc()
     d.a_mode, d.epilogue = a_mode, epilogue
     d.a0, d.a1 = N.ptr(a0), N.ptr(a1)
@@ -123,7 +126,27 @@ def gemm_desc(*, a0: torch.Tensor, w: torch.Tensor, out: torch.Tensor, N_: int,
     d.t_fp16 = 1 if t_fp16 else 0
     d.alpha_dev, d.alpha_step, d.alpha_stride = N.ptr(alpha_dev), N.ptr(alpha_step), alpha_stride
     d.chan_stats = N.ptr(chan_stats)
-    return Desc("gemm", d, [a0, a1, w, out, bias, rowvec, res1, res2, alpha_dev, alpha_step, chan_stats])
+    keep = [a0, a1, w, out, bias, rowvec, res1, res2, alpha_dev, alpha_step, chan_stats]
+    if ln is not None:
+        rec, u, eps = ln
+        if rec.dtype != torch.float32 or rec.dim() != 3 or rec.shape[-1] != 4 or not rec.is_contiguous():
+            raise ValueError("ln records must be a contiguous fp32 [nrec, ld, 4] tensor")
+        if u.dtype != torch.float32 or u.numel() != N_ or not u.is_contiguous():
+            raise ValueError("ln_u must be a contiguous fp32 [N] tensor")
+        d.ln_rec, d.ln_nrec, d.ln_ld, d.ln_u, d.ln_eps = N.ptr(rec), rec.shape[0], rec.shape[1], N.ptr(u), eps
+        keep += [rec, u]
+    return Desc("gemm", d, keep)
+
+
+def gemm_row_stats_records(desc: Desc) -> int:
+    """host-only: per-row LayerNorm records this GEMM can emit from its epilogue (0: it cannot)"""
+    return int(N.lib().pp_gemm_row_stats_records(C.byref(desc.c)))
+
+
+def attach_row_stats(desc: Desc, rec: torch.Tensor) -> None:
+    """rec: fp32 [records, ld, 4] with ld >= M"""
+    desc.c.row_stats, desc.c.row_stats_ld = N.ptr(rec), rec.shape[1]
+    desc.keep.append(rec)
 
 
 def gemm_stats_geometry(desc: Desc) -> "N.StatsGeom":
@@ -337,6 +360,7 @@ class Program:
         self._h = N.vp()
         N.check(N.lib().pp_program_create(C.byref(self._h)), "pp_program_create")
         self._keep = []
+        self.labels = []  # one short label per recorded op (diagnostics: `run_range`)
         self._graph = False
 
     def __del__(self):
@@ -354,50 +378,60 @@ class Program:
               "unipc": L.pp_program_add_unipc}[desc.kind]
         N.check(fn(self._h, C.byref(desc.c)), f"pp_program_add_{desc.kind}")
         self._keep.append(desc.keep)
+        self.labels.append(desc.kind)
 
     def add_layer_norm(self, x, y, gamma, beta, rows, c, eps):
         N.check(N.lib().pp_program_add_layer_norm(self._h, N.ptr(x), N.ptr(y), N.ptr(gamma), N.ptr(beta),
                                                   rows, c, eps), "pp_program_add_layer_norm")
         self._keep.append((x, y, gamma, beta))
+        self.labels.append("layer_norm")
 
     def add_upsample2x(self, x, y, nb, h, w, c):
         N.check(N.lib().pp_program_add_upsample2x(self._h, N.ptr(x), N.ptr(y), nb, h, w, c),
                 "pp_program_add_upsample2x")
         self._keep.append((x, y))
+        self.labels.append("upsample2x")
 
     def add_upsample_nearest(self, x, y, nb, h, w, c, ho, wo):
         N.check(N.lib().pp_program_add_upsample_nearest(self._h, N.ptr(x), N.ptr(y), nb, h, w, c, ho, wo),
                 "pp_program_add_upsample_nearest")
         self._keep.append((x, y))
+        self.labels.append("upsample_nearest")
 
     def add_softmax_rows(self, s, p, rows, cols, ld_s, ld_p):
         N.check(N.lib().pp_program_add_softmax_rows(self._h, N.ptr(s), N.ptr(p), rows, cols, ld_s, ld_p),
                 "pp_program_add_softmax_rows")
         self._keep.append((s, p))
+        self.labels.append("softmax_rows")
 
     def add_embed_gather(self, idx, base, ext, pos, out, rows, vocab, seq, dim):
         N.check(N.lib().pp_program_add_embed_gather(self._h, N.ptr(idx), N.ptr(base), N.ptr(ext), N.ptr(pos), N.ptr(out),
                                                     rows, vocab, seq, dim), "pp_program_add_embed_gather")
         self._keep.append((idx, base, ext, pos, out))
+        self.labels.append("embed_gather")
 
     def add_causal_attention_small(self, qkv, out, batch, seq, heads, d, scale):
         N.check(N.lib().pp_program_add_causal_attention_small(self._h, N.ptr(qkv), N.ptr(out), batch, seq, heads, d,
                                                               scale), "pp_program_add_causal_attention_small")
         self._keep.append((qkv, out))
+        self.labels.append("causal_attention_small")
 
     def add_add(self, a, b, y, n):
         N.check(N.lib().pp_program_add_add(self._h, N.ptr(a), N.ptr(b), N.ptr(y), n), "pp_program_add_add")
         self._keep.append((a, b, y))
+        self.labels.append("add")
 
     def add_time_embed(self, timesteps, step_idx, out, batch, dim):
         N.check(N.lib().pp_program_add_time_embed(self._h, N.ptr(timesteps), N.ptr(step_idx), N.ptr(out),
                                                   batch, dim), "pp_program_add_time_embed")
         self._keep.append((timesteps, step_idx, out))
+        self.labels.append("time_embed")
 
     def add_memset(self, t: torch.Tensor):
         N.check(N.lib().pp_program_add_memset(self._h, N.ptr(t), t.numel() * t.element_size()),
                 "pp_program_add_memset")
         self._keep.append((t,))
+        self.labels.append("memset")
 
     @property
     def num_ops(self) -> int:
@@ -409,6 +443,10 @@ class Program:
 
     def run(self) -> None:
         N.check(N.lib().pp_program_run(self._h, N.current_stream()), "pp_program_run")
+
+    def run_range(self, first: int, count: int) -> None:
+        """diagnostic: replay ops [first, first + count) as plain launches"""
+        N.check(N.lib().pp_program_run_range(self._h, first, count, N.current_stream()), "pp_program_run_range")
 
     def build_graph(self) -> None:
         """capture the recorded launches into a CUDA graph. Capture does not execute anything and cannot run on the

@@ -101,6 +101,57 @@ def lnorm(rows, c):
     return lambda: ops.layer_norm(x, y, gamma, beta, 1e-5)
 
 
+def ln_block(M, C, fold, part=None):
+    """norm1 -> q|k and V^T of one BasicTransformerBlock, either as LayerNorm kernel + two GEMMs or folded:
+    the producer (proj_in-like GEMM) emits per-row records and the two consumers finish the normalisation"""
+    a = torch.randn(M, C, device=dev, generator=g).to(BF)
+    wp = (torch.randn(C, C, device=dev, generator=g) / math.sqrt(C)).to(BF)
+    x = torch.empty(M, C, device=dev, dtype=BF)
+    pd = ops.gemm_desc(a0=a, w=wp, out=x, N_=C, M=M, bias=torch.zeros(C, device=dev))
+    wqk = (torch.randn(2 * C, C, device=dev, generator=g) / math.sqrt(C)).to(BF)
+    wv = (torch.randn(C, C, device=dev, generator=g) / math.sqrt(C)).to(BF)
+    qk = torch.empty(M, 2 * C, device=dev, dtype=BF)
+    hw = 4096 if M % 4096 == 0 else M
+    vt = torch.empty(M // hw, C, hw, device=dev, dtype=torch.float16)
+    ones, zeros = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+    if fold:
+        nrec = ops.gemm_row_stats_records(pd)
+        rec = torch.empty(nrec, M, 4, device=dev)
+        ops.attach_row_stats(pd, rec)
+        uqk, uv = wqk.float().sum(1).contiguous(), wv.float().sum(1).contiguous()
+        d1 = ops.gemm_desc(a0=x, w=wqk, out=qk, N_=2 * C, M=M, bias=torch.zeros(2 * C, device=dev), ln=(rec, uqk, 1e-5))
+        d2 = ops.gemm_desc(a0=x, w=wv, out=vt, N_=C, M=M, bias=zeros, epilogue=nat.PP_EPI_TRANSPOSED, t_rows=hw, t_ld=hw,
+                           t_fp16=True, ln=(rec, uv, 1e-5))
+
+        def run():
+            ops.run(pd); ops.run(d1); ops.run(d2)
+        if part == "producer":
+            return lambda: ops.run(pd)
+        if part == "qk":
+            ops.run(pd)
+            return lambda: ops.run(d1)
+        if part == "vt":
+            ops.run(pd)
+            return lambda: ops.run(d2)
+    else:
+        l1 = torch.empty_like(x)
+        d1 = ops.gemm_desc(a0=l1, w=wqk, out=qk, N_=2 * C, M=M)
+        d2 = ops.gemm_desc(a0=l1, w=wv, out=vt, N_=C, M=M, epilogue=nat.PP_EPI_TRANSPOSED, t_rows=hw, t_ld=hw, t_fp16=True)
+
+        def run():
+            ops.run(pd); ops.layer_norm(x, l1, ones, zeros, 1e-5); ops.run(d1); ops.run(d2)
+    return run
+
+
+def vt_only(M, C):
+    x = torch.randn(M, C, device=dev, generator=g).to(BF)
+    wv = (torch.randn(C, C, device=dev, generator=g) / math.sqrt(C)).to(BF)
+    hw = 4096
+    vt = torch.empty(M // hw, C, hw, device=dev, dtype=torch.float16)
+    d2 = ops.gemm_desc(a0=x, w=wv, out=vt, N_=C, M=M, epilogue=nat.PP_EPI_TRANSPOSED, t_rows=hw, t_ld=hw, t_fp16=True)
+    return lambda: ops.run(d2)
+
+
 cases = [
     ("conv 320->320 @64x64 b16", conv(16, 64, 64, 320, 320), 2 * 16 * 4096 * 320 * 2880),
     ("conv 640->640 @32x32 b16", conv(16, 32, 32, 640, 640), 2 * 16 * 1024 * 640 * 5760),
@@ -108,6 +159,13 @@ cases = [
     ("conv 1280->1280 @8x8 b16", conv(16, 8, 8, 1280, 1280), 2 * 16 * 64 * 1280 * 11520),
     ("conv 2560->1280 @16x16 b16", conv(16, 16, 16, 2560, 1280), 2 * 16 * 256 * 1280 * 23040),
     ("linear 320->320 M=65536", linear(65536, 320, 320), 2 * 65536 * 320 * 320),
+    ("linear 320->640 M=65536 (q|k)", linear(65536, 320, 640), 2 * 65536 * 320 * 640),
+    ("linear 320->320 transposed fp16 (V^T)", vt_only(65536, 320), 2 * 65536 * 320 * 320),
+    ("proj + LayerNorm + q|k + V^T 320 M=65536 [unfused]", ln_block(65536, 320, False), 2 * 65536 * 320 * 320 * 4),
+    ("proj + q|k + V^T 320 M=65536 [LayerNorm folded]", ln_block(65536, 320, True), 2 * 65536 * 320 * 320 * 4),
+    ("  folded: producer 320->320 + row records (mode 3)", ln_block(65536, 320, True, "producer"), 2 * 65536 * 320 * 320),
+    ("  folded: q|k 320->640 (mode 4)", ln_block(65536, 320, True, "qk"), 2 * 65536 * 320 * 640),
+    ("  folded: V^T 320->320 transposed (mode 1 + LN)", ln_block(65536, 320, True, "vt"), 2 * 65536 * 320 * 320),
     ("geglu 320->2560 M=65536", linear(65536, 320, 2560, geglu=True), 2 * 65536 * 320 * 2560),
     ("linear 1280->320 M=65536", linear(65536, 1280, 320), 2 * 65536 * 1280 * 320),
     ("geglu 640->5120 M=16384", linear(16384, 640, 5120, geglu=True), 2 * 16384 * 640 * 5120),
@@ -140,4 +198,4 @@ for name, fn, flops in cases:
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / n * 1e3
-    print(f"{name:40s} {us:9.1f} us  {flops / us / 1e6:8.2f} {'TB/s' if 'TB/s' in name else 'TFLOP/s'}")
+    print(f"{name:52s} {us:9.1f} us  {flops / us / 1e6:8.2f} {'TB/s' if 'TB/s' in name else 'TFLOP/s'}")

@@ -546,3 +546,131 @@ def test_attention_16384_tokens_d40(ops):
     ref = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(B, n, C_)
     assert torch.isfinite(out.float()).all()
     assert _rel(out, ref) < 1.5e-2, _rel(out, ref)
+
+
+def test_attention_16384_tokens_full_grid_is_reproducible(ops):
+    """C4's launch (UNet batch 4 x 8 heads x 16384 tokens, 2048 CTAs, 128 key blocks each) repeated: every run must be
+    finite and bit-identical to the first. Guards the hand-over of P between the four softmax warps of a group: with
+    three score buffers a warp could run a block ahead and release PV(j) before a slower warp had written its rows
+    (seen as NaN rows in the C4 loop; the outcome changed from run to run)."""
+    B, H, d, n = 4, 8, 40, 16384
+    g = torch.Generator(device="cuda").manual_seed(12)
+    C_ = H * d
+    q = torch.randn(B, n, C_, device=_dev(), generator=g).to(BF16)
+    k = torch.randn(B, n, C_, device=_dev(), generator=g).to(BF16)
+    vt = torch.randn(B, C_, n, device=_dev(), generator=g).to(torch.float16)
+    outs = []
+    for _ in range(4):
+        out = torch.full((B, n, C_), float("nan"), device=_dev(), dtype=BF16)
+        ops.run(ops.attn_desc(q=q, k=k, vt=vt, out=out, batch=B, heads=H, d=d, nq=n, nk=n, q_ld=C_, k_ld=C_, vt_ld=n,
+                              o_ld=C_, q_batch_stride=n * C_, k_batch_stride=n * C_, scale=1.0 / math.sqrt(d)))
+        torch.cuda.synchronize()
+        assert torch.isfinite(out.float()).all()
+        assert out.float().abs().max().item() <= vt.float().abs().max().item()  # a convex combination of V rows
+        outs.append(out)
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+
+
+def _ln_fold_pack(w, gamma, beta, bias=None):
+    """host-side fold the engine performs (engine.NetEngine.w_ln_folded): W' = W * gamma (bf16), u = row sums of
+    the bf16 W', b' = W beta (+ bias)"""
+    wf = (w * gamma[None, :]).to(BF16)
+    u = wf.double().sum(1).float()
+    b = (w.double() @ beta.double()).float()
+    if bias is not None:
+        b = b + bias
+    return wf.contiguous(), u.contiguous(), b.contiguous()
+
+
+def _producer_with_row_stats(ops, M, C, K, seed, offset=0.0, bn=0):
+    """x = a @ wp^T + bias + res (+ a common offset) with per-row LayerNorm records from the epilogue"""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a = torch.randn(M, K, device=_dev(), generator=g).to(BF16)
+    wp = (torch.randn(C, K, device=_dev(), generator=g) / math.sqrt(K)).to(BF16)
+    bias = torch.randn(C, device=_dev(), generator=g) + offset
+    res = torch.randn(M, C, device=_dev(), generator=g).to(BF16)
+    x = torch.full((M, C), float("nan"), device=_dev(), dtype=BF16)
+    d = ops.gemm_desc(a0=a, w=wp, out=x, N_=C, M=M, bias=bias, res1=res, block_n=bn)
+    nrec = ops.gemm_row_stats_records(d)
+    assert nrec > 0
+    rec = torch.full((nrec, M + 3, 4), float("nan"), device=_dev(), dtype=torch.float32)  # ld > M on purpose
+    ops.attach_row_stats(d, rec)
+    ops.run(d)
+    torch.cuda.synchronize()
+    ref = a.float() @ wp.float().t() + bias + res.float()
+    assert _rel(x, ref) < 6e-3
+    return x, rec, ref
+
+
+@pytest.mark.parametrize("M,C,bn,offset", [(256, 320, 0, 0.0), (1000, 640, 0, 0.0), (300, 1280, 64, 0.0),
+                                           (128, 32, 0, 0.0), (512, 320, 256, 300.0)])
+def test_gemm_row_stats_records(ops, M, C, bn, offset):
+    """the records a producer emits combine to the mean / variance of the rows it computed — the fp32 values before
+    the bf16 rounding of the store, which is what an fp32 LayerNorm of the exact activations would see (for a large
+    common offset the stored bf16 values carry quantisation noise of their own: at 300 the bf16 step is 2) — also for
+    a large common offset (shifted sums: no cancellation)"""
+    x, rec, xf32 = _producer_with_row_stats(ops, M, C, 192, M + C, offset, bn)
+    r = rec[:, :M].double()
+    cnt = r[..., 3]
+    assert torch.isfinite(r).all() and (cnt.sum(0) == C).all()
+    mean_i = r[..., 2] + r[..., 0] / cnt.clamp(min=1)
+    mean = (mean_i * cnt).sum(0) / C
+    m2 = (r[..., 1] - r[..., 0] ** 2 / cnt.clamp(min=1) + cnt * (mean_i - mean[None]) ** 2).sum(0)
+    xf = xf32.double()
+    assert (mean - xf.mean(1)).abs().max().item() < 1e-4 * (1 + abs(offset))
+    var_ref = xf.var(1, unbiased=False)
+    assert ((m2 / C - var_ref).abs() / var_ref).max().item() < 2e-3
+
+
+@pytest.mark.parametrize("M,C,N,bn", [(256, 320, 640, 0), (1000, 640, 1280, 0), (300, 1280, 1280, 256), (128, 32, 64, 0)])
+def test_gemm_layer_norm_fold_plain(ops, M, C, N, bn):
+    """LayerNorm(x) @ W^T + b with the LayerNorm applied algebraically in the consumer's epilogue, against
+    F.layer_norm on the same bf16 x in fp32"""
+    x, rec, _ = _producer_with_row_stats(ops, M, C, 192, M + C + N)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    w = torch.randn(N, C, device=_dev(), generator=g) / math.sqrt(C)
+    gamma = 1 + 0.3 * torch.randn(C, device=_dev(), generator=g)
+    beta = 0.3 * torch.randn(C, device=_dev(), generator=g)
+    bias = torch.randn(N, device=_dev(), generator=g)
+    wf, u, b = _ln_fold_pack(w, gamma, beta, bias)
+    out = torch.full((M, N), float("nan"), device=_dev(), dtype=BF16)
+    ops.run(ops.gemm_desc(a0=x, w=wf, out=out, N_=N, M=M, bias=b, block_n=bn, ln=(rec, u, 1e-5)))
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5) @ w.t() + bias
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < 8e-3, _rel(out, ref)
+
+
+def test_gemm_layer_norm_fold_transposed_and_geglu(ops):
+    from powerpaint_b200 import _native as nat
+
+    M, C, hw = 512, 320, 256
+    x, rec, _ = _producer_with_row_stats(ops, M, C, 320, 77)
+    g = torch.Generator(device="cuda").manual_seed(12)
+    gamma = 1 + 0.3 * torch.randn(C, device=_dev(), generator=g)
+    beta = 0.3 * torch.randn(C, device=_dev(), generator=g)
+    lnx = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    # V^T: fp16 transposed store
+    wv = torch.randn(C, C, device=_dev(), generator=g) / math.sqrt(C)
+    wf, u, b = _ln_fold_pack(wv, gamma, beta)
+    vt = torch.zeros(M // hw, C, hw, device=_dev(), dtype=torch.float16)
+    ops.run(ops.gemm_desc(a0=x, w=wf, out=vt, N_=C, M=M, bias=b, epilogue=nat.PP_EPI_TRANSPOSED, t_rows=hw, t_ld=hw,
+                          t_fp16=True, ln=(rec, u, 1e-5)))
+    torch.cuda.synchronize()
+    ref = (lnx @ wv.t()).view(M // hw, hw, C).transpose(1, 2)
+    assert _rel(vt, ref) < 8e-3, _rel(vt, ref)
+    # GEGLU
+    Fh = 1280
+    wg = torch.randn(2 * Fh, C, device=_dev(), generator=g) / math.sqrt(C)
+    bg = torch.randn(2 * Fh, device=_dev(), generator=g)
+    wf, u, b = _ln_fold_pack(wg, gamma, beta, bg)
+    wi, ui = ops.pack_geglu_weight(wf.float(), u, 128)
+    _, bi = ops.pack_geglu_weight(wf.float(), b, 128)
+    out = torch.zeros(M, Fh, device=_dev(), dtype=BF16)
+    ops.run(ops.gemm_desc(a0=x, w=wi, out=out, N_=2 * Fh, M=M, bias=bi, epilogue=nat.PP_EPI_GEGLU, block_n=128,
+                          ln=(rec, ui, 1e-5)))
+    torch.cuda.synchronize()
+    y = lnx @ wg.t() + bg
+    ref = y[:, :Fh] * F.gelu(y[:, Fh:])
+    assert _rel(out, ref) < 8e-3, _rel(out, ref)

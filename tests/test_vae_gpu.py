@@ -83,7 +83,7 @@ def test_vae_uint8_fast_path_equals_float_path():
     mask[0, 0, :4, :4] = 127  # below the 0.5 threshold after / 255
     mask[0, 0, 4:8, :4] = 128  # at / above it
     a = pm.encode_uint8(img, mask)
-    imf = img.float() / 127.5 - 1.0
+    imf = (img.cpu().float() / 127.5 - 1.0).to(DEV)  # the reference divides on the CPU (true fp32 division)
     mf = (mask.float() / 255.0 >= 0.5).float()
     b = pm.encode(imf * (mf < 0.5)).latent_dist
     assert _rel(a.mean, b.mean) < 1e-6 and _rel(a.logvar, b.logvar) < 1e-6
@@ -104,10 +104,14 @@ def test_softmax_rows_and_image_kernels():
         assert (p[:, cols:] == 0).all()
     img = torch.randint(0, 256, (2, 3, 20, 12), device=DEV, generator=g, dtype=torch.uint8)
     out = ops.image_preprocess_u8(img, None, c_pad=8)
-    ref = (img.float() / 127.5 - 1).permute(0, 2, 3, 1).reshape(2, 240, 3)
+    # the reference normalises on the CPU (`image.to(torch.float32) / 127.5 - 1.0`, pipeline_PowerPaint.py:123-127):
+    # a true fp32 division. torch's CUDA kernel multiplies by the reciprocal instead, which differs in the last fp32
+    # bit for 111 of the 256 pixel values (one of them after bf16 rounding) — the CPU result is the contract.
+    ref = (img.cpu().float() / 127.5 - 1).permute(0, 2, 3, 1).reshape(2, 240, 3).to(DEV)
     assert torch.equal(out[..., :3].float(), ref.to(torch.bfloat16).float()) and (out[..., 3:] == 0).all()
     ctl = ops.image_preprocess_u8(img, None, c_pad=8, divisor=255.0, shift=0.0)
-    assert torch.equal(ctl[..., :3].float(), (img.float() / 255).permute(0, 2, 3, 1).reshape(2, 240, 3).to(torch.bfloat16).float())
+    cref = (img.cpu().float() / 255).permute(0, 2, 3, 1).reshape(2, 240, 3).to(DEV)
+    assert torch.equal(ctl[..., :3].float(), cref.to(torch.bfloat16).float())
 
 
 def test_pipeline_v1_uint8_request_equals_float_request():
