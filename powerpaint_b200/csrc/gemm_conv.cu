@@ -35,6 +35,20 @@
 #include "common.cuh"
 #include "ops.h"
 
+// -DGEMM_TRACE: CTA 0 records clock64() at the role hand-overs of its first tiles (profiles/gemm_trace.py reads them)
+#ifdef GEMM_TRACE
+__device__ long long g_gemm_trace[64 * 16];
+#define GT(tile_local, slot)                                                                     \
+    do {                                                                                         \
+        if (blockIdx.x == 0 && (tile_local) < 64) g_gemm_trace[(tile_local) * 16 + (slot)] = clock64(); \
+    } while (0)
+extern "C" int pp_debug_gemm_trace(long long* host_out, int n) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_gemm_trace, sizeof(long long) * (size_t)n);
+}
+#else
+#define GT(tile_local, slot) do {} while (0)
+#endif
+
 namespace pp {
 
 static constexpr int BLOCK_M = 128;
@@ -229,6 +243,10 @@ __device__ __forceinline__ void epilogue_store8(const GemmKParams& p, float alph
 __host__ __device__ constexpr int stages_for(int block_n) {
     return block_n <= 64 ? 8 : block_n <= 128 ? 5 : block_n <= 160 ? 5 : 3;
 }
+// CTA-pair mode: a stage holds the A tile and half of the weight tile
+__host__ __device__ constexpr int stages_pair_for(int block_n) {
+    return block_n <= 128 ? 7 : block_n <= 160 ? 6 : 4;
+}
 // Output staging tile: the epilogue writes its accumulator rows (bf16) into shared memory laid out as the boxes
 // of a TMA store — 64-column sub-tiles [128 rows][128 B] with the 128-byte swizzle (the 160-wide tile ends in a
 // 32-column sub-tile [128][64 B] with the 64-byte swizzle) — and ONE thread hands them to the TMA unit, which
@@ -251,12 +269,20 @@ __host__ __device__ constexpr int out_stage_bytes_for(int block_n) {
 // instruction footprint small): 0 = bf16 row-major output, N % 8 == 0 (bias, rowvec, two residuals,
 // alpha, SiLU), 1 = generic (fp32 / transposed / ragged N), 2 = GEGLU, 3 = mode 0 emitting the per-row records of the
 // consumer's LayerNorm, 4 = mode 0 with LayerNorm of A applied algebraically (bias only).
-template <int BLOCK_N, int MODE>
+// CG = 2: CTA-pair mode (cta_group::2). Two CTAs of a 2-CTA cluster own two consecutive m-tiles of one n-tile: each loads
+// its own A tile and HALF of the weight tile (BLOCK_N / 2 rows), the leader (cluster rank 0) issues one 256 x BLOCK_N MMA
+// that reads both CTAs' shared memory and writes both CTAs' tensor memory, and each CTA runs its own epilogue. Per CTA
+// and k-iteration the shared-memory traffic drops from 2 x 36 KB to 2 x 26 KB (BLOCK_N = 160): the 3x3 convs are bound
+// by exactly that (r02 experiments: the MMAs alone run at 1713 TFLOP/s from resident operands, 1300 with the TMA
+// writes next to the operand reads).
+template <int BLOCK_N, int MODE, int CG = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid_constant__ GemmKParams p) {
-    constexpr int STAGES = stages_for(BLOCK_N);
-    constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+    constexpr int STAGES = CG == 2 ? stages_pair_for(BLOCK_N) : stages_for(BLOCK_N);
+    constexpr int B_ROWS = BLOCK_N / CG;  // weight rows this CTA stages
+    constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
     constexpr int TMEM_COLS = tmem_cols_for(2 * BLOCK_N);
-    constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+    constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M * CG, BLOCK_N);
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -288,7 +314,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
 
     const int warp = threadIdx.x >> 5;
     const int n_tiles = p.n_tiles;
-    const int num_tiles = p.m_tiles * n_tiles;
+    // the persistent walk runs over pair tiles in pair mode (m_tiles is even there): unit u -> m-tile u_m * CG + rank
+    const int num_tiles = (p.m_tiles / CG) * n_tiles;
+    const int walk_first = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int walk_stride = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int num_k_iters = p.num_k_iters;
 
     // the two single-thread roles take the HIGHEST warp ids: the SM's issue arbiter favours higher
@@ -299,21 +328,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
         prefetch_tmap(&p.tmB);
         if constexpr (MODE != 1) prefetch_tmap(&p.tmOut[0]);
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar(s), 1);
+            mbar_init(full_bar(s), CG);  // pair mode: one arrive.expect_tx per CTA, on the leader's barrier
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full_bar(a), 1);
-            mbar_init(tmem_empty_bar(a), GEMM_EPI_WARPS);
+            mbar_init(tmem_empty_bar(a), GEMM_EPI_WARPS * CG);  // pair mode: both CTAs' epilogue warps, on the leader's
         }
         fence_mbar_init();
     }
     if (warp == W_MMA) {
-        tmem_alloc(tmem_slot, TMEM_COLS);
-        tmem_relinquish();
+        if constexpr (CG == 2) {
+            tmem_alloc_cg2(tmem_slot, TMEM_COLS);
+            tmem_relinquish_cg2();
+        } else {
+            tmem_alloc(tmem_slot, TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     // everything above touched only shared / tensor memory and kernel parameters; global memory
@@ -337,19 +372,47 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
             const int cpt = p.chunks0 + p.chunks1;  // chunks per tap
             int s = 0;                              // ring slot and its phase, carried across tiles
             uint32_t ph = 0;
-            TileWalk tw(blockIdx.x, gridDim.x, n_tiles);
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tw.next()) {
-                const int n_tile = tw.n, m_tile = tw.m;
+            TileWalk tw(walk_first, walk_stride, n_tiles);
+            for (int tile = walk_first; tile < num_tiles; tile += walk_stride, tw.next()) {
+                const int n_tile = tw.n, m_tile = tw.m * CG + (int)cta_rank;
                 int x0 = 0, y0 = 0, nb0 = 0;
                 if (p.a_mode != PP_A_MATRIX) tile_origin(m_tile, x0, y0, nb0);
                 int ky = 0, kx = 0, ch = 0;  // filter tap and 64-channel chunk of this k-iteration
                 for (int it = 0; it < num_k_iters; ++it) {
                     mbar_wait(empty_bar(s), ph ^ 1u);
-                    mbar_arrive_expect_tx(full_bar(s), p.a_bytes + B_STAGE_BYTES);
+                    if (it == 0) GT((tile - walk_first) / walk_stride, 0);
+                    if (it == num_k_iters - 1) GT((tile - walk_first) / walk_stride, 1);
+#if defined(GEMM_EXP_NOLOAD)  // experiment: no TMA traffic at all (operands are whatever the smem holds)
+                    mbar_arrive(full_bar(s));
+                    if (++ch == cpt) {
+                        ch = 0;
+                        if (++kx == 3) { kx = 0; ++ky; }
+                    }
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
+                    continue;
+#elif defined(GEMM_EXP_NOLOADB)  // experiment: activations only
+                    mbar_arrive_expect_tx(full_bar(s), p.a_bytes);
+#elif defined(GEMM_EXP_NOLOADA)  // experiment: weights only
+                    mbar_arrive_expect_tx(full_bar(s), B_STAGE_BYTES);
+#else
+                    if constexpr (CG == 2) mbar_arrive_expect_tx_cluster(full_bar(s) & PP_PEER_BIT_MASK, p.a_bytes + B_STAGE_BYTES);
+                    else mbar_arrive_expect_tx(full_bar(s), p.a_bytes + B_STAGE_BYTES);
+#endif
                     const uint32_t dstA = sA + s * A_STAGE_BYTES;
                     const uint32_t dstB = sB + s * B_STAGE_BYTES;
                     const int src = ch >= p.chunks0 ? 1 : 0;
                     const int cc = (src ? ch - p.chunks0 : ch) * BLOCK_K;
+#ifdef GEMM_EXP_NOLOADA
+                    if (false) {
+                    } else
+#endif
+                    if constexpr (CG == 2) {
+                        // pair mode serves the matrix and stride-1 conv operands (checked at prepare time)
+                        const uint32_t lbar = full_bar(s) & PP_PEER_BIT_MASK;
+                        if (p.a_mode == PP_A_MATRIX) tma_load_2d_cg2(dstA, &p.tmA[src], lbar, cc, m_tile * BLOCK_M);
+                        else tma_load_4d_cg2(dstA, &p.tmA[src], lbar, cc, x0 + kx - 1, y0 + ky - 1, nb0);
+                        tma_load_2d_cg2(dstB, &p.tmB, lbar, it * BLOCK_K, n_tile * BLOCK_N + (int)cta_rank * B_ROWS);
+                    } else
                     if (p.a_mode == PP_A_MATRIX) {
                         tma_load_2d(dstA, &p.tmA[src], full_bar(s), cc, m_tile * BLOCK_M);
                     } else if (p.a_mode == PP_A_CONV3X3) {
@@ -366,7 +429,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                         tma_load_4d(dstA, &p.tmA[(ky & 1) * 2 + (kx & 1)], full_bar(s), cc, x0 + (kx >> 1), y0 + (ky >> 1),
                                     nb0);
                     }
-                    tma_load_2d(dstB, &p.tmB, full_bar(s), it * BLOCK_K, n_tile * BLOCK_N);
+#ifndef GEMM_EXP_NOLOADB
+                    if constexpr (CG == 1) tma_load_2d(dstB, &p.tmB, full_bar(s), it * BLOCK_K, n_tile * BLOCK_N);
+#endif
                     if (++ch == cpt) {
                         ch = 0;
                         if (++kx == 3) { kx = 0; ++ky; }
@@ -377,30 +442,41 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
         }
     } else if (warp == W_MMA) {
         // ===================== MMA issuer =====================
-        if (elect_one()) {
+        if ((CG == 1 || cta_rank == 0) && elect_one()) {  // pair mode: the leader issues for both CTAs
             int s = 0;
             uint32_t ph = 0;
             uint32_t lt = 0;  // local tile counter
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            for (int tile = walk_first; tile < num_tiles; tile += walk_stride, ++lt) {
                 const uint32_t acc = lt & 1u;
                 const uint32_t acc_ph = (lt >> 1) & 1u;
                 mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u);  // epilogue drained this accumulator
+                GT(lt, 2);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
                 for (int it = 0; it < num_k_iters; ++it) {
                     mbar_wait(full_bar(s), ph);
+                    if (it == 0) GT(lt, 3);
+                    if (it == num_k_iters - 1) GT(lt, 4);
                     tc_fence_after();
                     const uint64_t da = umma_desc_kmajor_sw128(sA + s * A_STAGE_BYTES);
                     const uint64_t db = umma_desc_kmajor_sw128(sB + s * B_STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        umma_bf16_ss(tmem_d, umma_desc_advance_k(da, k * UMMA_K),
-                                     umma_desc_advance_k(db, k * UMMA_K), IDESC, (it | k) != 0);
+                        if constexpr (CG == 2)
+                            umma_bf16_ss_cg2(tmem_d, umma_desc_advance_k(da, k * UMMA_K),
+                                             umma_desc_advance_k(db, k * UMMA_K), IDESC, (it | k) != 0);
+                        else
+                            umma_bf16_ss(tmem_d, umma_desc_advance_k(da, k * UMMA_K),
+                                         umma_desc_advance_k(db, k * UMMA_K), IDESC, (it | k) != 0);
                     }
-                    umma_commit(empty_bar(s));  // frees the smem slot once these MMAs retire
+                    // frees the smem slot once these MMAs retire (pair mode: in both CTAs)
+                    if constexpr (CG == 2) umma_commit_cg2(empty_bar(s));
+                    else umma_commit(empty_bar(s));
                     if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
-                umma_commit(tmem_full_bar(acc));  // accumulator complete
+                // accumulator complete (pair mode: both CTAs' epilogues are told)
+                if constexpr (CG == 2) umma_commit_cg2(tmem_full_bar(acc));
+                else umma_commit(tmem_full_bar(acc));
             }
         }
         __syncwarp();
@@ -435,8 +511,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
             return v;
         };
         // stage the first tile's bias
-        TileWalk tw(blockIdx.x, gridDim.x, n_tiles);
-        if (blockIdx.x < num_tiles) {
+        TileWalk tw(walk_first, walk_stride, n_tiles);
+        if (walk_first < num_tiles) {
             const float b0 = load_bias(tw.n);
             const float u0 = load_u(tw.n);
             if (etid < BLOCK_N) {
@@ -446,15 +522,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
         }
         epi_sync();
         uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-            const int n_tile = tw.n, m_tile = tw.m;
+        for (int tile = walk_first; tile < num_tiles; tile += walk_stride, ++lt) {
+            const int n_tile = tw.n, m_tile = tw.m * CG + (int)cta_rank;
             tw.next();  // now at the tile after this one
             const uint32_t acc = lt & 1u;
             const uint32_t acc_ph = (lt >> 1) & 1u;
             const float* sbias = sbias_all + acc * BLOCK_N;
             const float* su = su_all + acc * BLOCK_N;
             // bias of the next tile: issue the load now, park it in smem at the end of this tile
-            const int next_tile = tile + gridDim.x;
+            const int next_tile = tile + walk_stride;
             const float bias_next = next_tile < num_tiles ? load_bias(tw.n) : 0.f;
             const float u_next = next_tile < num_tiles ? load_u(tw.n) : 0.f;
             // output row of this thread
@@ -555,6 +631,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 const bool full = ncols == BLOCK_N && __all_sync(0xffffffffu, valid);
                 const bool plain = !has_r1 && !has_r2 && !has_rv;
                 mbar_wait(tmem_full_bar(acc), acc_ph);
+                if (etid == 0) GT(lt, 5);  // accumulator ready (epilogue thread 0)
                 tc_fence_after();
                 // column split between the two warps of a lane quarter: alternating 32-column chunks, except for the
                 // 160-wide tile (5 chunks would split 3 / 2): there each warp takes one contiguous 80-column half
@@ -755,15 +832,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 }
             }
             // all TMEM reads of this accumulator stage are complete (wait::ld above)
+            if (etid == 0) GT(lt, 6);  // tile math done, staged
             tc_fence_before();
             __syncwarp();
-            if (lane_id() == 0) mbar_arrive(tmem_empty_bar(acc));
+            if (lane_id() == 0) {
+                if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty_bar(acc) & PP_PEER_BIT_MASK);  // the leader's barrier
+                else mbar_arrive(tmem_empty_bar(acc));
+            }
             if constexpr (MODE != 1) {
                 // hand the staged tile to the TMA unit: generic-proxy writes -> async proxy, one barrier, one thread
                 // issues the stores (one per sub-tile); the unit writes whole rows and clips out-of-range parts
                 fence_proxy_async_smem();
                 if (half == 0) s_row[r] = valid ? (long long)row : -1ll;
                 epi_sync();
+                if (etid == 0) GT(lt, 7);  // all epilogue warps staged
                 constexpr int OUT_COLS = MODE == 2 ? BLOCK_N / 2 : BLOCK_N;
                 constexpr int PIECES = OUT_COLS / 8;
                 if (etid == 0) {
@@ -782,6 +864,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
 #endif
                     }
                     bulk_commit_group();
+                    GT(lt, 8);  // TMA stores issued
                 }
                 if constexpr (MODE == 0 || MODE == 3 || MODE == 4) {
                     // GroupNorm partial sums of exactly the bf16 values the consumer will read
@@ -836,18 +919,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
             }
             if constexpr (MODE != 1) {
                 if (etid == 0) bulk_wait_read_all();  // the TMA unit has read the staged tile: it may be overwritten
+                if (etid == 0) GT(lt, 9);  // staged tile consumed by the TMA unit
             }
             epi_sync();
+            if (etid == 0) GT(lt, 10);
         }
         if constexpr (MODE != 1) {
             if (etid == 0) bulk_wait_all();  // global writes of the last tile performed before the CTA retires
         }
     }
 
-    __syncthreads();
-    if (warp == W_MMA) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (CG == 2) {
+        tc_fence_before();
+        cluster_sync_all();  // neither CTA retires while the other may still signal its barriers / read its operands
+        if (warp == W_MMA) {
+            tc_fence_after();
+            tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+        }
+    } else {
+        __syncthreads();
+        if (warp == W_MMA) {
+            tc_fence_after();
+            tmem_dealloc(tmem_base, TMEM_COLS);
+        }
     }
 }
 
@@ -857,8 +951,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int pad64(int c) { return ceil_div(c, 64) * 64; }
 
-static size_t smem_for_block_n(int bn) {
-    return (size_t)stages_for(bn) * (A_STAGE_BYTES + bn * BLOCK_K * 2) + 8 * (2 * stages_for(bn) + 6) + 4 * bn * 4 +
+static size_t smem_for_block_n(int bn, int cg = 1) {
+    const int st = cg == 2 ? stages_pair_for(bn) : stages_for(bn);
+    return (size_t)st * (A_STAGE_BYTES + (bn / cg) * BLOCK_K * 2) + 8 * (2 * st + 6) + 4 * bn * 4 +
            out_stage_bytes_for(bn) + 16 + 1024;  // out_stage_bytes_for includes the row table and the 1 KB alignment slack
 }
 
@@ -876,6 +971,24 @@ static int num_sms() {
 template <int BLOCK_N, int MODE>
 static int launch_variant(const GemmLaunch& l, cudaStream_t s) {
     PP_CUDA_CHECK(launch(gemm_conv_kernel<BLOCK_N, MODE>, l.grid, GEMM_THREADS, l.smem, s, l.p));
+    return PP_OK;
+}
+// CTA-pair flavour (mode 0 only): clusters of two CTAs
+template <int BLOCK_N>
+static int launch_pair(const GemmLaunch& l, cudaStream_t s) {
+    PP_CUDA_CHECK(launch_cluster(gemm_conv_kernel<BLOCK_N, 0, 2>, l.grid, GEMM_THREADS, l.smem, s, 2u, l.p));
+    return PP_OK;
+}
+template <int BLOCK_N>
+static int ensure_attr_pair() {
+    static bool done[PP_MAX_DEVICES] = {};
+    int dev = 0;
+    PP_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= PP_MAX_DEVICES || !done[dev]) {
+        PP_CUDA_CHECK(cudaFuncSetAttribute(gemm_conv_kernel<BLOCK_N, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem_for_block_n(BLOCK_N, 2)));
+        if (dev >= 0 && dev < PP_MAX_DEVICES) done[dev] = true;
+    }
     return PP_OK;
 }
 
@@ -925,6 +1038,15 @@ static int ensure_attr_for(int block_n, int mode) {
 }
 
 int gemm_launch(const GemmLaunch& l, cudaStream_t s) {
+    if (l.cg == 2) {
+        switch (l.block_n) {
+            case 128: return launch_pair<128>(l, s);
+            case 160: return launch_pair<160>(l, s);
+            case 256: return launch_pair<256>(l, s);
+        }
+        set_last_error("gemm_launch: no CTA-pair variant for block_n %d", l.block_n);
+        return PP_ERR_INVALID;
+    }
     PP_GEMM_DISPATCH(launch_variant, l.block_n, l.mode, l, s)
     set_last_error("gemm_launch: unsupported block_n %d / mode %d", l.block_n, l.mode);
     return PP_ERR_INVALID;
@@ -932,13 +1054,15 @@ int gemm_launch(const GemmLaunch& l, cudaStream_t s) {
 
 // Tile width: minimise (rounds over the SMs) x (per-tile cost ~ width + fixed overhead), where
 // padding beyond N is paid as well; ties go to the wider tile (fewer A re-reads).
-static int pick_block_n(int N, int m_tiles, bool geglu) {
+static int pick_block_n(int N, int m_tiles, bool geglu, int cg = 1) {
     const int cands[4] = {256, 160, 128, 64};
-    const int sms = num_sms();
+    const int sms = num_sms() / cg;  // pair mode: pair tiles over CTA pairs
+    m_tiles /= cg;
     int best = 0;
     double best_cost = 1e30;
     for (int c : cands) {
         if (geglu && (c == 64 || c == 160 || N % c != 0)) continue;  // 160: 80 output columns are no TMA-store box
+        if (cg == 2 && c == 64) continue;
         const int nt = ceil_div(N, c);
         const long tiles = (long)m_tiles * nt;
         const long rounds = (tiles + sms - 1) / sms;
@@ -954,7 +1078,21 @@ static int pick_block_n(int N, int m_tiles, bool geglu) {
 // Tile geometry of a launch (everything that needs no device or driver): validation of the shape
 // fields, the conv pixel box, the tile width and the walk. Shared by gemm_prepare and the host-only
 // statistics-geometry query.
-static int gemm_geometry(const pp_gemm_desc& d, GemmKParams& p, int* block_n_out) {
+static bool gemm_fast_mode(const pp_gemm_desc& d);
+
+// CTA-pair mode (cta_group::2) is chosen for the long-K contractions — the 3x3 convs and the K >= 1152 linears — in
+// the plain bf16 epilogue flavour, when the m-tiles pair up. PP_B200_PAIR=0 switches it off (A/B comparisons).
+static bool pair_mode_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("PP_B200_PAIR");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+static constexpr int PAIR_MIN_K_ITERS = 18;
+
+static int gemm_geometry(const pp_gemm_desc& d, GemmKParams& p, int* block_n_out, int* cg_out = nullptr) {
     PP_REQUIRE(d.a_mode >= PP_A_MATRIX && d.a_mode <= PP_A_CONV3X3_S2P0, "gemm: bad a_mode %d", d.a_mode);
     PP_REQUIRE(d.epilogue >= PP_EPI_PLAIN && d.epilogue <= PP_EPI_TRANSPOSED, "gemm: bad epilogue %d", d.epilogue);
     PP_REQUIRE(d.a0 && d.b && d.out, "gemm: null operand pointer");
@@ -1009,11 +1147,16 @@ static int gemm_geometry(const pp_gemm_desc& d, GemmKParams& p, int* block_n_out
     }
     p.N = d.N;
     const bool geglu = d.epilogue == PP_EPI_GEGLU;
-    int bn = d.block_n ? d.block_n : pick_block_n(d.N, m_tiles, geglu);
+    int cg = 1;
+    if (pair_mode_enabled() && (d.a_mode == PP_A_MATRIX || d.a_mode == PP_A_CONV3X3) && m_tiles % 2 == 0 &&
+        p.num_k_iters >= PAIR_MIN_K_ITERS && !geglu && gemm_fast_mode(d) && !d.row_stats && !d.ln_rec && d.block_n != 64)
+        cg = 2;
+    int bn = d.block_n ? d.block_n : pick_block_n(d.N, m_tiles, geglu, cg);
     PP_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "gemm: block_n %d unsupported", bn);
     p.m_tiles = m_tiles;
     p.n_tiles = ceil_div(d.N, bn);
     *block_n_out = bn;
+    if (cg_out) *cg_out = cg;
     return PP_OK;
 }
 
@@ -1069,11 +1212,12 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
     GemmLaunch l;
     memset(&l, 0, sizeof(l));
     GemmKParams& p = l.p;
-    int bn = 0;
+    int bn = 0, cg = 1;
     {
-        int rc = gemm_geometry(d, p, &bn);
+        int rc = gemm_geometry(d, p, &bn, &cg);
         if (rc) return rc;
     }
+    l.cg = cg;
     const int taps = d.a_mode == PP_A_MATRIX ? 1 : 9;
     const bool packed_k = taps == 9 || d.a1 != nullptr;
     const int64_t kw = packed_k ? (int64_t)taps * (pad64(d.c0) + pad64(d.c1)) : d.c0;
@@ -1134,7 +1278,7 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
     {
         uint64_t dims[2] = {(uint64_t)kw, (uint64_t)d.N};
         uint64_t str[1] = {(uint64_t)ldb * 2};
-        uint32_t box[2] = {64, (uint32_t)bn};
+        uint32_t box[2] = {64, (uint32_t)(bn / cg)};  // pair mode: each CTA stages half of the weight tile
         int rc = make_tmap_bf16(&p.tmB, d.b, 2, dims, str, box, true);
         if (rc) return rc;
     }
@@ -1177,10 +1321,10 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
         if (d.bias) PP_REQUIRE((reinterpret_cast<uintptr_t>(d.bias) & 15) == 0, "gemm: bias alignment");
     }
     {
-        const long tiles = (long)p.m_tiles * p.n_tiles;
-        l.grid = dim3((unsigned)std::min<long>(tiles, num_sms()), 1, 1);
+        const long tiles = (long)(p.m_tiles / cg) * p.n_tiles;  // pair mode: pair tiles over CTA pairs
+        l.grid = dim3((unsigned)(cg * std::min<long>(tiles, num_sms() / cg)), 1, 1);
     }
-    l.smem = smem_for_block_n(bn);
+    l.smem = smem_for_block_n(bn, cg);
     if (geglu) {
         l.mode = 2;
     } else {
@@ -1242,7 +1386,11 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
         p.ln_u = d.ln_u;
         p.ln_eps = d.ln_eps;
     }
-    {
+    if (cg == 2) {
+        PP_REQUIRE(l.mode == 0 && (bn == 128 || bn == 160 || bn == 256), "gemm: CTA-pair mode needs the plain bf16 epilogue");
+        int rc = bn == 128 ? ensure_attr_pair<128>() : bn == 160 ? ensure_attr_pair<160>() : ensure_attr_pair<256>();
+        if (rc) return rc;
+    } else {
         int rc = ensure_attr_for(bn, l.mode);
         if (rc) return rc;
     }

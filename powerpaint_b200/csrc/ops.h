@@ -65,6 +65,7 @@ struct GemmKParams {
 struct GemmLaunch {
     GemmKParams p;
     int block_n;
+    int cg;    // 1, or 2 = CTA-pair mode (cta_group::2): clusters of two CTAs share one 256-row MMA tile
     int mode;  // epilogue flavour: 0 fast bf16, 1 generic, 2 GEGLU, 3 fast bf16 + LayerNorm records out, 4 fast bf16 + LayerNorm of A
     dim3 grid;
     size_t smem;
