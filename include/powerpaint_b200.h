@@ -75,7 +75,10 @@ enum {
 enum {
     PP_EPI_PLAIN = 0,
     PP_EPI_GEGLU = 1,      /* out[:, j] = (acc_a + bias_a) * gelu(acc_g + bias_g); weights tile-interleaved */
-    PP_EPI_TRANSPOSED = 2  /* out[(m / t_rows) * N + n][m % t_rows], row pitch t_ld (V^T for attention) */
+    PP_EPI_TRANSPOSED = 2, /* out[(m / t_rows) * N + n][m % t_rows], row pitch t_ld (V^T for attention) */
+    PP_EPI_ROWS_THEN_TRANSPOSED = 3 /* columns [0, trans_from_col) row-major into `out` (pitch ldc), columns
+                               [trans_from_col, N) transposed into `out_t` like PP_EPI_TRANSPOSED with
+                               N - trans_from_col channels: to_q | to_k | to_v^T of one attention in ONE launch */
 };
 enum { PP_ACT_NONE = 0, PP_ACT_SILU = 1, PP_ACT_QUICK_GELU = 2 /* x * sigmoid(1.702 x): CLIP text encoder MLP */ };
 
@@ -140,18 +143,25 @@ typedef struct pp_gemm_desc {
     /* LayerNorm folded into the GEMMs either side of it (BasicTransformerBlock norm1/2/3):
        PRODUCER (PP_A_MATRIX, bf16 row-major output): row_stats != NULL makes the epilogue emit, per output row and
        per half n-tile, one record {sum of (x - shift), sum of (x - shift)^2, shift, count} (fp32 x 4) of the values
-       it stores, laid out [records][row_stats_ld] with records = pp_gemm_row_stats_records(desc).
-       CONSUMER: ln_rec != NULL applies LayerNorm(A) algebraically in the epilogue. With W' = W * gamma (folded into
-       b on the host), ln_u[n] = sum_k W'[n, k] and bias[n] = sum_k W[n, k] beta[k] (+ the layer's own bias):
-         acc' = rstd[m] * (acc - mean[m] * ln_u[n]),  mean / rstd from the ln_nrec records of row m (Chan's
-       combination, eps = ln_eps); everything after (bias, GEGLU gate, transposed store ...) is unchanged. */
+       it computes, laid out [records][row_stats_ld] with records = pp_gemm_row_stats_records(desc) — scratch of this
+       launch. The CTA that finishes the LAST n-tile of a 128-row block (row_ticket[m-tile], zero-initialised int32,
+       left at zero again) folds the records of its rows (Chan's combination) into
+         row_final[m] = {rstd, -rstd * mean}   (fp32 x 2, eps = ln_eps).
+       CONSUMER: ln_stats != NULL (a producer's row_final) applies LayerNorm(A) algebraically in the epilogue. With
+       W' = W * gamma (folded into b on the host), ln_u[n] = sum_k W'[n, k] and bias[n] = sum_k W[n, k] beta[k]
+       (+ the layer's own bias):  acc' = rstd[m] * acc - rstd[m] mean[m] * ln_u[n];  everything after (bias, GEGLU
+       gate, transposed store ...) is unchanged. */
     float* row_stats;
     int64_t row_stats_ld;
-    const float* ln_rec;
-    int32_t ln_nrec;
-    int64_t ln_ld;
+    float* row_final;
+    int32_t* row_ticket;
+    const float* ln_stats;
     const float* ln_u;
     float ln_eps;
+    /* PP_EPI_ROWS_THEN_TRANSPOSED: transposed destination and the first transposed column (a multiple of the tile
+       width: pass block_n explicitly). t_rows must be a multiple of 128 and divide M. */
+    void* out_t;
+    int32_t trans_from_col;
 } pp_gemm_desc;
 
 pp_status pp_gemm_conv(const pp_gemm_desc* d, pp_stream stream);

@@ -17,9 +17,9 @@ _lib = None
 
 # enums (mirror include/powerpaint_b200.h)
 PP_A_MATRIX, PP_A_CONV3X3, PP_A_CONV3X3_S2, PP_A_CONV3X3_S2P0 = 0, 1, 2, 3
-PP_EPI_PLAIN, PP_EPI_GEGLU, PP_EPI_TRANSPOSED = 0, 1, 2
+PP_EPI_PLAIN, PP_EPI_GEGLU, PP_EPI_TRANSPOSED, PP_EPI_ROWS_THEN_TRANSPOSED = 0, 1, 2, 3
 PP_ACT_NONE, PP_ACT_SILU, PP_ACT_QUICK_GELU = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 vp = C.c_void_p
 i32 = C.c_int32
@@ -53,8 +53,9 @@ class GemmDesc(C.Structure):
         ("block_n", i32), ("t_fp16", i32),
         ("alpha_dev", vp), ("alpha_step", vp), ("alpha_stride", i32),
         ("chan_stats", vp),
-        ("row_stats", vp), ("row_stats_ld", i64),
-        ("ln_rec", vp), ("ln_nrec", i32), ("ln_ld", i64), ("ln_u", vp), ("ln_eps", f32),
+        ("row_stats", vp), ("row_stats_ld", i64), ("row_final", vp), ("row_ticket", vp),
+        ("ln_stats", vp), ("ln_u", vp), ("ln_eps", f32),
+        ("out_t", vp), ("trans_from_col", i32),
     ]
 
 

@@ -268,7 +268,9 @@ __host__ __device__ constexpr int out_stage_bytes_for(int block_n) {
 // MODE selects the epilogue flavour at compile time (keeps the hot epilogue short and the
 // instruction footprint small): 0 = bf16 row-major output, N % 8 == 0 (bias, rowvec, two residuals,
 // alpha, SiLU), 1 = generic (fp32 / transposed / ragged N), 2 = GEGLU, 3 = mode 0 emitting the per-row records of the
-// consumer's LayerNorm, 4 = mode 0 with LayerNorm of A applied algebraically (bias only).
+// consumer's LayerNorm, 4 = mode 0 with LayerNorm of A applied algebraically (bias only), 5 = bias-only bf16 output
+// whose n-tiles from trans_first_tile on are stored TRANSPOSED through the staging tile (to_q | to_k | to_v^T of an
+// attention in one launch, or V^T alone), optionally with the LayerNorm fold.
 // CG = 2: CTA-pair mode (cta_group::2). Two CTAs of a 2-CTA cluster own two consecutive m-tiles of one n-tile: each loads
 // its own A tile and HALF of the weight tile (BLOCK_N / 2 rows), the leader (cluster rank 0) issues one 256 x BLOCK_N MMA
 // that reads both CTAs' shared memory and writes both CTAs' tensor memory, and each CTA runs its own epilogue. Per CTA
@@ -285,6 +287,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
     const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
 
     extern __shared__ uint8_t smem_raw[];
+    __shared__ int s_last_tile;  // mode 3: this CTA finished the last n-tile of its current row block
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = smem_base;
     const uint32_t sB = sA + STAGES * A_STAGE_BYTES;
@@ -502,7 +505,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
         };
         // LayerNorm of A folded into this epilogue: modes 1 and 2 decide at run time; of the fast bf16 flavours only
         // mode 4 carries it (and only mode 3 emits the records), so the big convs in mode 0 keep their register budget
-        const bool ln = (MODE == 1 || MODE == 2 || MODE == 4) && p.ln_rec != nullptr;
+        const bool ln = (MODE == 1 || MODE == 2 || MODE == 4 || MODE == 5) && p.ln_stats != nullptr;
         auto load_u = [&](int n_tile_of) -> float {
             const int n = n_tile_of * BLOCK_N + etid;
             float v = 0.f;
@@ -521,6 +524,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
             }
         }
         epi_sync();
+        float2 ln_cur = make_float2(1.f, 0.f);  // {rstd, -rstd * mean} of this thread's row in the current tile
+        if (ln && walk_first < num_tiles) {
+            const int64_t row0 = (int64_t)(tw.m * CG + (int)cta_rank) * BLOCK_M + r;
+            if (row0 < p.M) ln_cur = __ldg(p.ln_stats + row0);
+        }
         uint32_t lt = 0;
         for (int tile = walk_first; tile < num_tiles; tile += walk_stride, ++lt) {
             const int n_tile = tw.n, m_tile = tw.m * CG + (int)cta_rank;
@@ -555,54 +563,61 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
             }
             const int n_base = n_tile * BLOCK_N;
             const uint32_t taddr = tmem_base + lane_addr + acc * BLOCK_N;
-            // LayerNorm fold: acc' = ln_rs * acc + ln_nm * u[n] with ln_rs = rstd, ln_nm = -rstd * mean of this row,
-            // from the producer's per-row records (Chan's combination of the half-tile partials)
-            float ln_rs = 1.f, ln_nm = 0.f;
-            if (ln && valid) {
-                float cnt = 0.f, mean = 0.f, m2 = 0.f;
-                for (int i = 0; i < p.ln_nrec; ++i) {
-                    const float4 rc = __ldg(p.ln_rec + (int64_t)i * p.ln_ld + row);
-                    if (rc.w > 0.f) {
-                        const float inv = __fdividef(1.f, rc.w);
-                        const float mi = fmaf(rc.x, inv, rc.z);
-                        const float m2i = fmaxf(fmaf(-rc.x * inv, rc.x, rc.y), 0.f);
-                        const float tot = cnt + rc.w;
-                        const float wgt = __fdividef(rc.w, tot);
-                        const float dl = mi - mean;
-                        mean = fmaf(dl, wgt, mean);
-                        m2 += m2i + dl * dl * cnt * wgt;
-                        cnt = tot;
-                    }
-                }
-                const float var = cnt > 0.f ? __fdividef(m2, cnt) : 0.f;
-                ln_rs = rsqrtf(var + p.ln_eps);
-                ln_nm = -ln_rs * mean;
+            // mode 5: this tile's columns are stored transposed ([channel][token], V^T for the attention kernel)
+            const bool ttile = MODE == 5 && n_tile >= p.trans_first_tile;
+            // LayerNorm fold: acc' = ln_rs * acc + ln_nm * u[n] with {ln_rs, ln_nm} = {rstd, -rstd * mean} of this row, as
+            // left by the producer (row_final). The pair of the NEXT tile's row is fetched now, so that its global-memory
+            // latency is off the epilogue's serial path (a per-tile fold of the raw records cost ~2500 cycles a tile).
+            const float ln_rs = ln_cur.x, ln_nm = ln_cur.y;
+            if (ln) {
+                const int64_t nrow = (int64_t)(tw.m * CG + (int)cta_rank) * BLOCK_M + r;  // tw is already at the next tile
+                ln_cur = (next_tile < num_tiles && nrow < p.M) ? __ldg(p.ln_stats + nrow) : make_float2(1.f, 0.f);
             }
+            // The tile's results stay in registers (packed bf16, 8 columns per uint4) until the TMA unit has finished
+            // reading the PREVIOUS tile out of the staging buffer: that read (~1200 cycles) then overlaps this tile's
+            // tensor-memory loads and arithmetic instead of sitting between two tiles.
+            constexpr int PK_N = MODE == 2 ? BLOCK_N / 32 : MODE == 1 ? 1 : BLOCK_N / 16;
+            uint4 pk[PK_N];
             if constexpr (MODE == 2) {
                 constexpr int HALF = BLOCK_N / 2;
                 const int o_base = n_tile * HALF;  // output column of this tile
                 const int n_out = p.N / 2;
                 mbar_wait(tmem_full_bar(acc), acc_ph);
                 tc_fence_after();
-#pragma unroll 1
-                for (int c0 = half * 16; c0 < HALF; c0 += 32) {
+#pragma unroll
+                for (int k = 0; k < BLOCK_N / 64; ++k) {
+                    const int c0 = half * 16 + 32 * k;
                     uint32_t ra[16], rg[16];
                     tmem_ld16(taddr + c0, ra);
                     tmem_ld16(taddr + HALF + c0, rg);
                     tmem_wait_ld();
+                    pk[2 * k] = pk[2 * k + 1] = make_uint4(0u, 0u, 0u, 0u);
                     if (valid && o_base + c0 < n_out) {
 #pragma unroll
                         for (int h8 = 0; h8 < 16; h8 += 8) {
+                            // bias (and, with the LayerNorm fold, the weight row sums) of the 8 value / 8 gate columns
+                            // as 16-byte shared-memory loads: scalar loads made this epilogue LSU-bound
+                            float ba[8], bg[8], ua[8], ug[8];
+                            *reinterpret_cast<float4*>(&ba[0]) = *reinterpret_cast<const float4*>(sbias + c0 + h8);
+                            *reinterpret_cast<float4*>(&ba[4]) = *reinterpret_cast<const float4*>(sbias + c0 + h8 + 4);
+                            *reinterpret_cast<float4*>(&bg[0]) = *reinterpret_cast<const float4*>(sbias + HALF + c0 + h8);
+                            *reinterpret_cast<float4*>(&bg[4]) = *reinterpret_cast<const float4*>(sbias + HALF + c0 + h8 + 4);
+                            if (ln) {
+                                *reinterpret_cast<float4*>(&ua[0]) = *reinterpret_cast<const float4*>(su + c0 + h8);
+                                *reinterpret_cast<float4*>(&ua[4]) = *reinterpret_cast<const float4*>(su + c0 + h8 + 4);
+                                *reinterpret_cast<float4*>(&ug[0]) = *reinterpret_cast<const float4*>(su + HALF + c0 + h8);
+                                *reinterpret_cast<float4*>(&ug[4]) = *reinterpret_cast<const float4*>(su + HALF + c0 + h8 + 4);
+                            }
                             float v[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 float a = __uint_as_float(ra[h8 + j]), g = __uint_as_float(rg[h8 + j]);
                                 if (ln) {
-                                    a = fmaf(a, ln_rs, fmaf(ln_nm, su[c0 + h8 + j], sbias[c0 + h8 + j]));
-                                    g = fmaf(g, ln_rs, fmaf(ln_nm, su[HALF + c0 + h8 + j], sbias[HALF + c0 + h8 + j]));
+                                    a = fmaf(a, ln_rs, fmaf(ln_nm, ua[j], ba[j]));
+                                    g = fmaf(g, ln_rs, fmaf(ln_nm, ug[j], bg[j]));
                                 } else {
-                                    a += sbias[c0 + h8 + j];
-                                    g += sbias[HALF + c0 + h8 + j];
+                                    a += ba[j];
+                                    g += bg[j];
                                 }
                                 v[j] = a * gelu_tanh_f(g);
                             }
@@ -611,11 +626,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                             q.y = pack_bf16x2(v[2], v[3]);
                             q.z = pack_bf16x2(v[4], v[5]);
                             q.w = pack_bf16x2(v[6], v[7]);
-                            *reinterpret_cast<uint4*>(stage_ptr(r, c0 + h8)) = q;
+                            pk[2 * k + h8 / 8] = q;
                         }
                     }
                 }
-            } else if constexpr (MODE == 0 || MODE == 3 || MODE == 4) {
+            } else if constexpr (MODE == 0 || MODE == 3 || MODE == 4 || MODE == 5) {
                 // lean path: per-row base pointers, 32-bit column offsets, uniform flags hoisted.
                 // The epilogue runs with only two warps per scheduler, so it is latency-bound unless
                 // the four 8-column groups of a chunk are independent straight-line code: the common
@@ -637,8 +652,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 // 160-wide tile (5 chunks would split 3 / 2): there each warp takes one contiguous 80-column half
                 // as 32 + 32 + 16, so both finish together
                 constexpr bool kSplitHalves = BLOCK_N == 160;
+                constexpr int NCH = kSplitHalves ? 3 : BLOCK_N / 64;  // chunks per thread (160: 32 + 32 + 16 columns)
+                auto chunk_col = [&](int k) { return kSplitHalves ? half * 80 + 32 * k : half * 32 + 64 * k; };
                 uint32_t accA[32], accB[32];
-                tmem_ld32(taddr + (kSplitHalves ? half * 80 : half * 32), accA);
+                tmem_ld32(taddr + chunk_col(0), accA);
                 // per-row partial sums for the consumer's LayerNorm (this warp's columns of the row): shifted by the
                 // first value seen so a large common offset does not cancel in the variance
                 constexpr bool want_rows = MODE == 3;  // mode 3 is only selected with row_stats set
@@ -646,7 +663,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 uint64_t st_s1 = 0ull, st_s2 = 0ull;  // {even, odd} column lanes of sum and sum of squares
                 float st_shift = 0.f, st_cnt = 0.f;
                 // ---- store helper: 8 fp32 -> (silu) -> bf16 -> 16-byte store
-                auto store8 = [&](float (&v)[8], int col) {
+                auto store8 = [&](float (&v)[8], uint4& dst) {
                     if (want_rows) {
                         if (st_cnt == 0.f) st_shift = v[0];
                         const uint64_t sh2 = pack_f32x2(st_shift, st_shift);
@@ -666,21 +683,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                         for (int j = 0; j < 8; ++j) v[j] = quick_gelu_f(v[j]);
                     }
                     uint4 q;
-                    q.x = pack_bf16x2(v[0], v[1]);
-                    q.y = pack_bf16x2(v[2], v[3]);
-                    q.z = pack_bf16x2(v[4], v[5]);
-                    q.w = pack_bf16x2(v[6], v[7]);
-                    *reinterpret_cast<uint4*>(stage_ptr(r, col)) = q;
+                    if (MODE == 5 && ttile && p.t_fp16) {  // V^T is fp16 (P is fp16 in the attention kernel)
+                        q.x = pack_f16x2(v[0], v[1]);
+                        q.y = pack_f16x2(v[2], v[3]);
+                        q.z = pack_f16x2(v[4], v[5]);
+                        q.w = pack_f16x2(v[6], v[7]);
+                    } else {
+                        q.x = pack_bf16x2(v[0], v[1]);
+                        q.y = pack_bf16x2(v[2], v[3]);
+                        q.z = pack_bf16x2(v[4], v[5]);
+                        q.w = pack_bf16x2(v[6], v[7]);
+                    }
+                    dst = q;
                 };
-                // ---- one chunk of NG 8-column groups (32 or 16 columns)
-                auto process = [&](const uint32_t* accv, auto ng_tag, int c0) {
+                // ---- one chunk of NG 8-column groups (32 or 16 columns); results go to pk[PKB + g]
+                auto process = [&](const uint32_t* accv, auto ng_tag, int c0, auto pkb_tag) {
                     constexpr int NG = decltype(ng_tag)::value;
-                    if constexpr (MODE == 4) {
+                    constexpr int PKB = decltype(pkb_tag)::value;
+                    if (MODE == 4 || (MODE == 5 && ln)) {
                         // LayerNorm-folded consumer (q|k, cross-attention q): acc' = rstd * (acc - mean * u[n]) + bias
                         // fused as two FMAs; these launches carry no residual / row vector
 #pragma unroll
                         for (int g = 0; g < NG; ++g) {
                             const int col = c0 + g * 8;
+                            pk[PKB + g] = make_uint4(0u, 0u, 0u, 0u);
                             if (valid && col < ncols) {
                                 const float4 b0 = *reinterpret_cast<const float4*>(sbias + col);
                                 const float4 b1 = *reinterpret_cast<const float4*>(sbias + col + 4);
@@ -695,11 +721,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                                 v[5] = fmaf(__uint_as_float(accv[g * 8 + 5]), ln_rs, fmaf(ln_nm, u1.y, b1.y));
                                 v[6] = fmaf(__uint_as_float(accv[g * 8 + 6]), ln_rs, fmaf(ln_nm, u1.z, b1.z));
                                 v[7] = fmaf(__uint_as_float(accv[g * 8 + 7]), ln_rs, fmaf(ln_nm, u1.w, b1.w));
-                                store8(v, col);
+                                store8(v, pk[PKB + g]);
                             }
                         }
                         return;
-                    } else {
+                    }
+                    if constexpr (MODE != 4) {
                     if (full && plain) {
 #pragma unroll
                         for (int g = 0; g < NG; ++g) {
@@ -711,7 +738,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                             v[2] = (__uint_as_float(accv[g * 8 + 2]) + b0.z) * alpha; v[3] = (__uint_as_float(accv[g * 8 + 3]) + b0.w) * alpha;
                             v[4] = (__uint_as_float(accv[g * 8 + 4]) + b1.x) * alpha; v[5] = (__uint_as_float(accv[g * 8 + 5]) + b1.y) * alpha;
                             v[6] = (__uint_as_float(accv[g * 8 + 6]) + b1.z) * alpha; v[7] = (__uint_as_float(accv[g * 8 + 7]) + b1.w) * alpha;
-                            store8(v, col);
+                            store8(v, pk[PKB + g]);
                         }
                         return;
                     }
@@ -732,6 +759,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
 #pragma unroll
                     for (int g = 0; g < NG; ++g) {
                         const int col = c0 + g * 8;
+                        pk[PKB + g] = make_uint4(0u, 0u, 0u, 0u);
                         if (ok[g]) {
                             const float4 b0 = *reinterpret_cast<const float4*>(sbias + col);
                             const float4 b1 = *reinterpret_cast<const float4*>(sbias + col + 4);
@@ -744,44 +772,38 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                             v[2] = (v[2] + bf16_lo(q1[g].y)) * alpha + bf16_lo(q2[g].y); v[3] = (v[3] + bf16_hi(q1[g].y)) * alpha + bf16_hi(q2[g].y);
                             v[4] = (v[4] + bf16_lo(q1[g].z)) * alpha + bf16_lo(q2[g].z); v[5] = (v[5] + bf16_hi(q1[g].z)) * alpha + bf16_hi(q2[g].z);
                             v[6] = (v[6] + bf16_lo(q1[g].w)) * alpha + bf16_lo(q2[g].w); v[7] = (v[7] + bf16_hi(q1[g].w)) * alpha + bf16_hi(q2[g].w);
-                            store8(v, col);
+                            store8(v, pk[PKB + g]);
                         }
                     }
                     }
                 };
                 using G4 = std::integral_constant<int, 4>;
                 using G2 = std::integral_constant<int, 2>;
-#ifdef GEMM_EXP_NOEPI  // experiment: drain the accumulator only (what does the tile cost without the epilogue math?)
-                tmem_wait_ld();
-                if (false)
-#endif
-                if constexpr (kSplitHalves) {
-                    const int cb = half * 80;
-                    uint32_t accC[16];
-                    tmem_wait_ld();
-                    tmem_ld32(taddr + cb + 32, accB);
-                    process(accA, G4{}, cb);
-                    tmem_wait_ld();
-                    tmem_ld16(taddr + cb + 64, accC);
-                    process(accB, G4{}, cb + 32);
-                    tmem_wait_ld();
-                    process(accC, G2{}, cb + 64);
-                } else {
-#pragma unroll 1
-                    for (int c0 = half * 32; c0 < BLOCK_N; c0 += 128) {
+                // software pipeline over the chunks: the tensor-memory load of chunk k + 1 is in flight while chunk k is
+                // processed (one load in flight per warp: two collapse the tensor-memory read rate, profiles/ubench)
+                auto chunk = [&](auto k_tag, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
+                    constexpr int K = decltype(k_tag)::value;
+                    if constexpr (K < NCH) {
                         tmem_wait_ld();
-                        if (c0 + 64 < BLOCK_N) tmem_ld32(taddr + c0 + 64, accB);
-                        process(accA, G4{}, c0);
-                        if (c0 + 64 < BLOCK_N) {
-                            tmem_wait_ld();
-                            if (c0 + 128 < BLOCK_N) tmem_ld32(taddr + c0 + 128, accA);
-                            process(accB, G4{}, c0 + 64);
+                        if constexpr (K + 1 < NCH) {
+                            if constexpr (kSplitHalves && K + 1 == 2) tmem_ld16(taddr + chunk_col(K + 1), reinterpret_cast<uint32_t(&)[16]>(nxt));
+                            else tmem_ld32(taddr + chunk_col(K + 1), nxt);
                         }
+#ifndef GEMM_EXP_NOEPI  // experiment: drain the accumulator only (what does the tile cost without the epilogue math?)
+                        if constexpr (kSplitHalves && K == 2) process(cur, G2{}, chunk_col(K), std::integral_constant<int, 4 * K>{});
+                        else process(cur, G4{}, chunk_col(K), std::integral_constant<int, 4 * K>{});
+#endif
                     }
+                };
+                chunk(std::integral_constant<int, 0>{}, accA, accB);
+                chunk(std::integral_constant<int, 1>{}, accB, accA);
+                chunk(std::integral_constant<int, 2>{}, accA, accB);
+                chunk(std::integral_constant<int, 3>{}, accB, accA);
+                if constexpr (want_rows) {
+                    if (valid)
+                        p.row_stats[(int64_t)(n_tile * 2 + half) * p.row_stats_ld + row] =
+                            make_float4(f32x2_lo(st_s1) + f32x2_hi(st_s1), f32x2_lo(st_s2) + f32x2_hi(st_s2), st_shift, st_cnt);
                 }
-                if (want_rows && valid)
-                    p.row_stats[(int64_t)(n_tile * 2 + half) * p.row_stats_ld + row] =
-                        make_float4(f32x2_lo(st_s1) + f32x2_hi(st_s1), f32x2_lo(st_s2) + f32x2_hi(st_s2), st_shift, st_cnt);
             } else {
                 // residuals of a 32-column chunk are fetched one chunk ahead (the first chunk's
                 // before the accumulator is even ready), so their latency hides behind TMEM
@@ -831,42 +853,132 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                     for (int g = 0; g < 4; ++g) { c1[g] = x1[g]; c2[g] = x2[g]; }
                 }
             }
-            // all TMEM reads of this accumulator stage are complete (wait::ld above)
-            if (etid == 0) GT(lt, 6);  // tile math done, staged
+            // all TMEM reads of this accumulator stage are complete (wait::ld above): hand it back to the MMA issuer
+            if (etid == 0) GT(lt, 6);  // tile math done (results in registers)
             tc_fence_before();
             __syncwarp();
             if (lane_id() == 0) {
                 if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty_bar(acc) & PP_PEER_BIT_MASK);  // the leader's barrier
                 else mbar_arrive(tmem_empty_bar(acc));
             }
+            // park the next tile's bias in the other staging buffer: its last readers (tile lt - 1) all passed that
+            // tile's second barrier, and the barrier below orders these writes before tile lt + 1 reads them
+            if (etid < BLOCK_N) {
+                sbias_all[(acc ^ 1u) * BLOCK_N + etid] = bias_next;
+                su_all[(acc ^ 1u) * BLOCK_N + etid] = u_next;
+            }
             if constexpr (MODE != 1) {
-                // hand the staged tile to the TMA unit: generic-proxy writes -> async proxy, one barrier, one thread
-                // issues the stores (one per sub-tile); the unit writes whole rows and clips out-of-range parts
+                // the TMA unit must have read the previous tile out of the staging buffer before it is overwritten
+                if (etid == 0) bulk_wait_read_all();
+                if (etid == 0) GT(lt, 9);  // previous staged tile consumed by the TMA unit
+            }
+            epi_sync();
+            if constexpr (MODE != 1) {
+                // stage the tile (generic-proxy writes -> async proxy), one barrier, one thread issues the TMA stores
+                // (one per sub-tile); the unit writes whole rows and clips out-of-range parts
+#pragma unroll
+                for (int i = 0; i < PK_N; ++i) {
+                    int col;
+                    if constexpr (MODE == 2) col = half * 16 + 32 * (i / 2) + 8 * (i % 2);
+                    else if constexpr (BLOCK_N == 160) col = half * 80 + 8 * i;
+                    else col = half * 32 + 64 * (i / 4) + 8 * (i % 4);
+                    if (MODE == 5 && ttile) {
+                        // transposed staging: [column][128 rows] 16-bit, 64-column sub-tiles of 16 KB — the boxes of the
+                        // transposed TMA store; a warp's 32 lanes write 64 contiguous bytes per column (conflict-free)
+                        uint8_t* tb = s_out + (col >> 6) * 16384 + (col & 63) * 256 + r * 2;
+                        const uint32_t w[4] = {pk[i].x, pk[i].y, pk[i].z, pk[i].w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            *reinterpret_cast<uint16_t*>(tb + (2 * j) * 256) = (uint16_t)(w[j] & 0xFFFFu);
+                            *reinterpret_cast<uint16_t*>(tb + (2 * j + 1) * 256) = (uint16_t)(w[j] >> 16);
+                        }
+                    } else {
+                        *reinterpret_cast<uint4*>(stage_ptr(r, col)) = pk[i];
+                    }
+                }
                 fence_proxy_async_smem();
                 if (half == 0) s_row[r] = valid ? (long long)row : -1ll;
+                if constexpr (MODE == 3) {
+                    // every warp's records were written before the barrier above: the CTA that takes the last
+                    // ticket of this 128-row block folds the block's records into {rstd, -rstd * mean} per row
+                    if (etid == 0) {
+                        // the barrier above ordered every warp's record stores before this thread; its fence is
+                        // cumulative, so they are visible device-wide before the ticket is (one fence, not 256)
+                        __threadfence();
+                        const int t = atomicAdd(p.row_ticket + m_tile, 1);
+                        s_last_tile = (t == n_tiles - 1) ? 1 : 0;
+                        if (t == n_tiles - 1) p.row_ticket[m_tile] = 0;  // ready for the next launch
+                    }
+                }
                 epi_sync();
                 if (etid == 0) GT(lt, 7);  // all epilogue warps staged
+                if constexpr (MODE == 3) {
+                    if (s_last_tile && half == 0 && valid) {
+                        __threadfence();
+                        const int nrec = 2 * n_tiles;
+                        float cnt = 0.f, mean = 0.f, m2 = 0.f;
+                        for (int i0 = 0; i0 < nrec; i0 += 4) {
+                            float4 rc[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)  // four independent L2 loads in flight (nrec is even, mostly 4)
+                                rc[u] = i0 + u < nrec ? __ldcg(p.row_stats + (int64_t)(i0 + u) * p.row_stats_ld + row)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (rc[u].w > 0.f) {  // Chan's combination of (count, mean, M2)
+                                    const float inv = __fdividef(1.f, rc[u].w);
+                                    const float mi = fmaf(rc[u].x, inv, rc[u].z);
+                                    const float m2i = fmaxf(fmaf(-rc[u].x * inv, rc[u].x, rc[u].y), 0.f);
+                                    const float tot = cnt + rc[u].w;
+                                    const float wgt = __fdividef(rc[u].w, tot);
+                                    const float dl = mi - mean;
+                                    mean = fmaf(dl, wgt, mean);
+                                    m2 += m2i + dl * dl * cnt * wgt;
+                                    cnt = tot;
+                                }
+                            }
+                        }
+                        const float var = cnt > 0.f ? __fdividef(m2, cnt) : 0.f;
+                        const float rs = rsqrtf(var + p.ln_eps);
+                        p.row_final[row] = make_float2(rs, -rs * mean);
+                    }
+                }
                 constexpr int OUT_COLS = MODE == 2 ? BLOCK_N / 2 : BLOCK_N;
                 constexpr int PIECES = OUT_COLS / 8;
                 if (etid == 0) {
                     const int out_base = n_tile * OUT_COLS;
-                    const int n_out = MODE == 2 ? p.N / 2 : p.N;
+                    const int n_out = MODE == 2 ? p.N / 2 : MODE == 5 ? p.trans_first_tile * BLOCK_N : p.N;
                     int x0 = 0, y0 = 0, nb0 = 0;
                     if (p.a_mode != PP_A_MATRIX) tile_origin(m_tile, x0, y0, nb0);
+                    if (MODE == 5 && ttile) {
+                        // (token, channel, sample) coordinates of the transposed destination; tiles never straddle samples
+                        const int row0 = m_tile * BLOCK_M;
+                        const int sb = row0 / p.t_rows, t0 = row0 - sb * p.t_rows;
+                        const int cbase = (n_tile - p.trans_first_tile) * BLOCK_N;
 #pragma unroll
-                    for (int sub = 0; sub * 64 < OUT_COLS; ++sub) {
-                        const int col = out_base + sub * 64;
-                        if (col >= n_out) break;
-                        const CUtensorMap* tm = (OUT_COLS - sub * 64) >= 64 ? &p.tmOut[0] : &p.tmOut[1];
-#ifndef GEMM_EXP_NOSTORE  // experiment: no global write of the tile
-                        if (p.a_mode == PP_A_MATRIX) tma_store_2d(tm, s_out_addr + sub * 16384, col, m_tile * BLOCK_M);
-                        else tma_store_4d(tm, s_out_addr + sub * 16384, col, x0, y0, nb0);
+                        for (int sub = 0; sub * 64 < BLOCK_N; ++sub) {
+                            if (n_base + sub * 64 >= p.N) break;
+                            const CUtensorMap* tm = (BLOCK_N - sub * 64) >= 64 ? &p.tmOutT[0] : &p.tmOutT[1];
+#ifndef GEMM_EXP_NOSTORE
+                            tma_store_3d(tm, s_out_addr + sub * 16384, t0, cbase + sub * 64, sb);
 #endif
+                        }
+                    } else {
+#pragma unroll
+                        for (int sub = 0; sub * 64 < OUT_COLS; ++sub) {
+                            const int col = out_base + sub * 64;
+                            if (col >= n_out) break;
+                            const CUtensorMap* tm = (OUT_COLS - sub * 64) >= 64 ? &p.tmOut[0] : &p.tmOut[1];
+#ifndef GEMM_EXP_NOSTORE  // experiment: no global write of the tile
+                            if (p.a_mode == PP_A_MATRIX) tma_store_2d(tm, s_out_addr + sub * 16384, col, m_tile * BLOCK_M);
+                            else tma_store_4d(tm, s_out_addr + sub * 16384, col, x0, y0, nb0);
+#endif
+                        }
                     }
                     bulk_commit_group();
                     GT(lt, 8);  // TMA stores issued
                 }
-                if constexpr (MODE == 0 || MODE == 3 || MODE == 4) {
+                if constexpr (MODE == 0 || MODE == 3 || MODE == 4) {  // (never mode 5: transposed tiles hold no rows)
                     // GroupNorm partial sums of exactly the bf16 values the consumer will read
                     if (p.chan_stats) {
                         constexpr int L = (BLOCK_N <= 128) ? 16 : 8;
@@ -911,17 +1023,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                     }
                 }
             }
-            // park the next tile's bias in the other staging buffer; everyone has finished reading
-            // the buffer of tile lt-1 (same slot) long ago, the barrier orders this tile's writes
-            if (etid < BLOCK_N) {
-                sbias_all[(acc ^ 1u) * BLOCK_N + etid] = bias_next;
-                su_all[(acc ^ 1u) * BLOCK_N + etid] = u_next;
-            }
-            if constexpr (MODE != 1) {
-                if (etid == 0) bulk_wait_read_all();  // the TMA unit has read the staged tile: it may be overwritten
-                if (etid == 0) GT(lt, 9);  // staged tile consumed by the TMA unit
-            }
-            epi_sync();
             if (etid == 0) GT(lt, 10);
         }
         if constexpr (MODE != 1) {
@@ -1018,6 +1119,10 @@ static int ensure_attr() {
         case 160 * 8 + 3: return FN<160, 3>(__VA_ARGS__);                        \
         case 256 * 8 + 3: return FN<256, 3>(__VA_ARGS__);                        \
         case 64 * 8 + 4: return FN<64, 4>(__VA_ARGS__);                          \
+        case 64 * 8 + 5: return FN<64, 5>(__VA_ARGS__);                          \
+        case 128 * 8 + 5: return FN<128, 5>(__VA_ARGS__);                        \
+        case 160 * 8 + 5: return FN<160, 5>(__VA_ARGS__);                        \
+        case 256 * 8 + 5: return FN<256, 5>(__VA_ARGS__);                        \
         case 128 * 8 + 4: return FN<128, 4>(__VA_ARGS__);                        \
         case 160 * 8 + 4: return FN<160, 4>(__VA_ARGS__);                        \
         case 256 * 8 + 4: return FN<256, 4>(__VA_ARGS__);                        \
@@ -1079,6 +1184,13 @@ static int pick_block_n(int N, int m_tiles, bool geglu, int cg = 1) {
 // fields, the conv pixel box, the tile width and the walk. Shared by gemm_prepare and the host-only
 // statistics-geometry query.
 static bool gemm_fast_mode(const pp_gemm_desc& d);
+// transposed columns through the staging tile + TMA store (mode 5): whole 128-row tiles inside one sample, bias only
+static bool gemm_trans_staged(const pp_gemm_desc& d) {
+    const bool t = d.epilogue == PP_EPI_TRANSPOSED || d.epilogue == PP_EPI_ROWS_THEN_TRANSPOSED;
+    return t && d.a_mode == PP_A_MATRIX && !d.out_fp32 && d.N % 8 == 0 && d.t_rows > 0 && d.t_rows % BLOCK_M == 0 &&
+           d.M % d.t_rows == 0 && d.t_ld % 8 == 0 && !d.a1 && !d.rowvec && !d.res1 && !d.res2 && d.act == PP_ACT_NONE &&
+           d.alpha == 1.0f && !d.alpha_dev && !d.chan_stats && !d.row_stats;
+}
 
 // CTA-pair mode (cta_group::2) is chosen for the long-K contractions — the 3x3 convs and the K >= 1152 linears — in
 // the plain bf16 epilogue flavour, when the m-tiles pair up. PP_B200_PAIR=0 switches it off (A/B comparisons).
@@ -1094,7 +1206,7 @@ static constexpr int PAIR_MIN_K_ITERS = 18;
 
 static int gemm_geometry(const pp_gemm_desc& d, GemmKParams& p, int* block_n_out, int* cg_out = nullptr) {
     PP_REQUIRE(d.a_mode >= PP_A_MATRIX && d.a_mode <= PP_A_CONV3X3_S2P0, "gemm: bad a_mode %d", d.a_mode);
-    PP_REQUIRE(d.epilogue >= PP_EPI_PLAIN && d.epilogue <= PP_EPI_TRANSPOSED, "gemm: bad epilogue %d", d.epilogue);
+    PP_REQUIRE(d.epilogue >= PP_EPI_PLAIN && d.epilogue <= PP_EPI_ROWS_THEN_TRANSPOSED, "gemm: bad epilogue %d", d.epilogue);
     PP_REQUIRE(d.a0 && d.b && d.out, "gemm: null operand pointer");
     PP_REQUIRE(d.c0 > 0 && d.c0 % 8 == 0, "gemm: c0=%d must be a positive multiple of 8", d.c0);
     PP_REQUIRE((d.a1 == nullptr) == (d.c1 == 0), "gemm: a1/c1 mismatch");
@@ -1149,7 +1261,7 @@ static int gemm_geometry(const pp_gemm_desc& d, GemmKParams& p, int* block_n_out
     const bool geglu = d.epilogue == PP_EPI_GEGLU;
     int cg = 1;
     if (pair_mode_enabled() && (d.a_mode == PP_A_MATRIX || d.a_mode == PP_A_CONV3X3) && m_tiles % 2 == 0 &&
-        p.num_k_iters >= PAIR_MIN_K_ITERS && !geglu && gemm_fast_mode(d) && !d.row_stats && !d.ln_rec && d.block_n != 64)
+        p.num_k_iters >= PAIR_MIN_K_ITERS && !geglu && gemm_fast_mode(d) && !d.row_stats && !d.ln_stats && d.block_n != 64)
         cg = 2;
     int bn = d.block_n ? d.block_n : pick_block_n(d.N, m_tiles, geglu, cg);
     PP_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "gemm: block_n %d unsupported", bn);
@@ -1199,7 +1311,11 @@ int gemm_stats_geometry(const pp_gemm_desc& d, pp_stats_geom* g) {
 
 // records per row a GEMM emits for the consumer's LayerNorm: one per half n-tile (the two epilogue warps that share a
 // TMEM lane quarter each own a set of columns); 0 = this launch cannot emit them
-int gemm_row_stats_records(const pp_gemm_desc& d) {
+int gemm_row_stats_records(const pp_gemm_desc& d0) {
+    // the query comes before the record buffer exists: answer for the launch WITH row_stats attached (that one never
+    // runs in CTA-pair mode, which can pick a different tile width and hence a different record count)
+    pp_gemm_desc d = d0;
+    if (!d.row_stats) d.row_stats = reinterpret_cast<float*>(uintptr_t(16));
     GemmKParams p;
     memset(&p, 0, sizeof(p));
     int bn = 0;
@@ -1305,11 +1421,13 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
     p.t_rows = d.t_rows;
     p.t_ld = d.t_ld;
     p.t_fp16 = d.t_fp16;
-    if (d.epilogue == PP_EPI_TRANSPOSED) {
+    if (d.epilogue == PP_EPI_TRANSPOSED || d.epilogue == PP_EPI_ROWS_THEN_TRANSPOSED) {
         PP_REQUIRE(d.t_rows > 0 && d.t_ld >= d.t_rows, "gemm: transposed store needs t_rows/t_ld");
         PP_REQUIRE(!d.out_fp32, "gemm: transposed store is bf16 only");
-    } else {
-        PP_REQUIRE(d.ldc >= (geglu ? d.N / 2 : d.N), "gemm: ldc=%lld too small", (long long)d.ldc);
+    }
+    if (d.epilogue != PP_EPI_TRANSPOSED) {
+        const int n_rows_part = geglu ? d.N / 2 : d.epilogue == PP_EPI_ROWS_THEN_TRANSPOSED ? d.trans_from_col : d.N;
+        PP_REQUIRE(d.ldc >= n_rows_part, "gemm: ldc=%lld too small", (long long)d.ldc);
         if (d.N % 8 == 0) {
             PP_REQUIRE(d.ldc % (d.out_fp32 ? 4 : 8) == 0, "gemm: ldc=%lld breaks 16-byte store alignment", (long long)d.ldc);
             PP_REQUIRE((reinterpret_cast<uintptr_t>(d.out) & 15) == 0, "gemm: out pointer not 16-byte aligned");
@@ -1327,14 +1445,36 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
     l.smem = smem_for_block_n(bn, cg);
     if (geglu) {
         l.mode = 2;
+    } else if (gemm_trans_staged(d)) {
+        l.mode = 5;
+        const bool mixed = d.epilogue == PP_EPI_ROWS_THEN_TRANSPOSED;
+        if (mixed)
+            PP_REQUIRE(d.out_t && d.trans_from_col > 0 && d.trans_from_col < d.N && d.trans_from_col % bn == 0 &&
+                           (d.N - d.trans_from_col) % 8 == 0,
+                       "gemm: trans_from_col=%d must be a positive multiple of the tile width %d below N=%d",
+                       d.trans_from_col, bn, d.N);
+        p.trans_first_tile = mixed ? d.trans_from_col / bn : 0;
+        void* out_t = mixed ? d.out_t : d.out;
+        const uint64_t nt = (uint64_t)(d.N - (mixed ? d.trans_from_col : 0));
+        PP_REQUIRE((reinterpret_cast<uintptr_t>(out_t) & 15) == 0, "gemm: transposed output not 16-byte aligned");
+        for (int k = 0; k < 2; ++k) {
+            if (k == 1 && bn % 64 == 0) break;
+            uint64_t dims[3] = {(uint64_t)d.t_rows, nt, (uint64_t)(d.M / d.t_rows)};
+            uint64_t str[2] = {(uint64_t)d.t_ld * 2, nt * (uint64_t)d.t_ld * 2};
+            uint32_t box[3] = {(uint32_t)BLOCK_M, k == 0 ? 64u : 32u, 1u};
+            int rc = make_tmap_bf16_sw(&p.tmOutT[k], out_t, 3, dims, str, box, 0);
+            if (rc) return rc;
+        }
     } else {
-        PP_REQUIRE(!(d.row_stats && d.ln_rec), "gemm: a launch either emits LayerNorm records or consumes them");
-        l.mode = gemm_fast_mode(d) ? (d.row_stats ? 3 : d.ln_rec ? 4 : 0) : 1;
+        PP_REQUIRE(d.epilogue != PP_EPI_ROWS_THEN_TRANSPOSED, "gemm: PP_EPI_ROWS_THEN_TRANSPOSED needs a plain bf16 GEMM "
+                   "(bias only) whose t_rows is a multiple of 128 and divides M");
+        PP_REQUIRE(!(d.row_stats && d.ln_stats), "gemm: a launch either emits LayerNorm statistics or consumes them");
+        l.mode = gemm_fast_mode(d) ? (d.row_stats ? 3 : d.ln_stats ? 4 : 0) : 1;
     }
-    if (l.mode != 1) {
+    if (l.mode != 1 && !(l.mode == 5 && p.trans_first_tile == 0)) {
         // TMA-store boxes of the staged output tile: 64 columns (128-byte swizzle), and a 32-column box (64-byte
         // swizzle) for the tail of the 160-wide tile; tensor extents clip ragged tiles and columns >= N
-        const uint64_t n_out = geglu ? (uint64_t)d.N / 2 : (uint64_t)d.N;
+        const uint64_t n_out = geglu ? (uint64_t)d.N / 2 : l.mode == 5 ? (uint64_t)d.trans_from_col : (uint64_t)d.N;
         const int out_cols = geglu ? bn / 2 : bn;
         for (int k = 0; k < 2; ++k) {
             const uint32_t inner = k == 0 ? 64u : 32u;
@@ -1371,18 +1511,20 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
                    "(query pp_gemm_row_stats_records first)");
         PP_REQUIRE(d.row_stats_ld >= d.M && (reinterpret_cast<uintptr_t>(d.row_stats) & 15) == 0,
                    "gemm: row_stats_ld=%lld < M or row_stats not 16-byte aligned", (long long)d.row_stats_ld);
+        PP_REQUIRE(d.row_final && d.row_ticket && d.ln_eps > 0.f && (reinterpret_cast<uintptr_t>(d.row_final) & 7) == 0,
+                   "gemm: row_stats needs row_final (8-byte aligned), row_ticket and ln_eps > 0");
         p.row_stats = reinterpret_cast<float4*>(d.row_stats);
         p.row_stats_ld = d.row_stats_ld;
+        p.row_final = reinterpret_cast<float2*>(d.row_final);
+        p.row_ticket = d.row_ticket;
+        p.ln_eps = d.ln_eps;
     }
-    if (d.ln_rec) {
-        PP_REQUIRE(d.a_mode == PP_A_MATRIX && d.ln_u && d.ln_nrec > 0 && d.ln_ld >= d.M && d.ln_eps > 0.f,
-                   "gemm: LayerNorm fold needs PP_A_MATRIX, ln_u, ln_nrec > 0, ln_ld >= M, ln_eps > 0");
+    if (d.ln_stats) {
+        PP_REQUIRE(d.a_mode == PP_A_MATRIX && d.ln_u, "gemm: LayerNorm fold needs PP_A_MATRIX and ln_u");
         PP_REQUIRE(!d.res1 && !d.res2 && !d.rowvec && !d.a1 && d.alpha == 1.0f && !d.alpha_dev,
                    "gemm: LayerNorm-folded launches take bias only (no residual / row vector / alpha)");
-        PP_REQUIRE((reinterpret_cast<uintptr_t>(d.ln_rec) & 15) == 0, "gemm: ln_rec not 16-byte aligned");
-        p.ln_rec = reinterpret_cast<const float4*>(d.ln_rec);
-        p.ln_nrec = d.ln_nrec;
-        p.ln_ld = d.ln_ld;
+        PP_REQUIRE((reinterpret_cast<uintptr_t>(d.ln_stats) & 7) == 0, "gemm: ln_stats not 8-byte aligned");
+        p.ln_stats = reinterpret_cast<const float2*>(d.ln_stats);
         p.ln_u = d.ln_u;
         p.ln_eps = d.ln_eps;
     }

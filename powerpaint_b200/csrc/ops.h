@@ -17,6 +17,8 @@ struct GemmKParams {
     CUtensorMap tmA[4];  // matrix/conv: [src0, src1]; stride-2 conv: 4 parity maps
     CUtensorMap tmB;
     CUtensorMap tmOut[2];  // output tile store (modes 0 / 2): 64-column boxes, and the 32-column remainder box
+    CUtensorMap tmOutT[2];  // mode 5: transposed tile store, boxes of 128 rows (tokens) x 64 / 32 channels
+    int32_t trans_first_tile;  // mode 5: n-tiles from here on are stored transposed (into out_t)
     int32_t a_mode;
     int32_t M, N;            // GEMM extents (conv: M = nb*ho*wo)
     int32_t num_k_iters;     // total 64-wide K chunks
@@ -55,9 +57,9 @@ struct GemmKParams {
     // LayerNorm fold (see pp_gemm_desc): records emitted per row and half n-tile / consumed by the epilogue
     float4* row_stats;
     int64_t row_stats_ld;
-    const float4* ln_rec;
-    int32_t ln_nrec;
-    int64_t ln_ld;
+    float2* row_final;     // {rstd, -rstd * mean} per row, written by the CTA finishing a row block's last n-tile
+    int32_t* row_ticket;   // per m-tile arrival counter (self-resetting)
+    const float2* ln_stats;  // consumer: a producer's row_final
     const float* ln_u;
     float ln_eps;
 };
@@ -66,7 +68,8 @@ struct GemmLaunch {
     GemmKParams p;
     int block_n;
     int cg;    // 1, or 2 = CTA-pair mode (cta_group::2): clusters of two CTAs share one 256-row MMA tile
-    int mode;  // epilogue flavour: 0 fast bf16, 1 generic, 2 GEGLU, 3 fast bf16 + LayerNorm records out, 4 fast bf16 + LayerNorm of A
+    int mode;  // epilogue flavour: 0 fast bf16, 1 generic, 2 GEGLU, 3 fast bf16 + LayerNorm records out, 4 fast bf16 + LayerNorm of A,
+               // 5 row-major then transposed columns through the staging tile (optional LayerNorm of A)
     dim3 grid;
     size_t smem;
 };

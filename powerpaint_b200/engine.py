@@ -78,7 +78,8 @@ class Plan:
         self.free: Dict[int, List[torch.Tensor]] = {}  # size -> raw blocks whose last reader has been recorded
         self.raw_of: Dict[int, torch.Tensor] = {}      # data_ptr of a live view -> its raw block
         self.chan_stats: Dict[int, tuple] = {}         # data_ptr of a tensor -> (partials, geometry) its producer emits
-        self.row_stats: Dict[int, torch.Tensor] = {}   # data_ptr of a tensor -> per-row LayerNorm records of its producer
+        self.row_stats: Dict[int, torch.Tensor] = {}   # data_ptr of a tensor -> per-row {rstd, -rstd mean} its producer leaves
+        self.row_ticket: Optional[torch.Tensor] = None  # arrival counters of the LayerNorm-statistics producers (kept at zero)
         self.scale_dev: Optional[torch.Tensor] = None  # eager side-net forward: 1-float conditioning scale
 
 
@@ -147,6 +148,8 @@ class NetEngine:
 
     # LayerNorm folded into the GEMMs either side of it (PP_B200_LN_FOLD=0: standalone LayerNorm kernel)
     LN_FOLD = os.environ.get("PP_B200_LN_FOLD", "1") != "0"
+    # to_q | to_k | to_v^T of a self-attention as one launch (PP_B200_QKV_MERGED=0: q|k and V^T separately)
+    QKV_MERGED = os.environ.get("PP_B200_QKV_MERGED", "1") != "0"
 
     def w_ln_folded(self, key: str, wnames, ln_name: str, bias_name: Optional[str] = None, geglu: bool = False):
         """Weights of the GEMM that consumes LayerNorm(x): y = LN(x) W^T + b = rstd (x W'^T - mean u) + b' with
@@ -319,13 +322,23 @@ class NetEngine:
                              alpha_step=alpha_step, alpha_stride=alpha_stride, ln=ln)
         if stats_hw:
             self._with_stats(plan, desc, out)
+        rec = None
         if row_stats:
             nrec = ops.gemm_row_stats_records(desc)
             if nrec > 0:
+                # per-row LayerNorm statistics of the output: the records are scratch of this one launch (the CTA
+                # finishing a row block folds them into `final`), the ticket array is shared by all producers of the plan
                 rec = self._buf(plan, nrec, M, 4, dtype=torch.float32)
-                ops.attach_row_stats(desc, rec)
-                plan.row_stats[out.data_ptr()] = rec
+                final = self._buf(plan, M, 2, dtype=torch.float32)
+                n_t = _ceil(M, 128) // 128
+                if plan.row_ticket is None or plan.row_ticket.numel() < n_t:
+                    plan.row_ticket = torch.zeros(max(n_t, 1024), dtype=torch.int32, device=self.device)
+                    plan.buffers.append(plan.row_ticket)
+                ops.attach_row_stats(desc, rec, final, plan.row_ticket, 1e-5)
+                plan.row_stats[out.data_ptr()] = final
         prog.add(desc)
+        if rec is not None:
+            self._free(plan, rec)
         return out
 
     def _ln_of(self, plan, x):
@@ -385,7 +398,28 @@ class NetEngine:
         # the consumers multiply the raw t0 by W * gamma and finish the normalisation in their epilogues
         rec = self._ln_of(plan, t0)
         vt = self._buf(plan, nb, C, hw_ld, dtype=torch.float16)  # fp16 V^T: P is fp16 in pp_attention
-        if rec is not None:
+        # to_q | to_k | to_v^T in ONE launch when the tiles line up (whole 128-token tiles per sample, the V columns
+        # start on a tile boundary): t0 is read once, the V tiles leave through a transposed staging tile
+        qkv_bn = 160 if C % 160 == 0 else 128 if C % 128 == 0 else 0
+        merged = self.QKV_MERGED and qkv_bn and hw % 128 == 0
+        if merged:
+            names = [b + ".attn1.to_q", b + ".attn1.to_k", b + ".attn1.to_v"]
+            if rec is not None:
+                wqkv, uqkv, bqkv = self.w_ln_folded(b + ".attn1.qkv", names, b + ".norm1")
+                a_in, ln1 = t0, (rec, uqkv, 1e-5)
+            else:
+                l1 = self._buf(plan, M, C)
+                prog.add_layer_norm(t0, l1, self.vec(b + ".norm1.weight"), self.vec(b + ".norm1.bias"), M, C, 1e-5)
+                wqkv = self._cached("qkv:" + b, lambda: torch.cat([self._raw(n + ".weight") for n in names], 0)
+                                    .to(BF16).contiguous())
+                bqkv, a_in, ln1 = None, l1, None
+            qk = self._buf(plan, M, 2 * C)
+            prog.add(ops.gemm_desc(a0=a_in, w=wqkv, out=qk, N_=3 * C, M=M, bias=bqkv, ln=ln1, block_n=qkv_bn,
+                                   epilogue=N.PP_EPI_ROWS_THEN_TRANSPOSED, out_t=vt, trans_from_col=2 * C, t_rows=hw,
+                                   t_ld=hw_ld, t_fp16=True))
+            if rec is None:
+                self._free(plan, a_in)
+        elif rec is not None:
             wqk, uqk, bqk = self.w_ln_folded(b + ".attn1.qk", [b + ".attn1.to_q", b + ".attn1.to_k"], b + ".norm1")
             wv, uv, bv = self.w_ln_folded(b + ".attn1.v", [b + ".attn1.to_v"], b + ".norm1")
             qk = self._linear(plan, prog, t0, M, None, 2 * C, w=wqk, bias=bqk, ln=(rec, uqk, 1e-5))

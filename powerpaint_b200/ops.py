@@ -99,9 +99,9 @@ def gemm_desc(*, a0: torch.Tensor, w: torch.Tensor, out: torch.Tensor, N_: int,
               out_fp32: bool = False, t_rows: int = 0, t_ld: int = 0, block_n: int = 0, t_fp16: bool = False,
               alpha_dev: Optional[torch.Tensor] = None, alpha_step: Optional[torch.Tensor] = None,
               alpha_stride: int = 0, chan_stats: Optional[torch.Tensor] = None,
-              ln: Optional[tuple] = None) -> Desc:
-    """`ln` = (records [nrec, ld, 4] fp32, u [N] fp32, eps): LayerNorm of A folded into the epilogue — `w` must
-    carry gamma (W * gamma) and `bias` the W @ beta term (include/powerpaint_b200.h)"""
+              ln: Optional[tuple] = None, out_t: Optional[torch.Tensor] = None, trans_from_col: int = 0) -> Desc:
+    """`ln` = (row stats [M, 2] fp32 = a producer's `row_final`, u [N] fp32, eps): LayerNorm of A folded into the
+    epilogue — `w` must carry gamma (W * gamma) and `bias` the W @ beta term (include/powerpaint_b200.h)"""
     d = N.GemmDesc()
     d.a_mode, d.epilogue = a_mode, epilogue
     d.a0, d.a1 = N.ptr(a0), N.ptr(a1)
@@ -119,22 +119,24 @@ def gemm_desc(*, a0: torch.Tensor, w: torch.Tensor, out: torch.Tensor, N_: int,
     d.res2, d.ldr2 = N.ptr(res2), (ldr2 or N_)
     d.alpha, d.act = alpha, act
     d.out = N.ptr(out)
-    d.ldc = ldc or (N_ // 2 if epilogue == N.PP_EPI_GEGLU else N_)
+    d.ldc = ldc or (N_ // 2 if epilogue == N.PP_EPI_GEGLU else trans_from_col if epilogue == N.PP_EPI_ROWS_THEN_TRANSPOSED
+                    else N_)
     d.out_fp32 = 1 if out_fp32 else 0
     d.t_rows, d.t_ld = t_rows, t_ld
     d.block_n = block_n
     d.t_fp16 = 1 if t_fp16 else 0
     d.alpha_dev, d.alpha_step, d.alpha_stride = N.ptr(alpha_dev), N.ptr(alpha_step), alpha_stride
     d.chan_stats = N.ptr(chan_stats)
-    keep = [a0, a1, w, out, bias, rowvec, res1, res2, alpha_dev, alpha_step, chan_stats]
+    d.out_t, d.trans_from_col = N.ptr(out_t), trans_from_col  # PP_EPI_ROWS_THEN_TRANSPOSED
+    keep = [a0, a1, w, out, bias, rowvec, res1, res2, alpha_dev, alpha_step, chan_stats, out_t]
     if ln is not None:
-        rec, u, eps = ln
-        if rec.dtype != torch.float32 or rec.dim() != 3 or rec.shape[-1] != 4 or not rec.is_contiguous():
-            raise ValueError("ln records must be a contiguous fp32 [nrec, ld, 4] tensor")
+        st, u, eps = ln
+        if st.dtype != torch.float32 or st.dim() != 2 or st.shape[-1] != 2 or st.shape[0] < M or not st.is_contiguous():
+            raise ValueError("ln row stats must be a contiguous fp32 [>= M, 2] tensor")
         if u.dtype != torch.float32 or u.numel() != N_ or not u.is_contiguous():
             raise ValueError("ln_u must be a contiguous fp32 [N] tensor")
-        d.ln_rec, d.ln_nrec, d.ln_ld, d.ln_u, d.ln_eps = N.ptr(rec), rec.shape[0], rec.shape[1], N.ptr(u), eps
-        keep += [rec, u]
+        d.ln_stats, d.ln_u, d.ln_eps = N.ptr(st), N.ptr(u), eps
+        keep += [st, u]
     return Desc("gemm", d, keep)
 
 
@@ -143,10 +145,14 @@ def gemm_row_stats_records(desc: Desc) -> int:
     return int(N.lib().pp_gemm_row_stats_records(C.byref(desc.c)))
 
 
-def attach_row_stats(desc: Desc, rec: torch.Tensor) -> None:
-    """rec: fp32 [records, ld, 4] with ld >= M"""
+def attach_row_stats(desc: Desc, rec: torch.Tensor, final: torch.Tensor, ticket: torch.Tensor, eps: float) -> None:
+    """rec: fp32 scratch [records, ld >= M, 4]; final: fp32 [>= M, 2] receives {rstd, -rstd * mean} per row; ticket: int32
+    [>= ceil(M / 128)], zero-initialised (the kernel leaves it at zero)"""
+    if final.dtype != torch.float32 or final.shape[-1] != 2 or not final.is_contiguous() or ticket.dtype != torch.int32:
+        raise ValueError("row_final must be contiguous fp32 [M, 2], row_ticket int32")
     desc.c.row_stats, desc.c.row_stats_ld = N.ptr(rec), rec.shape[1]
-    desc.keep.append(rec)
+    desc.c.row_final, desc.c.row_ticket, desc.c.ln_eps = N.ptr(final), N.ptr(ticket), eps
+    desc.keep += [rec, final, ticket]
 
 
 def gemm_stats_geometry(desc: Desc) -> "N.StatsGeom":

@@ -116,8 +116,8 @@ def ln_block(M, C, fold, part=None):
     ones, zeros = torch.ones(C, device=dev), torch.zeros(C, device=dev)
     if fold:
         nrec = ops.gemm_row_stats_records(pd)
-        rec = torch.empty(nrec, M, 4, device=dev)
-        ops.attach_row_stats(pd, rec)
+        rec = torch.empty(M, 2, device=dev)  # {rstd, -rstd * mean} per row, left by the producer
+        ops.attach_row_stats(pd, torch.empty(nrec, M, 4, device=dev), rec, torch.zeros(M // 128, dtype=torch.int32, device=dev), 1e-5)
         uqk, uv = wqk.float().sum(1).contiguous(), wv.float().sum(1).contiguous()
         d1 = ops.gemm_desc(a0=x, w=wqk, out=qk, N_=2 * C, M=M, bias=torch.zeros(2 * C, device=dev), ln=(rec, uqk, 1e-5))
         d2 = ops.gemm_desc(a0=x, w=wv, out=vt, N_=C, M=M, bias=zeros, epilogue=nat.PP_EPI_TRANSPOSED, t_rows=hw, t_ld=hw,
@@ -127,6 +127,21 @@ def ln_block(M, C, fold, part=None):
             ops.run(pd); ops.run(d1); ops.run(d2)
         if part == "producer":
             return lambda: ops.run(pd)
+        if part == "qkv":
+            ops.run(pd)
+            w3 = torch.cat([wqk, wv], 0).contiguous()
+            d3 = ops.gemm_desc(a0=x, w=w3, out=qk, N_=3 * C, M=M, bias=torch.zeros(3 * C, device=dev), block_n=160,
+                               ln=(rec, w3.float().sum(1).contiguous(), 1e-5), epilogue=nat.PP_EPI_ROWS_THEN_TRANSPOSED,
+                               out_t=vt, trans_from_col=2 * C, t_rows=hw, t_ld=hw, t_fp16=True)
+            return lambda: ops.run(d3)
+        if part == "geglu":
+            ops.run(pd)
+            wg, bg = ops.pack_geglu_weight(torch.randn(8 * C, C, device=dev, generator=g) / math.sqrt(C),
+                                           torch.zeros(8 * C, device=dev), 128)
+            ffh = torch.empty(M, 4 * C, device=dev, dtype=BF)
+            dg = ops.gemm_desc(a0=x, w=wg, out=ffh, N_=8 * C, M=M, bias=bg, epilogue=nat.PP_EPI_GEGLU, block_n=128,
+                               ln=(rec, wg.float().sum(1).contiguous(), 1e-5))
+            return lambda: ops.run(dg)
         if part == "qk":
             ops.run(pd)
             return lambda: ops.run(d1)
@@ -166,6 +181,8 @@ cases = [
     ("  folded: producer 320->320 + row records (mode 3)", ln_block(65536, 320, True, "producer"), 2 * 65536 * 320 * 320),
     ("  folded: q|k 320->640 (mode 4)", ln_block(65536, 320, True, "qk"), 2 * 65536 * 320 * 640),
     ("  folded: V^T 320->320 transposed (mode 1 + LN)", ln_block(65536, 320, True, "vt"), 2 * 65536 * 320 * 320),
+    ("  folded: q|k|v^T 320->960 one launch (mode 5 + LN)", ln_block(65536, 320, True, "qkv"), 2 * 65536 * 320 * 960),
+    ("  folded: geglu 320->2560 (mode 2 + LN)", ln_block(65536, 320, True, "geglu"), 2 * 65536 * 320 * 2560),
     ("geglu 320->2560 M=65536", linear(65536, 320, 2560, geglu=True), 2 * 65536 * 320 * 2560),
     ("linear 1280->320 M=65536", linear(65536, 1280, 320), 2 * 65536 * 1280 * 320),
     ("geglu 640->5120 M=16384", linear(16384, 640, 5120, geglu=True), 2 * 16384 * 640 * 5120),

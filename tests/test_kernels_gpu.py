@@ -595,22 +595,36 @@ def _producer_with_row_stats(ops, M, C, K, seed, offset=0.0, bn=0):
     nrec = ops.gemm_row_stats_records(d)
     assert nrec > 0
     rec = torch.full((nrec, M + 3, 4), float("nan"), device=_dev(), dtype=torch.float32)  # ld > M on purpose
-    ops.attach_row_stats(d, rec)
-    ops.run(d)
+    final = torch.full((M, 2), float("nan"), device=_dev(), dtype=torch.float32)
+    ticket = torch.zeros((M + 127) // 128, device=_dev(), dtype=torch.int32)
+    ops.attach_row_stats(d, rec, final, ticket, 1e-5)
+    for _ in range(2):  # twice: the tickets must be back at zero after a launch
+        ops.run(d)
     torch.cuda.synchronize()
+    assert (ticket == 0).all()
     ref = a.float() @ wp.float().t() + bias + res.float()
     assert _rel(x, ref) < 6e-3
-    return x, rec, ref
+    # {rstd, -rstd * mean} of the fp32 rows the epilogue computed
+    mean, var = ref.double().mean(1), ref.double().var(1, unbiased=False)
+    rstd = (var + 1e-5).rsqrt()
+    assert torch.isfinite(final).all()
+    assert ((final[:, 0].double() - rstd).abs() / rstd).max().item() < 2e-3
+    assert (final[:, 1].double() + rstd * mean).abs().max().item() < 2e-3 * (1 + (rstd * mean).abs().max().item())
+    return x, rec, ref, final
 
 
-@pytest.mark.parametrize("M,C,bn,offset", [(256, 320, 0, 0.0), (1000, 640, 0, 0.0), (300, 1280, 64, 0.0),
-                                           (128, 32, 0, 0.0), (512, 320, 256, 300.0)])
-def test_gemm_row_stats_records(ops, M, C, bn, offset):
+@pytest.mark.parametrize("M,C,bn,offset,K", [(256, 320, 0, 0.0, 192), (1000, 640, 0, 0.0, 192), (300, 1280, 64, 0.0, 192),
+                                             (128, 32, 0, 0.0, 192), (512, 320, 256, 300.0, 192),
+                                             # K = 1280 with paired m-tiles: without row_stats this launch would run in
+                                             # CTA-pair mode with another tile width — the record count must be the one of
+                                             # the launch that actually runs
+                                             (1024, 1280, 0, 0.0, 1280)])
+def test_gemm_row_stats_records(ops, M, C, bn, offset, K):
     """the records a producer emits combine to the mean / variance of the rows it computed — the fp32 values before
     the bf16 rounding of the store, which is what an fp32 LayerNorm of the exact activations would see (for a large
     common offset the stored bf16 values carry quantisation noise of their own: at 300 the bf16 step is 2) — also for
     a large common offset (shifted sums: no cancellation)"""
-    x, rec, xf32 = _producer_with_row_stats(ops, M, C, 192, M + C, offset, bn)
+    x, rec, xf32, _ = _producer_with_row_stats(ops, M, C, K, M + C, offset, bn)
     r = rec[:, :M].double()
     cnt = r[..., 3]
     assert torch.isfinite(r).all() and (cnt.sum(0) == C).all()
@@ -627,7 +641,7 @@ def test_gemm_row_stats_records(ops, M, C, bn, offset):
 def test_gemm_layer_norm_fold_plain(ops, M, C, N, bn):
     """LayerNorm(x) @ W^T + b with the LayerNorm applied algebraically in the consumer's epilogue, against
     F.layer_norm on the same bf16 x in fp32"""
-    x, rec, _ = _producer_with_row_stats(ops, M, C, 192, M + C + N)
+    x, _, _, rec = _producer_with_row_stats(ops, M, C, 192, M + C + N)
     g = torch.Generator(device="cuda").manual_seed(11)
     w = torch.randn(N, C, device=_dev(), generator=g) / math.sqrt(C)
     gamma = 1 + 0.3 * torch.randn(C, device=_dev(), generator=g)
@@ -646,7 +660,7 @@ def test_gemm_layer_norm_fold_transposed_and_geglu(ops):
     from powerpaint_b200 import _native as nat
 
     M, C, hw = 512, 320, 256
-    x, rec, _ = _producer_with_row_stats(ops, M, C, 320, 77)
+    x, _, _, rec = _producer_with_row_stats(ops, M, C, 320, 77)
     g = torch.Generator(device="cuda").manual_seed(12)
     gamma = 1 + 0.3 * torch.randn(C, device=_dev(), generator=g)
     beta = 0.3 * torch.randn(C, device=_dev(), generator=g)
@@ -674,3 +688,36 @@ def test_gemm_layer_norm_fold_transposed_and_geglu(ops):
     y = lnx @ wg.t() + bg
     ref = y[:, :Fh] * F.gelu(y[:, Fh:])
     assert _rel(out, ref) < 8e-3, _rel(out, ref)
+
+
+@pytest.mark.parametrize("M,C,hw,bn,fold", [(1024, 320, 256, 160, False), (1024, 320, 256, 160, True), (512, 128, 128, 128, True),
+                                            (2048, 640, 1024, 160, True)])
+def test_gemm_rows_then_transposed_qkv(ops, M, C, hw, bn, fold):
+    """to_q | to_k | to_v^T of one self-attention as ONE launch: columns [0, 2C) row-major bf16, columns [2C, 3C)
+    transposed fp16 through the staging tile (optionally with the LayerNorm fold), against the three separate products"""
+    from powerpaint_b200 import _native as nat
+
+    g = torch.Generator(device="cuda").manual_seed(M + C)
+    w = torch.randn(3 * C, C, device=_dev(), generator=g) / math.sqrt(C)
+    qk = torch.full((M, 2 * C), float("nan"), device=_dev(), dtype=BF16)
+    vt = torch.full((M // hw, C, hw), float("nan"), device=_dev(), dtype=torch.float16)
+    if fold:
+        x, _, _, rec = _producer_with_row_stats(ops, M, C, 192, 5 * M + C)
+        gamma = 1 + 0.3 * torch.randn(C, device=_dev(), generator=g)
+        beta = 0.3 * torch.randn(C, device=_dev(), generator=g)
+        wf, u, b = _ln_fold_pack(w, gamma, beta)
+        d = ops.gemm_desc(a0=x, w=wf, out=qk, N_=3 * C, M=M, bias=b, ln=(rec, u, 1e-5), block_n=bn,
+                          epilogue=nat.PP_EPI_ROWS_THEN_TRANSPOSED, out_t=vt, trans_from_col=2 * C, t_rows=hw, t_ld=hw,
+                          t_fp16=True)
+        ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5) @ w.t()
+    else:
+        x = torch.randn(M, C, device=_dev(), generator=g).to(BF16)
+        d = ops.gemm_desc(a0=x, w=w.to(BF16), out=qk, N_=3 * C, M=M, block_n=bn, epilogue=nat.PP_EPI_ROWS_THEN_TRANSPOSED,
+                          out_t=vt, trans_from_col=2 * C, t_rows=hw, t_ld=hw, t_fp16=True)
+        ref = x.float() @ w.to(BF16).float().t()
+    ops.run(d)
+    torch.cuda.synchronize()
+    assert torch.isfinite(qk.float()).all() and torch.isfinite(vt.float()).all()
+    assert _rel(qk, ref[:, :2 * C]) < 8e-3, _rel(qk, ref[:, :2 * C])
+    vref = ref[:, 2 * C:].view(M // hw, hw, C).transpose(1, 2)
+    assert _rel(vt, vref) < 8e-3, _rel(vt, vref)
