@@ -869,7 +869,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
             }
             if constexpr (MODE != 1) {
                 // the TMA unit must have read the previous tile out of the staging buffer before it is overwritten
-                if (etid == 0) bulk_wait_read_all();
+                if ((etid & 31) == 0) bulk_wait_read_all();  // every thread that issued a sub-tile store waits for its own
                 if (etid == 0) GT(lt, 9);  // previous staged tile consumed by the TMA unit
             }
             epi_sync();
@@ -945,38 +945,40 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 }
                 constexpr int OUT_COLS = MODE == 2 ? BLOCK_N / 2 : BLOCK_N;
                 constexpr int PIECES = OUT_COLS / 8;
-                if (etid == 0) {
+                // one thread per 64-column sub-tile (lane 0 of the first warps) issues its store: a single thread issuing
+                // three stores back to back took ~600 cycles of the epilogue's serial path
+                if ((etid & 31) == 0 && (etid >> 5) * 64 < (MODE == 5 ? BLOCK_N : OUT_COLS)) {
+                    const int sub = etid >> 5;
                     const int out_base = n_tile * OUT_COLS;
                     const int n_out = MODE == 2 ? p.N / 2 : MODE == 5 ? p.trans_first_tile * BLOCK_N : p.N;
-                    int x0 = 0, y0 = 0, nb0 = 0;
-                    if (p.a_mode != PP_A_MATRIX) tile_origin(m_tile, x0, y0, nb0);
                     if (MODE == 5 && ttile) {
                         // (token, channel, sample) coordinates of the transposed destination; tiles never straddle samples
                         const int row0 = m_tile * BLOCK_M;
                         const int sb = row0 / p.t_rows, t0 = row0 - sb * p.t_rows;
                         const int cbase = (n_tile - p.trans_first_tile) * BLOCK_N;
-#pragma unroll
-                        for (int sub = 0; sub * 64 < BLOCK_N; ++sub) {
-                            if (n_base + sub * 64 >= p.N) break;
+                        if (n_base + sub * 64 < p.N) {
                             const CUtensorMap* tm = (BLOCK_N - sub * 64) >= 64 ? &p.tmOutT[0] : &p.tmOutT[1];
 #ifndef GEMM_EXP_NOSTORE
                             tma_store_3d(tm, s_out_addr + sub * 16384, t0, cbase + sub * 64, sb);
 #endif
                         }
                     } else {
-#pragma unroll
-                        for (int sub = 0; sub * 64 < OUT_COLS; ++sub) {
-                            const int col = out_base + sub * 64;
-                            if (col >= n_out) break;
+                        const int col = out_base + sub * 64;
+                        if (col < n_out) {
                             const CUtensorMap* tm = (OUT_COLS - sub * 64) >= 64 ? &p.tmOut[0] : &p.tmOut[1];
 #ifndef GEMM_EXP_NOSTORE  // experiment: no global write of the tile
-                            if (p.a_mode == PP_A_MATRIX) tma_store_2d(tm, s_out_addr + sub * 16384, col, m_tile * BLOCK_M);
-                            else tma_store_4d(tm, s_out_addr + sub * 16384, col, x0, y0, nb0);
+                            if (p.a_mode == PP_A_MATRIX) {
+                                tma_store_2d(tm, s_out_addr + sub * 16384, col, m_tile * BLOCK_M);
+                            } else {
+                                int x0, y0, nb0;
+                                tile_origin(m_tile, x0, y0, nb0);
+                                tma_store_4d(tm, s_out_addr + sub * 16384, col, x0, y0, nb0);
+                            }
 #endif
                         }
                     }
                     bulk_commit_group();
-                    GT(lt, 8);  // TMA stores issued
+                    if (etid == 0) GT(lt, 8);  // TMA stores issued
                 }
                 if constexpr (MODE == 0 || MODE == 3 || MODE == 4) {  // (never mode 5: transposed tiles hold no rows)
                     // GroupNorm partial sums of exactly the bf16 values the consumer will read
@@ -1026,7 +1028,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
             if (etid == 0) GT(lt, 10);
         }
         if constexpr (MODE != 1) {
-            if (etid == 0) bulk_wait_all();  // global writes of the last tile performed before the CTA retires
+            if ((etid & 31) == 0) bulk_wait_all();  // global writes of the last tile performed before the CTA retires
         }
     }
 
