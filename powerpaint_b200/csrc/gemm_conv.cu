@@ -287,7 +287,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
     const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
 
     extern __shared__ uint8_t smem_raw[];
-    __shared__ int s_last_tile;  // mode 3: this CTA finished the last n-tile of its current row block
+    // mode 3 (LayerNorm-statistics producer): mailbox between the epilogue and the ticket-server lane, and the verdict
+    // ("this CTA finished the last n-tile of the row block") of the tile whose records are folded next
+    __shared__ volatile int s_req_seq, s_req_mtile, s_resp_seq, s_resp_last;
+    __shared__ int s_last_tile;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = smem_base;
     const uint32_t sB = sA + STAGES * A_STAGE_BYTES;
@@ -339,6 +342,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
             mbar_init(tmem_empty_bar(a), GEMM_EPI_WARPS * CG);  // pair mode: both CTAs' epilogue warps, on the leader's
         }
         fence_mbar_init();
+        if constexpr (MODE == 3) { s_req_seq = 0; s_resp_seq = 0; s_req_mtile = 0; s_resp_last = 0; }
     }
     if (warp == W_MMA) {
         if constexpr (CG == 2) {
@@ -371,7 +375,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
 
     if (warp == W_PROD) {
         // ===================== TMA producer =====================
-        if (elect_one()) {
+        // mode 3: lane 0 produces and lane 31 serves the row-block tickets. The ticket of a tile (fence + atomic round
+        // trip, ~1500 cycles) used to sit between the epilogue's two barriers; the server takes it while the epilogue
+        // is already in the next tile, which collects the verdict at its first barrier.
+        const bool is_producer = MODE == 3 ? lane_id() == 0 : elect_one();
+        if (MODE == 3 && lane_id() == 31) {
+            for (int seq = 1;; ++seq) {
+                const uint64_t t0 = global_timer_ns();
+                uint32_t spins = 0;
+                while (s_req_seq < seq) {
+                    __nanosleep(40);
+                    if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > PP_WAIT_TIMEOUT_NS) {
+                        printf("pp: ticket server timed out (block %d seq %d)\n", blockIdx.x, seq);
+                        __trap();
+                    }
+                }
+                __threadfence_block();
+                const int mt = s_req_mtile;
+                if (mt < 0) break;  // the epilogue is done
+                // the epilogue's barrier ordered every warp's record stores before the request; this fence is
+                // cumulative, so they are visible device-wide before the ticket is
+                __threadfence();
+                const int t = atomicAdd(p.row_ticket + mt, 1);
+                if (t == n_tiles - 1) p.row_ticket[mt] = 0;  // ready for the next launch
+                s_resp_last = (t == n_tiles - 1) ? 1 : 0;
+                __threadfence_block();
+                s_resp_seq = seq;
+            }
+        }
+        if (is_producer) {
             const int cpt = p.chunks0 + p.chunks1;  // chunks per tap
             int s = 0;                              // ring slot and its phase, carried across tiles
             uint32_t ph = 0;
@@ -529,6 +561,53 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
             const int64_t row0 = (int64_t)(tw.m * CG + (int)cta_rank) * BLOCK_M + r;
             if (row0 < p.M) ln_cur = __ldg(p.ln_stats + row0);
         }
+        // ---- mode 3: verdict of the ticket server for request number `seq`, and the fold of a row's records
+        int64_t prev_row = 0;
+        bool prev_valid = false;
+        auto ticket_verdict = [&](int seq) -> int {
+            const uint64_t t0 = global_timer_ns();
+            uint32_t spins = 0;
+            while (s_resp_seq < seq) {
+                if ((++spins & 0xFFFu) == 0 && global_timer_ns() - t0 > PP_WAIT_TIMEOUT_NS) {
+                    printf("pp: ticket verdict timed out (block %d seq %d)\n", blockIdx.x, seq);
+                    __trap();
+                }
+            }
+            __threadfence_block();
+            return s_resp_last;
+        };
+        auto fold_row_records = [&](const float4 (&first)[4], int64_t frow) {
+            // Chan's combination of the (count, mean, M2) of the row's half-tile records -> {rstd, -rstd * mean}
+            float cnt = 0.f, mean = 0.f, m2 = 0.f;
+            auto fold = [&](const float4& rc) {
+                if (rc.w > 0.f) {
+                    const float inv = __fdividef(1.f, rc.w);
+                    const float mi = fmaf(rc.x, inv, rc.z);
+                    const float m2i = fmaxf(fmaf(-rc.x * inv, rc.x, rc.y), 0.f);
+                    const float tot = cnt + rc.w;
+                    const float wgt = __fdividef(rc.w, tot);
+                    const float dl = mi - mean;
+                    mean = fmaf(dl, wgt, mean);
+                    m2 += m2i + dl * dl * cnt * wgt;
+                    cnt = tot;
+                }
+            };
+#pragma unroll
+            for (int u = 0; u < 4; ++u) fold(first[u]);
+            const int nrec = 2 * n_tiles;
+            for (int i0 = 4; i0 < nrec; i0 += 4) {
+                float4 rc[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    rc[u] = i0 + u < nrec ? __ldcg(p.row_stats + (int64_t)(i0 + u) * p.row_stats_ld + frow)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) fold(rc[u]);
+            }
+            const float var = cnt > 0.f ? __fdividef(m2, cnt) : 0.f;
+            const float rs = rsqrtf(var + p.ln_eps);
+            p.row_final[frow] = make_float2(rs, -rs * mean);
+        };
         uint32_t lt = 0;
         for (int tile = walk_first; tile < num_tiles; tile += walk_stride, ++lt) {
             const int n_tile = tw.n, m_tile = tw.m * CG + (int)cta_rank;
@@ -872,7 +951,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 if ((etid & 31) == 0) bulk_wait_read_all();  // every thread that issued a sub-tile store waits for its own
                 if (etid == 0) GT(lt, 9);  // previous staged tile consumed by the TMA unit
             }
+            if constexpr (MODE == 3) {
+                if (etid == 0 && lt > 0) s_last_tile = ticket_verdict((int)lt);  // of tile lt - 1 (request number lt)
+            }
             epi_sync();
+            // mode 3: the previous tile was the last n-tile of its row block -> fold the block's records (first four loads
+            // now, the arithmetic after the hand-over to the TMA unit); then post this tile's ticket request
+            float4 frc[4];
+            bool fold_prev = false;
+            if constexpr (MODE == 3) {
+                fold_prev = lt > 0 && s_last_tile != 0 && half == 0 && prev_valid;
+                if (fold_prev) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        frc[u] = u < 2 * n_tiles ? __ldcg(p.row_stats + (int64_t)u * p.row_stats_ld + prev_row)
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (etid == 0) {
+                    s_req_mtile = m_tile;
+                    __threadfence_block();
+                    s_req_seq = (int)lt + 1;
+                }
+            }
             if constexpr (MODE != 1) {
                 // stage the tile (generic-proxy writes -> async proxy), one barrier, one thread issues the TMA stores
                 // (one per sub-tile); the unit writes whole rows and clips out-of-range parts
@@ -898,51 +998,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 }
                 fence_proxy_async_smem();
                 if (half == 0) s_row[r] = valid ? (long long)row : -1ll;
-                if constexpr (MODE == 3) {
-                    // every warp's records were written before the barrier above: the CTA that takes the last
-                    // ticket of this 128-row block folds the block's records into {rstd, -rstd * mean} per row
-                    if (etid == 0) {
-                        // the barrier above ordered every warp's record stores before this thread; its fence is
-                        // cumulative, so they are visible device-wide before the ticket is (one fence, not 256)
-                        __threadfence();
-                        const int t = atomicAdd(p.row_ticket + m_tile, 1);
-                        s_last_tile = (t == n_tiles - 1) ? 1 : 0;
-                        if (t == n_tiles - 1) p.row_ticket[m_tile] = 0;  // ready for the next launch
-                    }
-                }
                 epi_sync();
                 if (etid == 0) GT(lt, 7);  // all epilogue warps staged
-                if constexpr (MODE == 3) {
-                    if (s_last_tile && half == 0 && valid) {
-                        __threadfence();
-                        const int nrec = 2 * n_tiles;
-                        float cnt = 0.f, mean = 0.f, m2 = 0.f;
-                        for (int i0 = 0; i0 < nrec; i0 += 4) {
-                            float4 rc[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)  // four independent L2 loads in flight (nrec is even, mostly 4)
-                                rc[u] = i0 + u < nrec ? __ldcg(p.row_stats + (int64_t)(i0 + u) * p.row_stats_ld + row)
-                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                if (rc[u].w > 0.f) {  // Chan's combination of (count, mean, M2)
-                                    const float inv = __fdividef(1.f, rc[u].w);
-                                    const float mi = fmaf(rc[u].x, inv, rc[u].z);
-                                    const float m2i = fmaxf(fmaf(-rc[u].x * inv, rc[u].x, rc[u].y), 0.f);
-                                    const float tot = cnt + rc[u].w;
-                                    const float wgt = __fdividef(rc[u].w, tot);
-                                    const float dl = mi - mean;
-                                    mean = fmaf(dl, wgt, mean);
-                                    m2 += m2i + dl * dl * cnt * wgt;
-                                    cnt = tot;
-                                }
-                            }
-                        }
-                        const float var = cnt > 0.f ? __fdividef(m2, cnt) : 0.f;
-                        const float rs = rsqrtf(var + p.ln_eps);
-                        p.row_final[row] = make_float2(rs, -rs * mean);
-                    }
-                }
                 constexpr int OUT_COLS = MODE == 2 ? BLOCK_N / 2 : BLOCK_N;
                 constexpr int PIECES = OUT_COLS / 8;
                 // one thread per 64-column sub-tile (lane 0 of the first warps) issues its store: a single thread issuing
@@ -979,6 +1036,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                     }
                     bulk_commit_group();
                     if (etid == 0) GT(lt, 8);  // TMA stores issued
+                }
+                if constexpr (MODE == 3) {
+                    if (fold_prev) fold_row_records(frc, prev_row);
+                    prev_row = row;
+                    prev_valid = valid;
                 }
                 if constexpr (MODE == 0 || MODE == 3 || MODE == 4) {  // (never mode 5: transposed tiles hold no rows)
                     // GroupNorm partial sums of exactly the bf16 values the consumer will read
@@ -1026,6 +1088,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 }
             }
             if (etid == 0) GT(lt, 10);
+        }
+        if constexpr (MODE == 3) {
+            // the last tile's verdict and fold, then release the ticket server
+            if (etid == 0 && lt > 0) s_last_tile = ticket_verdict((int)lt);
+            epi_sync();
+            if (lt > 0 && s_last_tile != 0 && half == 0 && prev_valid) {
+                float4 frc[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    frc[u] = u < 2 * n_tiles ? __ldcg(p.row_stats + (int64_t)u * p.row_stats_ld + prev_row)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                fold_row_records(frc, prev_row);
+            }
+            if (etid == 0) {
+                s_req_mtile = -1;
+                __threadfence_block();
+                s_req_seq = (int)lt + 1;
+            }
         }
         if constexpr (MODE != 1) {
             if ((etid & 31) == 0) bulk_wait_all();  // global writes of the last tile performed before the CTA retires
