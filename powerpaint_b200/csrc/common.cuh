@@ -197,6 +197,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src,
                  "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
+// asynchronous 4-byte global -> shared copy (LDGSTS: no register, nothing to wait for until cp_async_wait_all)
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk groups have finished READING their shared-memory source (it may be overwritten)
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

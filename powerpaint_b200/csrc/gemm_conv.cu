@@ -37,10 +37,10 @@
 
 // -DGEMM_TRACE: CTA 0 records clock64() at the role hand-overs of its first tiles (profiles/gemm_trace.py reads them)
 #ifdef GEMM_TRACE
-__device__ long long g_gemm_trace[64 * 16];
+__device__ long long g_gemm_trace[64 * 32];
 #define GT(tile_local, slot)                                                                     \
     do {                                                                                         \
-        if (blockIdx.x == 0 && (tile_local) < 64) g_gemm_trace[(tile_local) * 16 + (slot)] = clock64(); \
+        if (blockIdx.x == 0 && (tile_local) < 64) g_gemm_trace[(tile_local) * 32 + (slot)] = clock64(); \
     } while (0)
 extern "C" int pp_debug_gemm_trace(long long* host_out, int n) {
     return (int)cudaMemcpyFromSymbol(host_out, g_gemm_trace, sizeof(long long) * (size_t)n);
@@ -610,16 +610,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
         };
         uint32_t lt = 0;
         for (int tile = walk_first; tile < num_tiles; tile += walk_stride, ++lt) {
+            if (etid == 0) GT(lt, 15);  // top of the tile
             const int n_tile = tw.n, m_tile = tw.m * CG + (int)cta_rank;
             tw.next();  // now at the tile after this one
             const uint32_t acc = lt & 1u;
             const uint32_t acc_ph = (lt >> 1) & 1u;
             const float* sbias = sbias_all + acc * BLOCK_N;
             const float* su = su_all + acc * BLOCK_N;
-            // bias of the next tile: issue the load now, park it in smem at the end of this tile
+            // bias (and LayerNorm weight row sums) of the NEXT tile: an asynchronous global -> shared copy straight into the
+            // other staging buffer (its readers, tile lt - 1, are all past that tile's second barrier). A value loaded
+            // into a register here had to live across the whole tile; with the kernel at its register cap it was spilled
+            // at once, which made every thread wait ~700 cycles for the load right here, in front of each tile.
             const int next_tile = tile + walk_stride;
-            const float bias_next = next_tile < num_tiles ? load_bias(tw.n) : 0.f;
-            const float u_next = next_tile < num_tiles ? load_u(tw.n) : 0.f;
+            if (etid < BLOCK_N) {
+                const int nn = tw.n * BLOCK_N + etid;
+                float* db = sbias_all + (acc ^ 1u) * BLOCK_N + etid;
+                float* du = su_all + (acc ^ 1u) * BLOCK_N + etid;
+                if (next_tile < num_tiles && p.bias && nn < p.N) cp_async_f32(db, p.bias + nn);
+                else *db = 0.f;
+                if (next_tile < num_tiles && ln && nn < p.N) cp_async_f32(du, p.ln_u + nn);
+                else *du = 0.f;
+            }
+            if (etid == 0) GT(lt, 16);
             // output row of this thread
             bool valid;
             int64_t row;
@@ -640,6 +652,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 row = ((int64_t)on * p.ho + oy) * p.wo + ox;
                 grp = on;
             }
+            if (etid == 0) GT(lt, 17);
             const int n_base = n_tile * BLOCK_N;
             const uint32_t taddr = tmem_base + lane_addr + acc * BLOCK_N;
             // mode 5: this tile's columns are stored transposed ([channel][token], V^T for the attention kernel)
@@ -666,8 +679,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
 #pragma unroll
                 for (int k = 0; k < BLOCK_N / 64; ++k) {
                     const int c0 = half * 16 + 32 * k;
+                    // one tensor-memory load in flight per warp: two collapse the read rate (profiles/ubench/tmem_rates:
+                    // 173 cycles for one x32 load, ~1000 for two issued back to back by each of 4 warps)
                     uint32_t ra[16], rg[16];
                     tmem_ld16(taddr + c0, ra);
+                    tmem_wait_ld();
                     tmem_ld16(taddr + HALF + c0, rg);
                     tmem_wait_ld();
                     pk[2 * k] = pk[2 * k + 1] = make_uint4(0u, 0u, 0u, 0u);
@@ -715,6 +731,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 // the four 8-column groups of a chunk are independent straight-line code: the common
                 // case (tile fully inside the matrix, all 32 rows of the warp valid) has no per-group
                 // branches at all, and launches without residual / row-vector terms skip those adds.
+                if (etid == 0) GT(lt, 18);
                 const float alpha = effective_alpha(p);
                 const bool has_r1 = p.res1 != nullptr, has_r2 = p.res2 != nullptr, has_rv = p.rowvec != nullptr;
                 const int act = p.act;
@@ -724,6 +741,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 const int ncols = min(BLOCK_N, p.N - n_base);  // multiple of 8
                 const bool full = ncols == BLOCK_N && __all_sync(0xffffffffu, valid);
                 const bool plain = !has_r1 && !has_r2 && !has_rv;
+                if (etid == 0) GT(lt, 14);  // tile set-up done, about to wait for the accumulator
                 mbar_wait(tmem_full_bar(acc), acc_ph);
                 if (etid == 0) GT(lt, 5);  // accumulator ready (epilogue thread 0)
                 tc_fence_after();
@@ -940,12 +958,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty_bar(acc) & PP_PEER_BIT_MASK);  // the leader's barrier
                 else mbar_arrive(tmem_empty_bar(acc));
             }
-            // park the next tile's bias in the other staging buffer: its last readers (tile lt - 1) all passed that
-            // tile's second barrier, and the barrier below orders these writes before tile lt + 1 reads them
-            if (etid < BLOCK_N) {
-                sbias_all[(acc ^ 1u) * BLOCK_N + etid] = bias_next;
-                su_all[(acc ^ 1u) * BLOCK_N + etid] = u_next;
-            }
+            // the next tile's bias has landed in the other staging buffer (asynchronous copies issued at the top of this
+            // tile); the barrier below publishes it before tile lt + 1 reads it
+            cp_async_wait_all();
             if constexpr (MODE != 1) {
                 // the TMA unit must have read the previous tile out of the staging buffer before it is overwritten
                 if ((etid & 31) == 0) bulk_wait_read_all();  // every thread that issued a sub-tile store waits for its own
@@ -955,6 +970,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 if (etid == 0 && lt > 0) s_last_tile = ticket_verdict((int)lt);  // of tile lt - 1 (request number lt)
             }
             epi_sync();
+            if (etid == 0) GT(lt, 11);  // first barrier passed
             // mode 3: the previous tile was the last n-tile of its row block -> fold the block's records (first four loads
             // now, the arithmetic after the hand-over to the TMA unit); then post this tile's ticket request
             float4 frc[4];
@@ -996,7 +1012,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                         *reinterpret_cast<uint4*>(stage_ptr(r, col)) = pk[i];
                     }
                 }
+                if (etid == 0) GT(lt, 12);  // staging stores issued
                 fence_proxy_async_smem();
+                if (etid == 0) GT(lt, 13);  // proxy fence done
                 if (half == 0) s_row[r] = valid ? (long long)row : -1ll;
                 epi_sync();
                 if (etid == 0) GT(lt, 7);  // all epilogue warps staged

@@ -170,7 +170,9 @@ class NetEngine:
             return wf.contiguous(), u.float().contiguous(), b.float().contiguous()
         return self._cached("lnf:" + key, make)
 
-    GEGLU_BLOCK_N = 128
+    # tile width of the GEGLU GEMMs (weights are interleaved per tile; 256: the fixed per-tile cost of the epilogue is paid half
+    # as often: 118 -> 108 us at 320 -> 2560, M = 65536). PP_B200_GEGLU_BN=128|256
+    GEGLU_BLOCK_N = int(os.environ.get("PP_B200_GEGLU_BN", "256"))
 
     def w_geglu(self, name: str):
         def make():

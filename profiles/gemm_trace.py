@@ -6,7 +6,8 @@
 Columns (cycles relative to the producer's first TMA issue of tile 0):
   P0/P1  producer: first / last TMA issue of the tile      M2 accumulator stage free   M3 first smem stage full
   M4 last k-iteration's stage full (its MMAs issue now)    E5 accumulator ready (epilogue)   E6 tile math done + staged
-  E7 all epilogue warps staged   E8 TMA stores issued   E9 staged tile read by the TMA unit   E10 after the closing barrier
+  E9 previous staged tile read by the TMA unit   B1 first barrier   STG staging stores issued   FNC proxy fence done
+  E7 second barrier (all warps staged)   E8 TMA stores issued   E10 end of tile   SET next tile set up, about to wait for its accumulator
 """
 import ctypes
 import math
@@ -45,13 +46,13 @@ for _ in range(3):
     ops.run(d)
 torch.cuda.synchronize()
 lib = ctypes.CDLL(str(nat.lib_path()))
-n = 64 * 16
+n = 64 * 32
 buf = (ctypes.c_longlong * n)()
 rc = lib.pp_debug_gemm_trace(buf, n)
 assert rc == 0, rc
-t = [[buf[i * 16 + j] for j in range(11)] for i in range(10)]
+t = [[buf[i * 32 + j] for j in range(19)] for i in range(10)]
 t0 = t[0][0]
-names = ["P0", "P1", "M2", "M3", "M4", "E5", "E6", "E7", "E8", "E9", "E10"]
+names = ["P0", "P1", "M2", "M3", "M4", "E5", "E6", "E7", "E8", "E9", "E10", "B1", "STG", "FNC", "SET", "TOP", "T16", "T17", "T18"]
 print(what, " ".join(f"{n_:>7s}" for n_ in names))
 for i, row in enumerate(t):
     if row[0] == 0 and i > 0:

@@ -30,10 +30,11 @@ def conv(nb, h, w, cin, cout, bn=0):
 def linear(M, K, N, geglu=False, bn=0):
     a = torch.randn(M, K, device=dev, generator=g).to(BF)
     if geglu:
+        gbn = bn or 128
         w, b = ops.pack_geglu_weight(torch.randn(N, K, device=dev, generator=g) / math.sqrt(K),
-                                     torch.zeros(N, device=dev), 128)
+                                     torch.zeros(N, device=dev), gbn)
         out = torch.empty(M, N // 2, device=dev, dtype=BF)
-        d = ops.gemm_desc(a0=a, w=w, out=out, N_=N, M=M, bias=b, epilogue=nat.PP_EPI_GEGLU, block_n=128)
+        d = ops.gemm_desc(a0=a, w=w, out=out, N_=N, M=M, bias=b, epilogue=nat.PP_EPI_GEGLU, block_n=gbn)
     else:
         w = (torch.randn(N, K, device=dev, generator=g) / math.sqrt(K)).to(BF)
         out = torch.empty(M, N, device=dev, dtype=BF)
@@ -186,6 +187,10 @@ cases = [
     ("geglu 320->2560 M=65536", linear(65536, 320, 2560, geglu=True), 2 * 65536 * 320 * 2560),
     ("linear 1280->320 M=65536", linear(65536, 1280, 320), 2 * 65536 * 1280 * 320),
     ("geglu 640->5120 M=16384", linear(16384, 640, 5120, geglu=True), 2 * 16384 * 640 * 5120),
+    ("geglu 320->2560 M=65536 tile 256", linear(65536, 320, 2560, geglu=True, bn=256), 2 * 65536 * 320 * 2560),
+    ("geglu 640->5120 M=16384 tile 256", linear(16384, 640, 5120, geglu=True, bn=256), 2 * 16384 * 640 * 5120),
+    ("geglu 1280->10240 M=4096", linear(4096, 1280, 10240, geglu=True), 2 * 4096 * 1280 * 10240),
+    ("geglu 1280->10240 M=4096 tile 256", linear(4096, 1280, 10240, geglu=True, bn=256), 2 * 4096 * 1280 * 10240),
     ("self-attn d40 N=4096 b16", attn(16, 8, 40, 4096, 4096), 4 * 16 * 8 * 4096 * 4096 * 40),
     ("cross-attn d40 N=4096x77 b16", attn(16, 8, 40, 4096, 77), 4 * 16 * 8 * 4096 * 77 * 40),
     ("self-attn d80 N=1024 b16", attn(16, 8, 80, 1024, 1024), 4 * 16 * 8 * 1024 * 1024 * 80),
