@@ -69,9 +69,13 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
     auto bar_kv_full = [&](int s) { return bars + 8u * (1 + s); };
     auto bar_kv_empty = [&](int s) { return bars + 8u * (1 + MAXS + s); };
     auto bar_s_full = [&](int i) { return bars + 8u * (1 + 2 * MAXS + i); };
-    auto bar_p_full = [&](int t) { return bars + 8u * (7 + 2 * MAXS + t); };
-    auto bar_pv_done = [&](int t) { return bars + 8u * (9 + 2 * MAXS + t); };
-    const uint32_t tmem_slot = bars + 8u * (11 + 2 * MAXS);
+    // P hand-over barriers: one per (tile, key-block parity). With three score buffers a softmax warp can be a whole key
+    // block ahead of a slower warp of its group (never two: S of block j + 2 needs PV(j + 1), i.e. every warp's P(j + 1));
+    // on a single barrier its arrival for block j + 1 could complete the 4-count phase of block j and release PV(j) over
+    // raw scores (NaN rows at 16384 tokens, r02). Alternating barriers keep the two blocks' arrivals apart for free.
+    auto bar_p_full = [&](int t, int j) { return bars + 8u * (7 + 2 * MAXS + 2 * t + (j & 1)); };
+    auto bar_pv_done = [&](int t) { return bars + 8u * (11 + 2 * MAXS + t); };
+    const uint32_t tmem_slot = bars + 8u * (13 + 2 * MAXS);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
 
     const int warp = threadIdx.x >> 5;
@@ -93,7 +97,8 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
             mbar_init(bar_s_full(i), 1);
         }
         for (int t = 0; t < 2; ++t) {
-            mbar_init(bar_p_full(t), 4);
+            mbar_init(bar_p_full(t, 0), 4);
+            mbar_init(bar_p_full(t, 1), 4);
             mbar_init(bar_pv_done(t), 1);
         }
         fence_mbar_init();
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
             for (int k = 0; k < NBUF && k < nprod; ++k) issue_s(k);
             for (int k = 0; k < nprod; ++k) {
                 const int j = k >> 1, t = k & 1;
-                mbar_wait(bar_p_full(t), j & 1);
+                mbar_wait(bar_p_full(t, j), (j >> 1) & 1);
                 tc_fence_after();
                 issue_pv(k);
                 if (t == 1) umma_commit(bar_kv_empty(j % S));  // both tiles' PV(j) precede this commit
@@ -321,16 +326,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
             }
             tc_fence_before();
             __syncwarp();
-            if (lane_id() == 0) {
-                // With three score buffers the scores of block j + 1 are in tensor memory before the group has
-                // finished block j, so a fast warp can run a whole block ahead of a slow one; its arrival for block
-                // j + 1 would then complete the 4-count phase of block j and release PV(j) while the slow warp's rows
-                // of P(j) are still raw scores (seen as NaN rows at 16384 tokens, where 128 blocks give the warps time
-                // to drift). A warp therefore hands over block j only once the whole group has handed over block j - 1.
-                // (NBUF == 2: S(k + 2) is issued after PV(k), which needs all four warps — no run-ahead.)
-                if (NBUF == 3 && j > 0) mbar_wait(bar_p_full(t), (j - 1) & 1);
-                mbar_arrive(bar_p_full(t));
-            }
+            if (lane_id() == 0) mbar_arrive(bar_p_full(t, j));
         }
         // epilogue: O[:, :d] / O[:, d]
         mbar_wait(bar_pv_done(t), (nkv - 1) & 1);
