@@ -162,11 +162,19 @@ typedef struct pp_gemm_desc {
        width: pass block_n explicitly). t_rows must be a multiple of 128 and divide M. */
     void* out_t;
     int32_t trans_from_col;
+    /* optional split-K x2 for long-K launches whose tiles fill at most half of the GPU (8x8-resolution layers): fp32
+       workspace of pp_gemm_splitk_bytes(desc) bytes and the same number of tiles of zero-initialised int32 flags (the
+       kernel leaves them at zero). NULL: never split. Results are deterministic (owner + donor, fixed order). */
+    float* splitk_ws;
+    int32_t* splitk_flags;
 } pp_gemm_desc;
 
 pp_status pp_gemm_conv(const pp_gemm_desc* d, pp_stream stream);
 /* host-only query: can this GEMM emit GroupNorm partial sums, and with which layout */
 pp_status pp_gemm_stats_geometry(const pp_gemm_desc* d, pp_stats_geom* out);
+/* host-only query: bytes of split-K workspace this launch could use (0: it would not split); flags: one int32 per
+   (m-tile, n-tile), i.e. bytes / (128 * block_n * 4) of them — pass `*tiles_out` to size the flag array */
+int64_t pp_gemm_splitk_bytes(const pp_gemm_desc* d, int32_t* tiles_out);
 /* host-only query: number of per-row LayerNorm records this GEMM emits through row_stats (0: it cannot emit them) */
 int32_t pp_gemm_row_stats_records(const pp_gemm_desc* d);
 

@@ -19,7 +19,7 @@ _lib = None
 PP_A_MATRIX, PP_A_CONV3X3, PP_A_CONV3X3_S2, PP_A_CONV3X3_S2P0 = 0, 1, 2, 3
 PP_EPI_PLAIN, PP_EPI_GEGLU, PP_EPI_TRANSPOSED, PP_EPI_ROWS_THEN_TRANSPOSED = 0, 1, 2, 3
 PP_ACT_NONE, PP_ACT_SILU, PP_ACT_QUICK_GELU = 0, 1, 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 vp = C.c_void_p
 i32 = C.c_int32
@@ -56,6 +56,7 @@ class GemmDesc(C.Structure):
         ("row_stats", vp), ("row_stats_ld", i64), ("row_final", vp), ("row_ticket", vp),
         ("ln_stats", vp), ("ln_u", vp), ("ln_eps", f32),
         ("out_t", vp), ("trans_from_col", i32),
+        ("splitk_ws", vp), ("splitk_flags", vp),
     ]
 
 
@@ -109,6 +110,7 @@ _SIGNATURES = {
     "pp_gemm_conv": (C.c_int, [C.POINTER(GemmDesc), vp]),
     "pp_gemm_stats_geometry": (C.c_int, [C.POINTER(GemmDesc), C.POINTER(StatsGeom)]),
     "pp_gemm_row_stats_records": (i32, [C.POINTER(GemmDesc)]),
+    "pp_gemm_splitk_bytes": (i64, [C.POINTER(GemmDesc), C.POINTER(i32)]),
     "pp_attention": (C.c_int, [C.POINTER(AttnDesc), vp]),
     "pp_group_norm": (C.c_int, [C.POINTER(GnDesc), vp]),
     "pp_group_norm_scratch_bytes": (i64, [i32, i32, i32, i32]),

@@ -279,12 +279,14 @@ __host__ __device__ constexpr int out_stage_bytes_for(int block_n) {
 // writes next to the operand reads).
 template <int BLOCK_N, int MODE, int CG = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid_constant__ GemmKParams p) {
-    constexpr int STAGES = CG == 2 ? stages_pair_for(BLOCK_N) : stages_for(BLOCK_N);
-    constexpr int B_ROWS = BLOCK_N / CG;  // weight rows this CTA stages
+    constexpr int NCTA = CG >= 2 ? 2 : 1;   // CTAs per MMA tile (CG: 1 single CTA, 2 CTA pair, 3 CTA pair + split-K)
+    constexpr bool kSplitK = CG == 3;
+    constexpr int STAGES = NCTA == 2 ? stages_pair_for(BLOCK_N) : stages_for(BLOCK_N);
+    constexpr int B_ROWS = BLOCK_N / NCTA;  // weight rows this CTA stages
     constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
     constexpr int TMEM_COLS = tmem_cols_for(2 * BLOCK_N);
-    constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M * CG, BLOCK_N);
-    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+    constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M * NCTA, BLOCK_N);
+    const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
 
     extern __shared__ uint8_t smem_raw[];
     // mode 3 (LayerNorm-statistics producer): mailbox between the epilogue and the ticket-server lane, and the verdict
@@ -321,10 +323,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
     const int warp = threadIdx.x >> 5;
     const int n_tiles = p.n_tiles;
     // the persistent walk runs over pair tiles in pair mode (m_tiles is even there): unit u -> m-tile u_m * CG + rank
-    const int num_tiles = (p.m_tiles / CG) * n_tiles;
-    const int walk_first = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int walk_stride = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int num_tiles = (p.m_tiles / NCTA) * n_tiles;
+    // Split-K (pair mode only, p.ksplit == 2): the launch has at most one work item per CTA pair, item = 2 * tile + half;
+    // the pair with half 1 ("donor") hands its fp32 partial accumulators to the pair with half 0 ("owner") through a global
+    // workspace and a flag, the owner adds them (always owner + donor: deterministic) and runs the epilogue. For the layers
+    // whose tiles fill less than half of the GPU (8x8 resolution; 16x16 at small batch) every CTA then streams half of K.
+    constexpr bool split = kSplitK;
+    const int pair_id = (int)(blockIdx.x >> 1);
+    const int khalf = split ? (pair_id & 1) : 0;
+    const int walk_first = NCTA == 2 ? (split ? pair_id >> 1 : pair_id) : (int)blockIdx.x;
+    const int walk_stride = NCTA == 2 ? (split ? num_tiles : (int)(gridDim.x >> 1)) : (int)gridDim.x;
     const int num_k_iters = p.num_k_iters;
+    const int k_begin = split ? khalf * (num_k_iters / 2) : 0;
+    const int k_end = split ? (khalf ? num_k_iters : num_k_iters / 2) : num_k_iters;
 
     // the two single-thread roles take the HIGHEST warp ids: the SM's issue arbiter favours higher
     // warp ids, and a starved producer / MMA issuer stalls the whole pipeline
@@ -334,18 +345,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
         prefetch_tmap(&p.tmB);
         if constexpr (MODE != 1) prefetch_tmap(&p.tmOut[0]);
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar(s), CG);  // pair mode: one arrive.expect_tx per CTA, on the leader's barrier
+            mbar_init(full_bar(s), NCTA);  // pair mode: one arrive.expect_tx per CTA, on the leader's barrier
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full_bar(a), 1);
-            mbar_init(tmem_empty_bar(a), GEMM_EPI_WARPS * CG);  // pair mode: both CTAs' epilogue warps, on the leader's
+            mbar_init(tmem_empty_bar(a), GEMM_EPI_WARPS * NCTA);  // pair mode: both CTAs' epilogue warps, on the leader's
         }
         fence_mbar_init();
         if constexpr (MODE == 3) { s_req_seq = 0; s_resp_seq = 0; s_req_mtile = 0; s_resp_last = 0; }
     }
     if (warp == W_MMA) {
-        if constexpr (CG == 2) {
+        if constexpr (NCTA == 2) {
             tmem_alloc_cg2(tmem_slot, TMEM_COLS);
             tmem_relinquish_cg2();
         } else {
@@ -354,7 +365,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
         }
     }
     tc_fence_before();
-    if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
+    if constexpr (NCTA == 2) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
@@ -409,14 +420,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
             uint32_t ph = 0;
             TileWalk tw(walk_first, walk_stride, n_tiles);
             for (int tile = walk_first; tile < num_tiles; tile += walk_stride, tw.next()) {
-                const int n_tile = tw.n, m_tile = tw.m * CG + (int)cta_rank;
+                const int n_tile = tw.n, m_tile = tw.m * NCTA + (int)cta_rank;
                 int x0 = 0, y0 = 0, nb0 = 0;
                 if (p.a_mode != PP_A_MATRIX) tile_origin(m_tile, x0, y0, nb0);
                 int ky = 0, kx = 0, ch = 0;  // filter tap and 64-channel chunk of this k-iteration
-                for (int it = 0; it < num_k_iters; ++it) {
+                if (k_begin) {  // second half of a split contraction: tap / chunk of its first k-iteration
+                    const int tap = k_begin / cpt;
+                    ch = k_begin - tap * cpt;
+                    ky = tap / 3;
+                    kx = tap - ky * 3;
+                }
+                for (int it = k_begin; it < k_end; ++it) {
                     mbar_wait(empty_bar(s), ph ^ 1u);
-                    if (it == 0) GT((tile - walk_first) / walk_stride, 0);
-                    if (it == num_k_iters - 1) GT((tile - walk_first) / walk_stride, 1);
+                    if (it == k_begin) GT((tile - walk_first) / walk_stride, 0);
+                    if (it == k_end - 1) GT((tile - walk_first) / walk_stride, 1);
 #if defined(GEMM_EXP_NOLOAD)  // experiment: no TMA traffic at all (operands are whatever the smem holds)
                     mbar_arrive(full_bar(s));
                     if (++ch == cpt) {
@@ -430,7 +447,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
 #elif defined(GEMM_EXP_NOLOADA)  // experiment: weights only
                     mbar_arrive_expect_tx(full_bar(s), B_STAGE_BYTES);
 #else
-                    if constexpr (CG == 2) mbar_arrive_expect_tx_cluster(full_bar(s) & PP_PEER_BIT_MASK, p.a_bytes + B_STAGE_BYTES);
+                    if constexpr (NCTA == 2) mbar_arrive_expect_tx_cluster(full_bar(s) & PP_PEER_BIT_MASK, p.a_bytes + B_STAGE_BYTES);
                     else mbar_arrive_expect_tx(full_bar(s), p.a_bytes + B_STAGE_BYTES);
 #endif
                     const uint32_t dstA = sA + s * A_STAGE_BYTES;
@@ -441,7 +458,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                     if (false) {
                     } else
 #endif
-                    if constexpr (CG == 2) {
+                    if constexpr (NCTA == 2) {
                         // pair mode serves the matrix and stride-1 conv operands (checked at prepare time)
                         const uint32_t lbar = full_bar(s) & PP_PEER_BIT_MASK;
                         if (p.a_mode == PP_A_MATRIX) tma_load_2d_cg2(dstA, &p.tmA[src], lbar, cc, m_tile * BLOCK_M);
@@ -465,7 +482,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                                     nb0);
                     }
 #ifndef GEMM_EXP_NOLOADB
-                    if constexpr (CG == 1) tma_load_2d(dstB, &p.tmB, full_bar(s), it * BLOCK_K, n_tile * BLOCK_N);
+                    if constexpr (NCTA == 1) tma_load_2d(dstB, &p.tmB, full_bar(s), it * BLOCK_K, n_tile * BLOCK_N);
 #endif
                     if (++ch == cpt) {
                         ch = 0;
@@ -477,7 +494,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
         }
     } else if (warp == W_MMA) {
         // ===================== MMA issuer =====================
-        if ((CG == 1 || cta_rank == 0) && elect_one()) {  // pair mode: the leader issues for both CTAs
+        if ((NCTA == 1 || cta_rank == 0) && elect_one()) {  // pair mode: the leader issues for both CTAs
             int s = 0;
             uint32_t ph = 0;
             uint32_t lt = 0;  // local tile counter
@@ -488,29 +505,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 GT(lt, 2);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-                for (int it = 0; it < num_k_iters; ++it) {
+                for (int it = k_begin; it < k_end; ++it) {
                     mbar_wait(full_bar(s), ph);
-                    if (it == 0) GT(lt, 3);
-                    if (it == num_k_iters - 1) GT(lt, 4);
+                    if (it == k_begin) GT(lt, 3);
+                    if (it == k_end - 1) GT(lt, 4);
                     tc_fence_after();
                     const uint64_t da = umma_desc_kmajor_sw128(sA + s * A_STAGE_BYTES);
                     const uint64_t db = umma_desc_kmajor_sw128(sB + s * B_STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        if constexpr (CG == 2)
+                        if constexpr (NCTA == 2)
                             umma_bf16_ss_cg2(tmem_d, umma_desc_advance_k(da, k * UMMA_K),
-                                             umma_desc_advance_k(db, k * UMMA_K), IDESC, (it | k) != 0);
+                                             umma_desc_advance_k(db, k * UMMA_K), IDESC, ((it - k_begin) | k) != 0);
                         else
                             umma_bf16_ss(tmem_d, umma_desc_advance_k(da, k * UMMA_K),
-                                         umma_desc_advance_k(db, k * UMMA_K), IDESC, (it | k) != 0);
+                                         umma_desc_advance_k(db, k * UMMA_K), IDESC, ((it - k_begin) | k) != 0);
                     }
                     // frees the smem slot once these MMAs retire (pair mode: in both CTAs)
-                    if constexpr (CG == 2) umma_commit_cg2(empty_bar(s));
+                    if constexpr (NCTA == 2) umma_commit_cg2(empty_bar(s));
                     else umma_commit(empty_bar(s));
                     if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
                 // accumulator complete (pair mode: both CTAs' epilogues are told)
-                if constexpr (CG == 2) umma_commit_cg2(tmem_full_bar(acc));
+                if constexpr (NCTA == 2) umma_commit_cg2(tmem_full_bar(acc));
                 else umma_commit(tmem_full_bar(acc));
             }
         }
@@ -558,7 +575,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
         epi_sync();
         float2 ln_cur = make_float2(1.f, 0.f);  // {rstd, -rstd * mean} of this thread's row in the current tile
         if (ln && walk_first < num_tiles) {
-            const int64_t row0 = (int64_t)(tw.m * CG + (int)cta_rank) * BLOCK_M + r;
+            const int64_t row0 = (int64_t)(tw.m * NCTA + (int)cta_rank) * BLOCK_M + r;
             if (row0 < p.M) ln_cur = __ldg(p.ln_stats + row0);
         }
         // ---- mode 3: verdict of the ticket server for request number `seq`, and the fold of a row's records
@@ -611,7 +628,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
         uint32_t lt = 0;
         for (int tile = walk_first; tile < num_tiles; tile += walk_stride, ++lt) {
             if (etid == 0) GT(lt, 15);  // top of the tile
-            const int n_tile = tw.n, m_tile = tw.m * CG + (int)cta_rank;
+            const int n_tile = tw.n, m_tile = tw.m * NCTA + (int)cta_rank;
             tw.next();  // now at the tile after this one
             const uint32_t acc = lt & 1u;
             const uint32_t acc_ph = (lt >> 1) & 1u;
@@ -662,7 +679,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
             // latency is off the epilogue's serial path (a per-tile fold of the raw records cost ~2500 cycles a tile).
             const float ln_rs = ln_cur.x, ln_nm = ln_cur.y;
             if (ln) {
-                const int64_t nrow = (int64_t)(tw.m * CG + (int)cta_rank) * BLOCK_M + r;  // tw is already at the next tile
+                const int64_t nrow = (int64_t)(tw.m * NCTA + (int)cta_rank) * BLOCK_M + r;  // tw is already at the next tile
                 ln_cur = (next_tile < num_tiles && nrow < p.M) ? __ldg(p.ln_stats + nrow) : make_float2(1.f, 0.f);
             }
             // The tile's results stay in registers (packed bf16, 8 columns per uint4) until the TMA unit has finished
@@ -749,6 +766,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                 // 160-wide tile (5 chunks would split 3 / 2): there each warp takes one contiguous 80-column half
                 // as 32 + 32 + 16, so both finish together
                 constexpr bool kSplitHalves = BLOCK_N == 160;
+                if constexpr (kSplitK) {
+                    if (!khalf) {  // owner: the donor's partial tile is complete (flag set after its fence)
+                        if (etid == 0) {
+                            volatile int32_t* fl = p.splitk_flags + (int64_t)m_tile * n_tiles + n_tile;
+                            const uint64_t t0 = global_timer_ns();
+                            uint32_t spins = 0;
+                            while (*fl == 0) {
+                                if ((++spins & 0xFFFu) == 0 && global_timer_ns() - t0 > PP_WAIT_TIMEOUT_NS) {
+                                    printf("pp: split-K owner timed out (block %d)\n", blockIdx.x);
+                                    __trap();
+                                }
+                            }
+                            __threadfence();
+                            *fl = 0;  // ready for the next launch
+                        }
+                        epi_sync();
+                    }
+                }
                 constexpr int NCH = kSplitHalves ? 3 : BLOCK_N / 64;  // chunks per thread (160: 32 + 32 + 16 columns)
                 auto chunk_col = [&](int k) { return kSplitHalves ? half * 80 + 32 * k : half * 32 + 64 * k; };
                 uint32_t accA[32], accB[32];
@@ -886,6 +921,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
                             if constexpr (kSplitHalves && K + 1 == 2) tmem_ld16(taddr + chunk_col(K + 1), reinterpret_cast<uint32_t(&)[16]>(nxt));
                             else tmem_ld32(taddr + chunk_col(K + 1), nxt);
                         }
+                        if constexpr (kSplitK) {
+                            // split-K: the donor's raw fp32 accumulators go to the workspace ([tile][row][BLOCK_N]); the
+                            // owner adds the donor's to its own (owner + donor, always in this order) before the epilogue
+                            constexpr int NQ = (kSplitHalves && K == 2) ? 4 : 8;  // float4 pieces of this chunk
+                            float4* wsp = reinterpret_cast<float4*>(
+                                p.splitk_ws + (((int64_t)m_tile * n_tiles + n_tile) * BLOCK_M + r) * BLOCK_N + chunk_col(K));
+                            if (khalf) {
+#pragma unroll
+                                for (int q = 0; q < NQ; ++q)
+                                    wsp[q] = make_float4(__uint_as_float(cur[4 * q]), __uint_as_float(cur[4 * q + 1]),
+                                                         __uint_as_float(cur[4 * q + 2]), __uint_as_float(cur[4 * q + 3]));
+                                return;
+                            }
+#pragma unroll
+                            for (int q = 0; q < NQ; ++q) {
+                                const float4 pp = __ldcg(wsp + q);
+                                cur[4 * q] = __float_as_uint(__uint_as_float(cur[4 * q]) + pp.x);
+                                cur[4 * q + 1] = __float_as_uint(__uint_as_float(cur[4 * q + 1]) + pp.y);
+                                cur[4 * q + 2] = __float_as_uint(__uint_as_float(cur[4 * q + 2]) + pp.z);
+                                cur[4 * q + 3] = __float_as_uint(__uint_as_float(cur[4 * q + 3]) + pp.w);
+                            }
+                        }
 #ifndef GEMM_EXP_NOEPI  // experiment: drain the accumulator only (what does the tile cost without the epilogue math?)
                         if constexpr (kSplitHalves && K == 2) process(cur, G2{}, chunk_col(K), std::integral_constant<int, 4 * K>{});
                         else process(cur, G4{}, chunk_col(K), std::integral_constant<int, 4 * K>{});
@@ -955,12 +1012,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
             tc_fence_before();
             __syncwarp();
             if (lane_id() == 0) {
-                if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty_bar(acc) & PP_PEER_BIT_MASK);  // the leader's barrier
+                if constexpr (NCTA == 2) mbar_arrive_cluster(tmem_empty_bar(acc) & PP_PEER_BIT_MASK);  // the leader's barrier
                 else mbar_arrive(tmem_empty_bar(acc));
             }
             // the next tile's bias has landed in the other staging buffer (asynchronous copies issued at the top of this
             // tile); the barrier below publishes it before tile lt + 1 reads it
             cp_async_wait_all();
+            if constexpr (kSplitK) {
+                if (khalf) {
+                    // donor: the partial tile is in the workspace; publish it and leave (no output of its own)
+                    __threadfence();
+                    epi_sync();
+                    if (etid == 0) {
+                        __threadfence();
+                        *(volatile int32_t*)(p.splitk_flags + (int64_t)m_tile * n_tiles + n_tile) = 1;
+                    }
+                    continue;
+                }
+            }
             if constexpr (MODE != 1) {
                 // the TMA unit must have read the previous tile out of the staging buffer before it is overwritten
                 if ((etid & 31) == 0) bulk_wait_read_all();  // every thread that issued a sub-tile store waits for its own
@@ -1130,7 +1199,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_conv_kernel(const __grid
         }
     }
 
-    if constexpr (CG == 2) {
+    if constexpr (NCTA == 2) {
         tc_fence_before();
         cluster_sync_all();  // neither CTA retires while the other may still signal its barriers / read its operands
         if (warp == W_MMA) {
@@ -1177,7 +1246,10 @@ static int launch_variant(const GemmLaunch& l, cudaStream_t s) {
 // CTA-pair flavour (mode 0 only): clusters of two CTAs
 template <int BLOCK_N>
 static int launch_pair(const GemmLaunch& l, cudaStream_t s) {
-    PP_CUDA_CHECK(launch_cluster(gemm_conv_kernel<BLOCK_N, 0, 2>, l.grid, GEMM_THREADS, l.smem, s, 2u, l.p));
+    if (l.p.ksplit == 2)
+        PP_CUDA_CHECK(launch_cluster(gemm_conv_kernel<BLOCK_N, 0, 3>, l.grid, GEMM_THREADS, l.smem, s, 2u, l.p));
+    else
+        PP_CUDA_CHECK(launch_cluster(gemm_conv_kernel<BLOCK_N, 0, 2>, l.grid, GEMM_THREADS, l.smem, s, 2u, l.p));
     return PP_OK;
 }
 template <int BLOCK_N>
@@ -1187,6 +1259,8 @@ static int ensure_attr_pair() {
     PP_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= PP_MAX_DEVICES || !done[dev]) {
         PP_CUDA_CHECK(cudaFuncSetAttribute(gemm_conv_kernel<BLOCK_N, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem_for_block_n(BLOCK_N, 2)));
+        PP_CUDA_CHECK(cudaFuncSetAttribute(gemm_conv_kernel<BLOCK_N, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem_for_block_n(BLOCK_N, 2)));
         if (dev >= 0 && dev < PP_MAX_DEVICES) done[dev] = true;
     }
@@ -1304,7 +1378,8 @@ static bool pair_mode_enabled() {
 }
 static constexpr int PAIR_MIN_K_ITERS = 18;
 
-static int gemm_geometry(const pp_gemm_desc& d, GemmKParams& p, int* block_n_out, int* cg_out = nullptr) {
+static int gemm_geometry(const pp_gemm_desc& d, GemmKParams& p, int* block_n_out, int* cg_out = nullptr,
+                         int* ksplit_out = nullptr) {
     PP_REQUIRE(d.a_mode >= PP_A_MATRIX && d.a_mode <= PP_A_CONV3X3_S2P0, "gemm: bad a_mode %d", d.a_mode);
     PP_REQUIRE(d.epilogue >= PP_EPI_PLAIN && d.epilogue <= PP_EPI_ROWS_THEN_TRANSPOSED, "gemm: bad epilogue %d", d.epilogue);
     PP_REQUIRE(d.a0 && d.b && d.out, "gemm: null operand pointer");
@@ -1364,11 +1439,30 @@ static int gemm_geometry(const pp_gemm_desc& d, GemmKParams& p, int* block_n_out
         p.num_k_iters >= PAIR_MIN_K_ITERS && !geglu && gemm_fast_mode(d) && !d.row_stats && !d.ln_stats && d.block_n != 64)
         cg = 2;
     int bn = d.block_n ? d.block_n : pick_block_n(d.N, m_tiles, geglu, cg);
+    // split-K x2 (needs the caller's workspace): pair-mode launches whose halves of K are still long and whose tiles,
+    // doubled, fit the CTA pairs in one round; the tile width is re-picked for the most work items that still fit
+    int ksplit = 1;
+    if (cg == 2 && d.splitk_ws && d.splitk_flags && p.num_k_iters >= 2 * PAIR_MIN_K_ITERS && p.num_k_iters % 2 == 0) {
+        const int pairs = num_sms() / 2;
+        int best = 0, best_items = 0;
+        const int cands[3] = {128, 160, 256};
+        for (int c : cands) {
+            if (d.block_n && c != d.block_n) continue;
+            const int items = 2 * (m_tiles / 2) * ceil_div(d.N, c);
+            if (items <= pairs && items > best_items) { best = c; best_items = items; }
+        }
+        const int plain_items = (m_tiles / 2) * ceil_div(d.N, bn);
+        if (best && best_items > plain_items) {  // more CTAs busy than without the split
+            bn = best;
+            ksplit = 2;
+        }
+    }
     PP_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "gemm: block_n %d unsupported", bn);
     p.m_tiles = m_tiles;
     p.n_tiles = ceil_div(d.N, bn);
     *block_n_out = bn;
     if (cg_out) *cg_out = cg;
+    if (ksplit_out) *ksplit_out = ksplit;
     return PP_OK;
 }
 
@@ -1428,9 +1522,9 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
     GemmLaunch l;
     memset(&l, 0, sizeof(l));
     GemmKParams& p = l.p;
-    int bn = 0, cg = 1;
+    int bn = 0, cg = 1, ksplit = 1;
     {
-        int rc = gemm_geometry(d, p, &bn, &cg);
+        int rc = gemm_geometry(d, p, &bn, &cg, &ksplit);
         if (rc) return rc;
     }
     l.cg = cg;
@@ -1541,6 +1635,14 @@ int gemm_prepare(const pp_gemm_desc& d, GemmLaunch* out) {
     {
         const long tiles = (long)(p.m_tiles / cg) * p.n_tiles;  // pair mode: pair tiles over CTA pairs
         l.grid = dim3((unsigned)(cg * std::min<long>(tiles, num_sms() / cg)), 1, 1);
+        // split-K x2 (decided with the geometry): two CTA pairs per tile, one work item each
+        p.ksplit = ksplit;
+        if (ksplit == 2) {
+            PP_REQUIRE((reinterpret_cast<uintptr_t>(d.splitk_ws) & 15) == 0, "gemm: splitk_ws not 16-byte aligned");
+            p.splitk_ws = d.splitk_ws;
+            p.splitk_flags = d.splitk_flags;
+            l.grid = dim3((unsigned)(4 * tiles), 1, 1);
+        }
     }
     l.smem = smem_for_block_n(bn, cg);
     if (geglu) {
@@ -1651,6 +1753,21 @@ extern "C" pp_status pp_gemm_stats_geometry(const pp_gemm_desc* d, pp_stats_geom
 }
 
 extern "C" int32_t pp_gemm_row_stats_records(const pp_gemm_desc* d) { return d ? pp::gemm_row_stats_records(*d) : 0; }
+
+extern "C" int64_t pp_gemm_splitk_bytes(const pp_gemm_desc* d0, int32_t* tiles_out) {
+    if (tiles_out) *tiles_out = 0;
+    if (!d0) return 0;
+    // the query comes before the workspace exists: answer for the launch WITH a workspace attached
+    pp_gemm_desc d = *d0;
+    if (!d.splitk_ws) d.splitk_ws = reinterpret_cast<float*>(uintptr_t(16));
+    if (!d.splitk_flags) d.splitk_flags = reinterpret_cast<int32_t*>(uintptr_t(16));
+    pp::GemmKParams p;
+    memset(&p, 0, sizeof(p));
+    int bn = 0, cg = 1, ksplit = 1;
+    if (pp::gemm_geometry(d, p, &bn, &cg, &ksplit) || ksplit != 2) return 0;
+    if (tiles_out) *tiles_out = p.m_tiles * p.n_tiles;
+    return (int64_t)p.m_tiles * p.n_tiles * pp::BLOCK_M * bn * 4;
+}
 
 extern "C" pp_status pp_gemm_conv(const pp_gemm_desc* d, pp_stream stream) {
     if (!d) {

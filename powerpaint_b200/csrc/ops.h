@@ -55,6 +55,10 @@ struct GemmKParams {
     int32_t stat_segs;           // samples per m-tile (1, 2 or 4 ...)
     int32_t stat_seg_rows_log2;  // rows of one sample inside the tile
     // LayerNorm fold (see pp_gemm_desc): records emitted per row and half n-tile / consumed by the epilogue
+    // split-K x2 of a CTA-pair launch (see pp_gemm_desc): 1 or 2
+    int32_t ksplit;
+    float* splitk_ws;
+    int32_t* splitk_flags;
     float4* row_stats;
     int64_t row_stats_ld;
     float2* row_final;     // {rstd, -rstd * mean} per row, written by the CTA finishing a row block's last n-tile

@@ -100,7 +100,7 @@ int make_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64
 extern "C" {
 
 const char* pp_last_error(void) { return pp::last_error(); }
-int pp_abi_version(void) { return 4; }
+int pp_abi_version(void) { return 5; }
 int pp_device_supported(void) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;

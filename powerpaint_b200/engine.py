@@ -78,6 +78,7 @@ class Plan:
         self.free: Dict[int, List[torch.Tensor]] = {}  # size -> raw blocks whose last reader has been recorded
         self.raw_of: Dict[int, torch.Tensor] = {}      # data_ptr of a live view -> its raw block
         self.chan_stats: Dict[int, tuple] = {}         # data_ptr of a tensor -> (partials, geometry) its producer emits
+        self.splitk_flags: Optional[torch.Tensor] = None  # split-K hand-over flags shared by the plan's launches (kept at zero)
         self.row_stats: Dict[int, torch.Tensor] = {}   # data_ptr of a tensor -> per-row {rstd, -rstd mean} its producer leaves
         self.row_ticket: Optional[torch.Tensor] = None  # arrival counters of the LayerNorm-statistics producers (kept at zero)
         self.scale_dev: Optional[torch.Tensor] = None  # eager side-net forward: 1-float conditioning scale
@@ -246,6 +247,25 @@ class NetEngine:
             if rec is not None:
                 self._free(plan, rec)
 
+    # split-K x2 for long-K launches whose tiles fill at most half of the GPU. Off by default: measured neutral (8x8 conv
+    # 1280 -> 1280: 40.9 us plain, 40.6 us split) — those layers are bound by L2 serving the same weight / activation
+    # tiles to every CTA, not by the number of busy SMs (profiles/r02_notes.md). PP_B200_SPLITK=1 switches it on.
+    SPLITK = os.environ.get("PP_B200_SPLITK", "0") == "1"
+
+    def _with_splitk(self, plan: Plan, desc):
+        """hand the launch a split-K workspace if it could use one; returns the scratch to release after recording"""
+        if not self.SPLITK:
+            return None
+        nbytes, tiles = ops.gemm_splitk_query(desc)
+        if nbytes <= 0:
+            return None
+        ws = self._buf(plan, nbytes // 4, dtype=torch.float32)
+        if plan.splitk_flags is None or plan.splitk_flags.numel() < tiles:
+            plan.splitk_flags = torch.zeros(max(tiles, 4096), dtype=torch.int32, device=self.device)  # self-resetting
+            plan.buffers.append(plan.splitk_flags)
+        ops.attach_splitk(desc, ws, plan.splitk_flags)
+        return ws
+
     def _with_stats(self, plan: Plan, desc, out: torch.Tensor) -> None:
         """let this GEMM / conv emit the GroupNorm partial sums of its output from the epilogue"""
         if not self.GN_FUSED:
@@ -307,7 +327,9 @@ class NetEngine:
                              res2=res2, alpha=alpha, out_fp32=out_fp32, act=act, ldc=ldc)
         if stats:
             self._with_stats(plan, desc, out)
+        ws = self._with_splitk(plan, desc)
         prog.add(desc)
+        self._free(plan, ws)  # scratch of this one launch
         return out
 
     def _linear(self, plan, prog, x, M, wname, n_out, *, w=None, bias=None, res1=None, res2=None, alpha=1.0,

@@ -140,6 +140,21 @@ def gemm_desc(*, a0: torch.Tensor, w: torch.Tensor, out: torch.Tensor, N_: int,
     return Desc("gemm", d, keep)
 
 
+def gemm_splitk_query(desc: Desc):
+    """host-only: (workspace bytes, tiles) if this launch could split K across two CTA pairs, else (0, 0)"""
+    t = N.i32(0)
+    b = int(N.lib().pp_gemm_splitk_bytes(C.byref(desc.c), C.byref(t)))
+    return b, int(t.value)
+
+
+def attach_splitk(desc: Desc, ws: torch.Tensor, flags: torch.Tensor) -> None:
+    """ws: fp32 workspace of at least the queried bytes; flags: zero-initialised int32, one per tile (left at zero)"""
+    if ws.dtype != torch.float32 or flags.dtype != torch.int32:
+        raise TypeError("split-K workspace must be fp32, flags int32")
+    desc.c.splitk_ws, desc.c.splitk_flags = N.ptr(ws), N.ptr(flags)
+    desc.keep += [ws, flags]
+
+
 def gemm_row_stats_records(desc: Desc) -> int:
     """host-only: per-row LayerNorm records this GEMM can emit from its epilogue (0: it cannot)"""
     return int(N.lib().pp_gemm_row_stats_records(C.byref(desc.c)))

@@ -27,6 +27,18 @@ def conv(nb, h, w, cin, cout, bn=0):
     return lambda: ops.run(d)
 
 
+def conv_splitk(nb, h, w, cin, cout):
+    x = torch.randn(nb, h * w, cin, device=dev, generator=g).to(BF)
+    wt = ops.pack_conv3x3_weight(torch.randn(cout, cin, 3, 3, device=dev, generator=g) / math.sqrt(9 * cin))
+    out = torch.empty(nb, h * w, cout, device=dev, dtype=BF)
+    d = ops.gemm_desc(a0=x, w=wt, out=out, N_=cout, a_mode=nat.PP_A_CONV3X3, c0=cin, nb=nb, h=h, w_=w,
+                      bias=torch.zeros(cout, device=dev))
+    nbytes, tiles = ops.gemm_splitk_query(d)
+    if nbytes > 0:
+        ops.attach_splitk(d, torch.empty(nbytes // 4, device=dev), torch.zeros(tiles, dtype=torch.int32, device=dev))
+    return lambda: ops.run(d)
+
+
 def linear(M, K, N, geglu=False, bn=0):
     a = torch.randn(M, K, device=dev, generator=g).to(BF)
     if geglu:
@@ -173,6 +185,9 @@ cases = [
     ("conv 640->640 @32x32 b16", conv(16, 32, 32, 640, 640), 2 * 16 * 1024 * 640 * 5760),
     ("conv 1280->1280 @16x16 b16", conv(16, 16, 16, 1280, 1280), 2 * 16 * 256 * 1280 * 11520),
     ("conv 1280->1280 @8x8 b16", conv(16, 8, 8, 1280, 1280), 2 * 16 * 64 * 1280 * 11520),
+    ("conv 1280->1280 @8x8 b16 split-K x2", conv_splitk(16, 8, 8, 1280, 1280), 2 * 16 * 64 * 1280 * 11520),
+    ("conv 1280->1280 @16x16 b4 (C4/C5)", conv(4, 16, 16, 1280, 1280), 2 * 4 * 256 * 1280 * 11520),
+    ("conv 1280->1280 @16x16 b4 split-K x2", conv_splitk(4, 16, 16, 1280, 1280), 2 * 4 * 256 * 1280 * 11520),
     ("conv 2560->1280 @16x16 b16", conv(16, 16, 16, 2560, 1280), 2 * 16 * 256 * 1280 * 23040),
     ("linear 320->320 M=65536", linear(65536, 320, 320), 2 * 65536 * 320 * 320),
     ("linear 320->640 M=65536 (q|k)", linear(65536, 320, 640), 2 * 65536 * 320 * 640),

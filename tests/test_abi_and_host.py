@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in the header but not exported"
     assert declared == set(_native.EXPORTED_SYMBOLS), declared ^ set(_native.EXPORTED_SYMBOLS)
-    assert _native.lib().pp_abi_version() == _native.ABI_VERSION == 4
+    assert _native.lib().pp_abi_version() == _native.ABI_VERSION == 5
     assert _native.lib().pp_device_supported() in (0, 1)
 
 

@@ -721,3 +721,50 @@ def test_gemm_rows_then_transposed_qkv(ops, M, C, hw, bn, fold):
     assert _rel(qk, ref[:, :2 * C]) < 8e-3, _rel(qk, ref[:, :2 * C])
     vref = ref[:, 2 * C:].view(M // hw, hw, C).transpose(1, 2)
     assert _rel(vt, vref) < 8e-3, _rel(vt, vref)
+
+
+@pytest.mark.parametrize("nb,h,w,cin,cout,two", [(16, 8, 8, 1280, 1280, False), (4, 16, 16, 1280, 1280, False),
+                                                 (16, 8, 8, 1280, 1280, True), (4, 8, 8, 640, 1280, False)])
+def test_conv3x3_split_k(ops, nb, h, w, cin, cout, two):
+    """8x8-resolution convs (few tiles, long K) with split-K x2 across two CTA pairs: the donor pair's fp32 partial tile
+    goes through the workspace, the owner adds it (owner + donor, fixed order) — same result run after run, flags back at
+    zero, residual / time-embedding / statistics epilogue unchanged"""
+    from powerpaint_b200 import _native as nat
+
+    g = torch.Generator(device="cuda").manual_seed(nb * 100 + cin + two)
+    c1 = cin if two else 0
+    x = torch.randn(nb, cin + c1, h, w, device=_dev(), generator=g).to(BF16)
+    wt = (torch.randn(cout, cin + c1, 3, 3, device=_dev(), generator=g) / math.sqrt(9 * (cin + c1))).to(BF16)
+    bias = torch.randn(cout, device=_dev(), generator=g)
+    temb = torch.randn(nb, cout, device=_dev(), generator=g)
+    res = torch.randn(nb, h, w, cout, device=_dev(), generator=g).to(BF16)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    x0 = x_nhwc[..., :cin].contiguous()
+    x1 = x_nhwc[..., cin:].contiguous() if two else None
+    wp = ops.pack_conv3x3_weight(wt.float(), cin if two else None)
+    outs = []
+    for split in (True, False):
+        out = torch.full((nb, h, w, cout), float("nan"), device=_dev(), dtype=BF16)
+        d = ops.gemm_desc(a0=x0, a1=x1, c1=c1, w=wp, out=out, N_=cout, a_mode=nat.PP_A_CONV3X3, c0=cin, nb=nb, h=h, w_=w,
+                          bias=bias, rowvec=temb, res1=res)
+        if split:
+            nbytes, tiles = ops.gemm_splitk_query(d)
+            assert nbytes > 0 and tiles > 0, "this shape is expected to split"
+            ws = torch.full((nbytes // 4,), float("nan"), device=_dev(), dtype=torch.float32)
+            flags = torch.zeros(tiles, device=_dev(), dtype=torch.int32)
+            ops.attach_splitk(d, ws, flags)
+        ops.run(d)
+        torch.cuda.synchronize()
+        first = out.clone()
+        ops.run(d)  # again: flags must have been reset, result bit-identical
+        torch.cuda.synchronize()
+        assert torch.equal(out, first)
+        if split:
+            assert (flags == 0).all()
+        outs.append(out)
+    ref = F.conv2d(x.float(), wt.float(), bias, padding=1) + temb[:, :, None, None] + res.permute(0, 3, 1, 2).float()
+    for out in outs:
+        got = out.permute(0, 3, 1, 2).float()
+        assert torch.isfinite(got).all()
+        assert _rel(got, ref) < 6e-3, _rel(got, ref)
+    assert _rel(outs[0], outs[1]) < 4e-3
