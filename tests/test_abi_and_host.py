@@ -182,3 +182,34 @@ def test_gemm_stats_geometry_is_a_pure_host_query():
     assert g.supported and g.segs == 2 and g.seg_rows == 64
     lin = ops.gemm_desc(a0=a, w=a, out=a, N_=320, M=2 * 8560, c0=320, rows_per_group=8560)
     assert not ops.gemm_stats_geometry(lin).supported  # 80 x 107 latent: samples straddle the 128-row tiles
+
+
+def test_layer_norm_record_and_split_k_queries_are_pure_host_queries():
+    """host-only geometry answers that must describe the launch that actually runs: the per-row LayerNorm record count
+    (a producer never runs in CTA-pair mode, whatever the plain launch of the same shape would pick) and the split-K
+    workspace (only for long-K launches whose doubled tiles fit the CTA pairs of one round)"""
+    from powerpaint_b200 import _native as nat
+    from powerpaint_b200 import ops
+
+    a = torch.zeros(8, dtype=torch.bfloat16)  # only non-null pointers are needed: nothing is launched
+
+    def lin(M, K, N, **kw):
+        return ops.gemm_desc(a0=a, w=a, out=a, N_=N, M=M, c0=K, **kw)
+    # SD-1.5 transformer widths: records = 2 per n-tile of the single-CTA tile width
+    assert ops.gemm_row_stats_records(lin(65536, 320, 320)) == 4       # 2 x 160
+    assert ops.gemm_row_stats_records(lin(16384, 640, 640)) == 8       # 4 x 160
+    n1280 = ops.gemm_row_stats_records(lin(4096, 1280, 1280))          # K = 1280 would pair up without row_stats
+    assert n1280 > 0 and n1280 % 2 == 0
+    assert ops.gemm_row_stats_records(lin(4096, 1280, 1280, block_n=160)) == 16
+    assert ops.gemm_row_stats_records(lin(1024, 320, 324)) == 0        # ragged N: generic epilogue, no records
+    assert ops.gemm_row_stats_records(lin(1024, 320, 320, act=nat.PP_ACT_SILU)) == 0
+
+    def conv(nb, h, w, cin, cout):
+        return ops.gemm_desc(a0=a, w=a, out=a, N_=cout, a_mode=nat.PP_A_CONV3X3, c0=cin, nb=nb, h=h, w_=w)
+    nbytes, tiles = ops.gemm_splitk_query(conv(16, 8, 8, 1280, 1280))  # 8 m-tiles: few tiles, K = 180 iterations
+    assert nbytes > 0 and tiles > 0 and nbytes % (tiles * 128 * 4) == 0
+    bn = nbytes // (tiles * 128 * 4)
+    assert bn in (128, 160, 256) and tiles == 8 * ((1280 + bn - 1) // bn) and 2 * (tiles // 2) <= 74
+    assert ops.gemm_splitk_query(conv(16, 64, 64, 320, 320)) == (0, 0)  # 512 m-tiles: nothing to gain
+    assert ops.gemm_splitk_query(conv(16, 8, 8, 64, 1280)) == (0, 0)    # K = 9 iterations: too short to split
+    assert ops.gemm_splitk_query(lin(65536, 320, 320)) == (0, 0)
