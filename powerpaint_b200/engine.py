@@ -158,15 +158,11 @@ class NetEngine:
         Returns (W' bf16 [N, K], u fp32 [N], b' fp32 [N]); `geglu`: rows tile-interleaved like `w_geglu`."""
         def make():
             w = torch.cat([self._raw(n + ".weight").reshape(self._raw(n + ".weight").shape[0], -1) for n in wnames], 0)
-            gamma, beta = self._raw(ln_name + ".weight"), self._raw(ln_name + ".bias")
-            b = w.double() @ beta.double()
-            if bias_name is not None:
-                b = b + self._raw(bias_name).double()
-            wf = (w * gamma[None, :]).to(BF16)
-            u = wf.double().sum(1)
+            wf, u, b = ops.fold_layer_norm_into_linear(w, self._raw(ln_name + ".weight"), self._raw(ln_name + ".bias"),
+                                                       self._raw(bias_name) if bias_name is not None else None)
             if geglu:  # value / gate rows interleaved per tile; u and b' ride the same permutation
-                wi, u = ops.pack_geglu_weight(wf.float(), u.float(), self.GEGLU_BLOCK_N)
-                _, b = ops.pack_geglu_weight(wf.float(), b.float(), self.GEGLU_BLOCK_N)
+                wi, u = ops.pack_geglu_weight(wf.float(), u, self.GEGLU_BLOCK_N)
+                _, b = ops.pack_geglu_weight(wf.float(), b, self.GEGLU_BLOCK_N)
                 wf = wi  # bf16 -> fp32 -> bf16 is exact
             return wf.contiguous(), u.float().contiguous(), b.float().contiguous()
         return self._cached("lnf:" + key, make)

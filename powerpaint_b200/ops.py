@@ -78,6 +78,20 @@ def pack_geglu_weight(w: torch.Tensor, b: torch.Tensor, block_n: int = 128):
     return wi.to(BF16).contiguous(), bi.float().contiguous()
 
 
+def fold_layer_norm_into_linear(w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                                bias: Optional[torch.Tensor] = None):
+    """LayerNorm(x) W^T + b as a GEMM on the raw x:  rstd (x W'^T - mean u) + b'  with  W' = W * gamma (bf16, what the
+    tensor core multiplies), u = row sums of that bf16 W', b' = W beta (+ b). Returns (W' bf16 [N, K], u fp32 [N],
+    b' fp32 [N]); the statistics (mean, rstd) come from the producer of x at run time (pp_gemm_desc.ln_stats)."""
+    w = w.reshape(w.shape[0], -1).float()
+    b = w.double() @ beta.double()
+    if bias is not None:
+        b = b + bias.double()
+    wf = (w * gamma.float()[None, :]).to(BF16)
+    u = wf.double().sum(1)
+    return wf.contiguous(), u.float().contiguous(), b.float().contiguous()
+
+
 # --------------------------------------------------------------------------- descriptors
 class Desc:
     """A filled C descriptor plus the tensors it points into (kept alive)."""

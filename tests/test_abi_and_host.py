@@ -213,3 +213,39 @@ def test_layer_norm_record_and_split_k_queries_are_pure_host_queries():
     assert ops.gemm_splitk_query(conv(16, 64, 64, 320, 320)) == (0, 0)  # 512 m-tiles: nothing to gain
     assert ops.gemm_splitk_query(conv(16, 8, 8, 64, 1280)) == (0, 0)    # K = 9 iterations: too short to split
     assert ops.gemm_splitk_query(lin(65536, 320, 320)) == (0, 0)
+
+
+def test_layer_norm_fold_algebra_cpu():
+    """LayerNorm(x) W^T + b == rstd (x W'^T - mean u) + b' with the folded operands the engine hands to the GEMM
+    (ops.fold_layer_norm_into_linear), also through the GEGLU row interleave; the only difference left is the bf16
+    rounding of W' (the tensor core's operand)"""
+    from powerpaint_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    M, C, N = 64, 320, 256
+    x = (torch.randn(M, C, generator=g) * 2 + 0.7).to(torch.bfloat16).float()
+    w = torch.randn(N, C, generator=g) / C ** 0.5
+    gamma = 1 + 0.3 * torch.randn(C, generator=g)
+    beta = 0.3 * torch.randn(C, generator=g)
+    bias = torch.randn(N, generator=g)
+    wf, u, b = ops.fold_layer_norm_into_linear(w, gamma, beta, bias)
+    assert wf.dtype == torch.bfloat16 and u.dtype == b.dtype == torch.float32
+    assert torch.equal(u, wf.double().sum(1).float())  # row sums of exactly what the tensor core multiplies
+    mean = x.mean(1, keepdim=True)
+    rstd = (x.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
+    got = rstd * (x @ wf.float().t() - mean * u[None]) + b
+    ref = torch.nn.functional.layer_norm(x, (C,), gamma, beta, 1e-5) @ w.t() + bias
+    assert ((got - ref).norm() / ref.norm()).item() < 3e-3
+    # with an un-rounded W' the identity is exact to fp32 round-off
+    wx = w * gamma[None]
+    exact = rstd * (x @ wx.t() - mean * wx.sum(1)[None]) + (w @ beta + bias)
+    assert ((exact - ref).norm() / ref.norm()).item() < 1e-5
+    # GEGLU: value / gate rows interleaved per tile, u and b' permuted with them
+    for bn in (128, 256):
+        wi, ui = ops.pack_geglu_weight(wf.float(), u, bn)
+        _, bi = ops.pack_geglu_weight(wf.float(), b, bn)
+        y = rstd * (x @ wi.float().t() - mean * ui[None]) + bi
+        half = bn // 2
+        yv = torch.cat([y[:, t * bn:t * bn + half] for t in range(N // bn)], 1)
+        yg = torch.cat([y[:, t * bn + half:(t + 1) * bn] for t in range(N // bn)], 1)
+        assert torch.allclose(yv, got[:, :N // 2], atol=1e-5) and torch.allclose(yg, got[:, N // 2:], atol=1e-5)

@@ -573,14 +573,11 @@ def test_attention_16384_tokens_full_grid_is_reproducible(ops):
 
 
 def _ln_fold_pack(w, gamma, beta, bias=None):
-    """host-side fold the engine performs (engine.NetEngine.w_ln_folded): W' = W * gamma (bf16), u = row sums of
-    the bf16 W', b' = W beta (+ bias)"""
-    wf = (w * gamma[None, :]).to(BF16)
-    u = wf.double().sum(1).float()
-    b = (w.double() @ beta.double()).float()
-    if bias is not None:
-        b = b + bias
-    return wf.contiguous(), u.contiguous(), b.contiguous()
+    """the host-side fold the engine performs (ops.fold_layer_norm_into_linear, checked on the CPU in
+    tests/test_abi_and_host.py): W' = W * gamma (bf16), u = row sums of the bf16 W', b' = W beta (+ bias)"""
+    from powerpaint_b200 import ops as o
+
+    return o.fold_layer_norm_into_linear(w, gamma, beta, bias)
 
 
 def _producer_with_row_stats(ops, M, C, K, seed, offset=0.0, bn=0):
