@@ -28,14 +28,21 @@
  *                      pipeline_PowerPaint_Brushnet_CA.py:1390,1444-1449)
  *   pp_unipc_step     CFG combine + UniPCMultistepScheduler.step (the v2 app's scheduler, app.py:197)
  *   pp_upsample_nearest  Upsample2D with an explicit output size (unet_2d_condition.py:1120-1126,1311-1312)
+ *                     Also carries: LayerNorm of BasicTransformerBlock folded into the producing / consuming
+ *                     GEMMs (row_stats / ln_stats; diffusers LayerNorm norm1/2/3), and
+ *                     to_q | to_k | to_v^T of a self-attention as one launch (PP_EPI_ROWS_THEN_TRANSPOSED).
+ *                     Long-K launches run as 2-CTA clusters (tcgen05 cta_group::2) on their own.
  *   pp_gemm_stats_geometry  host-only: layout of the GroupNorm partial sums a GEMM / conv emits from its
  *                     epilogue (pp_gemm_desc.chan_stats -> pp_gn_desc.part0 / part1)
+ *   pp_gemm_row_stats_records, pp_gemm_splitk_bytes  host-only: scratch sizes of the LayerNorm-statistics
+ *                     producer and of the optional split-K workspace
  *   pp_softmax_rows, pp_image_preprocess_u8, pp_image_postprocess   VAE attention softmax and the uint8
  *                     pre/post-processing either side of vae.encode / vae.decode
  *                     (pipeline_PowerPaint.py:39-153,657-669,1051,1062)
  *   pp_embed_gather, pp_causal_attention_small   CLIP text encoder: embeddings with the task-prompt splice
  *                     (utils/utils.py:256-483) and the causal 77-token attention (pipeline_PowerPaint.py:317-518)
- *   pp_program_*      a recorded list of the above, replayed per denoising step
+ *   pp_program_*      a recorded list of the above, replayed per denoising step (pp_program_run_range: a slice
+ *                     of it as plain launches, for bisecting a step op by op)
  *                     (the `for i, t in enumerate(timesteps)` loops,
  *                      pipeline_PowerPaint.py:988-1041, Brushnet_CA.py:1384-1466,
  *                      ControlNet.py:1663-1741)

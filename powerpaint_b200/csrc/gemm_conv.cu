@@ -23,10 +23,15 @@
 //    mbarriers that keeps running across tile boundaries; two TMEM accumulator stages, so the epilogue
 //    of one tile overlaps the main loop of the next. tcgen05.commit releases ring slots and publishes
 //    the accumulator.
+//  * CTA pairs (CG = 2): the long-K launches run as 2-CTA clusters sharing one 256-row tcgen05.mma.cta_group::2 tile
+//    (each CTA stages its A tile and half of the weight tile); see the comment at the kernel.
 //  * Epilogue (fused): + bias[n] + time-embedding row vector + residual (skip / shortcut)
 //    → × alpha (1/output_scale_factor or BrushNet conditioning_scale) → + second residual
 //    (BrushNet / ControlNet feature injection, unet_2d_condition.py:1223,1300) → SiLU /
-//    GEGLU gate → bf16 or fp32 store, optionally transposed (V^T for the attention kernel).
+//    GEGLU gate → bf16 or fp32 store, optionally transposed (V^T for the attention kernel; q | k | v^T of an attention
+//    leave one launch, the V tiles through a transposed staging tile). The LayerNorms of BasicTransformerBlock live in
+//    the epilogues either side of them: the producer leaves {rstd, -rstd * mean} per row, the consumer multiplies the
+//    raw activations by W * gamma and finishes the normalisation with two FMAs per element.
 #include <algorithm>
 #include <type_traits>
 
