@@ -5,7 +5,11 @@ PyTorch on already-prepared tensors (the part of `__call__` that is the hot path
   v2 BrushNet powerpaint/pipelines/pipeline_PowerPaint_Brushnet_CA.py:1384-1449
   ControlNet  powerpaint/pipelines/pipeline_PowerPaint_ControlNet.py:1663-1735
 
-PARITY UNPINNED (see oracle/blocks.py): the reference pipelines cannot be imported here.
+PINNED for what the reference's own files decide: tests/golden/pipeline_{v1,brushnet,controlnet}_call.npz are the final
+latents of the reference's own `__call__` (its pipeline files and its UNet / BrushNet imported unmodified over
+tests/golden/diffusers_shim, generator: tests/golden/make_pipeline_golden.py); tests/test_pipeline_golden.py runs the
+product's `__call__` over these loops' arithmetic against them. The arithmetic of the diffusers blocks inside the nets
+stays unpinned (oracle/blocks.py).
 """
 from __future__ import annotations
 

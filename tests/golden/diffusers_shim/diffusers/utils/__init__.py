@@ -54,3 +54,15 @@ def is_torch_version(op, version):
 
     ops = {">": operator.gt, ">=": operator.ge, "<": operator.lt, "<=": operator.le, "==": operator.eq}
     return ops[op](V.parse(torch.__version__.split("+")[0]), V.parse(version))
+
+
+def is_accelerate_available():
+    return False
+
+
+def is_accelerate_version(op, version):
+    return False
+
+
+def replace_example_docstring(example):
+    return lambda fn: fn
