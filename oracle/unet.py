@@ -5,8 +5,10 @@ for the SD-1.5 family of configs, including every BrushNet hook (:1203-1207, :12
 and of `BrushNetModel` (powerpaint/models/BrushNet_CA.py:139-454 layout, :456-542 from_unet,
 :690-952 forward, non-guess-mode) and of diffusers' ControlNetModel.
 
-PARITY UNPINNED (see oracle/blocks.py header): no reference test / golden vector exists for
-this path and the reference modules cannot be imported here (diffusers absent).
+COMPOSITION PINNED: tests/golden/unet_composition.npz holds outputs of the reference's own model files (imported
+unmodified over tests/golden/diffusers_shim by tests/golden/make_unet_golden.py); tests/test_oracle_golden.py holds
+these classes to them. The arithmetic of the diffusers blocks they are built from stays PARITY UNPINNED
+(oracle/blocks.py header).
 """
 from __future__ import annotations
 
