@@ -264,7 +264,7 @@ class StableDiffusionInpaintPipeline:
         timesteps, num_inference_steps = self.get_timesteps(num_inference_steps, strength, device)
         if num_inference_steps < 1:
             raise ValueError(f"After adjusting the num_inference_steps by strength parameter: {strength}, the number "
-                             f"of pipeline steps is {num_inference_steps} which is < 1 and not appropriate for this "
+                             f"of pipelinesteps is {num_inference_steps} which is < 1 and not appropriate for this "
                              "pipeline.")
         if uint8_device_inputs(self.vae, image, mask):
             # device-resident uint8 request (< 1 MB per 512^2 image over PCIe): `image / 127.5 - 1`, the mask

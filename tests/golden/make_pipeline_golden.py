@@ -109,6 +109,26 @@ def main():
         out[f"{name}_latents"] = lat.numpy()
         out[f"{name}_timesteps"] = np.array(seen, dtype=np.int64)
         print(name, tuple(lat.shape), seen, float(lat.abs().mean()))
+    # two images per prompt (prompts repeat interleaved :441-443, masks / masked images tile :685-698) from caller latents
+    lat0 = torch.randn(2 * B, 4, H // 8, W // 8, generator=torch.Generator().manual_seed(77))
+    lat = pipe(image=img, mask=mask, prompt_embeds=pe, negative_prompt_embeds=ne, height=H, width=W,
+               num_images_per_prompt=2, latents=lat0, num_inference_steps=2, guidance_scale=7.5,
+               generator=generators(False), output_type="latent", return_dict=False)[0]
+    out["per_prompt2_latents"] = lat.numpy()
+    # what the reference raises for invalid calls (check_inputs :554-602, prepare_mask_and_masked_image :39-153, ...)
+    import json
+
+    from pipeline_cases import error_cases
+
+    errors = {}
+    for name, kw in error_cases(img, mask, pe, ne, H, W).items():
+        try:
+            pipe(**kw)
+            errors[name] = ["no error", ""]
+        except Exception as e:  # noqa: BLE001  (recording whatever the reference raises is the point)
+            errors[name] = [type(e).__name__, str(e)]
+    with open(os.path.join(os.environ.get("PP_GOLDEN_OUT", HERE), "pipeline_v1_errors.json"), "w") as f:
+        json.dump(errors, f, indent=1, sort_keys=True)
     # string prompts through the reference's `_encode_prompt` (tokenizer + text encoder, A/B trade-off :317-470)
     tok, te, _ = text_stack()
     pipe_t = RefPipe(vae=AutoencoderKL.synthetic(tiny=True), text_encoder=te, tokenizer=tok, unet=unet,
@@ -119,6 +139,19 @@ def main():
                  mask=mask, height=H, width=W, num_inference_steps=3, guidance_scale=7.5,
                  generator=generators(False), output_type="latent", return_dict=False)[0]
     out["prompts_latents"] = lat.numpy()
+    # 4-channel UNet: no mask channels; after every step the known region is reset to the noised original (:1025-1035,
+    # which indexes image_latents[:1] and mask[:1] — sample 0's image and mask serve the whole batch)
+    u4 = ref_unet(4)
+    u4.load_state_dict(synthetic_state_dict(cfg(4), "unet", 78), strict=True)
+    pipe4 = RefPipe(vae=AutoencoderKL.synthetic(tiny=True), text_encoder=None, tokenizer=None, unet=u4,
+                    scheduler=DDIMScheduler(), safety_checker=None, feature_extractor=None,
+                    requires_safety_checker=False)
+    for name, strength, steps in (("unet4_full", 1.0, 3), ("unet4_strength", 0.6, 5)):
+        lat = pipe4(image=img, mask=mask, prompt_embeds=pe, negative_prompt_embeds=ne, height=H, width=W,
+                    strength=strength, num_inference_steps=steps, guidance_scale=7.5, generator=generators(False),
+                    output_type="latent", return_dict=False)[0]
+        out[f"{name}_latents"] = lat.numpy()
+        print(name, tuple(lat.shape), float(lat.abs().mean()))
     save("pipeline_v1_call.npz", out)
     brushnet_golden()
     controlnet_golden()
@@ -162,12 +195,16 @@ BRUSHNET_CASES = {
     "full": dict(num_inference_steps=3, guidance_scale=7.5, brushnet_conditioning_scale=1.0),
     "window_scale": dict(num_inference_steps=4, guidance_scale=5.0, brushnet_conditioning_scale=0.8,
                          control_guidance_start=0.0, control_guidance_end=0.6),
+    "per_prompt2": dict(num_inference_steps=2, guidance_scale=7.5, brushnet_conditioning_scale=1.0,
+                        num_images_per_prompt=2),
     # (guidance_scale <= 1 is not a case: the reference's encode_prompt concatenates a None then, :627)
 }
 CONTROLNET_CASES = {
     "full": dict(strength=1.0, num_inference_steps=3, guidance_scale=5.0, controlnet_conditioning_scale=0.5),
     "strength_window": dict(strength=0.5, num_inference_steps=6, guidance_scale=7.5, controlnet_conditioning_scale=0.8,
                             control_guidance_start=0.3, control_guidance_end=1.0),
+    "per_prompt2": dict(strength=1.0, num_inference_steps=2, guidance_scale=7.5, controlnet_conditioning_scale=0.5,
+                        num_images_per_prompt=2),
 }
 
 
