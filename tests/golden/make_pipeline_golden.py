@@ -115,6 +115,16 @@ def main():
                num_images_per_prompt=2, latents=lat0, num_inference_steps=2, guidance_scale=7.5,
                generator=generators(False), output_type="latent", return_dict=False)[0]
     out["per_prompt2_latents"] = lat.numpy()
+    # fixtures for the GPU tests (tests/test_golden_gpu.py): same call, latent sizes the tiny GPU tests already exercise
+    from pipeline_cases import GPU_V1, GPU_V1_STRENGTH, sized_inputs
+
+    for name, case in (("gpu_v1", GPU_V1), ("gpu_v1_strength", GPU_V1_STRENGTH)):
+        gi, gm, gpe, gne, _ = sized_inputs(B, case["size"], case["size"], CROSS, case["seed"])
+        lat = pipe(image=gi, mask=gm, prompt_embeds=gpe, negative_prompt_embeds=gne, height=case["size"],
+                   width=case["size"], generator=torch.Generator().manual_seed(case["gen_seed"]), output_type="latent",
+                   return_dict=False, **case["kw"])[0]
+        out[f"{name}_latents"] = lat.numpy()
+        print(name, tuple(lat.shape), float(lat.abs().mean()))
     # what the reference raises for invalid calls (check_inputs :554-602, prepare_mask_and_masked_image :39-153, ...)
     import json
 
@@ -231,6 +241,14 @@ def controlnet_golden():
                    width=W, generator=generators(False), output_type="latent", return_dict=False, **kw)[0]
         out[f"{name}_latents"] = lat.numpy()
         print("controlnet", name, tuple(lat.shape), float(lat.abs().mean()))
+    from pipeline_cases import GPU_CONTROLNET as case, sized_inputs
+
+    gi, gm, gpe, gne, gctl = sized_inputs(B, case["size"], case["size"], CROSS, case["seed"])
+    lat = pipe(image=gi, mask=gm, control_image=gctl, prompt_embeds=gpe, negative_prompt_embeds=gne,
+               height=case["size"], width=case["size"], generator=torch.Generator().manual_seed(case["gen_seed"]),
+               output_type="latent", return_dict=False, **case["kw"])[0]
+    out["gpu_controlnet_latents"] = lat.numpy()
+    print("gpu_controlnet", tuple(lat.shape), float(lat.abs().mean()))
     save("pipeline_controlnet_call.npz", out)
 
 

@@ -31,3 +31,24 @@ def error_cases(img, mask, pe, ne, H, W):
         "too_few_steps": c(strength=0.1, num_inference_steps=2),
         "generator_list_length": c(generator=[torch.Generator().manual_seed(0)] * 3),
     }
+
+
+def sized_inputs(batch, h, w, cross, seed):
+    """image in [-1, 1], two-rectangle mask, prompt / negative embeddings and a control image for an h x w request
+    (the fixtures the GPU tests use: latent sizes the tiny GPU tests already exercise)"""
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(batch, 3, h, w, generator=g) * 2 - 1
+    mask = torch.zeros(batch, 1, h, w)
+    mask[0, :, h // 8:5 * h // 8, w // 4:5 * w // 8] = 1
+    mask[1:, :, h // 4:, w // 16:w // 2] = 1
+    pe = torch.randn(batch, 77, cross, generator=g) * 0.5
+    ne = torch.randn(batch, 77, cross, generator=g) * 0.5
+    ctl = torch.rand(batch, 3, h, w, generator=g)
+    return img, mask, pe, ne, ctl
+
+
+GPU_V1 = dict(size=128, seed=51, gen_seed=11, kw=dict(num_inference_steps=6, guidance_scale=7.5))
+GPU_V1_STRENGTH = dict(size=128, seed=52, gen_seed=12, kw=dict(num_inference_steps=10, strength=0.6, guidance_scale=7.5))
+GPU_CONTROLNET = dict(size=64, seed=53, gen_seed=13,
+                      kw=dict(num_inference_steps=6, guidance_scale=7.5, controlnet_conditioning_scale=0.5,
+                              control_guidance_start=0.0, control_guidance_end=0.7))
