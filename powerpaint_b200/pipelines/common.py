@@ -106,6 +106,72 @@ def prepare_mask_and_masked_image(image, mask, height, width, return_image: bool
     return mask, masked_image
 
 
+_IMAGE_KINDS = ("one of PIL image, numpy array, torch tensor, list of PIL images, list of numpy arrays or list of torch "
+                "tensors")
+
+
+def _is_image_input(x) -> bool:
+    one = (PIL.Image.Image, torch.Tensor, np.ndarray)
+    return isinstance(x, one) or (isinstance(x, list) and len(x) > 0 and isinstance(x[0], one))
+
+
+def check_image(image, prompt, prompt_embeds, mask=None, with_mask: bool = False):
+    """`check_image` of the ControlNet / BrushNet pipelines (ref:pipeline_PowerPaint_ControlNet.py:788-827,
+    ref:pipeline_PowerPaint_Brushnet_CA.py:868-922): accepted container types, then the image batch against the prompt
+    batch — same exception types and messages."""
+    if not _is_image_input(image):
+        raise TypeError(f"image must be passed and be {_IMAGE_KINDS}, but is {type(image)}")
+    if with_mask and not _is_image_input(mask):
+        raise TypeError(f"mask must be passed and be {_IMAGE_KINDS}, but is {type(mask)}")
+    image_batch_size = 1 if isinstance(image, PIL.Image.Image) else len(image)
+    if prompt is not None and isinstance(prompt, str):
+        prompt_batch_size = 1
+    elif prompt is not None and isinstance(prompt, list):
+        prompt_batch_size = len(prompt)
+    else:
+        prompt_batch_size = prompt_embeds.shape[0]
+    if image_batch_size != 1 and image_batch_size != prompt_batch_size:
+        raise ValueError("If image batch size is not 1, image batch size must be same as prompt batch size. image batch "
+                         f"size: {image_batch_size}, prompt batch size: {prompt_batch_size}")
+
+
+def check_prompt_arguments(prompt, negative_prompt, prompt_embeds, negative_prompt_embeds):
+    """the prompt / embedding exclusivity rules every reference `check_inputs` shares
+    (ref:pipeline_PowerPaint.py:575-602, ref:pipeline_PowerPaint_Brushnet_CA.py:782-807, ref:…ControlNet.py:675-700)"""
+    if prompt is not None and prompt_embeds is not None:
+        raise ValueError(f"Cannot forward both `prompt`: {prompt} and `prompt_embeds`: {prompt_embeds}. Please make "
+                         "sure to only forward one of the two.")
+    elif prompt is None and prompt_embeds is None:
+        raise ValueError("Provide either `prompt` or `prompt_embeds`. Cannot leave both `prompt` and `prompt_embeds` "
+                         "undefined.")
+    elif prompt is not None and not isinstance(prompt, (str, list)):
+        raise ValueError(f"`prompt` has to be of type `str` or `list` but is {type(prompt)}")
+    if negative_prompt is not None and negative_prompt_embeds is not None:
+        raise ValueError(f"Cannot forward both `negative_prompt`: {negative_prompt} and `negative_prompt_embeds`:"
+                         f" {negative_prompt_embeds}. Please make sure to only forward one of the two.")
+    if prompt_embeds is not None and negative_prompt_embeds is not None:
+        if prompt_embeds.shape != negative_prompt_embeds.shape:
+            raise ValueError("`prompt_embeds` and `negative_prompt_embeds` must have the same shape when passed "
+                             f"directly, but got: `prompt_embeds` {prompt_embeds.shape} != "
+                             f"`negative_prompt_embeds` {negative_prompt_embeds.shape}.")
+
+
+def check_control_guidance(control_guidance_start, control_guidance_end):
+    """ref:pipeline_PowerPaint_Brushnet_CA.py:836-855, ref:pipeline_PowerPaint_ControlNet.py:768-786"""
+    if len(control_guidance_start) != len(control_guidance_end):
+        raise ValueError(f"`control_guidance_start` has {len(control_guidance_start)} elements, but "
+                         f"`control_guidance_end` has {len(control_guidance_end)} elements. Make sure to provide the "
+                         "same number of elements to each list.")
+    for start, end in zip(control_guidance_start, control_guidance_end):
+        if start >= end:
+            raise ValueError(f"control guidance start: {start} cannot be larger or equal to control guidance end: "
+                             f"{end}.")
+        if start < 0.0:
+            raise ValueError(f"control guidance start: {start} can't be smaller than 0.")
+        if end > 1.0:
+            raise ValueError(f"control guidance end: {end} can't be larger than 1.0.")
+
+
 def preprocess_image(image, height=None, width=None, do_normalize=True) -> torch.Tensor:
     """VaeImageProcessor.preprocess: PIL/np/tensor -> float32 NCHW, resized (lanczos), [-1,1] if
     do_normalize (the control-image processor uses do_normalize=False,

@@ -20,7 +20,8 @@ import torch
 
 from ..denoise import FusedDenoiser
 from ..models.unet_2d_condition import BrushNetModel, UNet2DConditionModel
-from .common import StableDiffusionPipelineOutput, decode_latents, encode_text, preprocess_image, randn_tensor
+from .common import (StableDiffusionPipelineOutput, check_control_guidance, check_image, check_prompt_arguments,
+                     decode_latents, encode_text, preprocess_image, randn_tensor)
 from .pipeline_PowerPaint import StableDiffusionInpaintPipeline
 
 
@@ -103,38 +104,43 @@ class StableDiffusionPowerPaintBrushNetPipeline(StableDiffusionInpaintPipeline):
             return torch.cat([negative_prompt_embeds, prompt_embeds])
         return prompt_embeds
 
-    # ------------------------------------------------------------------ checks (:753-922, hot-path subset)
-    def check_inputs_brushnet(self, prompt, image, mask, callback_steps, negative_prompt, prompt_embeds,
-                              negative_prompt_embeds, brushnet_conditioning_scale, control_guidance_start,
-                              control_guidance_end):
+    # ------------------------------------------------------------------ checks (:753-922)
+    _callback_tensor_inputs = ["latents", "prompt_embeds", "negative_prompt_embeds"]
+
+    def check_inputs_brushnet(self, prompt, image, mask, callback_steps, negative_prompt=None, prompt_embeds=None,
+                              negative_prompt_embeds=None, ip_adapter_image=None, ip_adapter_image_embeds=None,
+                              brushnet_conditioning_scale=1.0, control_guidance_start=0.0, control_guidance_end=1.0,
+                              callback_on_step_end_tensor_inputs=None):
+        """the reference's `check_inputs` (:753-866) in its order, same exception types and messages"""
         if callback_steps is not None and (not isinstance(callback_steps, int) or callback_steps <= 0):
             raise ValueError(f"`callback_steps` has to be a positive integer but is {callback_steps} of type"
                              f" {type(callback_steps)}.")
-        if prompt is not None and prompt_embeds is not None:
-            raise ValueError(f"Cannot forward both `prompt`: {prompt} and `prompt_embeds`: {prompt_embeds}.")
-        elif prompt is None and prompt_embeds is None:
-            raise ValueError("Provide either `prompt` or `prompt_embeds`. Cannot leave both undefined.")
-        elif prompt is not None and not isinstance(prompt, (str, list)):
-            raise ValueError(f"`prompt` has to be of type `str` or `list` but is {type(prompt)}")
-        if negative_prompt is not None and negative_prompt_embeds is not None:
-            raise ValueError("Cannot forward both `negative_prompt` and `negative_prompt_embeds`.")
-        if prompt_embeds is not None and negative_prompt_embeds is not None:
-            if prompt_embeds.shape != negative_prompt_embeds.shape:
-                raise ValueError("`prompt_embeds` and `negative_prompt_embeds` must have the same shape.")
+        if callback_on_step_end_tensor_inputs is not None and not all(
+                k in self._callback_tensor_inputs for k in callback_on_step_end_tensor_inputs):
+            bad = [k for k in callback_on_step_end_tensor_inputs if k not in self._callback_tensor_inputs]
+            raise ValueError(f"`callback_on_step_end_tensor_inputs` has to be in {self._callback_tensor_inputs}, but "
+                             f"found {bad}")
+        check_prompt_arguments(prompt, negative_prompt, prompt_embeds, negative_prompt_embeds)
         if not isinstance(self.brushnet, BrushNetModel):
             assert False
+        check_image(image, prompt, prompt_embeds, mask=mask, with_mask=True)
         if not isinstance(brushnet_conditioning_scale, float):
             raise TypeError("For single brushnet: `brushnet_conditioning_scale` must be type `float`.")
-        if len(control_guidance_start) != len(control_guidance_end):
-            raise ValueError("`control_guidance_start` and `control_guidance_end` must have the same length")
-        for start, end in zip(control_guidance_start, control_guidance_end):
-            if start >= end:
-                raise ValueError(f"control guidance start: {start} cannot be larger or equal to control guidance "
-                                 f"end: {end}.")
-            if start < 0.0:
-                raise ValueError(f"control guidance start: {start} can't be smaller than 0.")
-            if end > 1.0:
-                raise ValueError(f"control guidance end: {end} can't be larger than 1.0.")
+        if not isinstance(control_guidance_start, (tuple, list)):
+            control_guidance_start = [control_guidance_start]
+        if not isinstance(control_guidance_end, (tuple, list)):
+            control_guidance_end = [control_guidance_end]
+        check_control_guidance(control_guidance_start, control_guidance_end)
+        if ip_adapter_image is not None and ip_adapter_image_embeds is not None:
+            raise ValueError("Provide either `ip_adapter_image` or `ip_adapter_image_embeds`. Cannot leave both "
+                             "`ip_adapter_image` and `ip_adapter_image_embeds` defined.")
+        if ip_adapter_image_embeds is not None:
+            if not isinstance(ip_adapter_image_embeds, list):
+                raise ValueError("`ip_adapter_image_embeds` has to be of type `list` but is "
+                                 f"{type(ip_adapter_image_embeds)}")
+            elif ip_adapter_image_embeds[0].ndim not in [3, 4]:
+                raise ValueError("`ip_adapter_image_embeds` has to be a list of 3D or 4D tensors but is "
+                                 f"{ip_adapter_image_embeds[0].ndim}D")
 
     def prepare_image(self, image, width, height, batch_size, num_images_per_prompt, device, dtype,
                       do_classifier_free_guidance=False, guess_mode=False):
@@ -170,6 +176,19 @@ class StableDiffusionPowerPaintBrushNetPipeline(StableDiffusionInpaintPipeline):
         prompt_embedsU = kwargs.pop("prompt_embedsU", None)
         if kwargs:
             raise TypeError(f"unexpected keyword arguments: {sorted(kwargs)}")
+        # align format for control guidance (:1197-1205), then the reference's checks in the reference's order (:1208-1224)
+        if not isinstance(control_guidance_start, list) and isinstance(control_guidance_end, list):
+            control_guidance_start = len(control_guidance_end) * [control_guidance_start]
+        elif not isinstance(control_guidance_end, list) and isinstance(control_guidance_start, list):
+            control_guidance_end = len(control_guidance_start) * [control_guidance_end]
+        elif not isinstance(control_guidance_start, list) and not isinstance(control_guidance_end, list):
+            control_guidance_start, control_guidance_end = [control_guidance_start], [control_guidance_end]
+        prompt, negative_prompt = promptA, negative_promptA
+        self.check_inputs_brushnet(prompt, image, mask, callback_steps, negative_prompt, prompt_embeds,
+                                   negative_prompt_embeds, ip_adapter_image, ip_adapter_image_embeds,
+                                   brushnet_conditioning_scale, control_guidance_start, control_guidance_end,
+                                   callback_on_step_end_tensor_inputs)
+        # valid for the reference, outside the hot path here
         if ip_adapter_image is not None or ip_adapter_image_embeds is not None:
             raise NotImplementedError("IP-adapter inputs are outside the hot path (unused by app.py)")
         if guess_mode:
@@ -178,14 +197,6 @@ class StableDiffusionPowerPaintBrushNetPipeline(StableDiffusionInpaintPipeline):
             raise NotImplementedError("cross_attention_kwargs (LoRA scale) is outside the hot path")
         if timesteps is not None:
             raise NotImplementedError("custom `timesteps` are not supported by the DDIM schedule table")
-        if not isinstance(control_guidance_start, list):
-            control_guidance_start = [control_guidance_start]
-        if not isinstance(control_guidance_end, list):
-            control_guidance_end = [control_guidance_end]
-        prompt, negative_prompt = promptA, negative_promptA
-        self.check_inputs_brushnet(prompt, image, mask, callback_steps, negative_prompt, prompt_embeds,
-                                   negative_prompt_embeds, brushnet_conditioning_scale, control_guidance_start,
-                                   control_guidance_end)
         self._guidance_scale = guidance_scale
         if prompt is not None and isinstance(prompt, str):
             batch_size = 1
@@ -212,6 +223,10 @@ class StableDiffusionPowerPaintBrushNetPipeline(StableDiffusionInpaintPipeline):
         ts = self.scheduler.timesteps
         num_channels_latents = self.unet.config.in_channels
         shape = (total, num_channels_latents, height // self.vae_scale_factor, width // self.vae_scale_factor)
+        if isinstance(generator, list) and len(generator) != total:  # (:957-962)
+            raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an "
+                             f"effective batch size of {total}. Make sure the batch size matches the length of the "
+                             "generators.")
         if latents is None:
             noise = randn_tensor(shape, generator=generator, device=device, dtype=torch.float32)
         else:

@@ -16,8 +16,9 @@ import torch
 
 from ..denoise import FusedDenoiser
 from ..models.unet_2d_condition import ControlNetModel, UNet2DConditionModel
-from .common import (StableDiffusionPipelineOutput, decode_latents, prepare_mask_and_masked_image,
-                     preprocess_image, randn_tensor, uint8_device_inputs)
+from .common import (StableDiffusionPipelineOutput, check_control_guidance, check_image, check_prompt_arguments,
+                     decode_latents, prepare_mask_and_masked_image, preprocess_image, randn_tensor,
+                     uint8_device_inputs)
 from .pipeline_PowerPaint import StableDiffusionInpaintPipeline
 
 
@@ -38,6 +39,36 @@ class StableDiffusionControlNetInpaintPipeline(StableDiffusionInpaintPipeline):
             self._denoiser = FusedDenoiser(self.unet, self.controlnet, mode="controlnet")
             self._denoiser_unet, self._denoiser_side = self.unet, self.controlnet
         return self._denoiser
+
+    def check_inputs_controlnet(self, prompt, image, height, width, callback_steps, negative_prompt=None,
+                                prompt_embeds=None, negative_prompt_embeds=None, controlnet_conditioning_scale=1.0,
+                                control_guidance_start=0.0, control_guidance_end=1.0):
+        """the reference's `check_inputs` (:651-786; `image` = the control image) in its order, same exception types
+        and messages. Unlike the v1 pipeline it does not look at `strength`."""
+        if height % 8 != 0 or width % 8 != 0:
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+        if callback_steps is None or not isinstance(callback_steps, int) or callback_steps <= 0:
+            raise ValueError(f"`callback_steps` has to be a positive integer but is {callback_steps} of type"
+                             f" {type(callback_steps)}.")
+        check_prompt_arguments(prompt, negative_prompt, prompt_embeds, negative_prompt_embeds)
+        if not isinstance(self.controlnet, ControlNetModel):
+            assert False
+        check_image(image, prompt, prompt_embeds)
+        if not isinstance(controlnet_conditioning_scale, float):
+            raise TypeError("For single controlnet: `controlnet_conditioning_scale` must be type `float`.")
+        check_control_guidance(control_guidance_start, control_guidance_end)
+
+    def _default_height_width(self, height, width, image):
+        """missing sizes come from the init image, rounded down to a multiple of 8 (:914-937)"""
+        while isinstance(image, list):
+            image = image[0]
+        if height is None:
+            height = image.height if hasattr(image, "height") else image.shape[2]
+            height = (height // 8) * 8
+        if width is None:
+            width = image.width if hasattr(image, "width") else image.shape[3]
+            width = (width // 8) * 8
+        return height, width
 
     def prepare_control_image(self, image, width, height, batch_size, num_images_per_prompt, device, dtype,
                               do_classifier_free_guidance=False, guess_mode=False):
@@ -63,23 +94,23 @@ class StableDiffusionControlNetInpaintPipeline(StableDiffusionInpaintPipeline):
                  controlnet_conditioning_scale: Union[float, List[float]] = 0.5, guess_mode: bool = False,
                  control_guidance_start: Union[float, List[float]] = 0.0,
                  control_guidance_end: Union[float, List[float]] = 1.0):
+        height, width = self._default_height_width(height, width, image)
+        prompt, negative_prompt = promptA, negative_promptA
+        # align format for control guidance (:1491-1502), then the reference's checks (:1505-1517)
+        if not isinstance(control_guidance_start, list) and isinstance(control_guidance_end, list):
+            control_guidance_start = len(control_guidance_end) * [control_guidance_start]
+        elif not isinstance(control_guidance_end, list) and isinstance(control_guidance_start, list):
+            control_guidance_end = len(control_guidance_start) * [control_guidance_end]
+        elif not isinstance(control_guidance_start, list) and not isinstance(control_guidance_end, list):
+            control_guidance_start, control_guidance_end = [control_guidance_start], [control_guidance_end]
+        self.check_inputs_controlnet(prompt, control_image, height, width, callback_steps, negative_prompt,
+                                     prompt_embeds, negative_prompt_embeds, controlnet_conditioning_scale,
+                                     control_guidance_start, control_guidance_end)
+        # valid for the reference, outside the hot path here
         if guess_mode:
             raise NotImplementedError("guess_mode is outside the hot path")
         if cross_attention_kwargs:
             raise NotImplementedError("cross_attention_kwargs (LoRA scale) is outside the hot path")
-        if isinstance(controlnet_conditioning_scale, list):
-            controlnet_conditioning_scale = controlnet_conditioning_scale[0]
-        if not isinstance(control_guidance_start, list):
-            control_guidance_start = [control_guidance_start]
-        if not isinstance(control_guidance_end, list):
-            control_guidance_end = [control_guidance_end]
-        height = height or self.unet.config.sample_size * self.vae_scale_factor
-        width = width or self.unet.config.sample_size * self.vae_scale_factor
-        prompt, negative_prompt = promptA, negative_promptA
-        self.check_inputs(prompt, height, width, strength, callback_steps, negative_prompt, prompt_embeds,
-                          negative_prompt_embeds)
-        if control_image is None:
-            raise ValueError("`control_image` input cannot be undefined.")
         if prompt is not None and isinstance(prompt, str):
             batch_size = 1
         elif prompt is not None and isinstance(prompt, list):

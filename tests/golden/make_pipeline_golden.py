@@ -126,19 +126,9 @@ def main():
         out[f"{name}_latents"] = lat.numpy()
         print(name, tuple(lat.shape), float(lat.abs().mean()))
     # what the reference raises for invalid calls (check_inputs :554-602, prepare_mask_and_masked_image :39-153, ...)
-    import json
-
     from pipeline_cases import error_cases
 
-    errors = {}
-    for name, kw in error_cases(img, mask, pe, ne, H, W).items():
-        try:
-            pipe(**kw)
-            errors[name] = ["no error", ""]
-        except Exception as e:  # noqa: BLE001  (recording whatever the reference raises is the point)
-            errors[name] = [type(e).__name__, str(e)]
-    with open(os.path.join(os.environ.get("PP_GOLDEN_OUT", HERE), "pipeline_v1_errors.json"), "w") as f:
-        json.dump(errors, f, indent=1, sort_keys=True)
+    record_errors(pipe, error_cases(img, mask, pe, ne, H, W), "pipeline_v1_errors.json")
     # string prompts through the reference's `_encode_prompt` (tokenizer + text encoder, A/B trade-off :317-470)
     tok, te, _ = text_stack()
     pipe_t = RefPipe(vae=AutoencoderKL.synthetic(tiny=True), text_encoder=te, tokenizer=tok, unet=unet,
@@ -165,6 +155,21 @@ def main():
     save("pipeline_v1_call.npz", out)
     brushnet_golden()
     controlnet_golden()
+
+
+def record_errors(pipe, cases, name):
+    import json
+
+    errors = {}
+    for case, kw in cases.items():
+        try:
+            pipe(**kw)
+            errors[case] = ["no error", ""]
+        except Exception as e:  # noqa: BLE001  (recording whatever the reference raises is the point)
+            errors[case] = [type(e).__name__, str(e)]
+    with open(os.path.join(os.environ.get("PP_GOLDEN_OUT", HERE), name), "w") as f:
+        json.dump(errors, f, indent=1, sort_keys=True)
+    print("wrote", name, sum(v[0] != "no error" for v in errors.values()), "errors of", len(errors), "cases")
 
 
 def save(name, out):
@@ -199,6 +204,9 @@ def brushnet_golden():
         out[f"{name}_latents"] = lat.numpy()
         print("brushnet", name, tuple(lat.shape), float(lat.abs().mean()))
     save("pipeline_brushnet_call.npz", out)
+    from pipeline_cases import brushnet_error_cases
+
+    record_errors(pipe, brushnet_error_cases(img, mask, PROMPTS, CROSS), "pipeline_brushnet_errors.json")
 
 
 BRUSHNET_CASES = {
@@ -250,6 +258,10 @@ def controlnet_golden():
     out["gpu_controlnet_latents"] = lat.numpy()
     print("gpu_controlnet", tuple(lat.shape), float(lat.abs().mean()))
     save("pipeline_controlnet_call.npz", out)
+    from pipeline_cases import controlnet_error_cases
+
+    img, mask, pe, ne = call_inputs()
+    record_errors(pipe, controlnet_error_cases(img, mask, pe, ne, ctl, H, W), "pipeline_controlnet_errors.json")
 
 
 if __name__ == "__main__":

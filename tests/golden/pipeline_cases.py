@@ -52,3 +52,62 @@ GPU_V1_STRENGTH = dict(size=128, seed=52, gen_seed=12, kw=dict(num_inference_ste
 GPU_CONTROLNET = dict(size=64, seed=53, gen_seed=13,
                       kw=dict(num_inference_steps=6, guidance_scale=7.5, controlnet_conditioning_scale=0.5,
                               control_guidance_start=0.0, control_guidance_end=0.7))
+
+
+def brushnet_error_cases(img, mask, prompts, cross):
+    """invalid v2 (BrushNet) calls: name -> kwargs"""
+    base = dict(**prompts, tradoff=0.7, tradoff_nag=0.4, image=img, mask=mask, num_inference_steps=2,
+                guidance_scale=7.5, output_type="latent", return_dict=False)
+    pe = torch.randn(img.shape[0], 77, cross, generator=torch.Generator().manual_seed(3))
+
+    def c(**kw):
+        return {**base, **kw}
+
+    return {
+        "scale_int": c(brushnet_conditioning_scale=1),
+        "scale_list": c(brushnet_conditioning_scale=[1.0]),
+        "callback_steps_zero": c(callback_steps=0),
+        "prompt_and_embeds": c(prompt_embeds=pe),
+        "no_prompt": c(promptA=None, promptB=None),
+        "prompt_type": c(promptA=3, promptB=3),
+        "negative_prompt_and_embeds": c(negative_prompt_embeds=pe),
+        "image_type": c(image="x"),
+        "mask_type": c(mask=3.0),
+        "image_batch_mismatch": c(image=torch.cat([img, img[:1]])),
+        "guidance_start_ge_end": c(control_guidance_start=0.5, control_guidance_end=0.5),
+        "guidance_start_negative": c(control_guidance_start=-0.1),
+        "guidance_end_above_one": c(control_guidance_end=1.5),
+        "guidance_length_mismatch": c(control_guidance_start=[0.0, 0.1], control_guidance_end=[1.0]),
+        "callback_tensor_inputs": c(callback_on_step_end_tensor_inputs=["nope"]),
+        "generator_list_length": c(generator=[torch.Generator().manual_seed(0)] * 3),
+        "ip_adapter_both": c(ip_adapter_image=img, ip_adapter_image_embeds=[pe]),
+    }
+
+
+def controlnet_error_cases(img, mask, pe, ne, ctl, H, W):
+    """invalid ControlNet calls: name -> kwargs (strength outside [0, 1] is NOT one: the reference does not check it)"""
+    base = dict(image=img, mask=mask, control_image=ctl, prompt_embeds=pe, negative_prompt_embeds=ne, height=H, width=W,
+                num_inference_steps=2, guidance_scale=7.5, output_type="latent", return_dict=False)
+
+    def c(**kw):
+        return {**base, **kw}
+
+    return {
+        "height_not_multiple_of_8": c(height=60),
+        "callback_steps_zero": c(callback_steps=0),
+        "prompt_and_embeds": c(promptA="a cat", promptB="a cat"),
+        "no_prompt": c(prompt_embeds=None, negative_prompt_embeds=None),
+        "negative_prompt_and_embeds": c(negative_promptA="x", negative_promptB="x"),
+        "embeds_shape_mismatch": c(negative_prompt_embeds=ne[:1]),
+        "scale_int": c(controlnet_conditioning_scale=1),
+        "scale_list": c(controlnet_conditioning_scale=[0.5]),
+        "control_image_type": c(control_image="x"),
+        "control_image_none": c(control_image=None),
+        "control_image_batch": c(control_image=torch.cat([ctl, ctl[:1]])),
+        "guidance_start_ge_end": c(control_guidance_start=0.5, control_guidance_end=0.5),
+        "guidance_start_negative": c(control_guidance_start=-0.1),
+        "guidance_end_above_one": c(control_guidance_end=1.5),
+        "image_none": c(image=None),
+        "mask_range": c(mask=mask + 1.5),
+        "generator_list_length": c(generator=[torch.Generator().manual_seed(0)] * 3),
+    }
