@@ -100,6 +100,14 @@ def main():
     mask_np = (rng.random((H, W)) > 0.6).astype(np.float32)
     m2, mi2 = ref_prepare(img_u8, mask_np, H, W)
     out["prepare_np_mask"], out["prepare_np_masked_image"] = m2.numpy(), mi2.numpy()
+    # every input container prepare_mask_and_masked_image accepts, as digests (bit-exact without storing the tensors)
+    import json
+
+    from pipeline_cases import digest_prepare, prepare_input_kinds
+
+    kinds = {k: digest_prepare(ref_prepare, i, m, H, W) for k, (i, m) in prepare_input_kinds(H, W).items()}
+    with open(os.path.join(os.environ.get("PP_GOLDEN_OUT", HERE), "prepare_input_kinds.json"), "w") as f:
+        json.dump(kinds, f, indent=1, sort_keys=True)
     for name, (strength, steps, gs, eta, per_sample) in CASES.items():
         seen = []
         lat = pipe(image=img, mask=mask, prompt_embeds=pe, negative_prompt_embeds=ne, height=H, width=W,

@@ -111,3 +111,42 @@ def controlnet_error_cases(img, mask, pe, ne, ctl, H, W):
         "mask_range": c(mask=mask + 1.5),
         "generator_list_length": c(generator=[torch.Generator().manual_seed(0)] * 3),
     }
+
+
+def prepare_input_kinds(H, W):
+    """every input container `prepare_mask_and_masked_image` accepts (ref:pipeline_PowerPaint.py:39-153): PIL (resized
+    with LANCZOS / NEAREST), lists, numpy HWC / HW, tensors of every rank, plus two rejected combinations"""
+    import PIL.Image
+
+    rng = np.random.default_rng(0)
+    pil = PIL.Image.fromarray(rng.integers(0, 256, (100, 80, 3), dtype=np.uint8))
+    pm = PIL.Image.fromarray((rng.random((100, 80)) > 0.5).astype(np.uint8) * 255).convert("L")
+    npimg = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    npm = (rng.random((H, W)) > 0.5).astype(np.float32)
+    g = torch.Generator().manual_seed(0)
+    t3 = torch.rand(3, H, W, generator=g) * 2 - 1
+    tm2 = (torch.rand(H, W, generator=g) > 0.5).float()
+    return {
+        "pil": (pil, pm),
+        "pil_list": ([pil, pil.transpose(PIL.Image.FLIP_LEFT_RIGHT)], [pm, pm]),
+        "np": (npimg, npm),
+        "np_list": ([npimg, npimg[::-1].copy()], [npm, npm]),
+        "np_batch4d": (np.stack([npimg, npimg]), np.stack([npm, npm])[:, None]),
+        "tensor3d_mask2d": (t3, tm2),
+        "tensor4d_mask3d": (t3[None], tm2[None]),
+        "tensor_batch_mask_single": (torch.stack([t3, t3 * 0.5]), tm2[None, None]),
+        "pil_image_np_mask": (pil.resize((W, H)), npm),
+        "np_mask_255": (npimg, (npm * 255).astype(np.uint8)),
+    }
+
+
+def digest_prepare(fn, image, mask, H, W):
+    """shapes + sha256 of the three outputs (bit-exact comparison without storing them), or the exception"""
+    import hashlib
+
+    try:
+        outs = fn(image, mask, H, W, return_image=True)
+    except Exception as e:  # noqa: BLE001
+        return {"error": [type(e).__name__, str(e)]}
+    return {"shapes": [list(o.shape) for o in outs],
+            "sha256": [hashlib.sha256(o.contiguous().numpy().tobytes()).hexdigest() for o in outs]}
