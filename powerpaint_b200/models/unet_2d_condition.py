@@ -66,7 +66,15 @@ def _make_config(cfg: NetConfig, **extra) -> _Config:
                   num_attention_heads=None, class_embed_type=None, num_class_embeds=None,
                   upcast_attention=False, resnet_time_scale_shift="default", downsample_padding=1,
                   projection_class_embeddings_input_dim=None, mid_block_type="UNetMidBlock2DCrossAttn",
-                  center_input_sample=False, addition_embed_type=None))
+                  center_input_sample=False, addition_embed_type=None,
+                  # the remaining constructor arguments of the reference class (unet_2d_condition.py:166-218) at the
+                  # only values the hot path implements, so that `config.<name>` reads the same on both sides
+                  addition_embed_type_num_heads=64, addition_time_embed_dim=None, attention_type="default",
+                  class_embeddings_concat=False, conv_in_kernel=3, conv_out_kernel=3, cross_attention_norm=None,
+                  dropout=0.0, dual_cross_attention=False, encoder_hid_dim=None, encoder_hid_dim_type=None,
+                  mid_block_only_cross_attention=None, resnet_out_scale_factor=1.0, resnet_skip_time_act=False,
+                  reverse_transformer_layers_per_block=None, time_embedding_act_fn=None, time_embedding_dim=None,
+                  time_embedding_type="positional", timestep_post_act=None, transformer_layers_per_block=1))
     d.update(extra)
     return _Config(**d)
 

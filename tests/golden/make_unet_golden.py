@@ -87,6 +87,15 @@ def main():
     x9, ctx9, _ = inputs(19, 9, 8, 8)
     out["unet9_controlnet_residuals"] = u9(x9, 500, ctx9, down_block_additional_residuals=dres,
                                            mid_block_additional_residual=mres).sample.numpy()
+    # the `config` surface of the reference classes (every constructor argument, unet_2d_condition.py:166-218,
+    # BrushNet_CA.py:139-186), for the product's `.config.<name>` to be held to
+    import json
+
+    def plain(cfg):
+        return {k: (list(v) if isinstance(v, tuple) else v) for k, v in dict(cfg).items()}
+
+    with open(os.path.join(HERE, "model_configs.json"), "w") as f:
+        json.dump({"unet9": plain(u9.config), "brushnet": plain(bn.config)}, f, indent=1, sort_keys=True)
     path = os.path.join(HERE, "unet_composition.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in list(out.items())[:4]}, "...", len(out), "arrays")
