@@ -75,3 +75,26 @@ def test_vae_param_layout_matches_torch_restatement():
 
     with pytest.raises(RuntimeError):
         p.encode(torch.zeros(1, 3, 64, 64))  # CPU parameters: there is no CPU path
+
+
+def test_safetensors_load_model_like_the_app(tmp_path):
+    """the app loads checkpoints with `safetensors.torch.load_model(pipe.unet | pipe.brushnet, path)`
+    (ref:app.py:111,188-191): diffusers-named tensors in, nothing missing or unexpected, the recorded programs of the
+    previous weights invalidated"""
+    import pytest
+
+    st = pytest.importorskip("safetensors.torch")
+    from powerpaint_b200.models import BrushNetModel, UNet2DConditionModel
+
+    for cls, kind, cin in ((UNet2DConditionModel, "unet", 9), (BrushNetModel, "brushnet", 4)):
+        _, n = _cfgs(True, cin)
+        sd = synthetic_state_dict(n, kind, 3)
+        path = str(tmp_path / f"{kind}.safetensors")
+        st.save_file({k: v.contiguous() for k, v in sd.items()}, path)
+        m = cls(n)
+        before = m.generation
+        missing, unexpected = st.load_model(m, path)
+        assert not missing and not unexpected
+        assert m.generation > before
+        got = m.state_dict()
+        assert all(torch.equal(got[k].float(), v) for k, v in sd.items())
