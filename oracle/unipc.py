@@ -6,7 +6,10 @@ The v2 app swaps the pipeline's scheduler for `UniPCMultistepScheduler.from_conf
 "bh2" variant, data prediction) for the configuration that call produces: solver_order 2, predict_x0,
 prediction_type epsilon, lower_order_final, no thresholding / Karras sigmas, and the beta schedule / timestep
 spacing / steps_offset inherited from the DDIM config. Tensor arithmetic in fp32 torch like the original.
-PARITY UNPINNED: diffusers is absent here, so no golden vectors of the original exist.
+PARITY UNPINNED against diffusers (absent here: no golden vectors of the original exist). Held to the mathematics
+instead: tests/test_scheduler.py::test_unipc_has_the_published_order_of_accuracy measures this class (and the product's
+folded scalars) against the closed-form probability-flow solution for Gaussian data: third-order convergence for
+solver_order 2, second for 1 — a wrong coefficient anywhere drops it to first order.
 """
 from __future__ import annotations
 

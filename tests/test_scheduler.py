@@ -136,3 +136,115 @@ def test_unipc_folded_coefficients_match_stepwise_oracle():
 
     with pytest.raises(NotImplementedError):
         UniPCMultistepScheduler(solver_order=3)
+
+
+def _gaussian_denoiser_eps(x, alpha, sigma, s2):
+    """optimal epsilon-prediction for data ~ N(0, s2): E[x0 | x_t] = alpha s2 / (alpha^2 s2 + sigma^2) x_t"""
+    return (x - alpha * (alpha * s2 / (alpha * alpha * s2 + sigma * sigma)) * x) / sigma
+
+
+def test_unipc_has_the_published_order_of_accuracy():
+    """No output of diffusers' UniPCMultistepScheduler can be produced here, so the stepwise restatement
+    (oracle/unipc.py) AND the product's folded per-step scalars are held to the mathematics: for data ~ N(0, s^2) the
+    probability-flow ODE has the closed form x_t = x_T sqrt(alpha_t^2 s^2 + sigma_t^2) / sqrt(alpha_T^2 s^2 + sigma_T^2)
+    and the optimal denoiser is linear, so the global error of a run is measurable exactly. UniPC-p = UniP-p + UniC-p has
+    order of accuracy p + 1 (Zhao et al. 2023, Thm 3.1): halving the step must cut the error ~8x for solver_order 2 (~4x
+    for 1); any wrong coefficient (rho, B(h), r_k, the lambda differences) drops it to first order. The comparison point
+    is t = 199 (the smooth part of the schedule; the last steps towards t = 0 have h = O(1) whatever the step count)."""
+    import math
+
+    import torch
+
+    from oracle.unipc import UniPCOracle
+    from powerpaint_b200.schedulers import UniPCMultistepScheduler
+
+    s2 = 0.25
+    x_init = torch.tensor([1.3, -0.7, 0.2], dtype=torch.float64)
+
+    def exact(a0, s0, a1, s1):
+        return x_init * math.sqrt(a1 * a1 * s2 + s1 * s1) / math.sqrt(a0 * a0 * s2 + s0 * s0)
+
+    def oracle_error(n, k, order):
+        o = UniPCOracle(timestep_spacing="trailing", solver_order=order)
+        o.set_timesteps(n)
+        o.sigmas = o.sigmas.double()
+        x = x_init.clone()
+        a0, s0 = [float(v) for v in o._alpha_sigma(o.sigmas[0])]
+        for i in range(k):
+            a, s = o._alpha_sigma(o.sigmas[o.step_index])
+            x = o.step(_gaussian_denoiser_eps(x, a, s, s2), int(o.timesteps[i]), x)
+        assert int(o.timesteps[k]) == 199
+        a1, s1 = [float(v) for v in o._alpha_sigma(o.sigmas[k])]
+        ref = exact(a0, s0, a1, s1)
+        return ((x - ref).norm() / ref.norm()).item()
+
+    def product_error(n, k):
+        s = UniPCMultistepScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                    timestep_spacing="trailing")
+        s.set_timesteps(n)
+        assert int(s.timesteps[k]) == 199
+        u = s.unipc_coefficients().double()
+        alpha = [1.0 / float(r[0]) for r in u]          # m = x / alpha - sigma / alpha * eps
+        sigma = [-float(r[1]) / float(r[0]) for r in u]
+        xs = x_init.clone()
+        last, m1, m2 = torch.zeros_like(xs), torch.zeros_like(xs), torch.zeros_like(xs)
+        for i in range(k):  # the update pp_unipc_step applies (same recursion as the folding test above)
+            r = u[i]
+            eps = _gaussian_denoiser_eps(xs, alpha[i], sigma[i], s2)
+            mt = r[0] * xs + r[1] * eps
+            xc = r[3] * last + r[4] * m1 + r[5] * m2 + r[6] * mt if r[2] != 0 else xs
+            last, m2, m1, xs = xc, m1, mt, r[7] * xc + r[8] * mt + r[9] * m1
+        ref = exact(alpha[0], sigma[0], alpha[k], sigma[k])
+        return ((xs - ref).norm() / ref.norm()).item()
+
+    grid = [(10, 8), (20, 16), (40, 32)]  # trailing spacing: steps of 100 / 50 / 25 from t = 999 down to t = 199
+    e1 = [oracle_error(n, k, 1) for n, k in grid]
+    e2 = [oracle_error(n, k, 2) for n, k in grid]
+    ep = [product_error(n, k) for n, k in grid]
+    order1 = [math.log2(e1[i] / e1[i + 1]) for i in range(2)]
+    order2 = [math.log2(e2[i] / e2[i + 1]) for i in range(2)]
+    orderp = [math.log2(ep[i] / ep[i + 1]) for i in range(2)]
+    assert all(1.4 < o < 2.4 for o in order1), (e1, order1)          # UniPC-1: second order
+    assert all(o > 2.7 for o in order2) and e2[-1] < 5e-5, (e2, order2)  # UniPC-2: third order (or better)
+    assert all(o > 2.7 for o in orderp) and ep[-1] < 5e-5, (ep, orderp)
+    # same iterates, folded (fp32 scalars) or stepwise (fp64 here)
+    assert all(abs(a - b) <= 1e-2 * b for a, b in zip(ep, e2)), (ep, e2)
+
+
+def test_ddim_converges_to_the_exact_flow_with_first_order():
+    """the same closed-form problem for DDIM (eta = 0), oracle step and the product's coefficient rows: the error at
+    t = 201 halves when the step halves (first-order exponential integrator) and the two agree"""
+    import math
+
+    import torch
+
+    from oracle.ddim import DDIMOracle
+    from powerpaint_b200.schedulers import DDIMScheduler
+
+    s2 = 0.25
+    x_init = torch.tensor([1.3, -0.7, 0.2], dtype=torch.float64)
+    errs_o, errs_p = [], []
+    for n in (10, 20, 40):
+        so, sp = DDIMOracle(), DDIMScheduler()
+        so.set_timesteps(n)
+        sp.set_timesteps(n)
+        ts = [int(t) for t in so.timesteps]
+        k = ts.index(201)
+        ac = so.alphas_cumprod.double()
+        coef = sp.step_coefficients(sp.timesteps).double()
+        xo, xp = x_init.clone(), x_init.clone()
+        for i in range(k):
+            a, s = float(ac[ts[i]]) ** 0.5, float(1 - ac[ts[i]]) ** 0.5
+            xo = so.step(_gaussian_denoiser_eps(xo, a, s, s2), ts[i], xo)
+            eps = _gaussian_denoiser_eps(xp, a, s, s2)
+            sa, s1a, sap, dirc = [float(v) for v in coef[i, :4]]
+            xp = sap * ((xp - s1a * eps) / sa) + dirc * eps
+        a0, s0 = float(ac[ts[0]]) ** 0.5, float(1 - ac[ts[0]]) ** 0.5
+        a1, s1 = float(ac[201]) ** 0.5, float(1 - ac[201]) ** 0.5
+        ref = x_init * math.sqrt(a1 * a1 * s2 + s1 * s1) / math.sqrt(a0 * a0 * s2 + s0 * s0)
+        errs_o.append(((xo - ref).norm() / ref.norm()).item())
+        errs_p.append(((xp - ref).norm() / ref.norm()).item())
+    for errs in (errs_o, errs_p):
+        orders = [math.log2(errs[i] / errs[i + 1]) for i in range(2)]
+        assert all(0.7 < o < 1.4 for o in orders) and errs[-1] < 2e-2, (errs, orders)
+    assert all(abs(a - b) <= 1e-3 * b for a, b in zip(errs_p, errs_o)), (errs_p, errs_o)
