@@ -420,6 +420,43 @@ class AutoencoderKL(nn.Module):
             img, nb, H, W = self._decode_nhwc(z)
             return ops.image_postprocess(img, nb, H, W, uint8=uint8)
 
+    # ---- checkpoint directories in the diffusers layout (`<root>/vae`)
+    @classmethod
+    def from_config(cls, config: dict) -> "AutoencoderKL":
+        if config.get("act_fn", "silu") != "silu":
+            raise NotImplementedError(f"config.act_fn = {config['act_fn']!r}: the SD VAE uses silu")
+        keys = ("in_channels", "out_channels", "latent_channels", "block_out_channels", "layers_per_block",
+                "norm_num_groups", "scaling_factor")
+        return cls(**{k: (tuple(config[k]) if isinstance(config[k], list) else config[k]) for k in keys if k in config})
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder: Optional[str] = None, torch_dtype=None,
+                        revision: Optional[str] = None, variant: Optional[str] = None, local_files_only: bool = False,
+                        cache_dir: Optional[str] = None, **unused) -> "AutoencoderKL":
+        """`config.json` + `diffusion_pytorch_model[.variant].safetensors | .bin`; the deprecated attention parameter
+        names of older VAE checkpoints (query / key / value / proj_attn) are renamed like diffusers does"""
+        from ..loading import load_json, load_weights, rename_deprecated_vae_attention, resolve_checkpoint_dir
+
+        d = resolve_checkpoint_dir(pretrained_model_name_or_path, subfolder, revision, local_files_only, cache_dir)
+        model = cls.from_config(load_json(d, "config.json"))
+        model.load_state_dict(rename_deprecated_vae_attention(load_weights(d, variant)), strict=True)
+        if torch_dtype is not None:
+            model.to(dtype=torch_dtype)
+        return model
+
+    def save_pretrained(self, save_directory, variant: Optional[str] = None, **unused):
+        import json
+        import os
+
+        from ..loading import save_weights
+
+        os.makedirs(save_directory, exist_ok=True)
+        cfg = {"_class_name": "AutoencoderKL", "_diffusers_version": "0.27.0", "act_fn": "silu"}
+        cfg.update({k: (list(v) if isinstance(v, tuple) else v) for k, v in vars(self.config).items()})
+        with open(os.path.join(save_directory, "config.json"), "w") as f:
+            json.dump(cfg, f, indent=2, sort_keys=True)
+        save_weights(self.state_dict(), save_directory, variant=variant)
+
     @classmethod
     def synthetic(cls, seed: int = 4321, tiny: bool = False, **kw) -> "AutoencoderKL":
         """deterministic random weights (no checkpoint reachable offline); `tiny` = small widths for tests"""

@@ -127,6 +127,42 @@ class _HotPathModel(nn.Module):
     def synthetic(cls, cfg: NetConfig, seed: int = 1234, **kw):
         return cls.from_state_dict(cfg, synthetic_state_dict(cfg, cls.KIND, seed), **kw)
 
+    # ---- checkpoint directories in the diffusers layout (ref:app.py:121-123,141-147,165-171)
+    @classmethod
+    def from_config(cls, config, **kw):
+        """a diffusers `config.json` dictionary (or another model's `.config`) -> an uninitialised model"""
+        from ..loading import net_config_from_diffusers
+
+        d = dict(vars(config)) if not isinstance(config, dict) else dict(config)
+        return cls(net_config_from_diffusers(d, cls.KIND), sample_size=d.get("sample_size") or 64, **kw)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder: Optional[str] = None, torch_dtype=None,
+                        revision: Optional[str] = None, variant: Optional[str] = None, local_files_only: bool = False,
+                        cache_dir: Optional[str] = None, **unused):
+        """`ModelMixin.from_pretrained` for a local directory or a cached hub snapshot: `config.json` +
+        `diffusion_pytorch_model[.variant].safetensors | .bin`, strict load, on the CPU. `torch_dtype` selects the
+        dtype of returned tensors (compute is bf16 x bf16 -> fp32 whatever it says)."""
+        from ..loading import load_json, load_weights, resolve_checkpoint_dir
+
+        d = resolve_checkpoint_dir(pretrained_model_name_or_path, subfolder, revision, local_files_only, cache_dir)
+        model = cls.from_config(load_json(d, "config.json"))
+        model.load_state_dict(load_weights(d, variant), strict=True)
+        if torch_dtype is not None:
+            model.to(dtype=torch_dtype)
+        return model
+
+    def save_pretrained(self, save_directory, variant: Optional[str] = None, **unused):
+        import json
+        import os
+
+        from ..loading import net_config_to_diffusers, save_weights
+
+        os.makedirs(save_directory, exist_ok=True)
+        with open(os.path.join(save_directory, "config.json"), "w") as f:
+            json.dump(net_config_to_diffusers(self._cfg, self.KIND, self.config), f, indent=2, sort_keys=True)
+        save_weights(self.state_dict(), save_directory, variant=variant)
+
     # ---- diffusers-like surface
     @property
     def dtype(self) -> torch.dtype:

@@ -50,6 +50,84 @@ class StableDiffusionInpaintPipeline:
         self._denoiser_unet = None
         self._progress_bar_config = {}
 
+    # ------------------------------------------------------------------ checkpoint directories (ref:app.py:91-93,157-164)
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, torch_dtype=None, revision: Optional[str] = None,
+                        variant: Optional[str] = None, local_files_only: bool = False,
+                        cache_dir: Optional[str] = None, **kwargs):
+        """`DiffusionPipeline.from_pretrained` for a local directory or a cached hub snapshot in the diffusers layout
+        (`model_index.json` + one subfolder per component). Constructor arguments passed as keywords replace the
+        stored component, like upstream (`brushnet=`, `text_encoder_brushnet=`, `safety_checker=None`, ...). The nets and
+        the VAE load as this package's classes, text encoder and tokenizer through transformers (the injected
+        dependencies they are upstream), the scheduler as DDIM (or UniPC) built from `scheduler_config.json`. A stored
+        safety checker is not loaded. Everything is on the CPU afterwards: `pipe = pipe.to("cuda")` as in the app."""
+        import inspect
+        import os
+
+        from ..loading import load_json, resolve_checkpoint_dir
+
+        root = resolve_checkpoint_dir(pretrained_model_name_or_path, None, revision, local_files_only, cache_dir)
+        index = load_json(root, "model_index.json")
+        params = [p for p in inspect.signature(cls.__init__).parameters if p != "self"]
+        passed = {k: kwargs.pop(k) for k in list(kwargs) if k in params}
+        for ignored in ("low_cpu_mem_usage", "use_safetensors", "device_map", "force_download", "resume_download",
+                        "proxies", "token", "use_auth_token", "custom_pipeline"):
+            kwargs.pop(ignored, None)
+        if kwargs:
+            raise TypeError(f"unexpected keyword arguments: {sorted(kwargs)}")
+        components = {}
+        for name in params:
+            if name in passed:
+                components[name] = passed[name]
+            elif name in ("safety_checker", "feature_extractor", "image_encoder"):
+                components[name] = None
+            elif name == "requires_safety_checker":
+                components[name] = False
+            else:
+                entry = index.get(name)
+                if not entry or entry[0] is None:
+                    raise ValueError(f"Pipeline {cls} expected {name}, but it is neither stored in "
+                                     f"{os.path.join(root, 'model_index.json')} nor passed as a keyword argument.")
+                components[name] = cls._load_component(name, os.path.join(root, name), entry, torch_dtype, variant)
+        return cls(**components)
+
+    @staticmethod
+    def _load_component(name: str, directory: str, entry, torch_dtype, variant):
+        """one subfolder of a pipeline directory; `entry` = [library, class name] of model_index.json"""
+        from ..loading import load_json
+        from ..models import AutoencoderKL, BrushNetModel, ControlNetModel
+        from ..schedulers import DDIMScheduler, UniPCMultistepScheduler
+
+        if name == "unet":
+            return UNet2DConditionModel.from_pretrained(directory, torch_dtype=torch_dtype, variant=variant)
+        if name == "brushnet":
+            return BrushNetModel.from_pretrained(directory, torch_dtype=torch_dtype, variant=variant)
+        if name == "controlnet":
+            return ControlNetModel.from_pretrained(directory, torch_dtype=torch_dtype, variant=variant)
+        if name == "vae":
+            return AutoencoderKL.from_pretrained(directory, torch_dtype=torch_dtype, variant=variant)
+        if name in ("text_encoder", "text_encoder_brushnet"):
+            import transformers
+
+            te = transformers.CLIPTextModel.from_pretrained(directory)
+            return te.to(torch_dtype) if torch_dtype is not None else te
+        if name == "tokenizer":
+            import transformers
+
+            return transformers.CLIPTokenizer.from_pretrained(directory)
+        if name == "scheduler":
+            cfg = load_json(directory, "scheduler_config.json")
+            stored = cfg.get("_class_name")
+            if stored == "UniPCMultistepScheduler":
+                return UniPCMultistepScheduler.from_config(cfg)
+            if stored not in (None, "DDIMScheduler"):
+                import warnings
+
+                warnings.warn(f"powerpaint_b200: the stored scheduler {stored} is replaced by DDIMScheduler built from "
+                              "the same noise schedule (the fused step kernels implement DDIM and UniPC)", stacklevel=3)
+            return DDIMScheduler.from_config(cfg)
+        raise ValueError(f"unknown pipeline component {name!r} ({entry})")
+
     # ------------------------------------------------------------------ small diffusers surface
     @property
     def _execution_device(self) -> torch.device:
@@ -59,20 +137,36 @@ class StableDiffusionInpaintPipeline:
     def device(self) -> torch.device:
         return self.unet.device
 
+    # every module the reference pipelines register (`register_modules`, ref:pipeline_PowerPaint.py:247-255,
+    # ref:pipeline_PowerPaint_Brushnet_CA.py:212-222, ref:pipeline_PowerPaint_ControlNet.py:308-317)
+    _components = ("vae", "text_encoder", "text_encoder_brushnet", "unet", "brushnet", "controlnet", "safety_checker")
+
     def to(self, device=None, dtype=None):
-        for name in ("vae", "text_encoder", "unet"):
+        """`DiffusionPipeline.to`: every registered module moves (the app does `pipe = pipe.to("cuda")`,
+        ref:app.py:113,135,200). A dtype only selects the dtype of the tensors the hot-path nets return."""
+        if isinstance(device, torch.dtype):
+            device, dtype = None, device
+        for name in self._components:
             m = getattr(self, name, None)
-            if m is not None and device is not None:
+            if m is None or not hasattr(m, "to"):
+                continue
+            if device is not None:
                 m.to(device)
-        if dtype is not None:
-            self.unet.to(dtype=dtype)
+            if dtype is not None and name in ("unet", "brushnet", "controlnet"):
+                m.to(dtype=dtype)
         return self
 
     def set_progress_bar_config(self, **kwargs):
         self._progress_bar_config = kwargs
 
     def enable_model_cpu_offload(self, gpu_id=0):
-        raise NotImplementedError("CPU offload is not supported: the hot path has no CPU fallback (SURVEY.md §5)")
+        """The v2 app calls this right before `pipe.to("cuda")` (ref:app.py:199-200). Nothing is offloaded here: the
+        recorded step programs hold device pointers into the packed weights, which stay resident (a B200 has 180 GB;
+        UNet + BrushNet are 3.5 GB in bf16). Kept callable so the app runs unchanged; it only says so."""
+        import warnings
+
+        warnings.warn("powerpaint_b200: enable_model_cpu_offload() keeps all models resident on the GPU (the hot path "
+                      "has no CPU side to offload to)", stacklevel=2)
 
     def denoiser(self) -> FusedDenoiser:
         if not isinstance(self.unet, UNet2DConditionModel):

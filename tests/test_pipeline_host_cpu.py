@@ -252,3 +252,37 @@ def test_brushnet_call_host_side_matches_oracle_loop():
     so.set_timesteps(steps)
     ref = loop_brushnet(ou, ob, so, lat, torch.cat([ne, pe]), peU, cond, 7.5, 1.0)
     assert torch.allclose(out, ref, atol=2e-4, rtol=1e-4), (out - ref).abs().max()
+
+
+def test_pipeline_to_moves_every_registered_module():
+    """`pipe = pipe.to("cuda")` (ref:app.py:113,135,200) is DiffusionPipeline.to: vae, both text encoders, unet, brushnet /
+    controlnet all move (checked with the meta device on the CPU), the pipeline returns itself, a dtype selects the dtype
+    of the tensors the hot-path nets return"""
+    from oracle.vae import AutoencoderKLOracle
+    from powerpaint_b200.engine import NetConfig
+    from powerpaint_b200.models import BrushNetModel, ControlNetModel, UNet2DConditionModel
+    from powerpaint_b200.pipelines import (StableDiffusionControlNetInpaintPipeline,
+                                           StableDiffusionPowerPaintBrushNetPipeline)
+    from powerpaint_b200.schedulers import DDIMScheduler
+
+    o = UNetConfig.tiny(4)
+
+    def cfg(cin):
+        return NetConfig(in_channels=cin, block_out_channels=o.block_out_channels, attention_head_dim=o.attention_head_dim,
+                         cross_attention_dim=o.cross_attention_dim, norm_num_groups=o.norm_num_groups)
+
+    te, te_b = torch.nn.Linear(4, 4), torch.nn.Linear(4, 4)  # stand-ins: any nn.Module is an injected dependency
+    pb = StableDiffusionPowerPaintBrushNetPipeline(
+        vae=AutoencoderKLOracle.synthetic(tiny=True), text_encoder=te, text_encoder_brushnet=te_b, tokenizer=None,
+        unet=UNet2DConditionModel(cfg(4)), brushnet=BrushNetModel(cfg(4)), scheduler=DDIMScheduler(), safety_checker=None)
+    assert pb.to("meta") is pb
+    for name in ("vae", "text_encoder", "text_encoder_brushnet", "unet", "brushnet"):
+        assert next(getattr(pb, name).parameters()).device.type == "meta", name
+    pb.to(torch.float16)
+    assert pb.unet._out_dtype == torch.float16 and pb.brushnet._out_dtype == torch.float16
+    pc = StableDiffusionControlNetInpaintPipeline(
+        vae=AutoencoderKLOracle.synthetic(tiny=True), text_encoder=te, tokenizer=None, unet=UNet2DConditionModel(cfg(9)),
+        controlnet=ControlNetModel(cfg(4)), scheduler=DDIMScheduler())
+    pc.to("meta")
+    for name in ("vae", "text_encoder", "unet", "controlnet"):
+        assert next(getattr(pc, name).parameters()).device.type == "meta", name
