@@ -293,6 +293,31 @@ class StableDiffusionInpaintPipeline:
             outputs += (image_latents,)
         return outputs
 
+    def _encode_vae_image(self, image: torch.Tensor, generator=None) -> torch.Tensor:
+        """ref:pipeline_PowerPaint.py:657-669: posterior sample (per-sample generators honoured) x scaling_factor"""
+        return vae_encode(self.vae, image, generator)
+
+    def run_safety_checker(self, image, device, dtype):
+        """ref:pipeline_PowerPaint.py:521-533 with `safety_checker=None` (what the app passes): nothing is flagged"""
+        return image, None
+
+    def decode_latents(self, latents: torch.Tensor):
+        """the deprecated helper of the ControlNet / BrushNet pipelines (ref:pipeline_PowerPaint_ControlNet.py:614-624):
+        float32 NHWC numpy in [0, 1]"""
+        return decode_latents(self.vae, latents, "np")
+
+    def enable_vae_slicing(self):
+        """accepted: decoding a batch slice by slice is numerically the decode of the batch (ref:…ControlNet.py:326-332)"""
+
+    def disable_vae_slicing(self):
+        pass
+
+    def enable_vae_tiling(self):
+        raise NotImplementedError("tiled VAE decoding (it blends tile borders, i.e. changes the result) is not built")
+
+    def disable_vae_tiling(self):
+        pass
+
     def prepare_mask_latents(self, mask, masked_image, batch_size, height, width, dtype, device, generator,
                              do_classifier_free_guidance):
         """nearest-resize the mask to latent resolution, VAE-encode the masked image (:671-710).

@@ -47,6 +47,22 @@ class StableDiffusionPowerPaintBrushNetPipeline(StableDiffusionInpaintPipeline):
             self._denoiser_unet, self._denoiser_side = self.unet, self.brushnet
         return self._denoiser
 
+    def check_image(self, image, mask, prompt, prompt_embeds):
+        """ref:pipeline_PowerPaint_Brushnet_CA.py:868-922"""
+        check_image(image, prompt, prompt_embeds, mask=mask, with_mask=True)
+
+    @property
+    def clip_skip(self):
+        return None  # `clip_skip` other than None is refused by `encode_prompt`
+
+    @property
+    def cross_attention_kwargs(self):
+        return None  # LoRA scaling is outside the hot path
+
+    @property
+    def num_timesteps(self):
+        return getattr(self, "_num_timesteps", None)
+
     @property
     def guidance_scale(self):
         return self._guidance_scale
@@ -221,6 +237,7 @@ class StableDiffusionPowerPaintBrushNetPipeline(StableDiffusionInpaintPipeline):
         height, width = image_t.shape[-2:]
         self.scheduler.set_timesteps(num_inference_steps, device="cpu")
         ts = self.scheduler.timesteps
+        self._num_timesteps = len(ts)
         num_channels_latents = self.unet.config.in_channels
         shape = (total, num_channels_latents, height // self.vae_scale_factor, width // self.vae_scale_factor)
         if isinstance(generator, list) and len(generator) != total:  # (:957-962)

@@ -58,6 +58,10 @@ class StableDiffusionControlNetInpaintPipeline(StableDiffusionInpaintPipeline):
             raise TypeError("For single controlnet: `controlnet_conditioning_scale` must be type `float`.")
         check_control_guidance(control_guidance_start, control_guidance_end)
 
+    def check_image(self, image, prompt, prompt_embeds):
+        """ref:pipeline_PowerPaint_ControlNet.py:788-827"""
+        check_image(image, prompt, prompt_embeds)
+
     def _default_height_width(self, height, width, image):
         """missing sizes come from the init image, rounded down to a multiple of 8 (:914-937)"""
         while isinstance(image, list):
