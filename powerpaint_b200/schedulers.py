@@ -81,6 +81,26 @@ class DDIMScheduler:
         d.update(kwargs)
         return cls(**d)
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, revision=None, local_files_only=False,
+                        cache_dir=None, **kwargs):
+        """`SchedulerMixin.from_pretrained`: `<dir>[/<subfolder>]/scheduler_config.json` of a checkpoint in the diffusers
+        layout (keys of other scheduler classes that have no meaning here are dropped by the constructor)"""
+        from .loading import load_json, resolve_checkpoint_dir
+
+        d = resolve_checkpoint_dir(pretrained_model_name_or_path, subfolder, revision, local_files_only, cache_dir)
+        return cls.from_config(load_json(d, "scheduler_config.json"), **kwargs)
+
+    def save_pretrained(self, save_directory, **unused):
+        import json
+        import os
+
+        os.makedirs(save_directory, exist_ok=True)
+        cfg = {"_class_name": type(self).__name__, "_diffusers_version": "0.27.0"}
+        cfg.update({k: v for k, v in vars(self.config).items() if not k.startswith("_")})
+        with open(os.path.join(save_directory, "scheduler_config.json"), "w") as f:
+            json.dump(cfg, f, indent=2, sort_keys=True)
+
     def scale_model_input(self, sample: torch.Tensor, timestep=None) -> torch.Tensor:
         return sample
 

@@ -248,3 +248,20 @@ def test_ddim_converges_to_the_exact_flow_with_first_order():
         orders = [math.log2(errs[i] / errs[i + 1]) for i in range(2)]
         assert all(0.7 < o < 1.4 for o in orders) and errs[-1] < 2e-2, (errs, orders)
     assert all(abs(a - b) <= 1e-3 * b for a, b in zip(errs_p, errs_o)), (errs_p, errs_o)
+
+
+def test_scheduler_from_pretrained_round_trip(tmp_path):
+    """`scheduler/scheduler_config.json` of a checkpoint directory, and the app's swap-by-config (ref:app.py:197)"""
+    from powerpaint_b200.schedulers import DDIMScheduler, UniPCMultistepScheduler
+
+    s = DDIMScheduler()
+    s.save_pretrained(str(tmp_path / "scheduler"))
+    s2 = DDIMScheduler.from_pretrained(str(tmp_path), subfolder="scheduler")
+    assert vars(s2.config) == vars(s.config)
+    u = UniPCMultistepScheduler.from_config(s2.config)
+    u.save_pretrained(str(tmp_path / "unipc"))
+    u2 = UniPCMultistepScheduler.from_pretrained(str(tmp_path / "unipc"))
+    assert vars(u2.config) == vars(u.config) and u2.config.solver_order == 2
+    u2.set_timesteps(20)
+    u.set_timesteps(20)
+    assert [int(t) for t in u2.timesteps] == [int(t) for t in u.timesteps]
