@@ -80,6 +80,11 @@ class StableDiffusionInpaintPipeline:
             if name in passed:
                 components[name] = passed[name]
             elif name in ("safety_checker", "feature_extractor", "image_encoder"):
+                if name == "safety_checker" and (index.get(name) or [None])[0] is not None:
+                    import warnings
+
+                    warnings.warn("powerpaint_b200: the stored safety checker is not loaded (outside the hot path; pass "
+                                  "`safety_checker=None` like the app's v2 branch does to silence this)", stacklevel=2)
                 components[name] = None
             elif name == "requires_safety_checker":
                 components[name] = False
