@@ -249,3 +249,44 @@ def test_layer_norm_fold_algebra_cpu():
         yv = torch.cat([y[:, t * bn:t * bn + half] for t in range(N // bn)], 1)
         yg = torch.cat([y[:, t * bn + half:(t + 1) * bn] for t in range(N // bn)], 1)
         assert torch.allclose(yv, got[:, :N // 2], atol=1e-5) and torch.allclose(yg, got[:, N // 2:], atol=1e-5)
+
+
+def test_header_is_plain_c_and_every_struct_field_offset_matches_the_ctypes_binding(tmp_path):
+    """include/powerpaint_b200.h through a C compiler (`gcc -std=c99 -pedantic`, no C++): it links against the library,
+    fails loudly without a GPU, and sizeof / offsetof of every descriptor field equal the ctypes mirror in
+    powerpaint_b200/_native.py — the binding a maintainer would write cannot drift from the header"""
+    import shutil
+    import subprocess
+
+    from powerpaint_b200 import _native as N
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    structs = {"pp_stats_geom": N.StatsGeom, "pp_gemm_desc": N.GemmDesc, "pp_attn_desc": N.AttnDesc,
+               "pp_gn_desc": N.GnDesc, "pp_cfg_ddim_desc": N.CfgDdimDesc, "pp_unipc_desc": N.UniPCDesc}
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include <string.h>', '#include "powerpaint_b200.h"',
+             'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  pp_gemm_desc d; memset(&d, 0, sizeof d);',
+              '  printf("abi %d\\n", pp_abi_version());',
+              '  printf("status %d\\n", (int)pp_gemm_conv(&d, 0));',
+              '  printf("error %s\\n", pp_last_error());', '  return 0; }']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    libdir = os.path.join(root, "powerpaint_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                        str(src), "-o", str(exe), "-L", libdir, "-lpowerpaint_b200", f"-Wl,-rpath,{libdir}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = dict(ln.split(" ", 1) for ln in subprocess.run([str(exe)], capture_output=True, text=True,
+                                                        check=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(out[cname]) == ctypes.sizeof(cls), (cname, out[cname], ctypes.sizeof(cls))
+        for fname, _ in cls._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
+    assert int(out["abi"]) == N.ABI_VERSION and int(out["status"]) != 0 and out["error"].strip()
