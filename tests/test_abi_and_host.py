@@ -290,3 +290,16 @@ def test_header_is_plain_c_and_every_struct_field_offset_matches_the_ctypes_bind
         for fname, _ in cls._fields_:
             assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
     assert int(out["abi"]) == N.ABI_VERSION and int(out["status"]) != 0 and out["error"].strip()
+
+
+def test_integration_md_stub_lists_the_descriptor_fields_of_the_binding():
+    """the ctypes stub printed in INTEGRATION.md is the binding: same field names in the same order"""
+    import re
+
+    from powerpaint_b200 import _native as N
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = md[md.index("class pp_gemm_desc"):md.index("lib.pp_gemm_conv.argtypes")]
+    assert re.findall(r'\("(\w+)", C\.', block) == [f for f, _ in N.GemmDesc._fields_]
+    assert f"pp_abi_version() == {N.ABI_VERSION}" in block
