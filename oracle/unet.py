@@ -308,3 +308,15 @@ def init_synthetic_(module: nn.Module, seed: int = 1234, zero_conv_scale: float 
             else:
                 p.copy_(0.02 * torch.randn(p.shape, generator=g))
     return module
+
+
+def build_synthetic(cls, cfg: "UNetConfig", seed: int = 1234, **kw) -> nn.Module:
+    """`init_synthetic_(cls(cfg))` without torch's default initialisation: the module is laid out on the meta device
+    and materialised empty, then every parameter is written by `init_synthetic_` (the oracle nets hold no buffers), so
+    the result is the same tensor for tensor. Constructing the SD-1.5-size net the ordinary way spends minutes in
+    `kaiming_uniform_` on a small host."""
+    with torch.device("meta"):
+        m = cls(cfg)
+    assert not list(m.buffers()), "to_empty() would leave buffers uninitialised"
+    return init_synthetic_(m.to_empty(device="cpu"), seed, **kw).eval()
+

@@ -8,13 +8,16 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(*args, timeout=600):
+def _run(*args, timeout=600, env=None):
     return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], cwd=ROOT, capture_output=True,
-                          text=True, timeout=timeout)
+                          text=True, timeout=timeout, env=dict(os.environ, **(env or {})))
 
 
 def test_reference_arm_prints_one_contract_line():
-    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0")
+    # a small net on 128x128 pixels instead of the metric's workload: the line's format is what is checked here, and
+    # building + running the SD-1.5-size fp32 net costs ~10 minutes on an 8-vCPU host (the sample string of such a line
+    # says that it is not the metric's workload)
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0", env={"PP_BENCH_CPU_FORMAT_CHECK": "1"})
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1, r.stdout
@@ -25,6 +28,7 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["ms_per_step"] > 0 and "workload" in d["config"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert "PP_BENCH_CPU_FORMAT_CHECK=1" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
