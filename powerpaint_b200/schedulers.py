@@ -176,7 +176,11 @@ class DDIMScheduler:
         prev = lat.view(nb, h, w, 4).permute(0, 3, 1, 2).contiguous().to(sample.dtype)
         if not return_dict:
             return (prev,)
-        return DDIMSchedulerOutput(prev_sample=prev, pred_original_sample=None)
+        # x0 prediction of the output object (diffusers' `pred_original_sample`, epsilon parametrisation); the loop never
+        # reads it: one elementwise expression on the caller's tensors, outside the fused kernel
+        a_t, _ = self._alphas(int(timestep))
+        x0 = ((sample.float() - math.sqrt(1 - a_t) * model_output.float()) / math.sqrt(a_t)).to(sample.dtype)
+        return DDIMSchedulerOutput(prev_sample=prev, pred_original_sample=x0)
 
     def add_noise(self, original_samples: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
         a = self.alphas_cumprod.to(original_samples.device)[timesteps.to(original_samples.device)]

@@ -105,3 +105,15 @@ def test_resampling_rules():
     assert torch.allclose(u(y, output_size=(7, 10)),
                           F.conv2d(F.interpolate(y, size=(7, 10), mode="nearest"), u.conv.weight, u.conv.bias, padding=1),
                           atol=1e-6)
+
+
+def test_build_synthetic_equals_default_construction_then_init():
+    """oracle.unet.build_synthetic (meta-device layout, no default initialisation) writes the same parameters as
+    init_synthetic_ on an ordinarily constructed net — bench.py's CPU leg relies on it"""
+    from oracle.unet import BrushNetOracle, UNet2DConditionOracle, UNetConfig, build_synthetic, init_synthetic_
+
+    for cls, cin in ((UNet2DConditionOracle, 9), (BrushNetOracle, 4)):
+        a = build_synthetic(cls, UNetConfig.tiny(cin), seed=7).state_dict()
+        b = init_synthetic_(cls(UNetConfig.tiny(cin)), seed=7).state_dict()
+        assert list(a) == list(b)
+        assert all(torch.equal(a[k], b[k]) for k in a)
