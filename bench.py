@@ -21,7 +21,8 @@ per-GPU batch.
          read back to the host (output_type="uint8": the device-side form of the uint8 arrays "pil" is built from).
   roofline  tensor-bound: algorithmic FLOPs of one denoising step / mean device time of one recorded step program
          (one CUDA-graph replay), against the measured sustained bf16 peak of MEASURED_PEAKS.json.
-  cpu_baseline  the fp32 oracle port of the v1 loop on the host cores (bounded sample, fixed thread count).
+  cpu_baseline  the fp32 oracle port of the config's loop on the host cores (bounded sample, fixed thread count);
+         `--impl reference` prints the same measurement as its own line, with the same `config` object.
   gpu_library_baseline  the oracle modules in torch bf16 eager (cuDNN / cuBLAS / SDPA: the library path the
          reference reaches through diffusers) on the same GPU, same UNet batch — the practical "reference-GPU" bar.
   parity_spot_check  2 steps of the bench shape against the fp32 oracle (GPU), rel-L2 / cosine; all outputs finite.
@@ -130,7 +131,7 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU arm (oracle port)
-_CPU_UNET = None
+_CPU_NETS = {}
 
 
 def cpu_threads() -> int:
@@ -155,46 +156,65 @@ def _cpu_format_check_only() -> bool:
     return os.environ.get("PP_BENCH_CPU_FORMAT_CHECK", "0") == "1"
 
 
-def cpu_oracle_rate(threads: int, ddim_steps_sample: int = 1, repeats: int = 2):
-    """images/s of the fp32 oracle port of the v1 loop on the host cores, extrapolated from a bounded sample:
-    1 image at 512x512 (UNet batch 2 with CFG), `ddim_steps_sample` of the 50 steps, best of `repeats` after one
-    untimed warm-up pass (first-touch page faults and oneDNN primitive creation otherwise dominate)."""
+def cpu_sample_text(cfg) -> str:
+    if _cpu_format_check_only():
+        return ("NOT THE METRIC'S WORKLOAD (PP_BENCH_CPU_FORMAT_CHECK=1: small nets, 1 image at a quarter of the side, "
+                "1 of 50 DDIM steps, extrapolated x50)")
+    side = 8 * cfg["latent"]
+    nets = {"v1": "UNet", "brushnet": "BrushNet + UNet", "controlnet": "ControlNet + UNet"}[cfg["mode"]]
+    return (f"fp32 oracle port of the {cfg['mode']} loop ({nets}), 1 image x {side}x{side} (net batch 2, CFG), 1 of 50 DDIM "
+            "steps, warm-up pass + best of 2, extrapolated x50")
+
+
+def cpu_oracle_rate(threads: int, cfg, ddim_steps_sample: int = 1, repeats: int = 2):
+    """images/s of the fp32 oracle port of the config's loop (oracle/pipelines.py: v1 / BrushNet / ControlNet) on the host
+    cores, extrapolated from a bounded sample: 1 image at the config's resolution (net batch 2 with CFG),
+    `ddim_steps_sample` of the 50 steps, best of `repeats` after one untimed warm-up pass (first-touch page faults and
+    oneDNN primitive creation otherwise dominate)."""
     from oracle.ddim import DDIMOracle
-    from oracle.pipelines import loop_v1
-    from oracle.unet import UNet2DConditionOracle, UNetConfig, build_synthetic
+    from oracle.unet import BrushNetOracle, ControlNetOracle, UNet2DConditionOracle, UNetConfig, build_synthetic
 
     torch.set_num_threads(threads)
     torch.manual_seed(0)
-    global _CPU_UNET
-    if _CPU_UNET is None:
-        _CPU_UNET = build_synthetic(UNet2DConditionOracle,
-                                    UNetConfig.tiny(9) if _cpu_format_check_only() else UNetConfig.sd15(9))
-    unet = _CPU_UNET
+    tiny = _cpu_format_check_only()
+    mk = UNetConfig.tiny if tiny else UNetConfig.sd15
+    key = (cfg["mode"], tiny)
+    if key not in _CPU_NETS:
+        ou = build_synthetic(UNet2DConditionOracle, mk(4 if cfg["mode"] == "brushnet" else 9))
+        side = None
+        if cfg["mode"] == "brushnet":
+            side = build_synthetic(BrushNetOracle, mk(4), seed=99)
+        elif cfg["mode"] == "controlnet":
+            side = build_synthetic(ControlNetOracle, mk(4), seed=77)
+        _CPU_NETS[key] = (ou, side)
+    ou, side = _CPU_NETS[key]
+    one = dict(cfg, batch=1, latent=cfg["latent"] // 4 if tiny else cfg["latent"])
+    kw = resident_inputs(one, torch.device("cpu"), 0, cross=ou.cfg.cross_attention_dim)
     sched = DDIMOracle()
-    sched.set_timesteps(DDIM_STEPS)
-    sched.timesteps = sched.timesteps[:ddim_steps_sample]
-    g = torch.Generator().manual_seed(0)
-    L = 16 if _cpu_format_check_only() else 64
-    lat = torch.randn(1, 4, L, L, generator=g)
-    emb = torch.randn(2, 77, unet.cfg.cross_attention_dim, generator=g) * 0.5
-    mask = (torch.rand(1, 1, L, L, generator=g) > 0.75).float()
-    ml = torch.randn(1, 4, L, L, generator=g)
-    loop_v1(unet, sched, lat, emb, mask, ml, GUIDANCE)  # warm-up, untimed
+
+    def one_pass():
+        sched.set_timesteps(DDIM_STEPS)
+        sched.timesteps = sched.timesteps[:ddim_steps_sample]
+        with torch.no_grad():
+            return oracle_loop(cfg, ou, side, sched, kw, torch.float32)
+
+    one_pass()  # warm-up, untimed
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        loop_v1(unet, sched, lat, emb, mask, ml, GUIDANCE)
+        one_pass()
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     per_ddim_step = best / ddim_steps_sample
     return 1.0 / (per_ddim_step * DDIM_STEPS), per_ddim_step
 
 
-CPU_SAMPLE = ("fp32 oracle port, 1 image x 512x512 (UNet batch 2, CFG), 1 of 50 DDIM steps, warm-up pass + best of 2, "
-              "extrapolated x50")
-if _cpu_format_check_only():
-    CPU_SAMPLE = ("NOT THE METRIC'S WORKLOAD (PP_BENCH_CPU_FORMAT_CHECK=1: small net, 1 image x 128x128, 1 of 50 DDIM "
-                  "steps, extrapolated x50)")
+def line_config(name: str, cfg, world: int) -> dict:
+    """the `config` object of the JSON line: the same for both arms of one (config, N)"""
+    B = cfg["batch"]
+    return {"workload": cfg["workload"], "name": name, "per_gpu_batch": B, "global_batch": B * world,
+            "ddim_steps": DDIM_STEPS, "parallelism": f"batch-sharded x{world}, no collective inside the loop",
+            "l2": "working set per step (1.7+ GB weights + activations) exceeds the 126 MB L2"}
 
 
 def run_reference_arm(args):
@@ -202,9 +222,10 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     threads = cpu_threads()
+    cfg = CONFIGS[args.config]
     vals = []
     for i in range(args.warmup + args.steps):
-        v, per = cpu_oracle_rate(threads, ddim_steps_sample=1, repeats=2 if i >= args.warmup else 1)
+        v, per = cpu_oracle_rate(threads, cfg, ddim_steps_sample=1, repeats=2 if i >= args.warmup else 1)
         if i >= args.warmup:
             vals.append((v, per))
     v = max(x[0] for x in vals)
@@ -213,13 +234,13 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per * DDIM_STEPS * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "PowerPaint-v1 text-guided inpaint 512x512, 50 DDIM steps, CFG 7.5 (C2 shape, "
-                               "bounded CPU sample)"},
+        "config": line_config(args.config, cfg, world),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
-                         "sample": CPU_SAMPLE},
+                         "sample": cpu_sample_text(cfg)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference's own diffusers pipeline cannot run here (diffusers==0.27.0 absent, no network); "
-                "this times the fp32 oracle port of its loop (oracle/) on the host cores",
+                "this times the fp32 oracle port of its loop (oracle/) on the host cores of rank 0's box, one bounded "
+                "sample per bench step (`cpu_baseline.sample`), `value` and `ms_per_step` extrapolated to 50 DDIM steps",
     }
     print(json.dumps(line))
     return 0
@@ -276,19 +297,19 @@ def synth_requests(cfg, seed):
     return out
 
 
-def resident_inputs(cfg, dev, rank):
+def resident_inputs(cfg, dev, rank, cross: int = 768):
     """device-resident loop inputs for `value` (what the pipeline's preparation would hand to the loop)"""
     B, L = cfg["batch"], cfg["latent"]
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     kw = dict(latents=torch.randn(B, 4, L, L, device=dev, generator=g),
-              prompt_embeds=torch.randn(2 * B, 77, 768, device=dev, generator=g) * 0.5)
+              prompt_embeds=torch.randn(2 * B, 77, cross, device=dev, generator=g) * 0.5)
     mask = torch.zeros(B, 1, L, L, device=dev)
     mask[:, :, L // 4:3 * L // 4, L // 4:3 * L // 4] = 1.0
     ml = torch.randn(B, 4, L, L, device=dev, generator=g)
     if cfg["mode"] == "brushnet":
         cond = torch.cat([ml, mask], 1)
         kw.update(extra=torch.cat([cond, cond]), side_scale=1.0,
-                  side_prompt_embeds=torch.randn(2 * B, 77, 768, device=dev, generator=g) * 0.5)
+                  side_prompt_embeds=torch.randn(2 * B, 77, cross, device=dev, generator=g) * 0.5)
     else:
         kw.update(extra=torch.cat([mask, ml], 1))
     if cfg["mode"] == "controlnet":
@@ -457,10 +478,8 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": cfg["workload"], "name": args.config, "per_gpu_batch": B, "global_batch": B * world,
-                       "ddim_steps": DDIM_STEPS, "parallelism": f"batch-sharded x{world}, no collective inside the loop",
-                       "l2": "working set per step (1.7+ GB weights + activations) exceeds the 126 MB L2",
-                       "ms_per_ddim_step": step_mean, "plan_activation_bytes": int(plan_bytes)},
+            "config": line_config(args.config, cfg, world),
+            "detail": {"ms_per_ddim_step": step_mean, "plan_activation_bytes": int(plan_bytes)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "calls_timed": k_e2e,
                     "includes": "per-rank H2D of uint8 image/mask + prompt embeddings from pinned host memory, "
@@ -520,9 +539,9 @@ def run_gpu_arm(args):
         del ou, oside
         torch.cuda.empty_cache()
         th = cpu_threads()
-        cpu_v, cpu_per = cpu_oracle_rate(th, ddim_steps_sample=1, repeats=2)
+        cpu_v, cpu_per = cpu_oracle_rate(th, cfg, ddim_steps_sample=1, repeats=2)
         line["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": th, "kind": "port", "host_cpus": os.cpu_count(),
-                                "sample": CPU_SAMPLE + f" ({cpu_per:.2f} s per DDIM step)"}
+                                "sample": cpu_sample_text(cfg) + f" ({cpu_per:.2f} s per DDIM step)"}
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

@@ -30,6 +30,26 @@ def test_reference_arm_prints_one_contract_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert "PP_BENCH_CPU_FORMAT_CHECK=1" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # both arms of one (config, N) carry the same `config` object
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert d["config"] == bench.line_config("C2", bench.CONFIGS["C2"], 1)
+
+
+def test_reference_arm_times_the_loop_of_the_named_config():
+    """--config C3 / C5: the CPU arm runs the BrushNet / ControlNet oracle loop, and says so"""
+    for name, word in (("C3", "BrushNet"), ("C5", "ControlNet")):
+        r = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--config", name,
+                 env={"PP_BENCH_CPU_FORMAT_CHECK": "1"})
+        assert r.returncode == 0, r.stderr[-2000:]
+        d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+        assert d["config"]["name"] == name and word in d["config"]["workload"] and d["value"] > 0
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert "BrushNet + UNet" in bench.cpu_sample_text(bench.CONFIGS["C3"])
+    assert "1024x1024" in bench.cpu_sample_text(bench.CONFIGS["C4"])
 
 
 def test_product_arm_refuses_to_run_without_a_gpu():
