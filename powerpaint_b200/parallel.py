@@ -54,3 +54,64 @@ def gather_images(images: torch.Tensor, dst: int = 0, group=None) -> Optional[to
     bufs = [torch.empty_like(images) for _ in range(world)] if rank == dst else None
     dist.gather(images.contiguous(), bufs, dst=dst, group=group)
     return torch.cat(bufs, dim=0) if rank == dst else None
+
+
+def scatter_batch(tensors: Optional[Sequence[torch.Tensor]], device, src: int = 0, group=None) -> List[torch.Tensor]:
+    """Ragged form of `scatter_requests`: rank `src` holds full-batch tensors [total, ...] (all with the same `total`;
+    the other ranks pass None and need to know nothing), rank r receives rows `shard_ranges(total, world)[r]` of each —
+    shards differ by at most one row and may be EMPTY when total < world (the caller skips its `__call__` then).
+    One object broadcast carries the shapes / dtypes; the payload travels as equal-sized (padded) scatter chunks."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if rank == src:
+        if not tensors:
+            raise ValueError("rank `src` must pass the full-batch tensors")
+        totals = {int(t.shape[0]) for t in tensors}
+        if len(totals) != 1:
+            raise ValueError(f"all tensors must share the batch dimension, got {sorted(totals)}")
+        meta = [[(tuple(t.shape), t.dtype) for t in tensors]]
+    else:
+        meta = [None]
+    dist.broadcast_object_list(meta, src=src, group=group)
+    out = []
+    for k, (shape, dt) in enumerate(meta[0]):
+        total = shape[0]
+        ranges = shard_ranges(total, world)
+        rows = max(e - s for s, e in ranges)  # == ceil(total / world)
+        s, e = ranges[rank]
+        dst = torch.empty((rows,) + tuple(shape[1:]), dtype=dt, device=device)
+        chunks = None
+        if rank == src:
+            full = tensors[k].to(device)
+            chunks = []
+            for cs, ce in ranges:
+                c = torch.zeros_like(dst)
+                c[: ce - cs] = full[cs:ce]
+                chunks.append(c)
+        if rows > 0:
+            dist.scatter(dst, chunks, src=src, group=group)
+        out.append(dst[: e - s].contiguous())
+    return out
+
+
+def gather_batch(local: torch.Tensor, total: int, dst: int = 0, group=None) -> Optional[torch.Tensor]:
+    """inverse of `scatter_batch`: rank r contributes its `shard_ranges(total, world)[r]` rows (possibly none; shape
+    [0, ...] with the right trailing dimensions and dtype), rank `dst` gets [total, ...] in rank order, others None"""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ranges = shard_ranges(total, world)
+    s, e = ranges[rank]
+    if local.shape[0] != e - s:
+        raise ValueError(f"rank {rank} holds {local.shape[0]} rows, its shard of {total} over {world} ranks is {e - s}")
+    rows = max(ce - cs for cs, ce in ranges)
+    if rows == 0:
+        return local if rank == dst else None
+    send = torch.zeros((rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    send[: e - s] = local
+    bufs = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    dist.gather(send, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([b[: ce - cs] for b, (cs, ce) in zip(bufs, ranges)], dim=0)
