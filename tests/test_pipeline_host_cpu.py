@@ -286,3 +286,74 @@ def test_pipeline_to_moves_every_registered_module():
     pc.to("meta")
     for name in ("vae", "text_encoder", "unet", "controlnet"):
         assert next(getattr(pc, name).parameters()).device.type == "meta", name
+
+
+def test_bench_style_uint8_requests_through_all_three_calls():
+    """the argument kinds bench.py's e2e leg hands to the three `__call__`s (uint8 NCHW images / masks / control images,
+    float prompt embeddings, output_type="uint8") on the CPU stand-ins: uint8 NHWC images come back, and the uint8
+    request gives the same latents as its float form (image / 127.5 - 1, mask / 255, control / 255)"""
+    from oracle.unet import BrushNetOracle, ControlNetOracle
+    from oracle.vae import AutoencoderKLOracle
+    from powerpaint_b200.engine import NetConfig
+    from powerpaint_b200.models import BrushNetModel, ControlNetModel, UNet2DConditionModel, synthetic_state_dict
+    from powerpaint_b200.pipelines import (StableDiffusionControlNetInpaintPipeline, StableDiffusionInpaintPipeline,
+                                           StableDiffusionPowerPaintBrushNetPipeline)
+    from powerpaint_b200.schedulers import DDIMScheduler
+
+    def pair(cls_o, cls_p, cin, kind, seed):
+        o = UNetConfig.tiny(cin)
+        n = NetConfig(in_channels=cin, block_out_channels=o.block_out_channels,
+                      attention_head_dim=o.attention_head_dim, cross_attention_dim=o.cross_attention_dim,
+                      norm_num_groups=o.norm_num_groups)
+        sd = synthetic_state_dict(n, kind, seed)
+        m = cls_o(o).eval()
+        m.load_state_dict(sd)
+        return m, cls_p.from_state_dict(n, sd), o
+
+    vae = AutoencoderKLOracle.synthetic(tiny=True)
+    B, H = 2, 64
+    g = torch.Generator().manual_seed(1)
+    img = torch.randint(0, 256, (B, 3, H, H), generator=g, dtype=torch.uint8)
+    mask = torch.zeros(B, 1, H, H, dtype=torch.uint8)
+    mask[:, :, 16:48, 16:48] = 255
+    ctl = (torch.rand(B, 3, H, H, generator=g) > 0.9).to(torch.uint8) * 255
+    ou9, pu9, o = pair(UNet2DConditionOracle, UNet2DConditionModel, 9, "unet", 3)
+    ou4, pu4, _ = pair(UNet2DConditionOracle, UNet2DConditionModel, 4, "unet", 11)
+    ob, pb, _ = pair(BrushNetOracle, BrushNetModel, 4, "brushnet", 12)
+    oc, pc, _ = pair(ControlNetOracle, ControlNetModel, 4, "controlnet", 6)
+    pe = torch.randn(B, 77, o.cross_attention_dim, generator=g) * 0.5
+    ne = torch.randn(B, 77, o.cross_attention_dim, generator=g) * 0.5
+    peU = torch.randn(2 * B, 77, o.cross_attention_dim, generator=g) * 0.5
+
+    def common(u8: bool, out: str):
+        return dict(image=img if u8 else img.float() / 127.5 - 1, mask=mask if u8 else mask.float() / 255,
+                    prompt_embeds=pe, negative_prompt_embeds=ne, height=H, width=H, num_inference_steps=3,
+                    guidance_scale=7.5, generator=torch.Generator().manual_seed(0), output_type=out)
+
+    v1 = StableDiffusionInpaintPipeline(vae=vae, text_encoder=None, tokenizer=None, unet=pu9,
+                                        scheduler=DDIMScheduler(), safety_checker=None)
+    f1 = _CoefficientDenoiser(ou9)
+    v1.denoiser = lambda: f1
+    bn = StableDiffusionPowerPaintBrushNetPipeline(vae=vae, text_encoder=None, text_encoder_brushnet=None,
+                                                   tokenizer=None, unet=pu4, brushnet=pb, scheduler=DDIMScheduler(),
+                                                   safety_checker=None)
+    f2 = _BrushNetCoefficientDenoiser(ou4, ob)
+    bn.denoiser = lambda: f2
+    cn = StableDiffusionControlNetInpaintPipeline(vae=vae, text_encoder=None, tokenizer=None, unet=pu9, controlnet=pc,
+                                                  scheduler=DDIMScheduler(), safety_checker=None)
+    f3 = _ControlNetCoefficientDenoiser(ou9, oc)
+    cn.denoiser = lambda: f3
+    calls = [
+        (v1, lambda u8: {}),
+        (bn, lambda u8: dict(prompt_embedsU=peU, brushnet_conditioning_scale=1.0)),
+        (cn, lambda u8: dict(control_image=ctl if u8 else ctl.float() / 255, controlnet_conditioning_scale=0.5)),
+    ]
+    for pipe, extra in calls:
+        torch.manual_seed(7)  # the BrushNet conditioning latents draw from the global RNG
+        res = pipe(**common(True, "uint8"), **extra(True)).images
+        assert res.dtype == torch.uint8 and res.shape == (B, H, H, 3), type(pipe).__name__
+        torch.manual_seed(7)
+        a = pipe(**common(True, "latent"), **extra(True)).images
+        torch.manual_seed(7)
+        b = pipe(**common(False, "latent"), **extra(False)).images
+        assert torch.allclose(a, b, atol=1e-5, rtol=1e-5), (type(pipe).__name__, (a - b).abs().max())
