@@ -53,7 +53,9 @@ class StableDiffusionPowerPaintBrushNetPipeline(StableDiffusionInpaintPipeline):
 
     @property
     def clip_skip(self):
-        return None  # `clip_skip` other than None is refused by `encode_prompt`
+        # what `__call__` was given (:1006-1007, :1227). Like the reference's `__call__`, ours never hands it to
+        # `encode_prompt` (:1268-1277), so it only shows here.
+        return getattr(self, "_clip_skip", None)
 
     @property
     def cross_attention_kwargs(self):
@@ -88,8 +90,6 @@ class StableDiffusionPowerPaintBrushNetPipeline(StableDiffusionInpaintPipeline):
     def encode_prompt(self, prompt, device, num_images_per_prompt, do_classifier_free_guidance, negative_prompt=None,
                       prompt_embeds=None, negative_prompt_embeds=None, lora_scale=None, clip_skip=None):
         """plain promptU through `text_encoder` (:442-629); returns [neg; pos] like the reference's caller expects"""
-        if clip_skip is not None:
-            raise NotImplementedError("clip_skip is outside the hot path")
         if prompt is not None and isinstance(prompt, str):
             batch_size = 1
             prompt = [prompt]
@@ -97,7 +97,14 @@ class StableDiffusionPowerPaintBrushNetPipeline(StableDiffusionInpaintPipeline):
             batch_size = len(prompt)
         else:
             batch_size = prompt_embeds.shape[0]
-        if prompt_embeds is None:
+        if prompt_embeds is None and clip_skip is not None:
+            # (:537-552) hidden state `clip_skip` layers before the last one, then the final LayerNorm; needs a text
+            # encoder that returns its hidden states (transformers' CLIPTextModel; the kernel-backed one refuses)
+            ids = self.tokenizer(prompt, padding="max_length", max_length=self.tokenizer.model_max_length,
+                                 truncation=True, return_tensors="pt").input_ids
+            hidden = self.text_encoder(ids.to(device), output_hidden_states=True)[-1][-(clip_skip + 1)]
+            prompt_embeds = self.text_encoder.text_model.final_layer_norm(hidden)
+        elif prompt_embeds is None:
             prompt_embeds = encode_text(self.tokenizer, self.text_encoder, prompt, device)
         prompt_embeds = prompt_embeds.to(device=device, dtype=torch.float32)
         bs, seq, _ = prompt_embeds.shape
@@ -211,9 +218,8 @@ class StableDiffusionPowerPaintBrushNetPipeline(StableDiffusionInpaintPipeline):
             raise NotImplementedError("guess_mode is outside the hot path (unused by app.py)")
         if cross_attention_kwargs:
             raise NotImplementedError("cross_attention_kwargs (LoRA scale) is outside the hot path")
-        if timesteps is not None:
-            raise NotImplementedError("custom `timesteps` are not supported by the DDIM schedule table")
         self._guidance_scale = guidance_scale
+        self._clip_skip = clip_skip
         if prompt is not None and isinstance(prompt, str):
             batch_size = 1
         elif prompt is not None and isinstance(prompt, list):
@@ -235,6 +241,17 @@ class StableDiffusionPowerPaintBrushNetPipeline(StableDiffusionInpaintPipeline):
                                            do_cfg)
         original_mask = (original_mask.sum(1)[:, None, :, :] < 0).to(image_t.dtype)
         height, width = image_t.shape[-2:]
+        if timesteps is not None:
+            # `retrieve_timesteps` (:114-122): DDIM and UniPC take no custom schedule — neither diffusers 0.27.0's nor
+            # the ones here — so the reference raises this ValueError at this point of the call
+            import inspect
+
+            if "timesteps" not in inspect.signature(self.scheduler.set_timesteps).parameters:
+                raise ValueError(f"The current scheduler class {self.scheduler.__class__}'s `set_timesteps` does not "
+                                 "support custom timestep schedules. Please check whether you are using the correct "
+                                 "scheduler.")
+            raise NotImplementedError("custom `timesteps`: the fused step kernels read the coefficient tables of "
+                                      "DDIMScheduler / UniPCMultistepScheduler (uniform spacing)")
         self.scheduler.set_timesteps(num_inference_steps, device="cpu")
         ts = self.scheduler.timesteps
         self._num_timesteps = len(ts)

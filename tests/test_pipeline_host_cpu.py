@@ -357,3 +357,61 @@ def test_bench_style_uint8_requests_through_all_three_calls():
         torch.manual_seed(7)
         b = pipe(**common(False, "latent"), **extra(False)).images
         assert torch.allclose(a, b, atol=1e-5, rtol=1e-5), (type(pipe).__name__, (a - b).abs().max())
+
+
+def test_brushnet_call_custom_timesteps_raise_like_retrieve_timesteps():
+    """ref:pipeline_PowerPaint_Brushnet_CA.py:114-122: a scheduler whose `set_timesteps` takes no `timesteps` (DDIM and
+    UniPC of diffusers 0.27.0, and the ones here) -> ValueError, raised after the prompt / image preparation"""
+    from oracle.unet import BrushNetOracle
+    from oracle.vae import AutoencoderKLOracle
+    from powerpaint_b200.engine import NetConfig
+    from powerpaint_b200.models import BrushNetModel, UNet2DConditionModel, synthetic_state_dict
+    from powerpaint_b200.pipelines import StableDiffusionPowerPaintBrushNetPipeline
+    from powerpaint_b200.schedulers import DDIMScheduler, UniPCMultistepScheduler
+
+    o = UNetConfig.tiny(4)
+    n = NetConfig(in_channels=4, block_out_channels=o.block_out_channels, attention_head_dim=o.attention_head_dim,
+                  cross_attention_dim=o.cross_attention_dim, norm_num_groups=o.norm_num_groups)
+    for sched in (DDIMScheduler(), UniPCMultistepScheduler()):
+        pipe = StableDiffusionPowerPaintBrushNetPipeline(
+            vae=AutoencoderKLOracle.synthetic(tiny=True), text_encoder=None, text_encoder_brushnet=None, tokenizer=None,
+            unet=UNet2DConditionModel.from_state_dict(n, synthetic_state_dict(n, "unet", 1)),
+            brushnet=BrushNetModel.from_state_dict(n, synthetic_state_dict(n, "brushnet", 2)), scheduler=sched,
+            safety_checker=None)
+        pipe.denoiser = lambda: (_ for _ in ()).throw(AssertionError("the loop must not be reached"))
+        img = torch.zeros(1, 3, 64, 64)
+        pe = torch.zeros(1, 77, o.cross_attention_dim)
+        with pytest.raises(ValueError, match="does not support custom timestep schedules"):
+            pipe(image=img, mask=torch.ones(1, 3, 64, 64), prompt_embeds=pe, negative_prompt_embeds=pe,
+                 prompt_embedsU=torch.zeros(2, 77, o.cross_attention_dim), timesteps=[900, 500, 100])
+
+
+def test_brushnet_encode_prompt_clip_skip_and_the_clip_skip_property():
+    """`encode_prompt(clip_skip=k)` (ref:pipeline_PowerPaint_Brushnet_CA.py:537-552): the hidden state k layers before
+    the last, through the final LayerNorm, for the positive prompt only (the negative branch :596-610 takes the last
+    hidden state); the property returns what `__call__` was given (:1006-1007,:1227)"""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from synthetic_clip import make_text_encoder, make_tokenizer
+
+    from powerpaint_b200.pipelines import StableDiffusionPowerPaintBrushNetPipeline
+
+    tok = make_tokenizer()
+    te = make_text_encoder(len(tok), seed=3).eval()
+    pipe = StableDiffusionPowerPaintBrushNetPipeline.__new__(StableDiffusionPowerPaintBrushNetPipeline)
+    pipe.tokenizer, pipe.text_encoder = tok, te
+    assert pipe.clip_skip is None
+    prompts = ["a photo of a cat", "a"]
+    with torch.no_grad():
+        plain = pipe.encode_prompt(prompts, "cpu", 1, True)
+        skipped = pipe.encode_prompt(prompts, "cpu", 1, True, clip_skip=1)
+        ids = tok(prompts, padding="max_length", max_length=tok.model_max_length, truncation=True,
+                  return_tensors="pt").input_ids
+        out = te(ids, output_hidden_states=True)
+        want = te.text_model.final_layer_norm(out.hidden_states[-2])
+    assert torch.equal(skipped[:2], plain[:2])  # negative half: unchanged
+    assert torch.allclose(skipped[2:], want, atol=1e-6) and not torch.allclose(skipped[2:], plain[2:], atol=1e-4)
+    pipe._clip_skip = 2
+    assert pipe.clip_skip == 2
