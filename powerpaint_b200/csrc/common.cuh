@@ -419,12 +419,14 @@ __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
     return r;
 }
 __device__ __forceinline__ float f32x2_lo(uint64_t v) {
-    float lo, hi;
+    float lo;
+    [[maybe_unused]] float hi;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
     return lo;
 }
 __device__ __forceinline__ float f32x2_hi(uint64_t v) {
-    float lo, hi;
+    [[maybe_unused]] float lo;
+    float hi;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
     return hi;
 }
