@@ -115,3 +115,75 @@ def gather_batch(local: torch.Tensor, total: int, dst: int = 0, group=None) -> O
     if rank != dst:
         return None
     return torch.cat([b[: ce - cs] for b, (cs, ce) in zip(bufs, ranges)], dim=0)
+
+
+def _split_batched(batched: dict, total: int):
+    """full-batch keywords -> (names, halves, tensors) to scatter; a [2 x total] keyword ([negative; positive], the
+    BrushNet pipeline's `prompt_embedsU`) travels as two [total] tensors (halves 1 and 2) so that each half is sharded
+    like the images; halves == 0 marks an ordinary [total] keyword"""
+    names, halves, tensors = [], [], []
+    for k, v in batched.items():
+        if v.shape[0] == total:
+            names.append(k), halves.append(0), tensors.append(v)
+        elif v.shape[0] == 2 * total:
+            names += [k, k]
+            halves += [1, 2]
+            tensors += [v[:total], v[total:]]
+        else:
+            raise ValueError(f"`{k}`: batch {v.shape[0]} is neither the request's {total} nor twice it")
+    return names, halves, tensors
+
+
+def _merge_shards(names, halves, shards) -> dict:
+    """inverse of `_split_batched` on one rank's shards: the two halves of a stacked keyword are concatenated again"""
+    kw = {}
+    for k, half, t in zip(names, halves, shards):
+        kw[k] = torch.cat([kw[k], t]) if half == 2 else t
+    return kw
+
+
+def sharded_call(pipe, batched: Optional[dict], device, seeds: Optional[Sequence[int]] = None, src: int = 0,
+                 group=None, **common) -> Optional[torch.Tensor]:
+    """One request batch over all ranks: rank `src` passes `batched` = {`__call__` keyword: full-batch tensor [total, ...]}
+    (image, mask, prompt_embeds, negative_prompt_embeds, control_image, ...; the other ranks pass None), every rank
+    passes the same `common` keywords (height, width, num_inference_steps, guidance_scale, output_type = "uint8" |
+    "latent" | "pt", ...). Each rank runs `pipe(...)` on its contiguous shard — no collective inside the call — and rank
+    `src` gets the images of the whole batch in request order (others None). `seeds[i]` seeds the generator of GLOBAL
+    image i, so the result does not depend on the number of ranks. A rank whose shard is empty skips the call.
+    Keywords whose batch is 2 x total (the BrushNet pipeline's `prompt_embedsU` = [negative; positive]) are split per
+    half."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if rank == src:
+        if not batched:
+            raise ValueError("rank `src` must pass the batched keywords")
+        total = int((batched["image"] if "image" in batched else next(iter(batched.values()))).shape[0])
+        names, halves, tensors = _split_batched(batched, total)
+        head = [(names, halves, total, None if seeds is None else [int(s) for s in seeds])]
+        if seeds is not None and len(seeds) != total:
+            raise ValueError(f"{len(seeds)} seeds for {total} images")
+    else:
+        tensors, head = None, [None]
+    dist.broadcast_object_list(head, src=src, group=group)
+    names, halves, total, seed_list = head[0]
+    shards = scatter_batch(tensors, device, src=src, group=group)
+    kw = _merge_shards(names, halves, shards)
+    s, e = shard_ranges(total, world)[rank]
+    out = None
+    if e > s:
+        if seed_list is not None:
+            common = dict(common, generator=[torch.Generator().manual_seed(seed_list[i]) for i in range(s, e)])
+        res = pipe(**kw, **common)
+        out = res.images if hasattr(res, "images") else res[0]
+        if not torch.is_tensor(out):
+            raise TypeError("sharded_call gathers tensors: use output_type 'uint8', 'pt' or 'latent'")
+    # ranks without a request take the trailing shape / dtype of the result from one that has it
+    meta = [None] * world
+    dist.all_gather_object(meta, None if out is None else (tuple(out.shape[1:]), out.dtype), group=group)
+    have = [m for m in meta if m is not None]
+    if not have:
+        return None
+    if out is None:
+        out = torch.empty((0,) + have[0][0], dtype=have[0][1], device=device)
+    return gather_batch(out.contiguous(), total, dst=src, group=group)
