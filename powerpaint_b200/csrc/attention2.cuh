@@ -297,6 +297,20 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
                     m_ref = mnew;
                 }
             } while (redo);
+            // The LAST block of the three-buffer instantiation: a warp can finish block nkv - 1 while a slower warp of its
+            // group still holds back PV(nkv - 2); bar_pv_done would then be two phases short of the parity the epilogue
+            // waits for, and that wait would pass at once (a parity wait cannot tell "two behind" from "done") — O read
+            // without the last two key blocks. Here, between the score wait and this warp's own arrival, the barrier is
+            // at most one phase short, so the wait is exact; the block's exponentials have just given PV(nkv - 2)
+            // ~3000 cycles to retire, so it rarely spins. It is the wait of the rescale path below, which
+            // test_attention_large_logits takes on its last block. With two score buffers S(k + 2) needs PV(k), so no
+            // warp gets that far ahead. (tests/test_attention_protocol_model.py explores every interleaving.)
+            if constexpr (NBUF == 3) {
+                if (j == nkv - 1 && j > 0) {
+                    mbar_wait(bar_pv_done(t), (j - 1) & 1);
+                    tc_fence_after();
+                }
+            }
             if (__any_sync(0xffffffffu, alpha != 1.f)) {
                 if (j > 0) {
                     mbar_wait(bar_pv_done(t), (j - 1) & 1);  // O holds blocks < j
