@@ -253,6 +253,14 @@ def test_every_interleaving_hands_over_complete_data(NBUF, S, W, nkv):
     assert n > 100
 
 
+@pytest.mark.skipif(os.environ.get("PP_SLOW_TESTS") != "1", reason="~2 min: set PP_SLOW_TESTS=1")
+def test_the_kernels_own_configuration():
+    """attn2_kernel<3,1,4> as it is launched: three score buffers, four ring stages, four warps per tile (1.4 M states),
+    and four key blocks on a two-stage ring (1.1 M states)"""
+    assert explore(3, 3, 4, 4, allow_rescale=False, max_states=20_000_000) > 1_000_000
+    assert explore(4, 3, 2, 4, allow_rescale=False, max_states=20_000_000) > 1_000_000
+
+
 def test_the_unguarded_epilogue_aliases():
     """the protocol as measured in round 2 (no wait on the last block): the epilogue's parity wait passes two phases
     early when a warp runs a block ahead at the end — three score buffers only"""
