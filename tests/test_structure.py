@@ -98,3 +98,47 @@ def test_safetensors_load_model_like_the_app(tmp_path):
         assert m.generation > before
         got = m.state_dict()
         assert all(torch.equal(got[k].float(), v) for k, v in sd.items())
+
+
+def test_every_kernel_waits_for_its_predecessor_grid():
+    """Every launch carries the programmatic-stream-serialization attribute, so a kernel may start while its predecessor
+    drains; `griddepcontrol.wait` (pdl_wait) is what orders its memory accesses after the predecessor's. The planner's
+    buffer recycling (a block handed to a later writer once its last reader has been RECORDED) additionally needs the
+    order to be transitive: kernel N + 1 waits for N only, so N itself must have waited for N - 1. Hence: every
+    __global__ function calls pdl_wait(), and before anything that could return."""
+    import glob
+    import os
+    import re
+
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "powerpaint_b200", "csrc")
+    seen = 0
+    for path in sorted(glob.glob(os.path.join(root, "*.cu")) + glob.glob(os.path.join(root, "*.cuh"))):
+        with open(path) as f:
+            src = f.read()
+        for m in re.finditer(r"__global__[^;{]*?\(", src):
+            i = src.find("{", m.end())
+            depth, j = 0, i
+            while True:
+                depth += (src[j] == "{") - (src[j] == "}")
+                if depth == 0:
+                    break
+                j += 1
+            body = src[i:j]
+            seen += 1
+            k = body.find("pdl_wait()")
+            assert k >= 0, f"{os.path.basename(path)}: a kernel near offset {m.start()} never calls pdl_wait()"
+            head = re.sub(r"//[^\n]*", "", body[:k])
+            while True:  # lambda bodies (address helpers) return values, not the kernel
+                lm = re.search(r"\[[&=]?\]\s*\([^)]*\)\s*(?:->\s*[\w:<>*& ]+?)?\s*\{", head)
+                if not lm:
+                    break
+                d, e = 0, lm.end() - 1
+                while e < len(head):
+                    d += (head[e] == "{") - (head[e] == "}")
+                    if d == 0:
+                        break
+                    e += 1
+                head = head[:lm.start()] + head[e + 1:]
+            assert "return" not in head, \
+                f"{os.path.basename(path)}: a kernel near offset {m.start()} can return before pdl_wait()"
+    assert seen >= 20
