@@ -36,6 +36,12 @@
 #ifndef ATT2_STAGGER
 #define ATT2_STAGGER 0
 #endif
+// 1: on the last key block the three-buffer instantiation waits for PV(nkv - 2) before it hands over P(nkv - 1), which
+// makes the epilogue's parity wait exact (see the softmax loop). 0 = the kernel as measured in round 2 (A/B only: that
+// kernel can read O two PV products early when a warp runs a key block ahead at the very end).
+#ifndef ATT2_FINAL_GUARD
+#define ATT2_FINAL_GUARD 1
+#endif
 
 namespace pp {
 
@@ -305,7 +311,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn2_kernel(const __grid_con
             // ~3000 cycles to retire, so it rarely spins. It is the wait of the rescale path below, which
             // test_attention_large_logits takes on its last block. With two score buffers S(k + 2) needs PV(k), so no
             // warp gets that far ahead. (tests/test_attention_protocol_model.py explores every interleaving.)
-            if constexpr (NBUF == 3) {
+            if constexpr (NBUF == 3 && ATT2_FINAL_GUARD != 0) {
                 if (j == nkv - 1 && j > 0) {
                     mbar_wait(bar_pv_done(t), (j - 1) & 1);
                     tc_fence_after();

@@ -306,8 +306,10 @@ def test_model_matches_the_source():
         "issue_s(k + NBUF);",
         "mbar_wait(bar_s_full(buf), (k / NBUF) & 1);",
         "mbar_wait(bar_pv_done(t), (j - 1) & 1);",
-        "if constexpr (NBUF == 3) {\n                if (j == nkv - 1 && j > 0) {\n                    mbar_wait(bar_pv_done(t), "
+        "if constexpr (NBUF == 3 && ATT2_FINAL_GUARD != 0) {\n                if (j == nkv - 1 && j > 0) {\n                    mbar_wait("
+        "bar_pv_done(t), "
         "(j - 1) & 1);",
+        "#define ATT2_FINAL_GUARD 1",
         "if (lane_id() == 0) mbar_arrive(bar_p_full(t, j));",
         "mbar_wait(bar_pv_done(t), (nkv - 1) & 1);",
     ]:

@@ -101,8 +101,9 @@ def test_safetensors_load_model_like_the_app(tmp_path):
 
 
 def test_every_kernel_waits_for_its_predecessor_grid():
-    """Every launch carries the programmatic-stream-serialization attribute, so a kernel may start while its predecessor
-    drains; `griddepcontrol.wait` (pdl_wait) is what orders its memory accesses after the predecessor's. The planner's
+    """With PP_B200_PDL=1 every launch carries the programmatic-stream-serialization attribute (off by default: measured
+    slower), so a kernel may start while its predecessor drains; `griddepcontrol.wait` (pdl_wait) is then what orders
+    its memory accesses after the predecessor's. The planner's
     buffer recycling (a block handed to a later writer once its last reader has been RECORDED) additionally needs the
     order to be transitive: kernel N + 1 waits for N only, so N itself must have waited for N - 1. Hence: every
     __global__ function calls pdl_wait(), and before anything that could return."""
